@@ -1,0 +1,173 @@
+/*
+ * ldsr_b200.h -- C ABI of the B200-native batched EM engine for ldsr's LDS model.
+ *
+ * Model (reference: vignettes/ldsr.Rmd:25-33, src/EM.cpp:20 -- scalar state, scalar output):
+ *     x[t+1] = A x[t] + B u[t] + w[t],  w ~ N(0,Q)
+ *     y[t]   = C x[t] + D v[t] + e[t],  e ~ N(0,R)
+ *
+ * This library replaces, as ONE batched call each, what the reference does one fit at a time
+ * through its Rcpp `.Call` entry points (src/RcppExports.cpp:133-136) fanned out by R's
+ * foreach (R/LDS_reconstruction.R:46, :242, :373-381):
+ *
+ *     reference entry point (file:line)                     replaced by
+ *     ----------------------------------------------------  -------------------------------
+ *     _ldsr_LDS_EM          src/RcppExports.cpp:40-53       ldsr_em_batch / ldsr_plan_em
+ *       + LDS_EM_restart    R/LDS_reconstruction.R:42-62      (restart fan-out + selection)
+ *       + one_lds_cv/cvLDS  R/LDS_reconstruction.R:270-285,     (hold-out folds = groups)
+ *                             :372-382
+ *     _ldsr_Kalman_smoother src/RcppExports.cpp:11-23       ldsr_smoother_batch
+ *     _ldsr_Mstep           src/RcppExports.cpp:26-37       ldsr_mstep_batch
+ *     _ldsr_propagate       src/RcppExports.cpp:56-68       ldsr_propagate_batch
+ *     one_LDS_rep / LDS_rep R/stochastics.R:18-63           ldsr_rep_batch
+ *
+ * Conventions
+ *   - All numerics are IEEE FP64 on the GPU.  There is NO CPU fallback: without a CUDA device
+ *     every compute entry point returns LDSR_ERR_CUDA.
+ *   - theta is flat, in the reference's own vector order (R/LDS_GA.R:6-16):
+ *         [A, B_1..B_p, C, D_1..D_q, Q, R, mu1, V1]          length p+q+6
+ *   - u is p x T, v is q x T, both COLUMN-major exactly as R stores them (the p-vector of one
+ *     time step is contiguous: u[t*p + j]); y has T entries with NaN / NA_real_ = missing.
+ *     +-Inf in y is rejected (LDSR_ERR_ARG): the reference treats it as observed in the filter
+ *     and as missing in the likelihood (EM.cpp:61 vs :113), which is garbage either way.
+ *   - u == NULL (v == NULL) replaces the reference's `matrix(0)` one-column sentinel
+ *     (EM.cpp:50,71,157,189; R/LDS_reconstruction.R:131-136): the input term is dropped and
+ *     B (D) is returned as zeros.  p (q) still gives the length of B (D) inside theta.
+ *   - Every function returns an LDSR_* code; on error a message is written to errbuf (if given).
+ *     Nothing is thrown across the ABI, nothing is retained after return except through an
+ *     explicit ldsr_plan / ldsr_ctx handle.  The caller owns every buffer it passes.
+ *   - Thread-safety: a ctx/plan must be used from one thread at a time.  Worker threads (one per
+ *     GPU) are internal and never call back into the host language; the optional poll callback
+ *     runs on the CALLING thread (so an R shim can run R_CheckUserInterrupt there).
+ */
+#ifndef LDSR_B200_H
+#define LDSR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDSR_ABI_VERSION 1
+
+/* return codes */
+#define LDSR_OK 0
+#define LDSR_ERR_ARG 1         /* bad argument (message says which) */
+#define LDSR_ERR_CUDA 2        /* CUDA runtime / no device / out of memory */
+#define LDSR_ERR_INTERRUPTED 3 /* poll callback asked to stop */
+#define LDSR_ERR_UNSUPPORTED 4 /* p or q beyond LDSR_MAX_PQ */
+
+/* per-fit status written to ldsr_em_result.status */
+#define LDSR_FIT_OK 0
+#define LDSR_FIT_SINGULAR 1  /* Gram block (u u' or v v' over the fit's steps) not invertible:
+                                the reference's arma::inv would throw (EM.cpp:166,198) */
+#define LDSR_FIT_NONFINITE 2 /* final log-likelihood is NaN/Inf (fit ran to niter) */
+
+#define LDSR_MAX_PQ 32 /* largest supported nrow(u), nrow(v) */
+
+/* ---- problem description (all HOST pointers) --------------------------------------------- */
+typedef struct {
+    /* series: one (y,u,v) triple.  LDS_reconstruction/cvLDS with a list of u/v (ensemble) or a
+     * multi-station job has several. */
+    int n_series;
+    const int *T;             /* [n_series] time steps (>= 2)                               */
+    const int *p;             /* [n_series] length of B                                      */
+    const int *q;             /* [n_series] length of D                                      */
+    const double *const *y;   /* [n_series] -> T doubles, NaN = missing                      */
+    const double *const *u;   /* [n_series] -> p*T doubles column-major, or NULL             */
+    const double *const *v;   /* [n_series] -> q*T doubles column-major, or NULL             */
+    /* groups: one (series, hold-out fold).  The fits of a group compete in the
+     * LDS_EM_restart selection (R/LDS_reconstruction.R:50-58).  held_idx lists the 0-based
+     * time steps forced to missing for the group (`y[instPeriod][z] <- NA`, :274), CSR. */
+    int n_groups;
+    const int *group_series;  /* [n_groups]                                                  */
+    const int *held_ptr;      /* [n_groups+1], may be NULL when no group holds anything out  */
+    const int *held_idx;      /* [held_ptr[n_groups]]                                        */
+    /* fits: one EM run from one initial theta.  Fits of one group must be contiguous and
+     * groups must appear in increasing order (fit_group non-decreasing). */
+    int n_fits;
+    const int *fit_group;     /* [n_fits]                                                    */
+    const double *theta0;     /* [n_fits * theta_stride] flat thetas                         */
+    int theta_stride;         /* >= max(p+q+6) over series                                   */
+} ldsr_batch;
+
+/* ---- EM results (HOST pointers; any pointer may be NULL = not wanted) ------------------- */
+typedef struct {
+    double *theta;   /* [n_fits * theta_stride] theta the LAST E-step ran with (EM.cpp:276)  */
+    double *lik;     /* [n_fits] final standardised log-likelihood (NaN if status==SINGULAR) */
+    int *iters;      /* [n_fits] number of E-steps = length(liks) of the reference           */
+    int *status;     /* [n_fits] LDSR_FIT_*                                                  */
+    double *liks;    /* [n_fits * niter] likelihood trace, NaN-padded                        */
+    int *best;       /* [n_groups] selected fit (index into the fit table), -1 if none       */
+    /* smoothed trajectories of each group's selected fit (fit$X, $Y, $V, $J of the winner),
+     * row g starts at traj_ptr[g] where traj_ptr is the exclusive prefix sum of T[series(g)].
+     * For groups with best == -1 the rows are NaN. */
+    double *X, *Y, *V, *J;
+} ldsr_em_result;
+
+typedef int (*ldsr_poll_fn)(void *arg); /* return nonzero to abort; called between chunks */
+
+typedef struct {
+    int n_devices;       /* 0 = all visible devices (never more than n_groups)               */
+    const int *devices;  /* [n_devices] CUDA ordinals, NULL = 0..n_devices-1                 */
+    int chunk_iters;     /* EM iterations per kernel launch between compactions; 0 = 100,
+                            the reference's interrupt-poll cadence (EM.cpp:261)             */
+    ldsr_poll_fn poll;   /* may be NULL                                                      */
+    void *poll_arg;
+    int variant;         /* 0 = auto; kernel-variant override for testing, see DESIGN.md     */
+    int trace_liks;      /* ldsr_plan_em only: record the likelihood trace so that
+                            ldsr_plan_fetch can return liks (ldsr_em_batch infers it from
+                            out->liks)                                                       */
+} ldsr_options;
+
+/* ---- context: owns per-device streams and reusable device/pinned arenas ------------------ */
+typedef struct ldsr_ctx ldsr_ctx;
+int ldsr_ctx_create(int n_devices, const int *devices, ldsr_ctx **out, char *errbuf, int errlen);
+void ldsr_ctx_destroy(ldsr_ctx *ctx);
+int ldsr_device_count(void); /* 0 when there is no usable CUDA device */
+int ldsr_abi_version(void);
+
+/* ---- the hot path: batched LDS_EM + restart selection ---------------------------------- */
+/* Host buffers in, host buffers out; shards groups across the ctx's devices (one worker
+ * thread + stream per device, no collective).  ctx may be NULL (a temporary one is made). */
+int ldsr_em_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int niter, double tol,
+                  const ldsr_options *opt, ldsr_em_result *out, char *errbuf, int errlen);
+
+/* Device-resident form: a plan holds the packed batch in HBM on ONE device. */
+typedef struct ldsr_plan ldsr_plan;
+int ldsr_plan_create(const ldsr_batch *batch, int device, ldsr_plan **out, char *errbuf, int errlen);
+/* Runs EM for every fit from the plan's resident theta0 on `stream` (a cudaStream_t, NULL =
+ * the plan's own stream); blocks until the results are resident in HBM.  Launch statistics
+ * (kernel launches issued, EM chunks) are returned through the optional int[4] `stats`:
+ * {kernel launches, chunks, total E-steps executed (all fits), reserved}. */
+int ldsr_plan_em(ldsr_plan *plan, int niter, double tol, const ldsr_options *opt, void *stream,
+                 long long *stats, char *errbuf, int errlen);
+int ldsr_plan_set_theta0(ldsr_plan *plan, const double *theta0_host, char *errbuf, int errlen);
+int ldsr_plan_fetch(ldsr_plan *plan, ldsr_em_result *out, char *errbuf, int errlen);
+void ldsr_plan_destroy(ldsr_plan *plan);
+
+/* ---- single-step entry points (the reference's other .Call functions, batched) ---------- */
+/* Kalman_smoother for every fit's theta0 on its group's (held-out) y.  X,Y,V,J are
+ * [sum over fits of T] with fit f's row at fit_ptr[f] (prefix sum of T[series(f)]);
+ * stdlik as in EM.cpp:22,124. */
+int ldsr_smoother_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int stdlik, double *X, double *Y,
+                        double *V, double *J, double *lik, char *errbuf, int errlen);
+/* Mstep: X,V,J rows (same layout as above) -> theta_out [n_fits*theta_stride], status. */
+int ldsr_mstep_batch(ldsr_ctx *ctx, const ldsr_batch *batch, const double *X, const double *V,
+                     const double *J, double *theta_out, int *status, char *errbuf, int errlen);
+/* propagate (EM.cpp:295-356): open-loop X,Y,V rows and lik for every fit's theta0. */
+int ldsr_propagate_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int stdlik, double *X, double *Y,
+                         double *V, double *lik, char *errbuf, int errlen);
+
+/* LDS_rep (R/stochastics.R:18-63): n_reps stochastic replicates of ONE model over n steps.
+ * Noise: if z != NULL it holds n_reps*(1+2n) standard-normal draws in the reference's draw order
+ * per replicate (x1, then n state draws, then n observation draws) -- this is the exact-parity
+ * path; else draws come from a counter-based generator keyed by (seed, replicate, index).
+ * Outputs are [n_reps*n] replicate-major (the reference's rbindlist order); any may be NULL. */
+int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n,
+                   int p, int q, int n_reps, const double *z, unsigned long long seed, double mu,
+                   int exp_trans, double *simX, double *simY, double *simQ, char *errbuf,
+                   int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDSR_B200_H */

@@ -1,0 +1,315 @@
+"""ctypes binding of libldsr_b200.so (include/ldsr_b200.h).  No fallback of any kind: if the
+library is missing or no CUDA device is present, calls raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libldsr_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+OK, ERR_ARG, ERR_CUDA, ERR_INTERRUPTED, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+FIT_OK, FIT_SINGULAR, FIT_NONFINITE = 0, 1, 2
+
+# every symbol include/ldsr_b200.h declares (checked by tests/test_abi_symbols.py)
+EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy",
+           "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
+           "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
+           "ldsr_propagate_batch", "ldsr_rep_batch")
+
+
+class LdsrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ldsr_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_series", C.c_int), ("T", _ip), ("p", _ip), ("q", _ip),
+                ("y", C.POINTER(_dp)), ("u", C.POINTER(_dp)), ("v", C.POINTER(_dp)),
+                ("n_groups", C.c_int), ("group_series", _ip), ("held_ptr", _ip), ("held_idx", _ip),
+                ("n_fits", C.c_int), ("fit_group", _ip), ("theta0", _dp), ("theta_stride", C.c_int)]
+
+
+class EmResult(C.Structure):
+    _fields_ = [("theta", _dp), ("lik", _dp), ("iters", _ip), ("status", _ip), ("liks", _dp),
+                ("best", _ip), ("X", _dp), ("Y", _dp), ("V", _dp), ("J", _dp)]
+
+
+POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Options(C.Structure):
+    _fields_ = [("n_devices", C.c_int), ("devices", _ip), ("chunk_iters", C.c_int),
+                ("poll", POLL_FN), ("poll_arg", C.c_void_p), ("variant", C.c_int),
+                ("trace_liks", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA shared library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise LdsrError(ERR_CUDA, "%s not built: run `python -m ldsr_b200.build` "
+                                      "(or __graft_entry__.build())" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        for name in EXPORTS:
+            getattr(L, name).restype = C.c_int
+        L.ldsr_ctx_destroy.restype = None
+        L.ldsr_plan_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def device_count():
+    return lib().ldsr_device_count()
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _colmajor(m):
+    """R-style [p, T] matrix -> flat column-major copy (time step contiguous)."""
+    if m is None:
+        return None, 0
+    m = np.asarray(m, dtype=np.float64)
+    if m.ndim == 1:
+        m = m[None, :]
+    return np.ascontiguousarray(m.T).ravel(), m.shape[0]
+
+
+class PackedBatch:
+    """Keeps every numpy buffer a C `ldsr_batch` points to alive."""
+
+    def __init__(self, series, group_series, held, fit_group, theta0):
+        ns = len(series)
+        self.ys, self.us, self.vs = [], [], []
+        Ts, ps, qs = [], [], []
+        for s in series:
+            y = np.ascontiguousarray(s["y"], dtype=np.float64).ravel()
+            uf, pu = _colmajor(s.get("u"))
+            vf, qv = _colmajor(s.get("v"))
+            if uf is not None and uf.size != pu * y.size:
+                raise ValueError("u must have %d columns" % y.size)
+            if vf is not None and vf.size != qv * y.size:
+                raise ValueError("v must have %d columns" % y.size)
+            self.ys.append(y)
+            self.us.append(uf)
+            self.vs.append(vf)
+            Ts.append(y.size)
+            ps.append(int(s.get("p", pu)))
+            qs.append(int(s.get("q", qv)))
+        self.T = np.asarray(Ts, dtype=np.int32)
+        self.p = np.asarray(ps, dtype=np.int32)
+        self.q = np.asarray(qs, dtype=np.int32)
+        PP = _dp * ns
+        null = C.cast(None, _dp)
+        self.yp = PP(*[_d(a) for a in self.ys])
+        self.up = PP(*[_d(a) if a is not None else null for a in self.us])
+        self.vp = PP(*[_d(a) if a is not None else null for a in self.vs])
+        self.group_series = np.ascontiguousarray(group_series, dtype=np.int32)
+        ng = self.group_series.size
+        self.held_ptr = self.held_idx = None
+        if held is not None:
+            hp = np.zeros(ng + 1, dtype=np.int32)
+            hp[1:] = np.cumsum([len(h) for h in held])
+            self.held_ptr = hp
+            self.held_idx = (np.concatenate([np.asarray(h, dtype=np.int32).ravel() for h in held])
+                             if hp[-1] > 0 else np.zeros(1, dtype=np.int32)).astype(np.int32)
+        self.fit_group = np.ascontiguousarray(fit_group, dtype=np.int32)
+        self.theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+        if self.theta0.ndim != 2 or self.theta0.shape[0] != self.fit_group.size:
+            raise ValueError("theta0 must be [n_fits, theta_stride]")
+        self.n_fits = self.fit_group.size
+        self.n_groups = ng
+        self.stride = self.theta0.shape[1]
+        self.traj_ptr = np.zeros(ng + 1, dtype=np.int64)
+        self.traj_ptr[1:] = np.cumsum(self.T[self.group_series])
+        self.fit_ptr = np.zeros(self.n_fits + 1, dtype=np.int64)
+        self.fit_ptr[1:] = np.cumsum(self.T[self.group_series[self.fit_group]])
+        self.c = Batch(ns, _i(self.T), _i(self.p), _i(self.q), self.yp, self.up, self.vp,
+                       ng, _i(self.group_series), _i(self.held_ptr), _i(self.held_idx),
+                       self.n_fits, _i(self.fit_group), _d(self.theta0), self.stride)
+
+
+def _check(rc, err):
+    if rc != OK:
+        raise LdsrError(rc, err.value.decode("utf-8", "replace"))
+
+
+def _options(n_devices=0, devices=None, chunk_iters=0, poll=None, trace_liks=False, keep=None):
+    o = Options()
+    o.n_devices = int(n_devices)
+    if devices is not None:
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        keep.append(dv)
+        o.devices = _i(dv)
+        o.n_devices = dv.size
+    o.chunk_iters = int(chunk_iters)
+    if poll is not None:
+        cb = POLL_FN(lambda _arg: int(bool(poll())))
+        keep.append(cb)
+        o.poll = cb
+    o.trace_liks = int(bool(trace_liks))
+    return o
+
+
+class EmOutputs:
+    """numpy buffers behind an ldsr_em_result."""
+
+    def __init__(self, pb, niter, want_liks=False, want_traj=True):
+        nf, ng = pb.n_fits, pb.n_groups
+        self.theta = np.full((nf, pb.stride), np.nan)
+        self.lik = np.full(nf, np.nan)
+        self.iters = np.zeros(nf, dtype=np.int32)
+        self.status = np.zeros(nf, dtype=np.int32)
+        self.best = np.full(ng, -1, dtype=np.int32)
+        self.liks = np.full((nf, niter), np.nan) if want_liks else None
+        tot = int(pb.traj_ptr[-1])
+        self.X, self.Y, self.V, self.J = ((np.full(tot, np.nan) for _ in range(4)) if want_traj
+                                          else (None,) * 4)
+        self.c = EmResult(_d(self.theta), _d(self.lik), _i(self.iters), _i(self.status),
+                          _d(self.liks), _i(self.best), _d(self.X), _d(self.Y), _d(self.V), _d(self.J))
+
+    def as_dict(self, pb):
+        d = dict(theta=self.theta, lik=self.lik, iters=self.iters, status=self.status,
+                 best=self.best, traj_ptr=pb.traj_ptr)
+        if self.liks is not None:
+            d["liks"] = self.liks
+        if self.X is not None:
+            d.update(X=self.X, Y=self.Y, V=self.V, J=self.J)
+        return d
+
+
+def em_batch(series, group_series, held, fit_group, theta0, niter=1000, tol=1e-5, n_devices=1,
+             devices=None, chunk_iters=0, poll=None, want_liks=False, want_traj=True, ctx=None):
+    """ldsr_em_batch with host (numpy) buffers.  Same argument shapes as oracle.em_batch."""
+    pb = PackedBatch(series, group_series, held, fit_group, theta0)
+    out = EmOutputs(pb, niter, want_liks, want_traj)
+    keep = []
+    opt = _options(n_devices, devices, chunk_iters, poll, keep=keep)
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_em_batch(ctx, C.byref(pb.c), int(niter), C.c_double(tol), C.byref(opt),
+                             C.byref(out.c), err, 512)
+    _check(rc, err)
+    return out.as_dict(pb)
+
+
+class Plan:
+    """Device-resident batch (ldsr_plan_*): inputs are uploaded once, EM runs from HBM."""
+
+    def __init__(self, series, group_series, held, fit_group, theta0, device=0):
+        self.pb = PackedBatch(series, group_series, held, fit_group, theta0)
+        self.h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib().ldsr_plan_create(C.byref(self.pb.c), int(device), C.byref(self.h), err, 512)
+        _check(rc, err)
+        self.niter = None
+
+    def em(self, niter=1000, tol=1e-5, chunk_iters=0, stream=None, trace_liks=False, poll=None):
+        keep = []
+        opt = _options(chunk_iters=chunk_iters, poll=poll, trace_liks=trace_liks, keep=keep)
+        stats = (C.c_longlong * 4)()
+        err = C.create_string_buffer(512)
+        rc = lib().ldsr_plan_em(self.h, int(niter), C.c_double(tol), C.byref(opt),
+                                C.c_void_p(stream or 0), stats, err, 512)
+        _check(rc, err)
+        self.niter = niter
+        self.trace = bool(trace_liks)
+        return dict(launches=stats[0], chunks=stats[1], esteps=stats[2])
+
+    def set_theta0(self, theta0):
+        th = np.ascontiguousarray(theta0, dtype=np.float64)
+        assert th.shape == self.pb.theta0.shape
+        err = C.create_string_buffer(512)
+        _check(lib().ldsr_plan_set_theta0(self.h, _d(th), err, 512), err)
+
+    def fetch(self, want_traj=True):
+        out = EmOutputs(self.pb, self.niter, self.trace, want_traj)
+        err = C.create_string_buffer(512)
+        _check(lib().ldsr_plan_fetch(self.h, C.byref(out.c), err, 512), err)
+        return out.as_dict(self.pb)
+
+    def close(self):
+        if self.h:
+            lib().ldsr_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _rows(flat, ptr):
+    return [flat[ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+
+
+def smoother_batch(series, group_series, held, fit_group, theta, stdlik=True, ctx=None):
+    pb = PackedBatch(series, group_series, held, fit_group, theta)
+    tot = int(pb.fit_ptr[-1])
+    X, Y, V, J = (np.empty(tot) for _ in range(4))
+    lik = np.empty(pb.n_fits)
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_smoother_batch(ctx, C.byref(pb.c), int(stdlik), _d(X), _d(Y), _d(V), _d(J), _d(lik), err, 512)
+    _check(rc, err)
+    return dict(X=_rows(X, pb.fit_ptr), Y=_rows(Y, pb.fit_ptr), V=_rows(V, pb.fit_ptr),
+                J=_rows(J, pb.fit_ptr), lik=lik)
+
+
+def mstep_batch(series, group_series, held, fit_group, X, V, J, theta_stride, ctx=None):
+    nf = len(fit_group)
+    pb = PackedBatch(series, group_series, held, fit_group, np.zeros((nf, theta_stride)))
+    Xf, Vf, Jf = (np.ascontiguousarray(np.concatenate([np.ravel(r) for r in a]), dtype=np.float64)
+                  for a in (X, V, J))
+    assert Xf.size == pb.fit_ptr[-1]
+    th = np.full((nf, theta_stride), np.nan)
+    st = np.zeros(nf, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_mstep_batch(ctx, C.byref(pb.c), _d(Xf), _d(Vf), _d(Jf), _d(th), _i(st), err, 512)
+    _check(rc, err)
+    return dict(theta=th, status=st)
+
+
+def propagate_batch(series, group_series, held, fit_group, theta, stdlik=True, ctx=None):
+    pb = PackedBatch(series, group_series, held, fit_group, theta)
+    tot = int(pb.fit_ptr[-1])
+    X, Y, V = (np.empty(tot) for _ in range(3))
+    lik = np.empty(pb.n_fits)
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_propagate_batch(ctx, C.byref(pb.c), int(stdlik), _d(X), _d(Y), _d(V), _d(lik), err, 512)
+    _check(rc, err)
+    return dict(X=_rows(X, pb.fit_ptr), Y=_rows(Y, pb.fit_ptr), V=_rows(V, pb.fit_ptr), lik=lik)
+
+
+def rep_batch(theta, u, v, n, n_reps, z=None, seed=0, mu=0.0, exp_trans=True, p=None, q=None,
+              want=("simX", "simY", "simQ"), ctx=None):
+    uf, pu = _colmajor(u)
+    vf, qv = _colmajor(v)
+    p = pu if p is None else p
+    q = qv if q is None else q
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    assert theta.size == p + q + 6
+    zz = None
+    if z is not None:
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        assert zz.size == n_reps * (1 + 2 * n)
+    outs = {k: (np.empty((n_reps, n)) if k in want else None) for k in ("simX", "simY", "simQ")}
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_rep_batch(ctx, _d(theta), _d(uf), _d(vf), int(n), int(p), int(q), int(n_reps), _d(zz),
+                              C.c_ulonglong(seed), C.c_double(mu), int(exp_trans), _d(outs["simX"]),
+                              _d(outs["simY"]), _d(outs["simQ"]), err, 512)
+    _check(rc, err)
+    return {k: v for k, v in outs.items() if v is not None}

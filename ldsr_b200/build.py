@@ -1,0 +1,69 @@
+"""Builds ldsr_b200/libldsr_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+One translation unit per padded input width PQ (kernels_inst.cu -DLDSR_PQ=n) plus the host/ABI
+unit; objects are compiled in parallel and linked with a static CUDA runtime so the library has
+no dependency beyond the driver.
+"""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+SO = os.path.join(HERE, "libldsr_b200.so")
+PQ_LIST = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 32)  # keep in sync with LDSR_PQ_LIST in ldsr_abi.cu
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
+
+
+def _sources():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files]
+    out.append(os.path.join(HERE, "..", "include", "ldsr_b200.h"))
+    return out
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def build(force=False, verbose=False, ptxas_info=False):
+    deps = _sources()
+    if not force and not _stale(SO, deps):
+        return SO
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    extra = ["-Xptxas", "-v"] if ptxas_info else []
+    for pq in PQ_LIST:
+        o = os.path.join(OBJ, "kernels_pq%d.o" % pq)
+        jobs.append((o, [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))
+    o_abi = os.path.join(OBJ, "ldsr_abi.o")
+    jobs.append((o_abi, [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, "ldsr_abi.cu"), "-o", o_abi]))
+    todo = [(o, c) for o, c in jobs if force or _stale(o, deps)]
+    logs = []
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        for out in ex.map(lambda j: _run(j[1]), todo):
+            logs.append(out)
+    objs = [o for o, _ in jobs]
+    logs.append(_run([NVCC, "-shared", "-o", SO] + objs + ["-cudart", "static", "-lpthread"]))
+    if verbose:
+        sys.stderr.write("".join(logs))
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))

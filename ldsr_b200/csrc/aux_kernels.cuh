@@ -1,0 +1,249 @@
+// aux_kernels.cuh -- set-up (hold-out masks, theta-independent Gram blocks), restart selection,
+// and the single-step batched kernels (Kalman_smoother, Mstep, propagate, LDS_rep).
+#pragma once
+#include "lds_math.cuh"
+
+namespace ldsr {
+
+// ------------------------------------------------------------------------------------------
+// Kalman_smoother for a list of jobs (EM.cpp:22-131), one lane per job, trajectories written to
+// global rows (X,Y,V,J of length T each).  Used for the winners after EM and for
+// ldsr_smoother_batch.  The filter pass parks Xu,Vu in the X,V rows; the backward pass then
+// overwrites them in place.
+// ------------------------------------------------------------------------------------------
+struct SmootherParams {
+    const SeriesDev *series;
+    const double *blobs;
+    const int *g_series;
+    const unsigned *masks;
+    const long long *g_mask_off;
+    const int *g_nobs;
+    int n_jobs;
+    const int *job_group;     // [n_jobs]
+    const int *job_theta;     // [n_jobs] row in theta (or -1: skip, rows become NaN)
+    const long long *job_row; // [n_jobs] offset of the job's output rows, in doubles
+    const double *theta;      // padded thetas
+    double *X, *Y, *V, *J, *lik;
+    int stdlik;
+};
+
+template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= P.n_jobs) return;
+    const int grp = P.job_group[job];
+    const SeriesDev S = P.series[P.g_series[grp]];
+    const int T = S.T;
+    const double *__restrict__ ys = P.blobs + S.blob_off + S.y_off;
+    const double *__restrict__ us = P.blobs + S.blob_off + S.u_off;
+    const double *__restrict__ vs = P.blobs + S.blob_off + S.v_off;
+    const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
+    double *X = P.X + P.job_row[job], *Y = P.Y + P.job_row[job], *V = P.V + P.job_row[job],
+           *J = P.J ? P.J + P.job_row[job] : nullptr;
+    if (P.job_theta[job] < 0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000ULL);
+        for (int t = 0; t < T; t++) {
+            X[t] = Y[t] = V[t] = nan;
+            if (J) J[t] = nan;
+        }
+        if (P.lik) P.lik[job] = nan;
+        return;
+    }
+    Theta<PQ> th;
+    load_theta<PQ>(th, P.theta + (size_t)P.job_theta[job] * theta_pad_len<PQ>());
+    const double A = th.A, A2 = th.A * th.A, Q = th.Q;
+    double Xp = th.mu1, Vp = th.V1, acc = 0.0;
+    for (int t = 0; t < T; t++) {
+        const bool obs = (mw[t >> 5] >> (t & 31)) & 1u;
+        double Xu = Xp, Vu = Vp;
+        if (obs) {
+            double dq, Sg;
+            measurement_update<PQ>(th, true, ys[t], vs + (size_t)t * PQ, Xp, Vp, Xu, Vu, dq, Sg);
+            acc += dq + log(Sg);
+        }
+        X[t] = Xu;
+        V[t] = Vu;
+        Xp = fma(A, Xu, dot_row<PQ>(th.B, us + (size_t)t * PQ));
+        Vp = fma(A2, Vu, Q);
+    }
+    if (P.lik) {
+        const double n = (double)P.g_nobs[grp];
+        double l = -0.5 * n * LOG_2PI - 0.5 * acc;
+        P.lik[job] = P.stdlik ? l / n : l;
+    }
+    // backward (EM.cpp:94-110)
+    {
+        const double VuT = V[T - 1];
+        if (J) J[T - 1] = VuT * A * (1.0 / fma(A2, VuT, Q)); // EM.cpp:98
+        Y[T - 1] = fma(th.C, X[T - 1], dot_row<PQ>(th.D, vs + (size_t)(T - 1) * PQ));
+    }
+    double Xs1 = X[T - 1], Vs1 = V[T - 1];
+    for (int t = T - 2; t >= 0; t--) {
+        const double Xu = X[t], Vu = V[t];
+        const double Xp1 = fma(A, Xu, dot_row<PQ>(th.B, us + (size_t)t * PQ));
+        const double Vp1 = fma(A2, Vu, Q);
+        const double Jt = Vu * A * (1.0 / Vp1);
+        const double Xs = fma(Jt, Xs1 - Xp1, Xu);
+        const double Vs = fma(Jt * (Vs1 - Vp1), Jt, Vu);
+        X[t] = Xs;
+        V[t] = Vs;
+        if (J) J[t] = Jt;
+        Y[t] = fma(th.C, Xs, dot_row<PQ>(th.D, vs + (size_t)t * PQ));
+        Xs1 = Xs;
+        Vs1 = Vs;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Mstep (EM.cpp:139-229) from caller-supplied smoothed rows X,V,J: one lane per fit gathers the
+// sums and calls the same mstep_from_stats the EM kernel uses.
+// ------------------------------------------------------------------------------------------
+struct MstepParams {
+    const SeriesDev *series;
+    const double *blobs;
+    const double *sconst;
+    const int *g_series;
+    const unsigned *masks;
+    const long long *g_mask_off;
+    const double *gconst;
+    const int *g_status;
+    int n_fits;
+    const int *f_group;
+    const long long *f_row;
+    const double *X, *V, *J;
+    double *theta_out;
+    int *status;
+};
+
+template <int PQ> __global__ void mstep_kernel(const MstepParams P) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P.n_fits) return;
+    const int grp = P.f_group[f];
+    const SeriesDev S = P.series[P.g_series[grp]];
+    const int T = S.T;
+    const double *__restrict__ ys = P.blobs + S.blob_off + S.y_off;
+    const double *__restrict__ us = P.blobs + S.blob_off + S.u_off;
+    const double *__restrict__ vs = P.blobs + S.blob_off + S.v_off;
+    const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
+    const double *X = P.X + P.f_row[f], *V = P.V + P.f_row[f], *J = P.J + P.f_row[f];
+    Stats<PQ> st;
+    st.zero();
+    for (int t = 0; t < T; t++) {
+        const double Xs = X[t], Vs = V[t];
+        if (t < T - 1) {
+            st.Tx1x = fma(X[t + 1], Xs, fma(V[t + 1], J[t], st.Tx1x));
+            st.Txx += fma(Xs, Xs, Vs);
+#pragma unroll
+            for (int k = 0; k < PQ; k++) {
+                st.Tx1u[k] = fma(X[t + 1], us[(size_t)t * PQ + k], st.Tx1u[k]);
+                st.Tux[k] = fma(us[(size_t)t * PQ + k], Xs, st.Tux[k]);
+            }
+        }
+        if ((mw[t >> 5] >> (t & 31)) & 1u) {
+            st.Syx = fma(ys[t], Xs, st.Syx);
+            st.Sxx += fma(Xs, Xs, Vs);
+#pragma unroll
+            for (int k = 0; k < PQ; k++) st.Sxv[k] = fma(Xs, vs[(size_t)t * PQ + k], st.Sxv[k]);
+        }
+    }
+    st.X0 = X[0];
+    st.V0 = V[0];
+    st.XT = X[T - 1];
+    st.VT = V[T - 1];
+    Theta<PQ> th;
+    mstep_from_stats<PQ>(st, P.gconst + (size_t)grp * gconst_stride(PQ), P.sconst + S.sconst_off, T, th);
+    store_theta<PQ>(th, P.theta_out + (size_t)f * theta_pad_len<PQ>());
+    P.status[f] = P.g_status[grp];
+}
+
+// ------------------------------------------------------------------------------------------
+// propagate (EM.cpp:295-356): open-loop prediction, one lane per job.
+// ------------------------------------------------------------------------------------------
+template <int PQ> __global__ void propagate_kernel(const SmootherParams P) {
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= P.n_jobs) return;
+    const int grp = P.job_group[job];
+    const SeriesDev S = P.series[P.g_series[grp]];
+    const int T = S.T;
+    const double *__restrict__ ys = P.blobs + S.blob_off + S.y_off;
+    const double *__restrict__ us = P.blobs + S.blob_off + S.u_off;
+    const double *__restrict__ vs = P.blobs + S.blob_off + S.v_off;
+    const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
+    double *X = P.X + P.job_row[job], *Y = P.Y + P.job_row[job], *V = P.V + P.job_row[job];
+    Theta<PQ> th;
+    load_theta<PQ>(th, P.theta + (size_t)P.job_theta[job] * theta_pad_len<PQ>());
+    const double A2 = th.A * th.A;
+    double Xp = th.mu1, Vp = th.V1, acc = 0.0;
+    for (int t = 0; t < T; t++) {
+        const double Yp = fma(th.C, Xp, dot_row<PQ>(th.D, vs + (size_t)t * PQ));
+        X[t] = Xp;
+        V[t] = Vp;
+        Y[t] = Yp;
+        if ((mw[t >> 5] >> (t & 31)) & 1u) {
+            const double delta = ys[t] - Yp, Sg = fma(th.C * Vp, th.C, th.R);
+            acc += delta / Sg * delta + log(Sg);
+        }
+        Xp = fma(th.A, Xp, dot_row<PQ>(th.B, us + (size_t)t * PQ));
+        Vp = fma(A2, Vp, th.Q);
+    }
+    const double n = (double)P.g_nobs[grp];
+    double l = -0.5 * n * LOG_2PI - 0.5 * acc;
+    P.lik[job] = P.stdlik ? l / n : l;
+}
+
+// ------------------------------------------------------------------------------------------
+// LDS_rep (R/stochastics.R:18-63): one lane per replicate.  The noise is either read from z
+// (n_reps x (1+2n), reference draw order) or generated from a counter-based generator
+// (splitmix64 -> Box-Muller) keyed by (seed, replicate, index).  Outputs are written
+// TIME-MAJOR into a [n][n_reps] staging layout so that warps store coalesced; the host-facing
+// layout (replicate-major) is produced by transpose_kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double counter_normal(unsigned long long seed, unsigned long long rep,
+                                                 unsigned long long idx) {
+    const unsigned long long k = splitmix64(seed ^ splitmix64(rep * 0xD1342543DE82EF95ULL + 1));
+    const unsigned long long a = splitmix64(k + 2 * idx), b = splitmix64(k + 2 * idx + 1);
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return sqrt(-2.0 * log(u1)) * c;
+}
+
+struct RepParams {
+    const double *theta; // padded, one model
+    const double *u, *v; // [n][PQ] padded, time-major (zeros when absent)
+    const double *z;     // optional caller noise [n_reps][1+2n]
+    unsigned long long seed;
+    int n, n_reps;
+    double mu;
+    int exp_trans;
+    double *simX, *simY, *simQ; // [n][n_reps] (time-major staging), any may be null
+};
+
+template <int PQ> __global__ void rep_kernel(const RepParams P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.n_reps) return;
+    Theta<PQ> th;
+    load_theta<PQ>(th, P.theta);
+    const double sQ = sqrt(th.Q), sR = sqrt(th.R), sV = sqrt(th.V1);
+    const int n = P.n;
+    const double *zr = P.z ? P.z + (size_t)r * (1 + 2 * n) : nullptr;
+    double x = (zr ? zr[0] : counter_normal(P.seed, r, 0)) * sV; // mean 0, not mu1 (stochastics.R:23)
+    for (int t = 0; t < n; t++) {
+        const double zq = zr ? zr[1 + t] : counter_normal(P.seed, r, 1 + t);
+        const double ze = zr ? zr[1 + n + t] : counter_normal(P.seed, r, 1 + n + t);
+        const double y = fma(th.C, x, dot_row<PQ>(th.D, P.v + (size_t)t * PQ)) + ze * sR;
+        const size_t o = (size_t)t * P.n_reps + r;
+        if (P.simX) P.simX[o] = x;
+        if (P.simY) P.simY[o] = y;
+        if (P.simQ) P.simQ[o] = P.exp_trans ? exp(y + P.mu) : y + P.mu;
+        x = fma(th.A, x, dot_row<PQ>(th.B, P.u + (size_t)t * PQ)) + zq * sQ;
+    }
+}
+
+} // namespace ldsr

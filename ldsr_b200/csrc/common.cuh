@@ -1,0 +1,74 @@
+// common.cuh -- device-side tables, PTX helpers (mbarrier + TMA bulk copy) shared by the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ldsr {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double LOG_2PI = 1.8378770664093454835606594728112; // log(2*pi), pi as in EM.cpp:3
+
+// One (y,u,v) triple, packed in HBM as a "blob" that one TMA bulk copy moves into shared memory:
+//   [ y : Ty doubles | u : T*PQ doubles, time-major, rows >= p zero | v : T*PQ (absent if same_uv) ]
+// PQ is the plan-wide padded input width (template parameter of the kernels).
+struct SeriesDev {
+    int T;
+    int p, q;            // lengths of B and D in the caller's theta
+    int has_u, has_v;    // 0 = the reference's matrix(0) sentinel (EM.cpp:71,77,157,189)
+    int same_uv;         // v is bit-identical to u: staged once
+    int y_off, u_off, v_off; // offsets inside the blob, in doubles
+    int blob_doubles;    // multiple of 2 (16-byte granularity of cp.async.bulk)
+    long long blob_off;  // offset of the blob in the blob arena, in doubles (even)
+    long long sconst_off; // -> TuuInv[PQ*PQ] in the constants arena
+    int fit_begin, fit_end; // this series' contiguous range in the (internally sorted) fit table
+    int n_seg_pad;       // unused padding
+};
+
+// per-group constants (theta-independent M-step blocks, EM.cpp:158,161 restricted to the group's
+// observed steps): [ Syy, n_obs, Syv[PQ], wy[PQ] = SvvInv*Syv, SvvInv[PQ*PQ] ]
+__host__ __device__ inline int gconst_stride(int pq) { return 2 + 2 * pq + pq * pq; }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    // make the initialised barrier visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// Stage `bytes` (multiple of 16) from global to shared with TMA bulk copies issued by one thread.
+// Pieces of <= 32 KB keep each transaction well inside the mbarrier tx-count range.
+__device__ __forceinline__ void stage_blob(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    mbar_arrive_expect_tx(bar, bytes);
+    const unsigned PIECE = 32768u;
+    for (unsigned off = 0; off < bytes; off += PIECE) {
+        unsigned n = bytes - off < PIECE ? bytes - off : PIECE;
+        bulk_g2s(static_cast<char *>(dst_smem) + off, static_cast<const char *>(src_gmem) + off, n, bar);
+    }
+}
+
+} // namespace ldsr

@@ -1,0 +1,297 @@
+// generic_kernels.cuh -- kernels that do not depend on the padded width PQ at compile time:
+// set-up (hold-out masks, theta-independent Gram blocks and their inverses), live-fit compaction,
+// CTA task list, restart selection, transposition.  Included by ldsr_abi.cu only.
+#pragma once
+#include "lds_math.cuh"
+
+namespace ldsr {
+
+// ------------------------------------------------------------------------------------------
+// In-place inverse of a symmetric positive-definite n x n matrix held in shared memory with
+// leading dimension ld, by Cholesky (one thread).  Returns false if a pivot is not > 0.
+// Stands in for the Gram-block part of arma::inv(P2)/inv(P4) (EM.cpp:166,198).
+// ------------------------------------------------------------------------------------------
+__device__ inline bool spd_inverse(double *a, int n, int ld, double *work /* n*n */) {
+    // a = L L'
+    for (int j = 0; j < n; j++) {
+        double d = a[j * ld + j];
+        for (int k = 0; k < j; k++) d -= a[j * ld + k] * a[j * ld + k];
+        if (!(d > 0.0) || !isfinite(d)) return false;
+        d = sqrt(d);
+        a[j * ld + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double s = a[i * ld + j];
+            for (int k = 0; k < j; k++) s -= a[i * ld + k] * a[j * ld + k];
+            a[i * ld + j] = s / d;
+        }
+    }
+    // work = inv(L) (lower)
+    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < n; i++) work[i * n + j] = 0.0;
+        work[j * n + j] = 1.0 / a[j * ld + j];
+        for (int i = j + 1; i < n; i++) {
+            double s = 0.0;
+            for (int k = j; k < i; k++) s -= a[i * ld + k] * work[k * n + j];
+            work[i * n + j] = s / a[i * ld + i];
+        }
+    }
+    // a = inv(L)' inv(L)
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+            for (int k = i; k < n; k++) s += work[k * n + i] * work[k * n + j];
+            a[i * ld + j] = s;
+            a[j * ld + i] = s;
+        }
+    return true;
+}
+
+struct SetupParams {
+    const SeriesDev *series;
+    const double *blobs;
+    int n_series, n_groups;
+    const int *g_series;
+    const int *held_ptr; // may be null
+    const int *held_idx;
+    unsigned *masks;
+    const long long *g_mask_off;
+    double *gconst;  // per group
+    double *sconst;  // per series (at SeriesDev.sconst_off)
+    int *g_status;
+    int *g_nobs;
+    int pq;
+};
+
+// One block per group (blockIdx < n_groups) or per series (the rest).
+//  group : observed-bit mask = finite(y) minus the hold-out list (R/LDS_reconstruction.R:274);
+//          Syy, Syv, Svv over the observed steps (EM.cpp:158,161), SvvInv, wy = SvvInv Syv.
+//  series: Tuu = sum_{t<T-1} u u' (EM.cpp:193) and its inverse.
+// Dynamic shared memory: (2*pq*pq + 2*pq + 4) doubles.
+__global__ void setup_kernel(const SetupParams P) {
+    extern __shared__ __align__(16) double sh[];
+    const int pq = P.pq;
+    double *M = sh, *work = sh + pq * pq, *vec = work + pq * pq, *wy = vec + pq;
+    __shared__ int ok_flag;
+    const bool is_group = (int)blockIdx.x < P.n_groups;
+    const int g = blockIdx.x, s = is_group ? P.g_series[g] : (int)blockIdx.x - P.n_groups;
+    const SeriesDev S = P.series[s];
+    const double *ys = P.blobs + S.blob_off + S.y_off;
+    const double *rows = P.blobs + S.blob_off + (is_group ? S.v_off : S.u_off);
+    const int T = S.T, nwords = (T + 31) / 32;
+    const int n_real = is_group ? (S.has_v ? S.q : 0) : (S.has_u ? S.p : 0);
+    unsigned *mw = is_group ? P.masks + P.g_mask_off[g] : nullptr;
+
+    if (is_group) {
+        for (int w = threadIdx.x; w < nwords; w += blockDim.x) {
+            unsigned bits = 0;
+            for (int b = 0; b < 32; b++) {
+                const int t = w * 32 + b;
+                if (t < T && isfinite(ys[t])) bits |= 1u << b;
+            }
+            mw[w] = bits;
+        }
+        __syncthreads();
+        if (P.held_ptr)
+            for (int k = P.held_ptr[g] + threadIdx.x; k < P.held_ptr[g + 1]; k += blockDim.x) {
+                const int t = P.held_idx[k];
+                atomicAnd(&mw[t >> 5], ~(1u << (t & 31)));
+            }
+        __syncthreads();
+    }
+    // Gram entries: thread e handles (a,b) of the pq x pq block; thread pq*pq+a handles Syv[a];
+    // thread pq*pq+pq handles Syy and n_obs.
+    const int n_ent = pq * pq + pq + 1;
+    for (int e = threadIdx.x; e < n_ent; e += blockDim.x) {
+        double acc = 0.0;
+        int cnt = 0;
+        const int a = e < pq * pq ? e / pq : e - pq * pq, b = e % pq;
+        const int t_end = is_group ? T : T - 1;
+        for (int t = 0; t < t_end; t++) {
+            if (is_group && !((mw[t >> 5] >> (t & 31)) & 1u)) continue;
+            if (e < pq * pq)
+                acc = fma(rows[(size_t)t * pq + a], rows[(size_t)t * pq + b], acc);
+            else if (e < pq * pq + pq)
+                acc = is_group ? fma(ys[t], rows[(size_t)t * pq + a], acc) : 0.0;
+            else {
+                acc = is_group ? fma(ys[t], ys[t], acc) : 0.0;
+                cnt++;
+            }
+        }
+        if (e < pq * pq)
+            M[e] = acc;
+        else if (e < pq * pq + pq)
+            vec[a] = acc;
+        else {
+            wy[pq] = acc;             // Syy
+            wy[pq + 1] = (double)cnt; // n_obs
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = true;
+        if (n_real > 0) ok = spd_inverse(M, n_real, pq, work);
+        // rows/cols beyond the real width belong to zero padding: their inverse block is zero
+        for (int a = 0; a < pq; a++)
+            for (int b = 0; b < pq; b++)
+                if (a >= n_real || b >= n_real) M[a * pq + b] = 0.0;
+        ok_flag = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (is_group) {
+        double *gc = P.gconst + (size_t)g * gconst_stride(pq);
+        for (int a = threadIdx.x; a < pq; a += blockDim.x) {
+            double acc = 0.0;
+            for (int b = 0; b < pq; b++) acc = fma(M[a * pq + b], vec[b], acc);
+            gc[2 + a] = vec[a];
+            gc[2 + pq + a] = acc;
+        }
+        for (int e = threadIdx.x; e < pq * pq; e += blockDim.x) gc[2 + 2 * pq + e] = M[e];
+        if (threadIdx.x == 0) {
+            gc[0] = wy[pq];
+            gc[1] = wy[pq + 1];
+            P.g_nobs[g] = (int)wy[pq + 1];
+            P.g_status[g] = ok_flag ? 0 : 1;
+        }
+    } else {
+        double *sc = P.sconst + S.sconst_off;
+        for (int e = threadIdx.x; e < pq * pq; e += blockDim.x) sc[e] = M[e];
+        if (threadIdx.x == 0) sc[pq * pq] = ok_flag ? 0.0 : 1.0; // series-level singular flag
+    }
+}
+
+// A series whose Tuu is singular makes every group of it singular.
+__global__ void merge_status_kernel(const SeriesDev *series, const double *sconst, const int *g_series, int n_groups,
+                                    int pq, int *g_status) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const SeriesDev S = series[g_series[g]];
+    if (sconst[S.sconst_off + pq * pq] != 0.0) g_status[g] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Restart selection, one thread per group (R/LDS_reconstruction.R:50-58): among fits with C > 0
+// the first with the largest non-NaN lik; if no fit has C > 0, the first largest non-NaN lik.
+// Also writes the per-fit status.
+// ------------------------------------------------------------------------------------------
+__global__ void select_kernel(int n_groups, const int *g_fit_ptr, const double *theta, int theta_len, int c_index,
+                              const double *lik, const int *g_status, int *best, int *f_status) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    int bpos = -1, ball = -1;
+    bool any_pos = false;
+    for (int f = g_fit_ptr[g]; f < g_fit_ptr[g + 1]; f++) {
+        const double l = lik[f], c = theta[(size_t)f * theta_len + c_index];
+        f_status[f] = g_status[g] ? 1 : (isfinite(l) ? 0 : 2);
+        if (l != l) continue;
+        if (c > 0.0) {
+            any_pos = true;
+            if (bpos < 0 || l > lik[bpos]) bpos = f;
+        }
+        if (ball < 0 || l > lik[ball]) ball = f;
+    }
+    // posC is decided on C alone, NaN liks included (which(allC > 0))
+    if (!any_pos)
+        for (int f = g_fit_ptr[g]; f < g_fit_ptr[g + 1]; f++)
+            if (theta[(size_t)f * theta_len + c_index] > 0.0) any_pos = true;
+    best[g] = any_pos ? bpos : ball;
+}
+
+// ---- compaction of live fits, per series (fits of a series are contiguous) --------------------
+// One block per series: writes the ids of its live fits to active[fit_begin ..) and the count to
+// n_live[series].
+__global__ void compact_kernel(const SeriesDev *series, const int *done, int *active, int *n_live) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    const SeriesDev S = series[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int f0 = S.fit_begin; f0 < S.fit_end; f0 += blockDim.x) {
+        const int f = f0 + threadIdx.x;
+        const bool lv = f < S.fit_end && done[f] == 0;
+        const unsigned bal = __ballot_sync(FULL, lv);
+        if (lane == 0) warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; w++) off += warp_sums[w];
+        if (lv) active[S.fit_begin + off + __popc(bal & ((1u << lane) - 1u))] = f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < nw; w++) tot += warp_sums[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_live[blockIdx.x] = base;
+}
+
+// Single block: turns the per-series live counts into the CTA task list.
+// counts[0] = number of CTA tasks, counts[1] = number of live fits.
+__global__ void build_tasks_kernel(const SeriesDev *series, int n_series, const int *n_live, int fits_per_cta,
+                                   int4 *tasks, int *task_off, int *counts) {
+    if (threadIdx.x == 0) {
+        int nt = 0, nl = 0;
+        for (int s = 0; s < n_series; s++) {
+            task_off[s] = nt;
+            nt += (n_live[s] + fits_per_cta - 1) / fits_per_cta;
+            nl += n_live[s];
+        }
+        task_off[n_series] = nt;
+        counts[0] = nt;
+        counts[1] = nl;
+    }
+    __syncthreads();
+    for (int s = 0; s < n_series; s++) {
+        const int n = task_off[s + 1] - task_off[s];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int first = i * fits_per_cta;
+            const int cnt = min(fits_per_cta, n_live[s] - first);
+            tasks[task_off[s] + i] = make_int4(s, series[s].fit_begin + first, cnt, 0);
+        }
+    }
+}
+
+// [rows][cols] -> [cols][rows] through a padded shared-memory tile.
+__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int cols) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+
+// initial EM state: theta <- theta0, no E-step done, lik = NaN
+__global__ void init_state_kernel(int n_fits, int theta_len, const double *theta0, double *theta, double *l1,
+                                  double *l2, double *lik, int *ne, int *done) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_fits * theta_len) theta[i] = theta0[i];
+    if (i < n_fits) {
+        l1[i] = 0.0;
+        l2[i] = 0.0;
+        lik[i] = __longlong_as_double(0x7ff8000000000000ULL);
+        ne[i] = 0;
+        done[i] = 0;
+    }
+}
+
+__global__ void fill_nan_kernel(double *p, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000ULL);
+}
+
+__global__ void sum_int_kernel(const int *v, int n, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned)v[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+} // namespace ldsr

@@ -1,0 +1,161 @@
+// lds_math.cuh -- per-fit (one lane = one fit) scalar-state Kalman / RTS / M-step arithmetic.
+//
+// What is computed follows the reference (src/EM.cpp:22-131 E-step, :139-229 M-step) term for
+// term; HOW it is computed is organised for the GPU: theta and the sufficient statistics live
+// in registers (PQ is a compile-time width), u/v/y are read through a warp-uniform pointer
+// (shared memory after a TMA stage, or global), and the two (p+1)^2 / (q+1)^2 inverses of the
+// reference are replaced by block elimination against the theta-independent Gram blocks
+// (Tuu = sum u u', Svv = sum_obs v v') whose inverses are precomputed once per series / group.
+#pragma once
+#include "common.cuh"
+
+namespace ldsr {
+
+template <int PQ> struct Theta {
+    double A, C, Q, R, mu1, V1;
+    double B[PQ], D[PQ];
+};
+
+// device-side flat layout of a padded theta: [A, B[PQ], C, D[PQ], Q, R, mu1, V1]
+template <int PQ> __host__ __device__ constexpr int theta_pad_len() { return 2 * PQ + 6; }
+
+template <int PQ> __device__ __forceinline__ void load_theta(Theta<PQ> &t, const double *g) {
+    t.A = g[0];
+#pragma unroll
+    for (int j = 0; j < PQ; j++) t.B[j] = g[1 + j];
+    t.C = g[1 + PQ];
+#pragma unroll
+    for (int j = 0; j < PQ; j++) t.D[j] = g[2 + PQ + j];
+    t.Q = g[2 + 2 * PQ];
+    t.R = g[3 + 2 * PQ];
+    t.mu1 = g[4 + 2 * PQ];
+    t.V1 = g[5 + 2 * PQ];
+}
+template <int PQ> __device__ __forceinline__ void store_theta(const Theta<PQ> &t, double *g) {
+    g[0] = t.A;
+#pragma unroll
+    for (int j = 0; j < PQ; j++) g[1 + j] = t.B[j];
+    g[1 + PQ] = t.C;
+#pragma unroll
+    for (int j = 0; j < PQ; j++) g[2 + PQ + j] = t.D[j];
+    g[2 + 2 * PQ] = t.Q;
+    g[3 + 2 * PQ] = t.R;
+    g[4 + 2 * PQ] = t.mu1;
+    g[5 + 2 * PQ] = t.V1;
+}
+
+template <int PQ> __device__ __forceinline__ double dot_row(const double (&w)[PQ], const double *__restrict__ row) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < PQ; j++) s = fma(w[j], row[j], s);
+    return s;
+}
+
+// Measurement update at one step (EM.cpp:61-68, 82-89).  `obs` is per lane; the caller only
+// enters when at least one lane of the warp observes this step.  Returns the innovation terms
+// for the likelihood (EM.cpp:115-122) through dq (delta^2/Sigma) and S (Sigma).
+template <int PQ>
+__device__ __forceinline__ void measurement_update(const Theta<PQ> &th, bool obs, double y, const double *__restrict__ vrow,
+                                                   double Xp, double Vp, double &Xu, double &Vu, double &dq,
+                                                   double &S) {
+    const double Dv = dot_row<PQ>(th.D, vrow);
+    S = fma(th.C * Vp, th.C, th.R);      // C*Vp*C + R
+    const double rS = 1.0 / S;
+    const double K = Vp * th.C * rS;     // Vp*C*inv(Sigma)
+    const double delta = y - fma(th.C, Xp, Dv);
+    Xu = obs ? fma(K, delta, Xp) : Xp;
+    Vu = obs ? (1.0 - K * th.C) * Vp : Vp;
+    dq = delta * rS * delta;
+}
+
+// Sufficient statistics of one E-step (EM.cpp:151-161, 180-193), theta-dependent part only.
+template <int PQ> struct Stats {
+    double Syx, Sxx;       // over observed steps
+    double Tx1x, Txx;      // over transitions t=0..T-2
+    double Sxv[PQ], Tx1u[PQ], Tux[PQ];
+    double X0, V0, XT, VT; // smoothed state at t=0 and t=T-1
+    __device__ __forceinline__ void zero() {
+        Syx = Sxx = Tx1x = Txx = 0.0;
+#pragma unroll
+        for (int j = 0; j < PQ; j++) Sxv[j] = Tx1u[j] = Tux[j] = 0.0;
+        X0 = V0 = XT = VT = 0.0;
+    }
+};
+
+// M-step from the statistics (EM.cpp:164-177, 196-214) by block elimination:
+//   [A B] = [Tx1x Tx1u] inv([[Txx,Txu],[Tux,Tuu]])
+//     z = TuuInv Tux, w = TuuInv Tx1u, A = (Tx1x - Tx1u.z)/(Txx - Tux.z), B = w - A z
+//   [C D] = [Syx Syv] inv([[Sxx,Sxv],[Svx,Svv]])
+//     z = SvvInv Sxv, C = (Syx - wy.Sxv)/(Sxx - Sxv.z), D = wy - C z,  wy = SvvInv Syv
+//   R = sum_obs (y - yhat) y / n_obs = (Syy - C Syx - D.Syv)/n_obs         (EM.cpp:177)
+//   Q = (Tx1x1 - A Tx1x - B.Tx1u)/(T-1)                                     (EM.cpp:210)
+// With TuuInv = 0 (no u) this reduces to A = Tx1x/Txx, B = 0 (EM.cpp:212-213); likewise C, D.
+// gc -> [Syy, n_obs, Syv[PQ], wy[PQ], SvvInv[PQ*PQ]] (per group), tuu_inv -> [PQ*PQ] (per series).
+template <int PQ>
+__device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const double *__restrict__ gc,
+                                                 const double *__restrict__ tuu_inv, int T, Theta<PQ> &th) {
+    const double Syy = gc[0], n_obs = gc[1];
+    const double *Syv = gc + 2, *wy = gc + 2 + PQ, *svv_inv = gc + 2 + 2 * PQ;
+    // ---- C, D, R
+    double z[PQ];
+    double num = s.Syx, den = s.Sxx;
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < PQ; b++) acc = fma(svv_inv[a * PQ + b], s.Sxv[b], acc);
+        z[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        num = fma(-wy[a], s.Sxv[a], num);
+        den = fma(-s.Sxv[a], z[a], den);
+    }
+    const double Cn = num / den;
+    double racc = fma(-Cn, s.Syx, Syy);
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        const double d = fma(-Cn, z[a], wy[a]);
+        th.D[a] = d;
+        racc = fma(-d, Syv[a], racc);
+    }
+    th.C = Cn;
+    th.R = racc / n_obs;
+    // ---- A, B, Q
+    double w[PQ];
+    num = s.Tx1x;
+    den = s.Txx;
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        double acc = 0.0, acw = 0.0;
+#pragma unroll
+        for (int b = 0; b < PQ; b++) {
+            const double m = tuu_inv[a * PQ + b];
+            acc = fma(m, s.Tux[b], acc);
+            acw = fma(m, s.Tx1u[b], acw);
+        }
+        z[a] = acc;
+        w[a] = acw;
+    }
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        num = fma(-s.Tx1u[a], z[a], num);
+        den = fma(-s.Tux[a], z[a], den);
+    }
+    const double An = num / den;
+    // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
+    const double Tx1x1 = s.Txx - fma(s.X0, s.X0, s.V0) + fma(s.XT, s.XT, s.VT);
+    double qacc = fma(-An, s.Tx1x, Tx1x1);
+#pragma unroll
+    for (int a = 0; a < PQ; a++) {
+        const double b = fma(-An, z[a], w[a]);
+        th.B[a] = b;
+        qacc = fma(-b, s.Tx1u[a], qacc);
+    }
+    th.A = An;
+    th.Q = qacc / (double)(T - 1);
+    th.mu1 = s.X0; // EM.cpp:218-219
+    th.V1 = s.V0;
+}
+
+} // namespace ldsr

@@ -1,0 +1,1141 @@
+// ldsr_abi.cu -- host side of the engine: packing, plans, the EM driver loop, multi-GPU sharding,
+// and the extern "C" surface declared in include/ldsr_b200.h.
+#include "../../include/ldsr_b200.h"
+#include "generic_kernels.cuh"
+#include "kernel_table.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ldsr {
+
+// ---- per-PQ kernel tables (kernels_inst.cu, one object per width) --------------------------
+#define LDSR_DECL(n) const KernelTable *kernel_table_pq##n();
+#define LDSR_PQ_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(24) X(32)
+LDSR_PQ_LIST(LDSR_DECL)
+const KernelTable *kernel_table_for(int need) {
+#define LDSR_PICK(n) \
+    if (need <= n) return kernel_table_pq##n();
+    LDSR_PQ_LIST(LDSR_PICK)
+    return nullptr;
+}
+
+// ---- errors ---------------------------------------------------------------------------------
+struct Err {
+    int code = LDSR_OK;
+    std::string msg;
+    bool ok() const { return code == LDSR_OK; }
+};
+static Err fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    Err e;
+    e.code = code;
+    e.msg = buf;
+    return e;
+}
+static int report(const Err &e, char *errbuf, int errlen) {
+    if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", e.msg.c_str());
+    return e.code;
+}
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) return fail(LDSR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- device memory pool: grow-only cache of cudaMalloc blocks, one per device ---------------
+class DevicePool {
+  public:
+    explicit DevicePool(int device) : device_(device) {}
+    ~DevicePool() {
+        cudaSetDevice(device_);
+        for (auto &b : blocks_) cudaFree(b.ptr);
+    }
+    cudaError_t alloc(size_t bytes, void **out) {
+        bytes = std::max<size_t>((bytes + 255) & ~size_t(255), 256);
+        std::lock_guard<std::mutex> lk(mu_);
+        int best = -1;
+        for (int i = 0; i < (int)blocks_.size(); i++)
+            if (!blocks_[i].used && blocks_[i].size >= bytes && blocks_[i].size <= 2 * bytes + 4096 &&
+                (best < 0 || blocks_[i].size < blocks_[best].size))
+                best = i;
+        if (best >= 0) {
+            blocks_[best].used = true;
+            *out = blocks_[best].ptr;
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+        blocks_.push_back({p, bytes, true});
+        *out = p;
+        return cudaSuccess;
+    }
+    void release(void *p) {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &b : blocks_)
+            if (b.ptr == p) b.used = false;
+    }
+    int device() const { return device_; }
+
+  private:
+    struct Block {
+        void *ptr;
+        size_t size;
+        bool used;
+    };
+    int device_;
+    std::mutex mu_;
+    std::vector<Block> blocks_;
+};
+
+} // namespace ldsr
+
+using namespace ldsr;
+
+struct ldsr_ctx {
+    std::vector<int> devices;
+    std::vector<std::unique_ptr<DevicePool>> pools;
+};
+
+// ---- plan -----------------------------------------------------------------------------------
+struct ldsr_plan {
+    int device = 0;
+    DevicePool *pool = nullptr;
+    std::unique_ptr<DevicePool> own_pool;
+    cudaStream_t stream = nullptr;
+    const KernelTable *kt = nullptr;
+    int PQ = 0, TL = 0;
+    int n_series = 0, n_groups = 0, n_fits = 0, theta_stride = 0;
+    int max_T = 0, max_seg = 0;
+    size_t max_blob_bytes = 0;
+    bool blob_in_smem = true;
+    int last_niter = 0;
+    // host metadata (internal order)
+    std::vector<SeriesDev> h_series;
+    std::vector<int> g_user, f_user, h_g_series, h_g_fit_ptr, h_f_group;
+    std::vector<int> s_p, s_q, s_T;
+    std::vector<long long> h_traj_ptr_user; // per USER group: offset of its trajectory row
+    long long traj_total = 0;
+    std::vector<void *> allocs;
+    // device
+    SeriesDev *d_series = nullptr;
+    double *d_blobs = nullptr, *d_sconst = nullptr, *d_gconst = nullptr;
+    int *d_g_series = nullptr, *d_g_status = nullptr, *d_g_nobs = nullptr, *d_g_fit_ptr = nullptr;
+    int *d_held_ptr = nullptr, *d_held_idx = nullptr;
+    unsigned *d_masks = nullptr;
+    long long *d_g_mask_off = nullptr;
+    int *d_f_group = nullptr, *d_f_user = nullptr;
+    double *d_theta0 = nullptr, *d_theta = nullptr, *d_l1 = nullptr, *d_l2 = nullptr, *d_lik = nullptr;
+    int *d_ne = nullptr, *d_done = nullptr, *d_status = nullptr;
+    double *d_liks = nullptr;
+    size_t liks_cap = 0;
+    int *d_active = nullptr, *d_task_off = nullptr, *d_n_live = nullptr, *d_counts = nullptr;
+    int4 *d_tasks = nullptr;
+    int max_tasks = 0;
+    unsigned long long *d_sum = nullptr;
+    double *d_ckpt = nullptr;
+    size_t ckpt_cap = 0;
+    int *d_best = nullptr;
+    // winners' trajectories (internal group order rows)
+    double *d_X = nullptr, *d_Y = nullptr, *d_V = nullptr, *d_J = nullptr;
+    int *d_job_group = nullptr, *d_job_theta = nullptr;
+    long long *d_job_row = nullptr;
+    int *h_counts = nullptr; // pinned
+    bool em_done = false;
+
+    template <class T> Err dalloc(T **out, size_t n) {
+        void *p = nullptr;
+        cudaError_t e = pool->alloc(std::max<size_t>(n, 1) * sizeof(T), &p);
+        if (e != cudaSuccess) return fail(LDSR_ERR_CUDA, "device allocation of %zu bytes failed: %s", n * sizeof(T),
+                                          cudaGetErrorString(e));
+        allocs.push_back(p);
+        *out = static_cast<T *>(p);
+        return Err();
+    }
+    template <class T> Err upload(T **out, const std::vector<T> &h) {
+        Err e = dalloc(out, h.size());
+        if (!e.ok()) return e;
+        if (!h.empty()) CU(cudaMemcpyAsync(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return Err();
+    }
+    ~ldsr_plan() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (void *p : allocs) pool->release(p);
+        if (h_counts) cudaFreeHost(h_counts);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace ldsr {
+
+// pad a caller theta (p,q) into the device layout (PQ,PQ).  Without u (v) the caller's B (D)
+// entries are not used by any kernel and come back as zeros (EM.cpp:186,154).
+static void pad_theta(const double *src, int p, int q, bool has_u, bool has_v, int PQ, double *dst) {
+    std::fill(dst, dst + 2 * PQ + 6, 0.0);
+    dst[0] = src[0];
+    if (has_u)
+        for (int j = 0; j < p; j++) dst[1 + j] = src[1 + j];
+    dst[1 + PQ] = src[1 + p];
+    if (has_v)
+        for (int j = 0; j < q; j++) dst[2 + PQ + j] = src[2 + p + j];
+    for (int k = 0; k < 4; k++) dst[2 + 2 * PQ + k] = src[2 + p + q + k];
+}
+static void unpad_theta(const double *src, int p, int q, bool has_u, bool has_v, int PQ, double *dst) {
+    dst[0] = src[0];
+    for (int j = 0; j < p; j++) dst[1 + j] = has_u ? src[1 + j] : 0.0;
+    dst[1 + p] = src[1 + PQ];
+    for (int j = 0; j < q; j++) dst[2 + p + j] = has_v ? src[2 + PQ + j] : 0.0;
+    for (int k = 0; k < 4; k++) dst[2 + p + q + k] = src[2 + 2 * PQ + k];
+}
+
+static Err validate(const ldsr_batch *b) {
+    if (!b) return fail(LDSR_ERR_ARG, "batch is NULL");
+    if (b->n_series < 1 || b->n_groups < 1 || b->n_fits < 1)
+        return fail(LDSR_ERR_ARG, "n_series, n_groups and n_fits must all be >= 1");
+    if (!b->T || !b->p || !b->q || !b->y || !b->group_series || !b->fit_group || !b->theta0)
+        return fail(LDSR_ERR_ARG, "a required table pointer is NULL");
+    for (int s = 0; s < b->n_series; s++) {
+        if (b->T[s] < 2) return fail(LDSR_ERR_ARG, "series %d: T=%d, need T >= 2", s, b->T[s]);
+        if (b->p[s] < 0 || b->q[s] < 0) return fail(LDSR_ERR_ARG, "series %d: negative p or q", s);
+        if (b->p[s] > LDSR_MAX_PQ || b->q[s] > LDSR_MAX_PQ)
+            return fail(LDSR_ERR_UNSUPPORTED, "series %d: p=%d q=%d exceeds LDSR_MAX_PQ=%d", s, b->p[s], b->q[s],
+                        LDSR_MAX_PQ);
+        if (!b->y[s]) return fail(LDSR_ERR_ARG, "series %d: y is NULL", s);
+        if (b->u && b->u[s] && b->p[s] < 1) return fail(LDSR_ERR_ARG, "series %d: u given but p=0", s);
+        if (b->v && b->v[s] && b->q[s] < 1) return fail(LDSR_ERR_ARG, "series %d: v given but q=0", s);
+        if (b->theta_stride < b->p[s] + b->q[s] + 6)
+            return fail(LDSR_ERR_ARG, "theta_stride=%d < p+q+6=%d (series %d)", b->theta_stride,
+                        b->p[s] + b->q[s] + 6, s);
+        for (int t = 0; t < b->T[s]; t++)
+            if (std::isinf(b->y[s][t])) return fail(LDSR_ERR_ARG, "series %d: y[%d] is +-Inf", s, t);
+    }
+    for (int g = 0; g < b->n_groups; g++) {
+        const int s = b->group_series[g];
+        if (s < 0 || s >= b->n_series) return fail(LDSR_ERR_ARG, "group %d: series id %d out of range", g, s);
+        if (b->held_ptr) {
+            if (b->held_ptr[g + 1] < b->held_ptr[g]) return fail(LDSR_ERR_ARG, "held_ptr not monotone at group %d", g);
+            for (int k = b->held_ptr[g]; k < b->held_ptr[g + 1]; k++)
+                if (b->held_idx[k] < 0 || b->held_idx[k] >= b->T[s])
+                    return fail(LDSR_ERR_ARG, "group %d: held-out step %d outside 0..%d", g, b->held_idx[k],
+                                b->T[s] - 1);
+        }
+    }
+    for (int f = 0; f < b->n_fits; f++) {
+        const int g = b->fit_group[f];
+        if (g < 0 || g >= b->n_groups) return fail(LDSR_ERR_ARG, "fit %d: group id %d out of range", f, g);
+        if (f > 0 && g < b->fit_group[f - 1])
+            return fail(LDSR_ERR_ARG, "fit_group must be non-decreasing (fit %d)", f);
+    }
+    return Err();
+}
+
+static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_plan **out) {
+    Err e = validate(b);
+    if (!e.ok()) return e;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(LDSR_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    std::unique_ptr<ldsr_plan> P(new ldsr_plan());
+    P->device = device;
+    if (pool)
+        P->pool = pool;
+    else {
+        P->own_pool.reset(new DevicePool(device));
+        P->pool = P->own_pool.get();
+    }
+    CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&P->h_counts, 8 * sizeof(int)));
+
+    const int ns = b->n_series, ng = b->n_groups, nf = b->n_fits;
+    P->n_series = ns;
+    P->n_groups = ng;
+    P->n_fits = nf;
+    P->theta_stride = b->theta_stride;
+    int need = 1;
+    for (int s = 0; s < ns; s++) {
+        const bool hu = b->u && b->u[s], hv = b->v && b->v[s];
+        if (hu) need = std::max(need, b->p[s]);
+        if (hv) need = std::max(need, b->q[s]);
+    }
+    P->kt = kernel_table_for(need);
+    if (!P->kt) return fail(LDSR_ERR_UNSUPPORTED, "input width %d has no kernel instantiation", need);
+    const int PQ = P->PQ = P->kt->pq;
+    P->TL = 2 * PQ + 6;
+    P->s_p.assign(b->p, b->p + ns);
+    P->s_q.assign(b->q, b->q + ns);
+    P->s_T.assign(b->T, b->T + ns);
+
+    // ---- internal order: groups sorted by series (stable), fits follow their groups
+    std::vector<int> fit_lo(ng, -1), fit_hi(ng, -1);
+    for (int f = 0; f < nf; f++) {
+        const int g = b->fit_group[f];
+        if (fit_lo[g] < 0) fit_lo[g] = f;
+        fit_hi[g] = f + 1;
+    }
+    P->g_user.resize(ng);
+    std::iota(P->g_user.begin(), P->g_user.end(), 0);
+    std::stable_sort(P->g_user.begin(), P->g_user.end(),
+                     [&](int a, int c) { return b->group_series[a] < b->group_series[c]; });
+    P->h_g_series.resize(ng);
+    P->h_g_fit_ptr.assign(ng + 1, 0);
+    P->f_user.clear();
+    P->h_f_group.clear();
+    for (int gi = 0; gi < ng; gi++) {
+        const int gu = P->g_user[gi];
+        P->h_g_series[gi] = b->group_series[gu];
+        P->h_g_fit_ptr[gi] = (int)P->f_user.size();
+        if (fit_lo[gu] >= 0)
+            for (int f = fit_lo[gu]; f < fit_hi[gu]; f++) {
+                P->f_user.push_back(f);
+                P->h_f_group.push_back(gi);
+            }
+    }
+    P->h_g_fit_ptr[ng] = (int)P->f_user.size();
+
+    // ---- series blobs
+    P->h_series.resize(ns);
+    std::vector<double> blobs;
+    long long sconst_off = 0;
+    for (int s = 0; s < ns; s++) {
+        SeriesDev &S = P->h_series[s];
+        std::memset(&S, 0, sizeof S);
+        const int T = b->T[s], p = b->p[s], q = b->q[s];
+        const double *u = b->u ? b->u[s] : nullptr, *v = b->v ? b->v[s] : nullptr;
+        S.T = T;
+        S.p = p;
+        S.q = q;
+        S.has_u = u != nullptr;
+        S.has_v = v != nullptr;
+        S.same_uv = (u && v && p == q && (u == v || std::memcmp(u, v, sizeof(double) * (size_t)p * T) == 0)) ||
+                    (!u && !v);
+        const int Ty = (T + 1) & ~1;
+        const int nuv = T * PQ;
+        S.y_off = 0;
+        S.u_off = Ty;
+        S.v_off = S.same_uv ? S.u_off : ((S.u_off + nuv + 1) & ~1);
+        S.blob_doubles = ((S.v_off + nuv) + 1) & ~1;
+        S.blob_off = (long long)blobs.size();
+        S.sconst_off = sconst_off;
+        sconst_off += PQ * PQ + 1;
+        blobs.resize(blobs.size() + S.blob_doubles, 0.0);
+        double *B = blobs.data() + S.blob_off;
+        for (int t = 0; t < T; t++) {
+            B[t] = b->y[s][t];
+            if (u)
+                for (int j = 0; j < p; j++) B[S.u_off + (size_t)t * PQ + j] = u[(size_t)t * p + j];
+            if (v && !S.same_uv)
+                for (int j = 0; j < q; j++) B[S.v_off + (size_t)t * PQ + j] = v[(size_t)t * q + j];
+        }
+        P->max_T = std::max(P->max_T, T);
+        P->max_blob_bytes = std::max(P->max_blob_bytes, (size_t)S.blob_doubles * 8);
+    }
+    // fit ranges per series (internal order is series-major)
+    {
+        int f = 0;
+        for (int s = 0; s < ns; s++) {
+            P->h_series[s].fit_begin = f;
+            while (f < (int)P->h_f_group.size() && P->h_g_series[P->h_f_group[f]] == s) f++;
+            P->h_series[s].fit_end = f;
+        }
+    }
+    P->max_seg = (P->max_T + EM_SEG - 1) / EM_SEG;
+    P->blob_in_smem = P->max_blob_bytes <= 200 * 1024;
+
+    // ---- masks, hold-outs (internal group order)
+    std::vector<long long> mask_off(ng);
+    long long nwords = 0;
+    std::vector<int> held_ptr(ng + 1, 0), held_idx;
+    for (int gi = 0; gi < ng; gi++) {
+        const int gu = P->g_user[gi];
+        mask_off[gi] = nwords;
+        nwords += (b->T[P->h_g_series[gi]] + 31) / 32;
+        if (b->held_ptr)
+            for (int k = b->held_ptr[gu]; k < b->held_ptr[gu + 1]; k++) held_idx.push_back(b->held_idx[k]);
+        held_ptr[gi + 1] = (int)held_idx.size();
+    }
+    // ---- trajectory rows: user-order prefix sum of T
+    P->h_traj_ptr_user.resize(ng + 1);
+    P->h_traj_ptr_user[0] = 0;
+    for (int g = 0; g < ng; g++) P->h_traj_ptr_user[g + 1] = P->h_traj_ptr_user[g] + b->T[b->group_series[g]];
+    P->traj_total = P->h_traj_ptr_user[ng];
+
+    // ---- thetas (internal order, padded)
+    std::vector<double> th0((size_t)nf * P->TL);
+    for (int fi = 0; fi < nf; fi++) {
+        const int s = P->h_g_series[P->h_f_group[fi]];
+        pad_theta(b->theta0 + (size_t)P->f_user[fi] * b->theta_stride, b->p[s], b->q[s], P->h_series[s].has_u != 0,
+                  P->h_series[s].has_v != 0, PQ, &th0[(size_t)fi * P->TL]);
+    }
+
+    // ---- upload
+    if (!(e = P->upload(&P->d_series, P->h_series)).ok()) return e;
+    if (!(e = P->upload(&P->d_blobs, blobs)).ok()) return e;
+    if (!(e = P->upload(&P->d_g_series, P->h_g_series)).ok()) return e;
+    if (!(e = P->upload(&P->d_g_fit_ptr, P->h_g_fit_ptr)).ok()) return e;
+    if (!(e = P->upload(&P->d_g_mask_off, mask_off)).ok()) return e;
+    if (!(e = P->upload(&P->d_held_ptr, held_ptr)).ok()) return e;
+    if (held_idx.empty()) held_idx.push_back(0);
+    if (!(e = P->upload(&P->d_held_idx, held_idx)).ok()) return e;
+    if (!(e = P->upload(&P->d_f_group, P->h_f_group)).ok()) return e;
+    if (!(e = P->upload(&P->d_f_user, P->f_user)).ok()) return e;
+    if (!(e = P->upload(&P->d_theta0, th0)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_masks, (size_t)nwords)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_sconst, (size_t)sconst_off)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_gconst, (size_t)ng * gconst_stride(PQ))).ok()) return e;
+    if (!(e = P->dalloc(&P->d_g_status, ng)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_g_nobs, ng)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_theta, (size_t)nf * P->TL)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_l1, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_l2, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_lik, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_ne, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_done, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_status, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_active, nf)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_n_live, ns)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_task_off, ns + 1)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_counts, 8)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_sum, 1)).ok()) return e;
+    P->max_tasks = nf / (32 * EM_WARPS) + ns + 1;
+    if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
+
+    // ---- set-up kernel: masks + Gram constants
+    SetupParams sp;
+    sp.series = P->d_series;
+    sp.blobs = P->d_blobs;
+    sp.n_series = ns;
+    sp.n_groups = ng;
+    sp.g_series = P->d_g_series;
+    sp.held_ptr = P->d_held_ptr;
+    sp.held_idx = P->d_held_idx;
+    sp.masks = P->d_masks;
+    sp.g_mask_off = P->d_g_mask_off;
+    sp.gconst = P->d_gconst;
+    sp.sconst = P->d_sconst;
+    sp.g_status = P->d_g_status;
+    sp.g_nobs = P->d_g_nobs;
+    sp.pq = PQ;
+    const size_t sh = (size_t)(2 * PQ * PQ + 2 * PQ + 4) * sizeof(double);
+    setup_kernel<<<ng + ns, 128, sh, P->stream>>>(sp);
+    CU(cudaGetLastError());
+    merge_status_kernel<<<(ng + 127) / 128, 128, 0, P->stream>>>(P->d_series, P->d_sconst, P->d_g_series, ng, PQ,
+                                                                 P->d_g_status);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(P->stream)); // host vectors above go out of scope
+    *out = P.release();
+    return Err();
+}
+
+// ---- the EM driver ---------------------------------------------------------------------------
+static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt, cudaStream_t st, bool want_liks,
+                   std::atomic<int> *abort_flag, long long *stats) {
+    if (niter < 2) return fail(LDSR_ERR_ARG, "niter=%d: the reference requires niter >= 2 (EM.cpp:247,256)", niter);
+    if (!(tol == tol)) return fail(LDSR_ERR_ARG, "tol is NaN");
+    CU(cudaSetDevice(P->device));
+    if (!st) st = P->stream;
+    const int nf = P->n_fits, ns = P->n_series, ng = P->n_groups;
+    const int chunk = (opt && opt->chunk_iters > 0) ? opt->chunk_iters : 100;
+    long long launches = 0, chunks = 0;
+    P->last_niter = niter;
+    P->em_done = false;
+
+    if (want_liks) {
+        const size_t need = (size_t)nf * niter;
+        if (P->liks_cap < need) {
+            Err e = P->dalloc(&P->d_liks, need);
+            if (!e.ok()) return e;
+            P->liks_cap = need;
+        }
+        fill_nan_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(P->d_liks, need);
+        launches++;
+    }
+    {
+        const int n = nf * P->TL;
+        init_state_kernel<<<(n + 255) / 256, 256, 0, st>>>(nf, P->TL, P->d_theta0, P->d_theta, P->d_l1, P->d_l2,
+                                                           P->d_lik, P->d_ne, P->d_done);
+        CU(cudaGetLastError());
+        launches++;
+    }
+    const size_t smem = P->blob_in_smem ? P->max_blob_bytes : 0;
+    CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
+
+    EmParams ep;
+    ep.series = P->d_series;
+    ep.blobs = P->d_blobs;
+    ep.sconst = P->d_sconst;
+    ep.g_series = P->d_g_series;
+    ep.masks = P->d_masks;
+    ep.g_mask_off = P->d_g_mask_off;
+    ep.gconst = P->d_gconst;
+    ep.g_status = P->d_g_status;
+    ep.f_group = P->d_f_group;
+    ep.theta = P->d_theta;
+    ep.l1 = P->d_l1;
+    ep.l2 = P->d_l2;
+    ep.lik = P->d_lik;
+    ep.ne = P->d_ne;
+    ep.done = P->d_done;
+    ep.liks = want_liks ? P->d_liks : nullptr;
+    ep.f_user = P->d_f_user;
+    ep.active = P->d_active;
+    ep.tasks = P->d_tasks;
+    ep.max_seg = P->max_seg;
+    ep.niter = niter;
+    ep.chunk = chunk;
+    ep.tol = tol;
+    ep.blob_in_smem = P->blob_in_smem ? 1 : 0;
+
+    for (;;) {
+        compact_kernel<<<ns, 256, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
+        build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, 32 * EM_WARPS, P->d_tasks, P->d_task_off,
+                                              P->d_counts);
+        launches += 2;
+        CU(cudaMemcpyAsync(P->h_counts, P->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int n_tasks = P->h_counts[0], n_live = P->h_counts[1];
+        if (n_live == 0) break;
+        if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
+        if (opt && opt->poll && !abort_flag && opt->poll(opt->poll_arg))
+            return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
+        const size_t need = (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
+        if (P->ckpt_cap < need) {
+            Err e = P->dalloc(&P->d_ckpt, need);
+            if (!e.ok()) return e;
+            P->ckpt_cap = need;
+        }
+        ep.ckpt = P->d_ckpt;
+        CU(P->kt->em_chunk(ep, n_tasks, smem, st));
+        launches++;
+        chunks++;
+    }
+    // ---- selection + the winners' smoothed trajectories
+    select_kernel<<<(ng + 127) / 128, 128, 0, st>>>(ng, P->d_g_fit_ptr, P->d_theta, P->TL, 1 + P->PQ, P->d_lik,
+                                                    P->d_g_status, P->d_best, P->d_status);
+    CU(cudaGetLastError());
+    launches++;
+    if (!P->d_X) {
+        Err e;
+        if (!(e = P->dalloc(&P->d_X, (size_t)P->traj_total)).ok()) return e;
+        if (!(e = P->dalloc(&P->d_Y, (size_t)P->traj_total)).ok()) return e;
+        if (!(e = P->dalloc(&P->d_V, (size_t)P->traj_total)).ok()) return e;
+        if (!(e = P->dalloc(&P->d_J, (size_t)P->traj_total)).ok()) return e;
+        std::vector<int> jg(ng);
+        std::vector<long long> jr(ng);
+        for (int gi = 0; gi < ng; gi++) {
+            jg[gi] = gi;
+            jr[gi] = P->h_traj_ptr_user[P->g_user[gi]];
+        }
+        cudaStream_t keep = P->stream;
+        P->stream = st;
+        if (!(e = P->upload(&P->d_job_group, jg)).ok()) return e;
+        if (!(e = P->upload(&P->d_job_row, jr)).ok()) return e;
+        P->stream = keep;
+        CU(cudaStreamSynchronize(st));
+    }
+    SmootherParams sp;
+    sp.series = P->d_series;
+    sp.blobs = P->d_blobs;
+    sp.g_series = P->d_g_series;
+    sp.masks = P->d_masks;
+    sp.g_mask_off = P->d_g_mask_off;
+    sp.g_nobs = P->d_g_nobs;
+    sp.n_jobs = ng;
+    sp.job_group = P->d_job_group;
+    sp.job_theta = P->d_best; // best fit (internal index) or -1
+    sp.job_row = P->d_job_row;
+    sp.theta = P->d_theta;
+    sp.X = P->d_X;
+    sp.Y = P->d_Y;
+    sp.V = P->d_V;
+    sp.J = P->d_J;
+    sp.lik = nullptr;
+    sp.stdlik = 1;
+    CU(P->kt->smoother(sp, st));
+    launches++;
+    CU(cudaMemsetAsync(P->d_sum, 0, sizeof(unsigned long long), st));
+    sum_int_kernel<<<64, 256, 0, st>>>(P->d_ne, nf, P->d_sum);
+    launches++;
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, P->d_sum, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    P->em_done = true;
+    if (stats) {
+        stats[0] = launches;
+        stats[1] = chunks;
+        stats[2] = (long long)total;
+        stats[3] = 0;
+    }
+    return Err();
+}
+
+static Err plan_fetch(ldsr_plan *P, ldsr_em_result *out) {
+    if (!P->em_done) return fail(LDSR_ERR_ARG, "ldsr_plan_fetch before a successful ldsr_plan_em");
+    if (!out) return fail(LDSR_ERR_ARG, "result struct is NULL");
+    CU(cudaSetDevice(P->device));
+    const int nf = P->n_fits, ng = P->n_groups, TL = P->TL;
+    std::vector<double> th, lik;
+    std::vector<int> tmp;
+    if (out->theta) {
+        th.resize((size_t)nf * TL);
+        CU(cudaMemcpy(th.data(), P->d_theta, th.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) {
+            const int s = P->h_g_series[P->h_f_group[fi]];
+            unpad_theta(&th[(size_t)fi * TL], P->s_p[s], P->s_q[s], P->h_series[s].has_u != 0,
+                        P->h_series[s].has_v != 0, P->PQ, out->theta + (size_t)P->f_user[fi] * P->theta_stride);
+        }
+    }
+    if (out->lik) {
+        lik.resize(nf);
+        CU(cudaMemcpy(lik.data(), P->d_lik, nf * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) out->lik[P->f_user[fi]] = lik[fi];
+    }
+    if (out->iters) {
+        tmp.resize(nf);
+        CU(cudaMemcpy(tmp.data(), P->d_ne, nf * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) out->iters[P->f_user[fi]] = tmp[fi];
+    }
+    if (out->status) {
+        tmp.resize(nf);
+        CU(cudaMemcpy(tmp.data(), P->d_status, nf * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) out->status[P->f_user[fi]] = tmp[fi];
+    }
+    if (out->liks) {
+        if (!P->d_liks) return fail(LDSR_ERR_ARG, "liks requested at fetch but not at ldsr_plan_em time");
+        CU(cudaMemcpy(out->liks, P->d_liks, (size_t)nf * P->last_niter * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (out->best) {
+        tmp.resize(ng);
+        CU(cudaMemcpy(tmp.data(), P->d_best, ng * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int gi = 0; gi < ng; gi++) out->best[P->g_user[gi]] = tmp[gi] < 0 ? -1 : P->f_user[tmp[gi]];
+    }
+    const size_t tb = (size_t)P->traj_total * sizeof(double);
+    if (out->X) CU(cudaMemcpy(out->X, P->d_X, tb, cudaMemcpyDeviceToHost));
+    if (out->Y) CU(cudaMemcpy(out->Y, P->d_Y, tb, cudaMemcpyDeviceToHost));
+    if (out->V) CU(cudaMemcpy(out->V, P->d_V, tb, cudaMemcpyDeviceToHost));
+    if (out->J) CU(cudaMemcpy(out->J, P->d_J, tb, cudaMemcpyDeviceToHost));
+    return Err();
+}
+
+// ---- sub-batch for one device: a subset of groups with their fits ---------------------------
+struct SubBatch {
+    ldsr_batch b;
+    std::vector<int> groups; // user group ids
+    std::vector<int> group_series, held_ptr, held_idx, fit_group, fits; // fits = user fit ids
+    std::vector<double> theta0;
+    std::vector<long long> traj_ptr; // local prefix sums of T
+};
+
+static void make_sub(const ldsr_batch *b, const std::vector<int> &groups, const std::vector<int> &fit_lo,
+                     const std::vector<int> &fit_hi, SubBatch &sb) {
+    sb.groups = groups;
+    sb.b = *b;
+    sb.held_ptr.assign(1, 0);
+    sb.traj_ptr.assign(1, 0);
+    for (int gl = 0; gl < (int)groups.size(); gl++) {
+        const int g = groups[gl];
+        sb.group_series.push_back(b->group_series[g]);
+        if (b->held_ptr)
+            for (int k = b->held_ptr[g]; k < b->held_ptr[g + 1]; k++) sb.held_idx.push_back(b->held_idx[k]);
+        sb.held_ptr.push_back((int)sb.held_idx.size());
+        sb.traj_ptr.push_back(sb.traj_ptr.back() + b->T[b->group_series[g]]);
+        for (int f = fit_lo[g]; f >= 0 && f < fit_hi[g]; f++) {
+            sb.fits.push_back(f);
+            sb.fit_group.push_back(gl);
+        }
+    }
+    sb.theta0.resize(sb.fits.size() * (size_t)b->theta_stride);
+    for (size_t i = 0; i < sb.fits.size(); i++)
+        std::memcpy(&sb.theta0[i * b->theta_stride], b->theta0 + (size_t)sb.fits[i] * b->theta_stride,
+                    sizeof(double) * b->theta_stride);
+    if (sb.held_idx.empty()) sb.held_idx.push_back(0);
+    sb.b.n_groups = (int)groups.size();
+    sb.b.group_series = sb.group_series.data();
+    sb.b.held_ptr = sb.held_ptr.data();
+    sb.b.held_idx = sb.held_idx.data();
+    sb.b.n_fits = (int)sb.fits.size();
+    sb.b.fit_group = sb.fit_group.data();
+    sb.b.theta0 = sb.theta0.data();
+}
+
+static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, const ldsr_options *opt,
+                    ldsr_em_result *out) {
+    Err e = validate(b);
+    if (!e.ok()) return e;
+    if (!out) return fail(LDSR_ERR_ARG, "result struct is NULL");
+    std::unique_ptr<ldsr_ctx> tmp_ctx;
+    if (!ctx) {
+        ldsr_ctx *c = nullptr;
+        char buf[256];
+        int rc = ldsr_ctx_create(opt ? opt->n_devices : 0, opt ? opt->devices : nullptr, &c, buf, sizeof buf);
+        if (rc != LDSR_OK) return fail(rc, "%s", buf);
+        tmp_ctx.reset(c);
+        ctx = c;
+    }
+    int nd = (int)ctx->devices.size();
+    if (opt && opt->n_devices > 0) nd = std::min(nd, opt->n_devices);
+    nd = std::max(1, std::min(nd, b->n_groups));
+    const bool want_liks = out->liks != nullptr;
+
+    // single device, whole batch: no sub-batch copies
+    if (nd == 1) {
+        ldsr_plan *P = nullptr;
+        e = plan_build(b, ctx->devices[0], ctx->pools[0].get(), &P);
+        if (!e.ok()) return e;
+        std::unique_ptr<ldsr_plan> guard(P);
+        e = plan_em(P, niter, tol, opt, nullptr, want_liks, nullptr, nullptr);
+        if (!e.ok()) return e;
+        return plan_fetch(P, out);
+    }
+
+    // ---- shard groups over devices: greedy by cost = restarts * T * (p+q+8)
+    const int ng = b->n_groups;
+    std::vector<int> fit_lo(ng, -1), fit_hi(ng, -1);
+    for (int f = 0; f < b->n_fits; f++) {
+        const int g = b->fit_group[f];
+        if (fit_lo[g] < 0) fit_lo[g] = f;
+        fit_hi[g] = f + 1;
+    }
+    std::vector<double> cost(ng);
+    for (int g = 0; g < ng; g++) {
+        const int s = b->group_series[g];
+        cost[g] = (double)(fit_hi[g] - std::max(fit_lo[g], 0)) * b->T[s] * (b->p[s] + b->q[s] + 8);
+    }
+    std::vector<int> order(ng);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+    std::vector<std::vector<int>> dev_groups(nd);
+    std::vector<double> load(nd, 0.0);
+    for (int g : order) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        dev_groups[d].push_back(g);
+        load[d] += cost[g];
+    }
+    for (auto &v : dev_groups) std::sort(v.begin(), v.end());
+
+    std::vector<SubBatch> subs(nd);
+    std::vector<Err> errs(nd);
+    std::atomic<int> abort_flag(0), running(nd);
+    struct Res {
+        std::vector<double> theta, lik, liks, X, Y, V, J;
+        std::vector<int> iters, status, best;
+    };
+    std::vector<Res> res(nd);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < nd; d++) {
+        make_sub(b, dev_groups[d], fit_lo, fit_hi, subs[d]);
+        workers.emplace_back([&, d]() {
+            SubBatch &sb = subs[d];
+            Res &r = res[d];
+            ldsr_plan *P = nullptr;
+            Err er = plan_build(&sb.b, ctx->devices[d], ctx->pools[d].get(), &P);
+            if (er.ok()) {
+                std::unique_ptr<ldsr_plan> guard(P);
+                er = plan_em(P, niter, tol, opt, nullptr, want_liks, &abort_flag, nullptr);
+                if (er.ok()) {
+                    const size_t nfl = sb.fits.size(), ngl = sb.groups.size();
+                    ldsr_em_result o;
+                    std::memset(&o, 0, sizeof o);
+                    if (out->theta) { r.theta.resize(nfl * b->theta_stride); o.theta = r.theta.data(); }
+                    if (out->lik) { r.lik.resize(nfl); o.lik = r.lik.data(); }
+                    if (out->iters) { r.iters.resize(nfl); o.iters = r.iters.data(); }
+                    if (out->status) { r.status.resize(nfl); o.status = r.status.data(); }
+                    if (out->liks) { r.liks.resize(nfl * (size_t)niter); o.liks = r.liks.data(); }
+                    if (out->best) { r.best.resize(ngl); o.best = r.best.data(); }
+                    const size_t tt = (size_t)sb.traj_ptr.back();
+                    if (out->X) { r.X.resize(tt); o.X = r.X.data(); }
+                    if (out->Y) { r.Y.resize(tt); o.Y = r.Y.data(); }
+                    if (out->V) { r.V.resize(tt); o.V = r.V.data(); }
+                    if (out->J) { r.J.resize(tt); o.J = r.J.data(); }
+                    er = plan_fetch(P, &o);
+                }
+            }
+            if (!er.ok()) abort_flag.store(1);
+            errs[d] = er;
+            running.fetch_sub(1);
+        });
+    }
+    // the poll callback runs HERE, on the calling thread
+    bool interrupted = false;
+    while (running.load() > 0) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(opt && opt->poll ? 20 : 2));
+        if (opt && opt->poll && !interrupted && opt->poll(opt->poll_arg)) {
+            interrupted = true;
+            abort_flag.store(1);
+        }
+    }
+    for (auto &w : workers) w.join();
+    if (interrupted) return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
+    for (int d = 0; d < nd; d++)
+        if (!errs[d].ok() && errs[d].code != LDSR_ERR_INTERRUPTED) return errs[d];
+    for (int d = 0; d < nd; d++)
+        if (!errs[d].ok()) return errs[d];
+
+    // ---- gather (host concatenation; no collective)
+    std::vector<long long> traj_ptr(ng + 1, 0);
+    for (int g = 0; g < ng; g++) traj_ptr[g + 1] = traj_ptr[g] + b->T[b->group_series[g]];
+    for (int d = 0; d < nd; d++) {
+        const SubBatch &sb = subs[d];
+        const Res &r = res[d];
+        for (size_t i = 0; i < sb.fits.size(); i++) {
+            const int f = sb.fits[i];
+            if (out->theta)
+                std::memcpy(out->theta + (size_t)f * b->theta_stride, &r.theta[i * b->theta_stride],
+                            sizeof(double) * b->theta_stride);
+            if (out->lik) out->lik[f] = r.lik[i];
+            if (out->iters) out->iters[f] = r.iters[i];
+            if (out->status) out->status[f] = r.status[i];
+            if (out->liks) std::memcpy(out->liks + (size_t)f * niter, &r.liks[i * (size_t)niter], sizeof(double) * niter);
+        }
+        for (size_t gl = 0; gl < sb.groups.size(); gl++) {
+            const int g = sb.groups[gl];
+            if (out->best) out->best[g] = r.best[gl] < 0 ? -1 : sb.fits[r.best[gl]];
+            const size_t n = (size_t)(traj_ptr[g + 1] - traj_ptr[g]);
+            if (out->X) std::memcpy(out->X + traj_ptr[g], &r.X[sb.traj_ptr[gl]], n * sizeof(double));
+            if (out->Y) std::memcpy(out->Y + traj_ptr[g], &r.Y[sb.traj_ptr[gl]], n * sizeof(double));
+            if (out->V) std::memcpy(out->V + traj_ptr[g], &r.V[sb.traj_ptr[gl]], n * sizeof(double));
+            if (out->J) std::memcpy(out->J + traj_ptr[g], &r.J[sb.traj_ptr[gl]], n * sizeof(double));
+        }
+    }
+    return Err();
+}
+
+// ---- single-step batched entry points (one device: ctx device 0) ----------------------------
+enum class StepKind { Smoother, Propagate };
+
+static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int stdlik, double *X, double *Y, double *V,
+                      double *J, double *lik) {
+    std::unique_ptr<ldsr_ctx> tmp_ctx;
+    if (!ctx) {
+        ldsr_ctx *c = nullptr;
+        char buf[256];
+        int rc = ldsr_ctx_create(1, nullptr, &c, buf, sizeof buf);
+        if (rc != LDSR_OK) return fail(rc, "%s", buf);
+        tmp_ctx.reset(c);
+        ctx = c;
+    }
+    if (!X || !Y || !V) return fail(LDSR_ERR_ARG, "X, Y and V outputs are required");
+    ldsr_plan *P = nullptr;
+    Err e = plan_build(b, ctx->devices[0], ctx->pools[0].get(), &P);
+    if (!e.ok()) return e;
+    std::unique_ptr<ldsr_plan> guard(P);
+    const int nf = P->n_fits;
+    // job rows follow the USER fit order
+    std::vector<long long> row_user(nf + 1, 0);
+    for (int f = 0; f < nf; f++) row_user[f + 1] = row_user[f] + b->T[b->group_series[b->fit_group[f]]];
+    std::vector<long long> jr(nf);
+    std::vector<int> jt(nf);
+    for (int fi = 0; fi < nf; fi++) {
+        jr[fi] = row_user[P->f_user[fi]];
+        jt[fi] = fi;
+    }
+    const size_t tot = (size_t)row_user[nf];
+    double *dX, *dY, *dV, *dJ = nullptr, *dlik;
+    int *d_jt;
+    long long *d_jr;
+    if (!(e = P->dalloc(&dX, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dY, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dV, tot)).ok()) return e;
+    if (J && !(e = P->dalloc(&dJ, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dlik, nf)).ok()) return e;
+    if (!(e = P->upload(&d_jt, jt)).ok()) return e;
+    if (!(e = P->upload(&d_jr, jr)).ok()) return e;
+    SmootherParams sp;
+    sp.series = P->d_series;
+    sp.blobs = P->d_blobs;
+    sp.g_series = P->d_g_series;
+    sp.masks = P->d_masks;
+    sp.g_mask_off = P->d_g_mask_off;
+    sp.g_nobs = P->d_g_nobs;
+    sp.n_jobs = nf;
+    sp.job_group = P->d_f_group;
+    sp.job_theta = d_jt;
+    sp.job_row = d_jr;
+    sp.theta = P->d_theta0;
+    sp.X = dX;
+    sp.Y = dY;
+    sp.V = dV;
+    sp.J = dJ;
+    sp.lik = dlik;
+    sp.stdlik = stdlik;
+    CU(kind == StepKind::Smoother ? P->kt->smoother(sp, P->stream) : P->kt->propagate(sp, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    CU(cudaMemcpy(X, dX, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(Y, dY, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(V, dV, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    if (J) CU(cudaMemcpy(J, dJ, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    if (lik) {
+        std::vector<double> l(nf);
+        CU(cudaMemcpy(l.data(), dlik, nf * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) lik[P->f_user[fi]] = l[fi];
+    }
+    return Err();
+}
+
+static Err mstep_batch(ldsr_ctx *ctx, const ldsr_batch *b, const double *X, const double *V, const double *J,
+                       double *theta_out, int *status) {
+    std::unique_ptr<ldsr_ctx> tmp_ctx;
+    if (!ctx) {
+        ldsr_ctx *c = nullptr;
+        char buf[256];
+        int rc = ldsr_ctx_create(1, nullptr, &c, buf, sizeof buf);
+        if (rc != LDSR_OK) return fail(rc, "%s", buf);
+        tmp_ctx.reset(c);
+        ctx = c;
+    }
+    if (!X || !V || !J || !theta_out) return fail(LDSR_ERR_ARG, "X, V, J and theta_out are required");
+    ldsr_plan *P = nullptr;
+    Err e = plan_build(b, ctx->devices[0], ctx->pools[0].get(), &P);
+    if (!e.ok()) return e;
+    std::unique_ptr<ldsr_plan> guard(P);
+    const int nf = P->n_fits;
+    std::vector<long long> row_user(nf + 1, 0);
+    for (int f = 0; f < nf; f++) row_user[f + 1] = row_user[f] + b->T[b->group_series[b->fit_group[f]]];
+    std::vector<long long> fr(nf);
+    for (int fi = 0; fi < nf; fi++) fr[fi] = row_user[P->f_user[fi]];
+    const size_t tot = (size_t)row_user[nf];
+    double *dX, *dV, *dJ, *dth;
+    int *dst;
+    long long *d_fr;
+    if (!(e = P->dalloc(&dX, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dV, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dJ, tot)).ok()) return e;
+    if (!(e = P->dalloc(&dth, (size_t)nf * P->TL)).ok()) return e;
+    if (!(e = P->dalloc(&dst, nf)).ok()) return e;
+    if (!(e = P->upload(&d_fr, fr)).ok()) return e;
+    CU(cudaMemcpyAsync(dX, X, tot * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    CU(cudaMemcpyAsync(dV, V, tot * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    CU(cudaMemcpyAsync(dJ, J, tot * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    MstepParams mp;
+    mp.series = P->d_series;
+    mp.blobs = P->d_blobs;
+    mp.sconst = P->d_sconst;
+    mp.g_series = P->d_g_series;
+    mp.masks = P->d_masks;
+    mp.g_mask_off = P->d_g_mask_off;
+    mp.gconst = P->d_gconst;
+    mp.g_status = P->d_g_status;
+    mp.n_fits = nf;
+    mp.f_group = P->d_f_group;
+    mp.f_row = d_fr;
+    mp.X = dX;
+    mp.V = dV;
+    mp.J = dJ;
+    mp.theta_out = dth;
+    mp.status = dst;
+    CU(P->kt->mstep(mp, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    std::vector<double> th((size_t)nf * P->TL);
+    std::vector<int> stt(nf);
+    CU(cudaMemcpy(th.data(), dth, th.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(stt.data(), dst, nf * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int fi = 0; fi < nf; fi++) {
+        const int s = P->h_g_series[P->h_f_group[fi]];
+        unpad_theta(&th[(size_t)fi * P->TL], P->s_p[s], P->s_q[s], P->h_series[s].has_u != 0,
+                    P->h_series[s].has_v != 0, P->PQ, theta_out + (size_t)P->f_user[fi] * P->theta_stride);
+        if (status) status[P->f_user[fi]] = stt[fi];
+    }
+    return Err();
+}
+
+static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n, int p, int q,
+                     int n_reps, const double *z, unsigned long long seed, double mu, int exp_trans, double *simX,
+                     double *simY, double *simQ) {
+    if (!theta || n < 1 || n_reps < 1 || p < 0 || q < 0) return fail(LDSR_ERR_ARG, "bad theta/n/n_reps/p/q");
+    if (p > LDSR_MAX_PQ || q > LDSR_MAX_PQ) return fail(LDSR_ERR_UNSUPPORTED, "p or q exceeds LDSR_MAX_PQ");
+    std::unique_ptr<ldsr_ctx> tmp_ctx;
+    if (!ctx) {
+        ldsr_ctx *c = nullptr;
+        char buf[256];
+        int rc = ldsr_ctx_create(1, nullptr, &c, buf, sizeof buf);
+        if (rc != LDSR_OK) return fail(rc, "%s", buf);
+        tmp_ctx.reset(c);
+        ctx = c;
+    }
+    CU(cudaSetDevice(ctx->devices[0]));
+    DevicePool *pool = ctx->pools[0].get();
+    const int need = std::max(1, std::max(u ? p : 0, v ? q : 0));
+    const KernelTable *kt = kernel_table_for(need);
+    if (!kt) return fail(LDSR_ERR_UNSUPPORTED, "no kernel for width %d", need);
+    const int PQ = kt->pq;
+    std::vector<double> th(2 * PQ + 6), up((size_t)n * PQ, 0.0), vp((size_t)n * PQ, 0.0);
+    pad_theta(theta, p, q, u != nullptr, v != nullptr, PQ, th.data());
+    for (int t = 0; t < n; t++) {
+        if (u)
+            for (int j = 0; j < p; j++) up[(size_t)t * PQ + j] = u[(size_t)t * p + j];
+        if (v)
+            for (int j = 0; j < q; j++) vp[(size_t)t * PQ + j] = v[(size_t)t * q + j];
+    }
+    std::vector<void *> held;
+    auto dal = [&](size_t bytes, void **pp) -> cudaError_t {
+        cudaError_t e = pool->alloc(bytes, pp);
+        if (e == cudaSuccess) held.push_back(*pp);
+        return e;
+    };
+    struct Rel {
+        DevicePool *pool;
+        std::vector<void *> *h;
+        ~Rel() {
+            for (void *p : *h) pool->release(p);
+        }
+    } rel{pool, &held};
+    const size_t tot = (size_t)n * n_reps;
+    double *dth, *du, *dv, *dz = nullptr, *dstage, *dout;
+    CU(dal(th.size() * 8, (void **)&dth));
+    CU(dal(up.size() * 8, (void **)&du));
+    CU(dal(vp.size() * 8, (void **)&dv));
+    CU(dal(tot * 8, (void **)&dstage));
+    CU(dal(tot * 8, (void **)&dout));
+    CU(cudaMemcpy(dth, th.data(), th.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(du, up.data(), up.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dv, vp.data(), vp.size() * 8, cudaMemcpyHostToDevice));
+    if (z) {
+        CU(dal((size_t)n_reps * (1 + 2 * (size_t)n) * 8, (void **)&dz));
+        CU(cudaMemcpy(dz, z, (size_t)n_reps * (1 + 2 * (size_t)n) * 8, cudaMemcpyHostToDevice));
+    }
+    // one pass per requested output keeps the staging footprint at 2 arrays
+    double *outs[3] = {simX, simY, simQ};
+    for (int k = 0; k < 3; k++) {
+        if (!outs[k]) continue;
+        RepParams rp;
+        rp.theta = dth;
+        rp.u = du;
+        rp.v = dv;
+        rp.z = dz;
+        rp.seed = seed;
+        rp.n = n;
+        rp.n_reps = n_reps;
+        rp.mu = mu;
+        rp.exp_trans = exp_trans;
+        rp.simX = k == 0 ? dstage : nullptr;
+        rp.simY = k == 1 ? dstage : nullptr;
+        rp.simQ = k == 2 ? dstage : nullptr;
+        CU(kt->rep(rp, 0));
+        dim3 grid((n_reps + 31) / 32, (n + 31) / 32), block(32, 8);
+        transpose_kernel<<<grid, block>>>(dstage, dout, n, n_reps); // [n][reps] -> [reps][n]
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(outs[k], dout, tot * 8, cudaMemcpyDeviceToHost));
+    }
+    return Err();
+}
+
+} // namespace ldsr
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+int ldsr_abi_version(void) { return LDSR_ABI_VERSION; }
+
+int ldsr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ldsr_ctx_create(int n_devices, const int *devices, ldsr_ctx **out, char *errbuf, int errlen) {
+    if (!out) return report(fail(LDSR_ERR_ARG, "out is NULL"), errbuf, errlen);
+    const int have = ldsr_device_count();
+    if (have < 1)
+        return report(fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)"), errbuf, errlen);
+    if (n_devices <= 0) n_devices = have;
+    std::unique_ptr<ldsr_ctx> c(new ldsr_ctx());
+    for (int i = 0; i < n_devices; i++) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= have)
+            return report(fail(LDSR_ERR_ARG, "device %d out of range (have %d)", d, have), errbuf, errlen);
+        c->devices.push_back(d);
+        c->pools.emplace_back(new DevicePool(d));
+    }
+    *out = c.release();
+    return LDSR_OK;
+}
+
+void ldsr_ctx_destroy(ldsr_ctx *ctx) { delete ctx; }
+
+int ldsr_em_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int niter, double tol, const ldsr_options *opt,
+                  ldsr_em_result *out, char *errbuf, int errlen) {
+    return report(em_batch(ctx, batch, niter, tol, opt, out), errbuf, errlen);
+}
+
+int ldsr_plan_create(const ldsr_batch *batch, int device, ldsr_plan **out, char *errbuf, int errlen) {
+    if (!out) return report(fail(LDSR_ERR_ARG, "out is NULL"), errbuf, errlen);
+    return report(plan_build(batch, device, nullptr, out), errbuf, errlen);
+}
+
+int ldsr_plan_em(ldsr_plan *plan, int niter, double tol, const ldsr_options *opt, void *stream, long long *stats,
+                 char *errbuf, int errlen) {
+    if (!plan) return report(fail(LDSR_ERR_ARG, "plan is NULL"), errbuf, errlen);
+    return report(plan_em(plan, niter, tol, opt, (cudaStream_t)stream, opt && opt->trace_liks != 0, nullptr, stats),
+                  errbuf, errlen);
+}
+
+int ldsr_plan_set_theta0(ldsr_plan *plan, const double *theta0_host, char *errbuf, int errlen) {
+    if (!plan || !theta0_host) return report(fail(LDSR_ERR_ARG, "plan or theta0 is NULL"), errbuf, errlen);
+    cudaSetDevice(plan->device);
+    std::vector<double> th0((size_t)plan->n_fits * plan->TL);
+    for (int fi = 0; fi < plan->n_fits; fi++) {
+        const int s = plan->h_g_series[plan->h_f_group[fi]];
+        pad_theta(theta0_host + (size_t)plan->f_user[fi] * plan->theta_stride, plan->s_p[s], plan->s_q[s],
+                  plan->h_series[s].has_u != 0, plan->h_series[s].has_v != 0, plan->PQ, &th0[(size_t)fi * plan->TL]);
+    }
+    cudaError_t e = cudaMemcpy(plan->d_theta0, th0.data(), th0.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return report(fail(LDSR_ERR_CUDA, "theta0 upload: %s", cudaGetErrorString(e)), errbuf, errlen);
+    return LDSR_OK;
+}
+
+int ldsr_plan_fetch(ldsr_plan *plan, ldsr_em_result *out, char *errbuf, int errlen) {
+    if (!plan) return report(fail(LDSR_ERR_ARG, "plan is NULL"), errbuf, errlen);
+    return report(plan_fetch(plan, out), errbuf, errlen);
+}
+
+void ldsr_plan_destroy(ldsr_plan *plan) { delete plan; }
+
+int ldsr_smoother_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int stdlik, double *X, double *Y, double *V, double *J,
+                        double *lik, char *errbuf, int errlen) {
+    return report(step_batch(ctx, batch, StepKind::Smoother, stdlik, X, Y, V, J, lik), errbuf, errlen);
+}
+
+int ldsr_mstep_batch(ldsr_ctx *ctx, const ldsr_batch *batch, const double *X, const double *V, const double *J,
+                     double *theta_out, int *status, char *errbuf, int errlen) {
+    return report(mstep_batch(ctx, batch, X, V, J, theta_out, status), errbuf, errlen);
+}
+
+int ldsr_propagate_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int stdlik, double *X, double *Y, double *V,
+                         double *lik, char *errbuf, int errlen) {
+    return report(step_batch(ctx, batch, StepKind::Propagate, stdlik, X, Y, V, nullptr, lik), errbuf, errlen);
+}
+
+int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n, int p, int q,
+                   int n_reps, const double *z, unsigned long long seed, double mu, int exp_trans, double *simX,
+                   double *simY, double *simQ, char *errbuf, int errlen) {
+    return report(rep_batch(ctx, theta, u, v, n, p, q, n_reps, z, seed, mu, exp_trans, simX, simY, simQ), errbuf,
+                  errlen);
+}
+
+} // extern "C"

@@ -1,0 +1,230 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ldsr_b200.api / _lib) against the CPU
+oracle and the reference's golden values.  Tolerances are BASELINE.json's: log-likelihood
+relative 1e-9, theta and reconstructed flow relative 1e-6 at the same iteration count, identical
+selected restart."""
+import numpy as np
+import pytest
+
+import ldsr_b200 as L
+from ldsr_b200 import _lib
+from oracle import oracle as O
+from tests import data
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-9
+THETA_RTOL = 1e-6
+
+
+def rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+def rand_theta0(rng, p, q, n):
+    return np.stack([np.concatenate([[rng.uniform()], rng.uniform(-1, 1, p), [rng.uniform()],
+                                     rng.uniform(-1, 1, q), [1, 1, 0, 1]]) for _ in range(n)])
+
+
+def assert_theta_close(a, b, rtol=THETA_RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), 1e-8)
+    assert np.max(np.abs(a - b) / scale) < rtol, np.max(np.abs(a - b) / scale)
+
+
+# ---- the reference's own known-answer tests, run on the GPU (tests/testthat/test-LDS-EM.R:21-41)
+def test_kat_first_two_iterations_p1():
+    y, u, th0, kat = data.p1_case()
+    tol = kat["tolerance"]
+    theta0 = L.vec_to_theta(th0, 7, 7)
+    s1 = L.Kalman_smoother(y, u, u, theta0)
+    th1 = L.Mstep(y, u, u, s1)
+    s2 = L.Kalman_smoother(y, u, u, th1)
+    th2 = L.Mstep(y, u, u, s2)
+    assert rel(s1["lik"], kat["smooth1_lik"]) < tol
+    assert rel(s1["X"][0], kat["smooth1_X_1_85"][0]) < tol
+    assert rel(s1["X"][84], kat["smooth1_X_1_85"][1]) < tol
+    for th, g in ((th1, kat["theta1"]), (th2, kat["theta2"])):
+        assert rel(th["A"], g["A"]) < tol
+        assert abs(th["C"] - g["C"]) < 1e-6
+        assert rel(th["Q"], g["Q"]) < tol
+    assert rel(s2["lik"], kat["smooth2_lik"]) < 5e-6
+    # and against the oracle to full precision
+    o1 = O.kalman_smoother(y, u, u, th0)
+    assert rel(s1["lik"], o1["lik"]) < 1e-12
+    for k in "XYVJ":
+        assert np.allclose(s1[k], o1[k], rtol=1e-11, atol=1e-13), k
+    assert_theta_close(L.theta_to_vec(th1), O.mstep(y, u, u, o1), 1e-10)
+
+
+def test_kat_convergence_p1():
+    y, u, th0, kat = data.p1_case()
+    fit = L.LDS_EM(y, u, u, L.vec_to_theta(th0, 7, 7), kat["em"]["niter"], kat["em"]["tol"])
+    assert len(fit["liks"]) == 68
+    assert abs(fit["lik"] - kat["em"]["lik"]) < 1e-6
+    o = O.em(y, u, u, th0, 100, 1e-5)
+    assert np.allclose(fit["liks"], o["liks"], rtol=LIK_RTOL, atol=0)
+    assert_theta_close(L.theta_to_vec(fit["theta"]), o["theta"])
+    for k in "XYVJ":
+        assert np.allclose(fit["fit"][k], o["fit"][k], rtol=1e-6, atol=1e-9), k
+
+
+def test_nplds_fixture_estep():
+    g = data.load("nplds.json")
+    y, u, mu, inst = data.np_case(1, 1200)
+    th = data.theta_of(g["theta"])
+    s = L.Kalman_smoother(y, u, u, L.vec_to_theta(th, 3, 3))
+    assert rel(s["lik"], g["lik"]) < LIK_RTOL
+    assert np.max(np.abs(s["X"] - np.array(g["rec"]["X"]))) < 1e-11
+    assert np.max(np.abs(np.exp(s["Y"] + mu) / np.array(g["rec"]["Q"]) - 1)) < 1e-11
+
+
+# ---- batched EM against the oracle
+def _np213():
+    y, u, mu, inst = data.np_case(601, 1800)
+    return y, u, mu, inst
+
+
+def check_batch(series, group_series, held, fit_group, th0, niter, tol, **kw):
+    g = _lib.em_batch(series, group_series, held, fit_group, th0, niter, tol, want_liks=True, **kw)
+    o = O.em_batch(series, group_series, held, fit_group, th0, niter, tol)
+    assert np.array_equal(g["status"], o["status"])
+    assert np.array_equal(g["iters"], o["iters"]), np.nonzero(g["iters"] != o["iters"])
+    assert np.allclose(g["lik"], o["lik"], rtol=LIK_RTOL, atol=0)
+    assert_theta_close(g["theta"], o["theta"])
+    assert np.array_equal(g["best"], o["best"])
+    # trace: filled up to iters, NaN after
+    for f in range(len(fit_group)):
+        n = g["iters"][f]
+        assert np.all(np.isfinite(g["liks"][f, :n])) and np.all(np.isnan(g["liks"][f, n:]))
+        assert g["liks"][f, n - 1] == g["lik"][f]
+    return g, o
+
+
+def test_em_batch_folds_restarts_np213():
+    y, u, mu, inst = _np213()
+    rng = np.random.default_rng(11)
+    n_folds, n_rest = 6, 20
+    held = [np.sort(rng.choice(inst, 11, replace=False)) for _ in range(n_folds)]
+    fg = np.repeat(np.arange(n_folds), n_rest)
+    th0 = rand_theta0(rng, 3, 3, n_folds * n_rest)
+    ser = [dict(y=y, u=u, v=u)]
+    g, o = check_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 300, 1e-5)
+    # winners' smoothed trajectories == oracle E-step with the winner's theta on the fold's y
+    for k in range(n_folds):
+        b = g["best"][k]
+        yy = y.copy()
+        yy[held[k]] = np.nan
+        s = O.kalman_smoother(yy, u, u, o["theta"][b])
+        row = slice(g["traj_ptr"][k], g["traj_ptr"][k + 1])
+        assert np.allclose(g["X"][row], s["X"], rtol=1e-6, atol=1e-9)
+        assert np.allclose(np.exp(g["Y"][row] + mu), np.exp(s["Y"] + mu), rtol=THETA_RTOL)
+        assert np.allclose(g["V"][row], s["V"], rtol=1e-6) and np.allclose(g["J"][row], s["J"], rtol=1e-6)
+
+
+def test_chunking_does_not_change_results():
+    y, u, mu, inst = _np213()
+    rng = np.random.default_rng(5)
+    th0 = rand_theta0(rng, 3, 3, 40)
+    ser = [dict(y=y, u=u, v=u)]
+    a = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=100)
+    b = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=7)
+    for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_sentinels_unequal_dims_and_ensemble():
+    # test-LDS-EM.R:58-77, test-ensemble.R:9-18: u=NULL, v=NULL, nrow(u)!=nrow(v), list of u/v
+    y, u, mu, inst = _np213()
+    rng = np.random.default_rng(3)
+    series = [dict(y=y, u=None, v=u, p=1, q=3), dict(y=y, u=u, v=None, p=3, q=1),
+              dict(y=y, u=u[:2], v=u), dict(y=y, u=u, v=u)]
+    stride = 12
+    th0, fg = [], []
+    for s_i, (p, q) in enumerate([(1, 3), (3, 1), (2, 3), (3, 3)]):
+        for t in rand_theta0(rng, p, q, 5):
+            th0.append(np.pad(t, (0, stride - t.size)))
+            fg.append(s_i)
+    held = [inst[:5], inst[5:9], np.array([], dtype=int), inst[-3:]]
+    g, o = check_batch(series, [0, 1, 2, 3], held, fg, np.stack(th0), 120, 1e-5)
+    assert np.all(g["theta"][0:5, 1] == 0)      # B == 0 without u
+    assert np.all(g["theta"][5:10, 5] == 0)     # D == 0 without v
+
+
+def test_api_restart_and_cv_shapes():
+    d = data.load("np.json")
+    Qa = dict(year=np.array(d["NPannual"]["year"]), Qa=np.array(d["NPannual"]["Qa"]))
+    pc = np.array([d["NPpc"][k] for k in ("PC1", "PC9", "PC13")])[:, 600:]
+    rng = np.random.default_rng(2)
+    fit = L.LDS_reconstruction(Qa, pc, pc, start_year=1800, num_restarts=4, rng=rng, niter=200, return_raw=True)
+    assert set(fit["rec"]) == {"year", "X", "Xl", "Xu", "Q", "Ql", "Qu"} and fit["rec"]["Q"].size == 213
+    assert np.all(fit["rec"]["Ql"] < fit["rec"]["Q"]) and np.all(fit["rec"]["Q"] < fit["rec"]["Qu"])
+    Z = L.make_Z(Qa["Qa"], 3, rng=rng)
+    cv = L.cvLDS(Qa, pc, pc, start_year=1800, num_restarts=3, Z=Z, rng=rng, niter=200)
+    assert cv["Ycv"].shape == (46, 3) and set(cv["metrics"]) == {"R2", "RE", "CE", "nRMSE", "KGE"}
+    ens = L.LDS_reconstruction(Qa, [pc, pc[:2]], [pc, pc[:2]], start_year=1800, num_restarts=2, rng=rng, niter=100)
+    assert len(ens["ensemble"]) == 2 and ens["rec"]["X"].size == 213
+    cv2 = L.cvLDS(Qa, [pc, pc[:2]], [pc, pc[:2]], start_year=1800, num_restarts=2,
+                  Z=L.make_Z(Qa["Qa"], 2, contiguous=False, rng=rng), rng=rng, niter=100)
+    assert cv2["Ycv"].shape == (46, 2)
+    for kw in (dict(u=None, v=pc), dict(u=pc, v=None), dict(u=pc[:2], v=pc)):
+        f = L.LDS_reconstruction(Qa, kw["u"], kw["v"], start_year=1800, num_restarts=2, rng=rng, niter=100)
+        assert np.isfinite(f["lik"])
+
+
+def test_propagate_and_rep_against_oracle():
+    d = data.load("np.json")
+    th = data.theta_of(d["theta"])
+    y, u, mu, inst = data.np_case(1, 1200)
+    g = L.propagate(L.vec_to_theta(th, 3, 3), u, u, y)
+    o = O.propagate(th, u, u, y)
+    assert rel(g["lik"], o["lik"]) < LIK_RTOL
+    for k in "XYV":
+        assert np.allclose(g[k], o[k], rtol=1e-12, atol=1e-14)
+    rng = np.random.default_rng(9)
+    n_reps, n = 7, 813
+    z = rng.standard_normal((n_reps, 1 + 2 * n))
+    r = L.LDS_rep(L.vec_to_theta(th, 3, 3), u, u, np.arange(1200, 2013), n_reps, mu=mu, z=z)
+    for i in range(n_reps):
+        oo = O.rep(th, u, u, n, z[i], mu=mu)
+        sl = slice(i * n, (i + 1) * n)
+        assert np.allclose(r["simX"][sl], oo["simX"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(r["simQ"][sl], oo["simQ"], rtol=1e-10)
+    # device generator: right moments, reproducible, different per replicate
+    r1 = L.LDS_rep(L.vec_to_theta(th, 3, 3), None, None, np.arange(2000), 2000, seed=1, exp_trans=False)
+    r2 = L.LDS_rep(L.vec_to_theta(th, 3, 3), None, None, np.arange(2000), 2000, seed=1, exp_trans=False)
+    assert np.array_equal(r1["simX"], r2["simX"])
+    X = r1["simX"].reshape(2000, 2000)[:, 500:]
+    a, q = th[0], th[8]
+    assert abs(X.mean()) < 0.02 and rel(X.var(), q / (1 - a * a)) < 0.02
+
+
+def test_singular_gram_block_is_flagged():
+    y, u, mu, inst = _np213()
+    uu = np.vstack([u[0], u[0], u[1]])  # duplicated row: Tuu singular -> arma::inv would throw
+    th0 = rand_theta0(np.random.default_rng(0), 3, 3, 3)
+    r = _lib.em_batch([dict(y=y, u=uu, v=u)], [0], None, [0, 0, 0], th0, 20, 1e-5)
+    assert np.all(r["status"] == _lib.FIT_SINGULAR) and np.all(np.isnan(r["lik"])) and r["best"][0] == -1
+
+
+def test_argument_errors():
+    y, u, mu, inst = _np213()
+    th0 = rand_theta0(np.random.default_rng(0), 3, 3, 2)
+    with pytest.raises(_lib.LdsrError) as e:
+        _lib.em_batch([dict(y=y, u=u, v=u)], [0], None, [0, 0], th0, 1, 1e-5)  # niter < 2
+    assert e.value.code == _lib.ERR_ARG
+    yy = y.copy()
+    yy[170] = np.inf
+    with pytest.raises(_lib.LdsrError):
+        _lib.em_batch([dict(y=yy, u=u, v=u)], [0], None, [0, 0], th0, 10, 1e-5)
+    with pytest.raises(_lib.LdsrError):
+        _lib.em_batch([dict(y=y, u=u, v=u)], [0], [np.array([999])], [0, 0], th0, 10, 1e-5)
+
+
+def test_poll_callback_interrupts():
+    y, u, mu, inst = _np213()
+    th0 = rand_theta0(np.random.default_rng(0), 3, 3, 8)
+    calls = []
+    with pytest.raises(_lib.LdsrError) as e:
+        _lib.em_batch([dict(y=y, u=u, v=u)], [0], None, np.zeros(8, dtype=int), th0, 1000, 0.0, chunk_iters=10,
+                      poll=lambda: calls.append(1) or len(calls) >= 3)
+    assert e.value.code == _lib.ERR_INTERRUPTED and len(calls) == 3
