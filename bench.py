@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""bench.py -- EM fits/sec of the batched LDS-EM hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # the reference's CPU algorithm (oracle)
+
+A "step" is one pass of the hot path over one batch: config[1] of BASELINE.json -- cvLDS on
+NPannual/NPpc (T=413, p=q=3), 100 make_Z hold-out folds x 100 restarts = 10 000 independent EM
+fits, niter=1000, tol=1e-5, followed by the per-fold restart selection and the winners' smoothed
+trajectories.  With N>1 (torchrun, one rank per GPU) every rank owns its own such batch
+(different folds / initial values): weak scaling, no data-path collective.
+
+Printed JSON (one line, rank 0): see the task contract; extra keys `roofline`, `cpu_baseline`.
+  value   fits/s, inputs resident in HBM (ldsr_plan_em), device time by CUDA events per step
+  e2e     fits/s through the public host-buffer call (ldsr_em_batch): packing, H2D of all inputs,
+          EM, D2H of all results inside the timed region (wall clock, synchronised)
+  roofline  em_chunk_kernel: algorithmic FP64 flops / its CUDA-event time, against
+          the DFMA rate measured in this run (MEASURED_PEAKS.json has no FP64 entry)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ldsr_b200 import workloads as W  # noqa: E402
+
+METRIC = "EM fits/sec (T~400, restarts x CV folds)"
+
+
+def build_workload(name, rank):
+    seed = W.SEED + 7919 * rank
+    if name == "np_cv":
+        return W.np_cv(100, 100, seed)
+    if name == "np_restarts":
+        return W.np_restarts(100, seed)
+    if name == "synthetic":
+        return W.synthetic_stations(seed=seed)
+    if name == "synthetic_small":
+        return W.synthetic_stations(n_stations=4, n_folds=25, n_restarts=100, seed=seed)
+    raise SystemExit("unknown workload " + name)
+
+
+def workload_config(w, args):
+    s = w["series"][0]
+    return {"workload": w["name"], "n_fits_per_gpu": int(w["fit_group"].size), "n_groups_per_gpu": int(len(w["group_series"])),
+            "n_series": len(w["series"]), "T": int(s["y"].size), "p": int(s["p"]), "q": int(s["q"]),
+            "niter": args.niter, "tol": args.tol, "chunk_iters": args.chunk or 100}
+
+
+def total_flops(w, iters):
+    """Algorithmic FP64 flops of the EM job."""
+    gs, fg = w["group_series"], w["fit_group"]
+    it_g = np.bincount(fg, weights=iters, minlength=len(gs))
+    n_g = np.bincount(fg, minlength=len(gs))
+    tot = 0.0
+    for g in range(len(gs)):
+        s = w["series"][gs[g]]
+        T = s["y"].size
+        n_obs = int(np.isfinite(s["y"]).sum()) - len(np.unique(w["held"][g]))
+        tot += it_g[g] * W.flops_per_iter(T, s["p"], s["q"], n_obs) + n_g[g] * T * (2 * s["q"] + 1)
+    return tot
+
+
+# ---- clocks sampler (B200_PROFILING.md "clocks DURING the timed region") ----------------------
+class ClockSampler:
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [ln for (ts, ln) in self.lines if t0 - 0.05 <= ts <= t1 + 0.1] or [ln for _, ln in self.lines]
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except Exception:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_groups(w, seconds, cores):
+    """How many groups of `w` give about `seconds` of oracle work on `cores` threads."""
+    s = w["series"][w["group_series"][0]]
+    per_fit = 1000 * s["y"].size * (30 + 4 * (s["p"] + s["q"])) * 1e-9  # ~50 ns/(iter*step) at p=q=3
+    fits_per_group = w["fit_group"].size / len(w["group_series"])
+    g = int(seconds * cores / (per_fit * fits_per_group))
+    return max(1, min(g, len(w["group_series"])))
+
+
+def run_oracle(sample, args, threads):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    r = O.em_batch(sample["series"], sample["group_series"], sample["held"], sample["fit_group"], sample["theta0"],
+                   args.niter, args.tol, n_threads=threads)
+    return time.perf_counter() - t0, r
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU algorithm (oracle/ldsr_oracle.c, restating src/EM.cpp) on all host threads.
+    The real Rcpp/Armadillo build cannot run here (no R): see DESIGN.md."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = O.max_threads()
+    w = build_workload(args.workload, 0)
+    K, Wm = args.steps, args.warmup
+    g = cpu_sample_groups(w, min(args.cpu_seconds, 150.0 / max(1, K + Wm)), cores)
+    sample = W.subset(w, g)
+    nf = int(sample["fit_group"].size)
+    for _ in range(Wm):
+        run_oracle(sample, args, cores)
+    times = []
+    esteps = 0
+    for _ in range(K):
+        dt, r = run_oracle(sample, args, cores)
+        times.append(dt)
+        esteps = int(r["iters"].sum())
+    tot = sum(times)
+    value = nf * K / tot
+    desc = "first %d of %d groups (%d fits) per step" % (g, len(w["group_series"]), nf)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": Wm, "ms_per_step": 1e3 * tot / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "bundled NP series + synthetic initial values/folds (seeded)",
+        "config": workload_config(w, args),
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iter_steps_per_s": esteps * w["series"][0]["y"].size / (tot / K),
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="np_cv")
+    ap.add_argument("--niter", type=int, default=1000)
+    ap.add_argument("--tol", type=float, default=1e-5)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="oracle work per cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ldsr_b200 import _lib
+
+    if not torch.cuda.is_available() or _lib.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = build_workload(args.workload, rank)
+    nf = int(w["fit_group"].size)
+    K, Wm = args.steps, args.warmup
+    fp64_peak = _lib.measure_fp64_peak(local)
+
+    # ---------------- device-resident path (value) ----------------
+    plan = _lib.Plan(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    for _ in range(Wm):
+        plan.em(args.niter, args.tol, chunk_iters=args.chunk, stream=stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid) if rank == 0 else None
+    time.sleep(0.6 if rank == 0 else 0.0)  # let nvidia-smi start sampling
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    stats = []
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed iterations (not inside the event pair)
+        ev[k][0].record()
+        stats.append(plan.em(args.niter, args.tol, chunk_iters=args.chunk, stream=stream))
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_ms = float(tot_ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    res = plan.fetch(want_traj=False)
+    iters = res["iters"].astype(np.float64)
+    value = world * nf * K / (tot_ms * 1e-3)
+
+    # ---------------- end-to-end through the public host-buffer API ----------------
+    ctx = _lib.Ctx(devices=[local])
+    call = lambda: _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], args.niter,
+                                 args.tol, chunk_iters=args.chunk, ctx=ctx)
+    for _ in range(2):
+        r_e2e = call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r_e2e = call()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * nf * K / float(e2e_s.item())
+    h2d = sum(s["y"].nbytes + (0 if s["u"] is None else s["u"].nbytes) + (0 if s["v"] is None else s["v"].nbytes)
+              for s in w["series"]) + w["theta0"].nbytes + w["fit_group"].nbytes + w["group_series"].nbytes + \
+        sum(h.nbytes for h in w["held"])
+    d2h = sum(r_e2e[k].nbytes for k in ("theta", "lik", "iters", "status", "best", "X", "Y", "V", "J"))
+    assert np.array_equal(r_e2e["iters"], res["iters"]) and np.array_equal(r_e2e["best"], res["best"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (em_chunk_kernel) ----------------
+    flops = total_flops(w, iters)  # per step
+    em_ns = float(np.mean([s["em_kernel_ns"] for s in stats]))
+    chunks = float(np.mean([s["chunks"] for s in stats]))
+    achieved = flops / (em_ns * 1e-9) / 1e12
+    roofline = {"bound": "fp64", "kernel": "em_chunk_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak, "traffic": None,
+                "peak_source": "DFMA microbenchmark in this run (ldsr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "flops_per_launch": flops / chunks, "launch_ms": em_ns * 1e-6 / chunks, "launches_per_step": chunks,
+                "kernel_share_of_step": em_ns * 1e-6 / (tot_ms / K)}
+
+    # ---------------- CPU baseline (oracle port of src/EM.cpp), bounded sample ----------------
+    cpu = None
+    if not args.no_cpu and world == 1:
+        from oracle import oracle as O
+        cores = O.max_threads()
+        g = cpu_sample_groups(w, args.cpu_seconds, cores)
+        sample = W.subset(w, g)
+        dt, ro = run_oracle(sample, args, cores)
+        ns = int(sample["fit_group"].size)
+        same = bool(np.array_equal(ro["iters"], res["iters"][:ns]) and np.array_equal(ro["best"], res["best"][:g])
+                    and np.allclose(ro["lik"], res["lik"][:ns], rtol=1e-9, atol=0))
+        cpu = {"value": ns / dt, "unit": "fits/s", "cores": cores, "kind": "port",
+               "sample": "first %d of %d groups (%d fits), %.1f s" % (g, len(w["group_series"]), ns, dt),
+               "gpu_matches_oracle_on_sample": same}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "bundled NP series (tests/golden/np.json) + synthetic initial values/folds (seeded)",
+        "config": dict(workload_config(w, args), l2="flushed (256 MiB write) between timed steps",
+                       mean_iters=float(iters.mean()), parallelism="groups sharded over %d GPU(s), no collective" % world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "timing": "wall clock around ldsr_em_batch (host packing + pageable H2D + EM + D2H)"},
+        "gpu_launches": int(sum(s["launches"] for s in stats)),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "iter_steps_per_s": world * float(iters.sum()) * w["series"][0]["y"].size / (tot_ms / K * 1e-3),
+        "step_ms": [round(x, 3) for x in step_ms],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -136,8 +136,10 @@ typedef struct ldsr_plan ldsr_plan;
 int ldsr_plan_create(const ldsr_batch *batch, int device, ldsr_plan **out, char *errbuf, int errlen);
 /* Runs EM for every fit from the plan's resident theta0 on `stream` (a cudaStream_t, NULL =
  * the plan's own stream); blocks until the results are resident in HBM.  Launch statistics
- * (kernel launches issued, EM chunks) are returned through the optional int[4] `stats`:
- * {kernel launches, chunks, total E-steps executed (all fits), reserved}. */
+ * are returned through the optional long long[8] `stats`:
+ * {kernel launches issued, EM chunks (= em_chunk_kernel launches), total E-steps executed (all
+ *  fits), summed device time of the em_chunk_kernel launches in ns (CUDA events on `stream`),
+ *  0, 0, 0, 0}. */
 int ldsr_plan_em(ldsr_plan *plan, int niter, double tol, const ldsr_options *opt, void *stream,
                  long long *stats, char *errbuf, int errlen);
 int ldsr_plan_set_theta0(ldsr_plan *plan, const double *theta0_host, char *errbuf, int errlen);
@@ -166,6 +168,11 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    int p, int q, int n_reps, const double *z, unsigned long long seed, double mu,
                    int exp_trans, double *simX, double *simY, double *simQ, char *errbuf,
                    int errlen);
+
+/* ---- measurement helper -------------------------------------------------------------------
+ * FP64 roofline denominator: runs a register-resident DFMA kernel (8 independent chains per
+ * thread, all SMs full) on `device` and returns the best-of-5 rate in TFLOP/s (FMA = 2 flops). */
+int ldsr_measure_fp64_peak(int device, double *tflops, char *errbuf, int errlen);
 
 #ifdef __cplusplus
 }

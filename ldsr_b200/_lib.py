@@ -18,7 +18,7 @@ FIT_OK, FIT_SINGULAR, FIT_NONFINITE = 0, 1, 2
 EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy",
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
-           "ldsr_propagate_batch", "ldsr_rep_batch")
+           "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_measure_fp64_peak")
 
 
 class LdsrError(RuntimeError):
@@ -165,6 +165,28 @@ def _options(n_devices=0, devices=None, chunk_iters=0, poll=None, trace_liks=Fal
     return o
 
 
+class Ctx:
+    """ldsr_ctx: device list + reusable device-memory pools (keeps cudaMalloc out of repeated calls)."""
+
+    def __init__(self, devices=None, n_devices=0):
+        self.h = C.c_void_p()
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        err = C.create_string_buffer(512)
+        rc = lib().ldsr_ctx_create(int(dv.size if dv is not None else n_devices), _i(dv), C.byref(self.h), err, 512)
+        _check(rc, err)
+
+    def close(self):
+        if self.h:
+            lib().ldsr_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class EmOutputs:
     """numpy buffers behind an ldsr_em_result."""
 
@@ -200,8 +222,8 @@ def em_batch(series, group_series, held, fit_group, theta0, niter=1000, tol=1e-5
     keep = []
     opt = _options(n_devices, devices, chunk_iters, poll, keep=keep)
     err = C.create_string_buffer(512)
-    rc = lib().ldsr_em_batch(ctx, C.byref(pb.c), int(niter), C.c_double(tol), C.byref(opt),
-                             C.byref(out.c), err, 512)
+    rc = lib().ldsr_em_batch(ctx.h if isinstance(ctx, Ctx) else ctx, C.byref(pb.c), int(niter), C.c_double(tol),
+                             C.byref(opt), C.byref(out.c), err, 512)
     _check(rc, err)
     return out.as_dict(pb)
 
@@ -220,14 +242,14 @@ class Plan:
     def em(self, niter=1000, tol=1e-5, chunk_iters=0, stream=None, trace_liks=False, poll=None):
         keep = []
         opt = _options(chunk_iters=chunk_iters, poll=poll, trace_liks=trace_liks, keep=keep)
-        stats = (C.c_longlong * 4)()
+        stats = (C.c_longlong * 8)()
         err = C.create_string_buffer(512)
         rc = lib().ldsr_plan_em(self.h, int(niter), C.c_double(tol), C.byref(opt),
                                 C.c_void_p(stream or 0), stats, err, 512)
         _check(rc, err)
         self.niter = niter
         self.trace = bool(trace_liks)
-        return dict(launches=stats[0], chunks=stats[1], esteps=stats[2])
+        return dict(launches=stats[0], chunks=stats[1], esteps=stats[2], em_kernel_ns=stats[3])
 
     def set_theta0(self, theta0):
         th = np.ascontiguousarray(theta0, dtype=np.float64)
@@ -313,3 +335,11 @@ def rep_batch(theta, u, v, n, n_reps, z=None, seed=0, mu=0.0, exp_trans=True, p=
                               _d(outs["simY"]), _d(outs["simQ"]), err, 512)
     _check(rc, err)
     return {k: v for k, v in outs.items() if v is not None}
+
+
+def measure_fp64_peak(device=0):
+    """Measured DFMA rate of the device in TFLOP/s (the FP64 roofline denominator)."""
+    t = C.c_double()
+    err = C.create_string_buffer(512)
+    _check(lib().ldsr_measure_fp64_peak(int(device), C.byref(t), err, 512), err)
+    return t.value

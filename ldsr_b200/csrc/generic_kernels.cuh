@@ -294,4 +294,24 @@ __global__ void sum_int_kernel(const int *v, int n, unsigned long long *out) {
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, no memory traffic.
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.6789) out[0] = s; // never true; keeps the chains alive
+}
+
 } // namespace ldsr

@@ -457,6 +457,20 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     const int nf = P->n_fits, ns = P->n_series, ng = P->n_groups;
     const int chunk = (opt && opt->chunk_iters > 0) ? opt->chunk_iters : 100;
     long long launches = 0, chunks = 0;
+    double em_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        CU(cudaEventCreate(&ev0));
+        CU(cudaEventCreate(&ev1));
+    }
+    struct EvGuard {
+        cudaEvent_t &a, &b;
+        ~EvGuard() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev_guard{ev0, ev1};
+    bool ev_pending = false;
     P->last_niter = niter;
     P->em_done = false;
 
@@ -513,6 +527,12 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         launches += 2;
         CU(cudaMemcpyAsync(P->h_counts, P->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (ev_pending) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ev0, ev1));
+            em_ms += ms;
+            ev_pending = false;
+        }
         const int n_tasks = P->h_counts[0], n_live = P->h_counts[1];
         if (n_live == 0) break;
         if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
@@ -525,7 +545,12 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             P->ckpt_cap = need;
         }
         ep.ckpt = P->d_ckpt;
+        if (stats) CU(cudaEventRecord(ev0, st));
         CU(P->kt->em_chunk(ep, n_tasks, smem, st));
+        if (stats) {
+            CU(cudaEventRecord(ev1, st));
+            ev_pending = true;
+        }
         launches++;
         chunks++;
     }
@@ -585,7 +610,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         stats[0] = launches;
         stats[1] = chunks;
         stats[2] = (long long)total;
-        stats[3] = 0;
+        stats[3] = (long long)(em_ms * 1e6);
+        stats[4] = stats[5] = stats[6] = stats[7] = 0;
     }
     return Err();
 }
@@ -1136,6 +1162,39 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    double *simY, double *simQ, char *errbuf, int errlen) {
     return report(rep_batch(ctx, theta, u, v, n, p, q, n_reps, z, seed, mu, exp_trans, simX, simY, simQ), errbuf,
                   errlen);
+}
+
+int ldsr_measure_fp64_peak(int device, double *tflops, char *errbuf, int errlen) {
+    auto run = [&]() -> Err {
+        if (!tflops) return fail(LDSR_ERR_ARG, "tflops is NULL");
+        if (ldsr_device_count() < 1) return fail(LDSR_ERR_CUDA, "no CUDA device available");
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        double *d = nullptr;
+        CU(cudaMalloc(&d, 64));
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
+        double best = 0.0;
+        for (int rep = 0; rep < 6; rep++) {
+            CU(cudaEventRecord(a));
+            dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            CU(cudaEventRecord(b));
+            CU(cudaEventSynchronize(b));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, a, b));
+            const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        cudaFree(d);
+        *tflops = best;
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
 }
 
 } // extern "C"
