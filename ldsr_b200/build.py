@@ -42,12 +42,20 @@ def _run(cmd):
 
 
 def build(force=False, verbose=False, ptxas_info=False):
+    """Env (development only): LDSR_PQ_LIST="3,10" builds just those widths; LDSR_SEG=4 overrides
+    the checkpoint segment length; LDSR_NVCC_EXTRA adds nvcc flags."""
+    global PQ_LIST
+    if os.environ.get("LDSR_PQ_LIST"):
+        PQ_LIST = tuple(int(x) for x in os.environ["LDSR_PQ_LIST"].split(","))
     deps = _sources()
     if not force and not _stale(SO, deps):
         return SO
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
     extra = ["-Xptxas", "-v"] if ptxas_info else []
+    if os.environ.get("LDSR_SEG"):
+        extra += ["-DLDSR_SEG=" + os.environ["LDSR_SEG"]]
+    extra += os.environ.get("LDSR_NVCC_EXTRA", "").split()
     for pq in PQ_LIST:
         o = os.path.join(OBJ, "kernels_pq%d.o" % pq)
         jobs.append((o, [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))

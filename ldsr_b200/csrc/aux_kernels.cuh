@@ -130,8 +130,10 @@ template <int PQ> __global__ void mstep_kernel(const MstepParams P) {
     for (int t = 0; t < T; t++) {
         const double Xs = X[t], Vs = V[t];
         if (t < T - 1) {
-            st.Tx1x = fma(X[t + 1], Xs, fma(V[t + 1], J[t], st.Tx1x));
-            st.Txx += fma(Xs, Xs, Vs);
+            st.Tx1x = fma(X[t + 1], Xs, st.Tx1x);
+            st.Tx1xv = fma(V[t + 1], J[t], st.Tx1xv);
+            st.Txx = fma(Xs, Xs, st.Txx);
+            st.Txxv += Vs;
 #pragma unroll
             for (int k = 0; k < PQ; k++) {
                 st.Tx1u[k] = fma(X[t + 1], us[(size_t)t * PQ + k], st.Tx1u[k]);
@@ -140,7 +142,8 @@ template <int PQ> __global__ void mstep_kernel(const MstepParams P) {
         }
         if ((mw[t >> 5] >> (t & 31)) & 1u) {
             st.Syx = fma(ys[t], Xs, st.Syx);
-            st.Sxx += fma(Xs, Xs, Vs);
+            st.Sxx = fma(Xs, Xs, st.Sxx);
+            st.Sxxv += Vs;
 #pragma unroll
             for (int k = 0; k < PQ; k++) st.Sxv[k] = fma(Xs, vs[(size_t)t * PQ + k], st.Sxv[k]);
         }

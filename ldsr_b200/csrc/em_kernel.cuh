@@ -6,8 +6,11 @@
 //   pass 1  forward Kalman filter: log-likelihood + a checkpoint (Xp,Vp) every SEG steps;
 //   stop rule (EM.cpp:272) -- a fit that stops keeps the theta this E-step ran with;
 //   pass 2  RTS smoother, segment by segment from the end: the segment's filter states are
-//           recomputed from its checkpoint into REGISTERS (Xu,Vu,Xp1 for SEG steps), then the
-//           backward recursion runs over them and accumulates the M-step sums on the fly;
+//           recomputed from its checkpoint into REGISTERS (Xu,Vu,Xp1,Vp1 for SEG steps), then the
+//           backward recursion runs over them and accumulates the M-step sums on the fly.  The
+//           recursion is written in affine form Xs = J*Xs1 + g, Vs = J^2*Vs1 + L with J, g, L
+//           computed off the dependency chain, so one warp alone keeps its FP64 pipe busy (the
+//           segment bodies are straight-line code: no votes, no bounds checks);
 //   M-step  closed form from the sums (lds_math.cuh).
 // No O(T) trajectory ever goes to memory: per fit and iteration the kernel touches 2 doubles per
 // SEG steps of checkpoint.  Steps no lane of the warp observes (warp vote on the mask bits) take a
@@ -51,8 +54,128 @@ __device__ __forceinline__ unsigned seg_bits(const unsigned *__restrict__ mw, in
     return (w >> (t0 & 31)) & ((seg_len == 32) ? 0xffffffffu : ((1u << seg_len) - 1u));
 }
 
-template <int PQ, int SEG, int W>
-__global__ void __launch_bounds__(W * 32) em_chunk_kernel(const EmParams P) {
+// ---- pass 1 over one segment -----------------------------------------------------------------
+// All lanes unobserved: pure prediction (EM.cpp:72-76 with Xu=Xp, Vu=Vp).
+template <int PQ, int SEG>
+__device__ __forceinline__ void fwd_unobserved(const Theta<PQ> &th, double A, double A2, double Q,
+                                               const double *__restrict__ useg, double &Xp, double &Vp) {
+    double Bu[SEG];
+#pragma unroll
+    for (int j = 0; j < SEG; j++) Bu[j] = dot_row<PQ>(th.B, useg + j * PQ);
+#pragma unroll
+    for (int j = 0; j < SEG; j++) {
+        Xp = fma(A, Xp, Bu[j]);
+        Vp = fma(A2, Vp, Q);
+    }
+}
+
+// Some lane observes some step: measurement update on every step, per-lane predicated, plus the
+// likelihood terms (EM.cpp:86-88, 115-122).  cnt (warp-uniform) <= SEG steps are valid.
+template <int PQ, int SEG>
+__device__ __forceinline__ void fwd_mixed(const Theta<PQ> &th, double A, double A2, double Q, unsigned bits, int cnt,
+                                          const double *__restrict__ yseg, const double *__restrict__ useg,
+                                          const double *__restrict__ vseg, double &Xp, double &Vp, double &acc) {
+#pragma unroll
+    for (int j = 0; j < SEG; j++) {
+        if (j < cnt) {
+            const bool obs = (bits >> j) & 1u;
+            const double Bu = dot_row<PQ>(th.B, useg + j * PQ);
+            const double Dv = dot_row<PQ>(th.D, vseg + j * PQ);
+            const double S = fma(th.C * Vp, th.C, th.R); // C*Vp*C + R
+            const double rS = fast_rcp(S);
+            const double K = Vp * th.C * rS;
+            const double delta = yseg[j] - fma(th.C, Xp, Dv);
+            const double Xu = obs ? fma(K, delta, Xp) : Xp;
+            const double Vu = obs ? (1.0 - K * th.C) * Vp : Vp;
+            const double term = delta * rS * delta + log(S);
+            acc += obs ? term : 0.0;
+            Xp = fma(A, Xu, Bu); // u lags one step (EM.cpp:74)
+            Vp = fma(A2, Vu, Q); // A*Vu*A + Q      (EM.cpp:76)
+        }
+    }
+}
+
+// ---- pass 2 over one segment -----------------------------------------------------------------
+// MIXED   : the segment holds observed steps for some lane -> measurement updates + observed sums
+// GUARDED : the segment is the last one: only cnt steps are valid and its last step is T-1
+template <int PQ, int SEG, bool MIXED, bool GUARDED>
+__device__ __forceinline__ void smooth_segment(const Theta<PQ> &th, double A, double A2, double Q, unsigned bits,
+                                               int cnt, const double *__restrict__ yseg,
+                                               const double *__restrict__ useg, const double *__restrict__ vseg,
+                                               double Xq, double Vq, double &Xs1, double &Vs1, Stats<PQ> &st) {
+    // Recompute the filter over the segment (EM.cpp:70-90) and, in the same sweep, the RTS gain and
+    // the affine form of the backward recursion (EM.cpp:100-102) -- all of it off the dependency
+    // chain of the smoother:
+    //      Xs_t = Xu + J (Xs1 - Xp1)   = J Xs1 + g,    g = Xu - J Xp1
+    //      Vs_t = Vu + J (Vs1 - Vp1) J = J^2 Vs1 + L,  L = Vu - J^2 Vp1
+    // Only J, g, L (3*SEG doubles) stay in registers.
+    double Jt[SEG], g[SEG], L[SEG];
+#pragma unroll
+    for (int j = 0; j < SEG; j++) {
+        if (!GUARDED || j < cnt) {
+            double xu = Xq, vu = Vq;
+            if (MIXED) {
+                const bool obs = (bits >> j) & 1u;
+                const double Dv = dot_row<PQ>(th.D, vseg + j * PQ);
+                const double S = fma(th.C * Vq, th.C, th.R);
+                const double K = Vq * th.C * fast_rcp(S);
+                const double delta = yseg[j] - fma(th.C, Xq, Dv);
+                xu = obs ? fma(K, delta, Xq) : Xq;
+                vu = obs ? (1.0 - K * th.C) * Vq : Vq;
+            }
+            Xq = fma(A, xu, dot_row<PQ>(th.B, useg + j * PQ));
+            Vq = fma(A2, vu, Q);
+            if (GUARDED && j == cnt - 1) { // t == T-1: smoothed = filtered (EM.cpp:94-95)
+                Jt[j] = 0.0;
+                g[j] = xu;
+                L[j] = vu;
+            } else {
+                const double J = vu * A * fast_rcp(Vq);
+                Jt[j] = J;
+                g[j] = fma(-J, Xq, xu);
+                L[j] = fma(-J * J, Vq, vu);
+            }
+        }
+    }
+    // ---- the chain and the sums of EM.cpp:151-161, 180-193
+#pragma unroll
+    for (int j = SEG - 1; j >= 0; j--) {
+        if (!GUARDED || j < cnt) {
+            const double J = Jt[j];
+            const double Xs = fma(J, Xs1, g[j]);
+            const double Vs = fma(J * J, Vs1, L[j]);
+            if (GUARDED && j == cnt - 1) {
+                st.XT = Xs;
+                st.VT = Vs;
+            } else {
+                st.Tx1x = fma(Xs1, Xs, st.Tx1x);
+                st.Tx1xv = fma(Vs1, J, st.Tx1xv);
+                st.Txx = fma(Xs, Xs, st.Txx);
+                st.Txxv += Vs;
+#pragma unroll
+                for (int k = 0; k < PQ; k++) {
+                    const double uk = useg[j * PQ + k];
+                    st.Tx1u[k] = fma(Xs1, uk, st.Tx1u[k]);
+                    st.Tux[k] = fma(uk, Xs, st.Tux[k]);
+                }
+            }
+            if (MIXED) {
+                const bool obs = (bits >> j) & 1u;
+                const double xo = obs ? Xs : 0.0, yo = obs ? yseg[j] : 0.0; // y is NaN where missing
+                st.Syx = fma(yo, xo, st.Syx);
+                st.Sxx = fma(xo, xo, st.Sxx);
+                st.Sxxv += obs ? Vs : 0.0;
+#pragma unroll
+                for (int k = 0; k < PQ; k++) st.Sxv[k] = fma(xo, vseg[j * PQ + k], st.Sxv[k]);
+            }
+            Xs1 = Xs;
+            Vs1 = Vs;
+        }
+    }
+}
+
+template <int PQ, int SEG, int W, bool STAGED>
+__global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -61,18 +184,16 @@ __global__ void __launch_bounds__(W * 32) em_chunk_kernel(const EmParams P) {
     const int T = S.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    const double *ser;
-    if (P.blob_in_smem) {
+    if (STAGED) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (threadIdx.x == 0) stage_blob(smem_raw, P.blobs + S.blob_off, (unsigned)S.blob_doubles * 8u, &bar);
-        ser = reinterpret_cast<const double *>(smem_raw);
-    } else {
-        ser = P.blobs + S.blob_off;
     }
+    const double *__restrict__ ser =
+        STAGED ? reinterpret_cast<const double *>(smem_raw) : (P.blobs + S.blob_off);
     const double *__restrict__ ys = ser + S.y_off;
     const double *__restrict__ us = ser + S.u_off;
     const double *__restrict__ vs = ser + S.v_off;
@@ -97,9 +218,10 @@ __global__ void __launch_bounds__(W * 32) em_chunk_kernel(const EmParams P) {
         lik = __longlong_as_double(0x7ff8000000000000ULL);
     }
     double *__restrict__ ck = P.ckpt + ((size_t)(blockIdx.x * W + warp) * P.max_seg) * 64 + lane;
-    const int nseg = (T + SEG - 1) / SEG;
+    const int nseg = (T + SEG - 1) / SEG;       // the last segment (full or not) holds step T-1
+    const int cnt_last = T - (nseg - 1) * SEG;  // 1..SEG valid steps in it
 
-    if (P.blob_in_smem) mbar_wait(&bar, 0);
+    if (STAGED) mbar_wait(&bar, 0);
     if (warp * 32 >= task.z) return; // whole warp has no fit
 
     for (int it = 0; it < P.chunk; ++it) {
@@ -114,32 +236,12 @@ __global__ void __launch_bounds__(W * 32) em_chunk_kernel(const EmParams P) {
             ck[(size_t)sg * 64] = Xp;
             ck[(size_t)sg * 64 + 32] = Vp;
             const unsigned bits = seg_bits(mw, t0, SEG);
-            if (__any_sync(FULL, bits != 0u)) {
-#pragma unroll
-                for (int j = 0; j < SEG; j++) {
-                    const int t = t0 + j;
-                    if (t < T) {
-                        const bool obs = (bits >> j) & 1u;
-                        double Xu = Xp, Vu = Vp;
-                        if (__any_sync(FULL, obs)) {
-                            double dq, Sg;
-                            measurement_update<PQ>(th, obs, ys[t], vs + (size_t)t * PQ, Xp, Vp, Xu, Vu, dq, Sg);
-                            if (obs) acc += dq + log(Sg);
-                        }
-                        Xp = fma(A, Xu, dot_row<PQ>(th.B, us + (size_t)t * PQ)); // u lags one step (EM.cpp:74)
-                        Vp = fma(A2, Vu, Q);                                      // A*Vu*A + Q (EM.cpp:76)
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < SEG; j++) {
-                    const int t = t0 + j;
-                    if (t < T) {
-                        Xp = fma(A, Xp, dot_row<PQ>(th.B, us + (size_t)t * PQ));
-                        Vp = fma(A2, Vp, Q);
-                    }
-                }
-            }
+            const double *__restrict__ useg = us + t0 * PQ;
+            if (sg == nseg - 1 || __any_sync(FULL, bits != 0u))
+                fwd_mixed<PQ, SEG>(th, A, A2, Q, bits, sg == nseg - 1 ? cnt_last : SEG, ys + t0, useg, vs + t0 * PQ,
+                                   Xp, Vp, acc);
+            else
+                fwd_unobserved<PQ, SEG>(th, A, A2, Q, useg, Xp, Vp);
         }
         // lik = (-0.5 n log 2pi - 0.5 acc)/n      (EM.cpp:122-124, stdlik = TRUE)
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs;
@@ -158,71 +260,22 @@ __global__ void __launch_bounds__(W * 32) em_chunk_kernel(const EmParams P) {
         Stats<PQ> st;
         st.zero();
         double Xs1 = 0.0, Vs1 = 0.0; // smoothed state of step t+1
-        for (int sg = nseg - 1; sg >= 0; --sg) {
+        {
+            const int sg = nseg - 1, t0 = sg * SEG;
+            smooth_segment<PQ, SEG, true, true>(th, A, A2, Q, seg_bits(mw, t0, SEG), cnt_last, ys + t0, us + t0 * PQ,
+                                                vs + t0 * PQ, ck[(size_t)sg * 64], ck[(size_t)sg * 64 + 32], Xs1, Vs1,
+                                                st);
+        }
+        for (int sg = nseg - 2; sg >= 0; --sg) {
             const int t0 = sg * SEG;
-            double Xq = ck[(size_t)sg * 64], Vq = ck[(size_t)sg * 64 + 32]; // (Xp,Vp) entering the segment
+            const double Xq = ck[(size_t)sg * 64], Vq = ck[(size_t)sg * 64 + 32]; // (Xp,Vp) entering the segment
             const unsigned bits = seg_bits(mw, t0, SEG);
-            const bool anyobs = __any_sync(FULL, bits != 0u);
-            double Xu[SEG], Vu[SEG], Xp1[SEG];
-            // ---- recompute the filter over the segment into registers
-#pragma unroll
-            for (int j = 0; j < SEG; j++) {
-                const int t = t0 + j;
-                if (t < T) {
-                    const bool obs = (bits >> j) & 1u;
-                    double xu = Xq, vu = Vq;
-                    if (anyobs && __any_sync(FULL, obs)) {
-                        double dq, Sg;
-                        measurement_update<PQ>(th, obs, ys[t], vs + (size_t)t * PQ, Xq, Vq, xu, vu, dq, Sg);
-                    }
-                    Xu[j] = xu;
-                    Vu[j] = vu;
-                    Xq = fma(A, xu, dot_row<PQ>(th.B, us + (size_t)t * PQ));
-                    Vq = fma(A2, vu, Q);
-                    Xp1[j] = Xq;
-                }
-            }
-            // ---- backward over the segment (EM.cpp:99-104) with the sums of EM.cpp:151-161,180-193
-#pragma unroll
-            for (int j = SEG - 1; j >= 0; j--) {
-                const int t = t0 + j;
-                if (t < T) {
-                    double Xs, Vs;
-                    if (t == T - 1) {
-                        Xs = Xu[j];
-                        Vs = Vu[j];
-                        st.XT = Xs;
-                        st.VT = Vs;
-                    } else {
-                        const double Vp1 = fma(A2, Vu[j], Q);
-                        const double J = Vu[j] * A * (1.0 / Vp1);
-                        Xs = fma(J, Xs1 - Xp1[j], Xu[j]);
-                        Vs = fma(J * (Vs1 - Vp1), J, Vu[j]);
-                        st.Tx1x = fma(Xs1, Xs, fma(Vs1, J, st.Tx1x));
-                        st.Txx += fma(Xs, Xs, Vs);
-                        const double *__restrict__ ut = us + (size_t)t * PQ;
-#pragma unroll
-                        for (int k = 0; k < PQ; k++) {
-                            st.Tx1u[k] = fma(Xs1, ut[k], st.Tx1u[k]);
-                            st.Tux[k] = fma(ut[k], Xs, st.Tux[k]);
-                        }
-                    }
-                    if (anyobs) {
-                        const bool obs = (bits >> j) & 1u;
-                        if (__any_sync(FULL, obs)) {
-                            const double yo = obs ? ys[t] : 0.0;
-                            const double xo = obs ? Xs : 0.0;
-                            st.Syx = fma(yo, xo, st.Syx);
-                            st.Sxx += obs ? fma(Xs, Xs, Vs) : 0.0;
-                            const double *__restrict__ vt = vs + (size_t)t * PQ;
-#pragma unroll
-                            for (int k = 0; k < PQ; k++) st.Sxv[k] = fma(xo, vt[k], st.Sxv[k]);
-                        }
-                    }
-                    Xs1 = Xs;
-                    Vs1 = Vs;
-                }
-            }
+            if (__any_sync(FULL, bits != 0u))
+                smooth_segment<PQ, SEG, true, false>(th, A, A2, Q, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
+                                                     Vq, Xs1, Vs1, st);
+            else
+                smooth_segment<PQ, SEG, false, false>(th, A, A2, Q, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
+                                                      Vq, Xs1, Vs1, st);
         }
         st.X0 = Xs1;
         st.V0 = Vs1;

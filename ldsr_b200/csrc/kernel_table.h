@@ -7,7 +7,10 @@
 
 namespace ldsr {
 
-constexpr int EM_SEG = 8;   // steps per checkpoint segment
+#ifndef LDSR_SEG
+#define LDSR_SEG 8
+#endif
+constexpr int EM_SEG = LDSR_SEG; // steps per checkpoint segment (divides 32)
 constexpr int EM_WARPS = 4; // warps per CTA (one per SM sub-partition)
 
 struct KernelTable {

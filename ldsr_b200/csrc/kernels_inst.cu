@@ -11,11 +11,14 @@ namespace {
 constexpr int PQ = LDSR_PQ;
 
 cudaError_t em_prepare(size_t smem_bytes) {
-    return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem_bytes);
+    return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
 cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
-    em_chunk_kernel<PQ, EM_SEG, EM_WARPS><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
+    if (p.blob_in_smem)
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, true><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
+    else
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, false><<<n_tasks, EM_WARPS * 32, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {

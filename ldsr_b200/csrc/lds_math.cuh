@@ -44,6 +44,21 @@ template <int PQ> __device__ __forceinline__ void store_theta(const Theta<PQ> &t
     g[5 + 2 * PQ] = t.V1;
 }
 
+// Reciprocal for the filter/smoother gains: MUFU.RCP64H seed + two Newton steps (~1 ulp, not
+// correctly rounded; the parity budget is 1e-9).  ~3x the throughput of the IEEE division
+// sequence (measured: 18 vs 125 issue cycles per warp, profiles/microbench_r01.txt).
+// Arguments are variances (Vp, Sigma): positive and far from the subnormal range in any fit that
+// still has a finite likelihood.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 template <int PQ> __device__ __forceinline__ double dot_row(const double (&w)[PQ], const double *__restrict__ row) {
     double s = 0.0;
 #pragma unroll
@@ -70,12 +85,12 @@ __device__ __forceinline__ void measurement_update(const Theta<PQ> &th, bool obs
 
 // Sufficient statistics of one E-step (EM.cpp:151-161, 180-193), theta-dependent part only.
 template <int PQ> struct Stats {
-    double Syx, Sxx;       // over observed steps
-    double Tx1x, Txx;      // over transitions t=0..T-2
+    double Syx, Sxx, Sxxv;          // over observed steps: sum yX, sum X^2, sum V
+    double Tx1x, Tx1xv, Txx, Txxv;  // over transitions t=0..T-2: sum X1 X, sum V1 J, sum X^2, sum V
     double Sxv[PQ], Tx1u[PQ], Tux[PQ];
     double X0, V0, XT, VT; // smoothed state at t=0 and t=T-1
     __device__ __forceinline__ void zero() {
-        Syx = Sxx = Tx1x = Txx = 0.0;
+        Syx = Sxx = Sxxv = Tx1x = Tx1xv = Txx = Txxv = 0.0;
 #pragma unroll
         for (int j = 0; j < PQ; j++) Sxv[j] = Tx1u[j] = Tux[j] = 0.0;
         X0 = V0 = XT = VT = 0.0;
@@ -98,7 +113,8 @@ __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const doubl
     const double *Syv = gc + 2, *wy = gc + 2 + PQ, *svv_inv = gc + 2 + 2 * PQ;
     // ---- C, D, R
     double z[PQ];
-    double num = s.Syx, den = s.Sxx;
+    const double Sxx = s.Sxx + s.Sxxv, Txx = s.Txx + s.Txxv, Tx1x = s.Tx1x + s.Tx1xv; // EM.cpp:152,180,181
+    double num = s.Syx, den = Sxx;
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
         double acc = 0.0;
@@ -123,8 +139,8 @@ __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const doubl
     th.R = racc / n_obs;
     // ---- A, B, Q
     double w[PQ];
-    num = s.Tx1x;
-    den = s.Txx;
+    num = Tx1x;
+    den = Txx;
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
         double acc = 0.0, acw = 0.0;
@@ -144,8 +160,8 @@ __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const doubl
     }
     const double An = num / den;
     // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
-    const double Tx1x1 = s.Txx - fma(s.X0, s.X0, s.V0) + fma(s.XT, s.XT, s.VT);
-    double qacc = fma(-An, s.Tx1x, Tx1x1);
+    const double Tx1x1 = Txx - fma(s.X0, s.X0, s.V0) + fma(s.XT, s.XT, s.VT);
+    double qacc = fma(-An, Tx1x, Tx1x1);
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
         const double b = fma(-An, z[a], w[a]);

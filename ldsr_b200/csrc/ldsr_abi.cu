@@ -21,12 +21,13 @@
 namespace ldsr {
 
 // ---- per-PQ kernel tables (kernels_inst.cu, one object per width) --------------------------
-#define LDSR_DECL(n) const KernelTable *kernel_table_pq##n();
+// weak: a development build may leave widths out (LDSR_PQ_LIST env of build.py); release has all
+#define LDSR_DECL(n) const KernelTable *kernel_table_pq##n() __attribute__((weak));
 #define LDSR_PQ_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(24) X(32)
 LDSR_PQ_LIST(LDSR_DECL)
 const KernelTable *kernel_table_for(int need) {
 #define LDSR_PICK(n) \
-    if (need <= n) return kernel_table_pq##n();
+    if (need <= n && kernel_table_pq##n) return kernel_table_pq##n();
     LDSR_PQ_LIST(LDSR_PICK)
     return nullptr;
 }
