@@ -43,9 +43,10 @@ struct EmParams {
     const int4 *tasks;        // per CTA: x = series, y = first index into active, z = count
     double *ckpt;             // checkpoint scratch: [global warp][seg][2][32]
     int max_seg;              // segments per warp slot in ckpt
+    int ckpt_smem_off;        // MODE 2: byte offset of the checkpoint area in dynamic shared memory
     int niter, chunk;
     double tol;
-    int blob_in_smem;         // 1: stage with TMA; 0: series too large, read it from global
+    int mode;                 // kernel MODE (see em_chunk_kernel)
 };
 
 __device__ __forceinline__ unsigned seg_bits(const unsigned *__restrict__ mw, int t0, int seg_len) {
@@ -55,86 +56,153 @@ __device__ __forceinline__ unsigned seg_bits(const unsigned *__restrict__ mw, in
 }
 
 // ---- pass 1 over one segment -----------------------------------------------------------------
-// All lanes unobserved: pure prediction (EM.cpp:72-76 with Xu=Xp, Vu=Vp).
-template <int PQ, int SEG>
-__device__ __forceinline__ void fwd_unobserved(const Theta<PQ> &th, double A, double A2, double Q,
-                                               const double *__restrict__ useg, double &Xp, double &Vp) {
-    double Bu[SEG];
+// All lanes unobserved: pure prediction (EM.cpp:72-76 with Xu=Xp, Vu=Vp) over SEG steps.  Pass 1
+// only needs the state at the end of the segment, so the SEG-step recursion is collapsed:
+//   Vp' = A2^SEG Vp + Q (1 + A2 + ... + A2^(SEG-1))            (one FMA, constants per iteration)
+//   Xp' = Ah (Ah Xp + h1) + h2,  Ah = A^(SEG/2), h1/h2 = Horner sums of B u over each half
+// which leaves two dependent FMAs on Xp instead of SEG.  (Pass 2 recomputes every step from the
+// checkpoint with the plain recursion.)
+template <int SEG> struct UnobsConst {
+    double Ah, aV, bV; // A^(SEG/2), A2^SEG, Q*sum_{k<SEG} A2^k
+    __device__ __forceinline__ void set(double A, double A2, double Q) {
+        double ah = 1.0, av = 1.0, sv = 0.0;
 #pragma unroll
-    for (int j = 0; j < SEG; j++) Bu[j] = dot_row<PQ>(th.B, useg + j * PQ);
+        for (int k = 0; k < SEG / 2; k++) ah *= A;
 #pragma unroll
-    for (int j = 0; j < SEG; j++) {
-        Xp = fma(A, Xp, Bu[j]);
-        Vp = fma(A2, Vp, Q);
+        for (int k = 0; k < SEG; k++) {
+            sv = fma(sv, A2, 1.0);
+            av *= A2;
+        }
+        Ah = ah;
+        aV = av;
+        bV = Q * sv;
     }
+};
+template <int PQ, int SEG>
+__device__ __forceinline__ void fwd_unobserved(const Theta<PQ> &th, double A, const UnobsConst<SEG> &uc,
+                                               const double *__restrict__ useg, double &Xp, double &Vp) {
+    static_assert(SEG % 2 == 0, "SEG must be even");
+    double h1 = 0.0, h2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < SEG / 2; j++) {
+        h1 = fma(A, h1, dot_row<PQ>(th.B, useg + j * PQ));
+        h2 = fma(A, h2, dot_row<PQ>(th.B, useg + (SEG / 2 + j) * PQ));
+    }
+    Xp = fma(uc.Ah, fma(uc.Ah, Xp, h1), h2);
+    Vp = fma(uc.aV, Vp, uc.bV);
 }
 
-// Some lane observes some step: measurement update on every step, per-lane predicated, plus the
-// likelihood terms (EM.cpp:86-88, 115-122).  cnt (warp-uniform) <= SEG steps are valid.
-template <int PQ, int SEG>
-__device__ __forceinline__ void fwd_mixed(const Theta<PQ> &th, double A, double A2, double Q, unsigned bits, int cnt,
-                                          const double *__restrict__ yseg, const double *__restrict__ useg,
-                                          const double *__restrict__ vseg, double &Xp, double &Vp, double &acc) {
+// ---- segments in which some lane observes some step ----------------------------------------
+// The variance recursion is run in homogeneous coordinates Vp = n/d (start of segment: n=Vp, d=1):
+//   observed   : d' = C^2 n + R d (= Sigma d),  n' = (A^2 R + Q C^2) n + Q R d        (EM.cpp:76,86-88)
+//   unobserved : d' = d,                        n' = A^2 n + Q d
+// so the dependency chain of a step is two multiply-adds instead of a reciprocal, and everything
+// else hangs off it:  1/Sigma = d/d',  K = C n/d',  Vu = nu/d' (nu = R n or n),  Vp' = n'/d',
+// J = A Vu/Vp' = A nu/n',  and  sum_obs log Sigma = log(d_end) (telescoping; d is rescaled by exact
+// powers of two mid-segment, the shift is added back).  The mean recursion becomes
+// Xp' = alpha Xp + beta with alpha = A(1-KC), beta = A K (y - D v) + B u computed off the chain.
+template <int PQ> struct MixedConst {
+    double C2, a11, a12, AC; // C^2, A^2 R + Q C^2, Q R, A C
+    __device__ __forceinline__ void set(const Theta<PQ> &th, double A2) {
+        C2 = th.C * th.C;
+        a11 = fma(A2, th.R, th.Q * C2);
+        a12 = th.Q * th.R;
+        AC = th.A * th.C;
+    }
+};
+
+__device__ __forceinline__ void rescale_pow2(double &n, double &d, int &shift) {
+    const int e = ((__double2hiint(d) >> 20) & 0x7ff) - 1023;
+    const double sc = __hiloint2double((1023 - e) << 20, 0);
+    n *= sc;
+    d *= sc;
+    shift += e;
+}
+
+// PASS2 = false: pass 1 (likelihood terms, state at the end of the segment)
+// PASS2 = true : recompute for the smoother: fills J, g, L (see smooth_segment)
+template <int PQ, int SEG, bool GUARDED, bool PASS2>
+__device__ __forceinline__ void mixed_forward(const Theta<PQ> &th, double A, double A2, double Q,
+                                              const MixedConst<PQ> &mc, unsigned bits, int cnt,
+                                              const double *__restrict__ yseg, const double *__restrict__ useg,
+                                              const double *__restrict__ vseg, double &Xq, double &Vq, double &acc,
+                                              double (&Jt)[SEG], double (&g)[SEG], double (&L)[SEG]) {
+    double n = Vq, d = 1.0;
+    int shift = 0;
 #pragma unroll
     for (int j = 0; j < SEG; j++) {
-        if (j < cnt) {
+        if (!GUARDED || j < cnt) {
             const bool obs = (bits >> j) & 1u;
+            const double m11 = obs ? mc.a11 : A2, m12 = obs ? mc.a12 : Q;
+            const double m21 = obs ? mc.C2 : 0.0, m22 = obs ? th.R : 1.0;
+            const double nn = fma(m11, n, m12 * d);
+            const double dd = fma(m21, n, m22 * d);
+            const double rho = fast_rcp(dd);
             const double Bu = dot_row<PQ>(th.B, useg + j * PQ);
             const double Dv = dot_row<PQ>(th.D, vseg + j * PQ);
-            const double S = fma(th.C * Vp, th.C, th.R); // C*Vp*C + R
-            const double rS = fast_rcp(S);
-            const double K = Vp * th.C * rS;
-            const double delta = yseg[j] - fma(th.C, Xp, Dv);
-            const double Xu = obs ? fma(K, delta, Xp) : Xp;
-            const double Vu = obs ? (1.0 - K * th.C) * Vp : Vp;
-            const double term = delta * rS * delta + log(S);
-            acc += obs ? term : 0.0;
-            Xp = fma(A, Xu, Bu); // u lags one step (EM.cpp:74)
-            Vp = fma(A2, Vu, Q); // A*Vu*A + Q      (EM.cpp:76)
+            const double K = obs ? th.C * n * rho : 0.0;
+            const double ymd = (obs ? yseg[j] : 0.0) - Dv; // y is NaN where missing
+            const double delta = fma(-th.C, Xq, ymd);      // y - (C Xp + D v)
+            const double alpha = fma(-mc.AC, K, A);
+            const double beta = fma(A * K, ymd, Bu);
+            if (!PASS2) {
+                const double w = delta * (d * rho); // delta / Sigma
+                acc = fma(obs ? w : 0.0, delta, acc);
+            }
+            const double Xn = fma(alpha, Xq, beta); // prior mean of the next step
+            if (PASS2) {
+                const double xu = fma(K, delta, Xq);
+                const double nu = obs ? th.R * n : n;
+                const double vu = nu * rho;
+                if (GUARDED && j == cnt - 1) { // t == T-1: smoothed = filtered (EM.cpp:94-95)
+                    Jt[j] = 0.0;
+                    g[j] = xu;
+                    L[j] = vu;
+                } else {
+                    const double J = A * nu * fast_rcp(nn);
+                    Jt[j] = J;
+                    g[j] = fma(-J, Xn, xu);
+                    L[j] = vu * fma(-A, J, 1.0); // Vu - J^2 Vp' with J Vp' = A Vu
+                }
+            }
+            Xq = Xn;
+            if (j == (GUARDED ? cnt - 1 : SEG - 1)) Vq = nn * rho; // prior variance entering the next segment
+            n = nn;
+            d = dd;
+            if (SEG > 4 && j == SEG / 2 - 1) rescale_pow2(n, d, shift);
         }
     }
+    if (!PASS2) acc += fma((double)shift, 0.693147180559945309417, log(d));
 }
 
 // ---- pass 2 over one segment -----------------------------------------------------------------
 // MIXED   : the segment holds observed steps for some lane -> measurement updates + observed sums
 // GUARDED : the segment is the last one: only cnt steps are valid and its last step is T-1
+// The filter is recomputed over the segment (EM.cpp:70-90) and, in the same sweep, the RTS gain and
+// the affine form of the backward recursion (EM.cpp:100-102) -- all off the smoother's chain:
+//      Xs_t = Xu + J (Xs1 - Xp1)   = J Xs1 + g,    g = Xu - J Xp1
+//      Vs_t = Vu + J (Vs1 - Vp1) J = J^2 Vs1 + L,  L = Vu - J^2 Vp1
+// Only J, g, L (3*SEG doubles) stay in registers.
 template <int PQ, int SEG, bool MIXED, bool GUARDED>
-__device__ __forceinline__ void smooth_segment(const Theta<PQ> &th, double A, double A2, double Q, unsigned bits,
-                                               int cnt, const double *__restrict__ yseg,
-                                               const double *__restrict__ useg, const double *__restrict__ vseg,
-                                               double Xq, double Vq, double &Xs1, double &Vs1, Stats<PQ> &st) {
-    // Recompute the filter over the segment (EM.cpp:70-90) and, in the same sweep, the RTS gain and
-    // the affine form of the backward recursion (EM.cpp:100-102) -- all of it off the dependency
-    // chain of the smoother:
-    //      Xs_t = Xu + J (Xs1 - Xp1)   = J Xs1 + g,    g = Xu - J Xp1
-    //      Vs_t = Vu + J (Vs1 - Vp1) J = J^2 Vs1 + L,  L = Vu - J^2 Vp1
-    // Only J, g, L (3*SEG doubles) stay in registers.
+__device__ __forceinline__ void smooth_segment(const Theta<PQ> &th, double A, double A2, double Q,
+                                               const MixedConst<PQ> &mc, unsigned bits, int cnt,
+                                               const double *__restrict__ yseg, const double *__restrict__ useg,
+                                               const double *__restrict__ vseg, double Xq, double Vq, double &Xs1,
+                                               double &Vs1, Stats<PQ> &st) {
     double Jt[SEG], g[SEG], L[SEG];
+    if (MIXED) {
+        double unused = 0.0;
+        mixed_forward<PQ, SEG, GUARDED, true>(th, A, A2, Q, mc, bits, cnt, yseg, useg, vseg, Xq, Vq, unused, Jt, g, L);
+    } else {
 #pragma unroll
-    for (int j = 0; j < SEG; j++) {
-        if (!GUARDED || j < cnt) {
-            double xu = Xq, vu = Vq;
-            if (MIXED) {
-                const bool obs = (bits >> j) & 1u;
-                const double Dv = dot_row<PQ>(th.D, vseg + j * PQ);
-                const double S = fma(th.C * Vq, th.C, th.R);
-                const double K = Vq * th.C * fast_rcp(S);
-                const double delta = yseg[j] - fma(th.C, Xq, Dv);
-                xu = obs ? fma(K, delta, Xq) : Xq;
-                vu = obs ? (1.0 - K * th.C) * Vq : Vq;
-            }
+        for (int j = 0; j < SEG; j++) {
+            const double xu = Xq, vu = Vq;
             Xq = fma(A, xu, dot_row<PQ>(th.B, useg + j * PQ));
             Vq = fma(A2, vu, Q);
-            if (GUARDED && j == cnt - 1) { // t == T-1: smoothed = filtered (EM.cpp:94-95)
-                Jt[j] = 0.0;
-                g[j] = xu;
-                L[j] = vu;
-            } else {
-                const double J = vu * A * fast_rcp(Vq);
-                Jt[j] = J;
-                g[j] = fma(-J, Xq, xu);
-                L[j] = fma(-J * J, Vq, vu);
-            }
+            const double J = vu * A * fast_rcp(Vq);
+            Jt[j] = J;
+            g[j] = fma(-J, Xq, xu);
+            L[j] = vu * fma(-A, J, 1.0);
         }
     }
     // ---- the chain and the sums of EM.cpp:151-161, 180-193
@@ -174,8 +242,12 @@ __device__ __forceinline__ void smooth_segment(const Theta<PQ> &th, double A, do
     }
 }
 
-template <int PQ, int SEG, int W, bool STAGED>
+// MODE 0: series and checkpoints in global memory (series too large for shared memory)
+//      1: series staged in shared memory by TMA, checkpoints in global memory
+//      2: series and checkpoints in shared memory
+template <int PQ, int SEG, int W, int MODE>
 __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
+    constexpr bool STAGED = MODE >= 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -217,7 +289,11 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         live = false;
         lik = __longlong_as_double(0x7ff8000000000000ULL);
     }
-    double *__restrict__ ck = P.ckpt + ((size_t)(blockIdx.x * W + warp) * P.max_seg) * 64 + lane;
+    // checkpoints: [warp][segment][Xp|Vp][lane]
+    double *__restrict__ ck =
+        (MODE == 2 ? reinterpret_cast<double *>(smem_raw + P.ckpt_smem_off) + (size_t)warp * P.max_seg * 64
+                   : P.ckpt + ((size_t)(blockIdx.x * W + warp) * P.max_seg) * 64) +
+        lane;
     const int nseg = (T + SEG - 1) / SEG;       // the last segment (full or not) holds step T-1
     const int cnt_last = T - (nseg - 1) * SEG;  // 1..SEG valid steps in it
 
@@ -227,6 +303,10 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     for (int it = 0; it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
         const double A = th.A, A2 = th.A * th.A, Q = th.Q;
+        UnobsConst<SEG> uc;
+        uc.set(A, A2, Q);
+        MixedConst<PQ> mc;
+        mc.set(th, A2);
 
         // ================= pass 1: forward filter, likelihood, checkpoints =================
         double Xp = th.mu1, Vp = th.V1; // prior of step 0 (EM.cpp:48-49)
@@ -237,11 +317,17 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
             ck[(size_t)sg * 64 + 32] = Vp;
             const unsigned bits = seg_bits(mw, t0, SEG);
             const double *__restrict__ useg = us + t0 * PQ;
-            if (sg == nseg - 1 || __any_sync(FULL, bits != 0u))
-                fwd_mixed<PQ, SEG>(th, A, A2, Q, bits, sg == nseg - 1 ? cnt_last : SEG, ys + t0, useg, vs + t0 * PQ,
-                                   Xp, Vp, acc);
+            if (sg == nseg - 1) {
+                double J_[SEG], g_[SEG], L_[SEG];
+                mixed_forward<PQ, SEG, true, false>(th, A, A2, Q, mc, bits, cnt_last, ys + t0, useg, vs + t0 * PQ, Xp,
+                                                    Vp, acc, J_, g_, L_);
+            } else if (__any_sync(FULL, bits != 0u)) {
+                double J_[SEG], g_[SEG], L_[SEG];
+                mixed_forward<PQ, SEG, false, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, useg, vs + t0 * PQ, Xp, Vp,
+                                                     acc, J_, g_, L_);
+            }
             else
-                fwd_unobserved<PQ, SEG>(th, A, A2, Q, useg, Xp, Vp);
+                fwd_unobserved<PQ, SEG>(th, A, uc, useg, Xp, Vp);
         }
         // lik = (-0.5 n log 2pi - 0.5 acc)/n      (EM.cpp:122-124, stdlik = TRUE)
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs;
@@ -262,7 +348,7 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         double Xs1 = 0.0, Vs1 = 0.0; // smoothed state of step t+1
         {
             const int sg = nseg - 1, t0 = sg * SEG;
-            smooth_segment<PQ, SEG, true, true>(th, A, A2, Q, seg_bits(mw, t0, SEG), cnt_last, ys + t0, us + t0 * PQ,
+            smooth_segment<PQ, SEG, true, true>(th, A, A2, Q, mc, seg_bits(mw, t0, SEG), cnt_last, ys + t0, us + t0 * PQ,
                                                 vs + t0 * PQ, ck[(size_t)sg * 64], ck[(size_t)sg * 64 + 32], Xs1, Vs1,
                                                 st);
         }
@@ -271,10 +357,10 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
             const double Xq = ck[(size_t)sg * 64], Vq = ck[(size_t)sg * 64 + 32]; // (Xp,Vp) entering the segment
             const unsigned bits = seg_bits(mw, t0, SEG);
             if (__any_sync(FULL, bits != 0u))
-                smooth_segment<PQ, SEG, true, false>(th, A, A2, Q, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
+                smooth_segment<PQ, SEG, true, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
                                                      Vq, Xs1, Vs1, st);
             else
-                smooth_segment<PQ, SEG, false, false>(th, A, A2, Q, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
+                smooth_segment<PQ, SEG, false, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
                                                       Vq, Xs1, Vs1, st);
         }
         st.X0 = Xs1;

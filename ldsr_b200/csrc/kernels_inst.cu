@@ -11,14 +11,19 @@ namespace {
 constexpr int PQ = LDSR_PQ;
 
 cudaError_t em_prepare(size_t smem_bytes) {
-    return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes);
 }
 cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
-    if (p.blob_in_smem)
-        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, true><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
+    if (p.mode == 2)
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 2><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
+    else if (p.mode == 1)
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 1><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
     else
-        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, false><<<n_tasks, EM_WARPS * 32, 0, st>>>(p);
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 0><<<n_tasks, EM_WARPS * 32, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {

@@ -492,7 +492,19 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         CU(cudaGetLastError());
         launches++;
     }
-    const size_t smem = P->blob_in_smem ? P->max_blob_bytes : 0;
+    // shared-memory plan: series blob (TMA-staged) [+ checkpoints of the CTA's warps]
+    const size_t blob_sm = (P->max_blob_bytes + 127) & ~size_t(127);
+    const size_t ck_sm = (size_t)EM_WARPS * P->max_seg * 64 * sizeof(double);
+    int mode = 0;
+    size_t smem = 0;
+    if (P->blob_in_smem) {
+        mode = 1;
+        smem = blob_sm;
+        if (blob_sm + ck_sm <= 220 * 1024 && !(opt && opt->variant == 1)) {
+            mode = 2;
+            smem = blob_sm + ck_sm;
+        }
+    }
     CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
 
     EmParams ep;
@@ -519,7 +531,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     ep.niter = niter;
     ep.chunk = chunk;
     ep.tol = tol;
-    ep.blob_in_smem = P->blob_in_smem ? 1 : 0;
+    ep.mode = mode;
+    ep.ckpt_smem_off = (int)blob_sm;
+    ep.ckpt = nullptr;
 
     for (;;) {
         compact_kernel<<<ns, 256, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
@@ -539,7 +553,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
         if (opt && opt->poll && !abort_flag && opt->poll(opt->poll_arg))
             return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
-        const size_t need = (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
+        const size_t need = mode == 2 ? 0 : (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
         if (P->ckpt_cap < need) {
             Err e = P->dalloc(&P->d_ckpt, need);
             if (!e.ok()) return e;
