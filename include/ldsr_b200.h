@@ -169,6 +169,12 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    int exp_trans, double *simX, double *simY, double *simQ, char *errbuf,
                    int errlen);
 
+/* ---- multi-GPU sharding (pure host logic, no device needed) ------------------------------
+ * The partition ldsr_em_batch uses: group g goes to shard group_shard[g] in 0..n_shards-1.
+ * All fits of a group stay on one device, so restart selection is device-local and the host only
+ * concatenates results -- there is no collective on the data path. */
+int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, char *errbuf, int errlen);
+
 /* ---- measurement helper -------------------------------------------------------------------
  * FP64 roofline denominator: runs a register-resident DFMA kernel (8 independent chains per
  * thread, all SMs full) on `device` and returns the best-of-5 rate in TFLOP/s (FMA = 2 flops). */

@@ -18,7 +18,7 @@ FIT_OK, FIT_SINGULAR, FIT_NONFINITE = 0, 1, 2
 EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy",
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
-           "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_measure_fp64_peak")
+           "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak")
 
 
 class LdsrError(RuntimeError):
@@ -343,3 +343,12 @@ def measure_fp64_peak(device=0):
     err = C.create_string_buffer(512)
     _check(lib().ldsr_measure_fp64_peak(int(device), C.byref(t), err, 512), err)
     return t.value
+
+
+def shard_groups(series, group_series, held, fit_group, theta0, n_shards):
+    """ldsr_shard_groups: the group -> device partition of ldsr_em_batch (host logic only)."""
+    pb = PackedBatch(series, group_series, held, fit_group, theta0)
+    out = np.empty(pb.n_groups, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    _check(lib().ldsr_shard_groups(C.byref(pb.c), int(n_shards), _i(out), err, 512), err)
+    return out

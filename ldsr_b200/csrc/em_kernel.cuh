@@ -300,6 +300,26 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     if (STAGED) mbar_wait(&bar, 0);
     if (warp * 32 >= task.z) return; // whole warp has no fit
 
+    // Which segments hold an observed step for some lane of this warp: fixed for the whole launch,
+    // so the vote is taken once here (bitmap in two registers covers 128 segments = T <= 128*SEG;
+    // longer series fall back to a vote per segment).
+    unsigned long long mix0 = 0ull, mix1 = 0ull;
+    const bool have_map = nseg <= 128;
+    if (have_map)
+        for (int sg = 0; sg < nseg; ++sg) {
+            const bool m = __any_sync(FULL, seg_bits(mw, sg * SEG, SEG) != 0u);
+            if (m) {
+                if (sg < 64)
+                    mix0 |= 1ull << sg;
+                else
+                    mix1 |= 1ull << (sg - 64);
+            }
+        }
+    auto seg_is_mixed = [&](int sg) -> bool {
+        if (have_map) return ((sg < 64 ? mix0 >> sg : mix1 >> (sg - 64)) & 1ull) != 0ull;
+        return __any_sync(FULL, seg_bits(mw, sg * SEG, SEG) != 0u);
+    };
+
     for (int it = 0; it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
         const double A = th.A, A2 = th.A * th.A, Q = th.Q;
@@ -315,19 +335,18 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
             const int t0 = sg * SEG;
             ck[(size_t)sg * 64] = Xp;
             ck[(size_t)sg * 64 + 32] = Vp;
-            const unsigned bits = seg_bits(mw, t0, SEG);
             const double *__restrict__ useg = us + t0 * PQ;
             if (sg == nseg - 1) {
                 double J_[SEG], g_[SEG], L_[SEG];
-                mixed_forward<PQ, SEG, true, false>(th, A, A2, Q, mc, bits, cnt_last, ys + t0, useg, vs + t0 * PQ, Xp,
-                                                    Vp, acc, J_, g_, L_);
-            } else if (__any_sync(FULL, bits != 0u)) {
+                mixed_forward<PQ, SEG, true, false>(th, A, A2, Q, mc, seg_bits(mw, t0, SEG), cnt_last, ys + t0, useg,
+                                                    vs + t0 * PQ, Xp, Vp, acc, J_, g_, L_);
+            } else if (seg_is_mixed(sg)) {
                 double J_[SEG], g_[SEG], L_[SEG];
-                mixed_forward<PQ, SEG, false, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, useg, vs + t0 * PQ, Xp, Vp,
-                                                     acc, J_, g_, L_);
-            }
-            else
+                mixed_forward<PQ, SEG, false, false>(th, A, A2, Q, mc, seg_bits(mw, t0, SEG), SEG, ys + t0, useg,
+                                                     vs + t0 * PQ, Xp, Vp, acc, J_, g_, L_);
+            } else {
                 fwd_unobserved<PQ, SEG>(th, A, uc, useg, Xp, Vp);
+            }
         }
         // lik = (-0.5 n log 2pi - 0.5 acc)/n      (EM.cpp:122-124, stdlik = TRUE)
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs;
@@ -355,13 +374,12 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         for (int sg = nseg - 2; sg >= 0; --sg) {
             const int t0 = sg * SEG;
             const double Xq = ck[(size_t)sg * 64], Vq = ck[(size_t)sg * 64 + 32]; // (Xp,Vp) entering the segment
-            const unsigned bits = seg_bits(mw, t0, SEG);
-            if (__any_sync(FULL, bits != 0u))
-                smooth_segment<PQ, SEG, true, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
-                                                     Vq, Xs1, Vs1, st);
+            if (seg_is_mixed(sg))
+                smooth_segment<PQ, SEG, true, false>(th, A, A2, Q, mc, seg_bits(mw, t0, SEG), SEG, ys + t0,
+                                                     us + t0 * PQ, vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
             else
-                smooth_segment<PQ, SEG, false, false>(th, A, A2, Q, mc, bits, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq,
-                                                      Vq, Xs1, Vs1, st);
+                smooth_segment<PQ, SEG, false, false>(th, A, A2, Q, mc, 0u, SEG, ys + t0, us + t0 * PQ, vs + t0 * PQ,
+                                                      Xq, Vq, Xs1, Vs1, st);
         }
         st.X0 = Xs1;
         st.V0 = Vs1;

@@ -720,6 +720,26 @@ static void make_sub(const ldsr_batch *b, const std::vector<int> &groups, const 
     sb.b.theta0 = sb.theta0.data();
 }
 
+// Greedy longest-processing-time partition of the groups over n_shards devices; the cost of a
+// group is restarts * T * (p+q+8) (iteration counts are not known in advance).  Deterministic.
+static void shard_groups(const ldsr_batch *b, int n_shards, int *group_shard) {
+    const int ng = b->n_groups;
+    std::vector<double> cost(ng, 0.0);
+    for (int f = 0; f < b->n_fits; f++) {
+        const int g = b->fit_group[f], s = b->group_series[g];
+        cost[g] += (double)b->T[s] * (b->p[s] + b->q[s] + 8);
+    }
+    std::vector<int> order(ng);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+    std::vector<double> load(n_shards, 0.0);
+    for (int g : order) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        group_shard[g] = d;
+        load[d] += cost[g];
+    }
+}
+
 static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, const ldsr_options *opt,
                     ldsr_em_result *out) {
     Err e = validate(b);
@@ -750,7 +770,7 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
         return plan_fetch(P, out);
     }
 
-    // ---- shard groups over devices: greedy by cost = restarts * T * (p+q+8)
+    // ---- shard groups over devices (no data-path collective: a group's restarts stay together)
     const int ng = b->n_groups;
     std::vector<int> fit_lo(ng, -1), fit_hi(ng, -1);
     for (int f = 0; f < b->n_fits; f++) {
@@ -758,22 +778,10 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
         if (fit_lo[g] < 0) fit_lo[g] = f;
         fit_hi[g] = f + 1;
     }
-    std::vector<double> cost(ng);
-    for (int g = 0; g < ng; g++) {
-        const int s = b->group_series[g];
-        cost[g] = (double)(fit_hi[g] - std::max(fit_lo[g], 0)) * b->T[s] * (b->p[s] + b->q[s] + 8);
-    }
-    std::vector<int> order(ng);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+    std::vector<int> shard(ng);
+    shard_groups(b, nd, shard.data());
     std::vector<std::vector<int>> dev_groups(nd);
-    std::vector<double> load(nd, 0.0);
-    for (int g : order) {
-        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        dev_groups[d].push_back(g);
-        load[d] += cost[g];
-    }
-    for (auto &v : dev_groups) std::sort(v.begin(), v.end());
+    for (int g = 0; g < ng; g++) dev_groups[shard[g]].push_back(g);
 
     std::vector<SubBatch> subs(nd);
     std::vector<Err> errs(nd);
@@ -1177,6 +1185,13 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    double *simY, double *simQ, char *errbuf, int errlen) {
     return report(rep_batch(ctx, theta, u, v, n, p, q, n_reps, z, seed, mu, exp_trans, simX, simY, simQ), errbuf,
                   errlen);
+}
+
+int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, char *errbuf, int errlen) {
+    Err e = validate(batch);
+    if (e.ok() && (n_shards < 1 || !group_shard)) e = fail(LDSR_ERR_ARG, "n_shards < 1 or group_shard is NULL");
+    if (e.ok()) shard_groups(batch, n_shards, group_shard);
+    return report(e, errbuf, errlen);
 }
 
 int ldsr_measure_fp64_peak(int device, double *tflops, char *errbuf, int errlen) {
