@@ -53,6 +53,19 @@ template <int CHAINS> __global__ void k_frcp(double *out, int iters, double a, d
     if (s == 1.2345) out[0] = s;
 }
 
+// only the first `active` lanes of each warp do the work: does the FP64 pipe skip idle half-warps?
+template <int CHAINS> __global__ void k_dfma_part(double *out, int iters, double a, double b, int active) {
+    if ((threadIdx.x & 31) >= active) return;
+    double x[CHAINS];
+    for (int c = 0; c < CHAINS; c++) x[c] = threadIdx.x + c;
+    for (int i = 0; i < iters; i++)
+#pragma unroll
+        for (int c = 0; c < CHAINS; c++) x[c] = fma(x[c], a, b);
+    double s = 0;
+    for (int c = 0; c < CHAINS; c++) s += x[c];
+    if (s == 1.2345) out[0] = s;
+}
+
 template <class F> float timeit(F f) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -99,6 +112,16 @@ int main() {
     {
         float ms = timeit([&] { k_dfma<8><<<148, 128>>>(d, iters, 1.0000001, 1e-9); });
         printf("full warps 8 chains: %.3f ms\n", ms);
+    }
+    for (int active : {32, 24, 16, 8, 1}) {
+        float ms = timeit([&] { k_dfma_part<8><<<148, 128>>>(d, iters, 1.0000001, 1e-9, active); });
+        printf("dfma 8 chains, %2d active lanes/warp, 1 warp/SMSP: %.3f ms -> %.2f cycles/op/warp\n", active, ms,
+               ms * 1e-3 * ghz * 1e9 / iters / 8);
+    }
+    for (int active : {32, 16}) {
+        float ms = timeit([&] { k_dfma_part<8><<<148, 256>>>(d, iters, 1.0000001, 1e-9, active); });
+        printf("dfma 8 chains, %2d active lanes/warp, 2 warps/SMSP: %.3f ms -> %.2f cycles/op/warp\n", active, ms,
+               ms * 1e-3 * ghz * 1e9 / iters / 8);
     }
     return 0;
 }
