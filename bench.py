@@ -267,12 +267,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (em_chunk_kernel) ----------------
+    # ---------------- roofline of the dominant kernel (the EM kernel) ----------------
     flops = total_flops(w, iters)  # per step
     em_ns = float(np.mean([s["em_kernel_ns"] for s in stats]))
     chunks = float(np.mean([s["chunks"] for s in stats]))
     achieved = flops / (em_ns * 1e-9) / 1e12
-    roofline = {"bound": "fp64", "kernel": "em_chunk_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": stats[0].get("kernel", "em_chunk_kernel"), "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak, "traffic": None,
                 "peak_source": "DFMA microbenchmark in this run (ldsr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flops_per_launch": flops / chunks, "launch_ms": em_ns * 1e-6 / chunks, "launches_per_step": chunks,

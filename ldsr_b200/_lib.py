@@ -148,8 +148,10 @@ def _check(rc, err):
         raise LdsrError(rc, err.value.decode("utf-8", "replace"))
 
 
-def _options(n_devices=0, devices=None, chunk_iters=0, poll=None, trace_liks=False, keep=None):
+def _options(n_devices=0, devices=None, chunk_iters=0, poll=None, trace_liks=False, keep=None, variant=None):
     o = Options()
+    # kernel variant (ldsr_options.variant): 0 auto; development override through LDSR_VARIANT
+    o.variant = int(os.environ.get("LDSR_VARIANT", "0")) if variant is None else int(variant)
     o.n_devices = int(n_devices)
     if devices is not None:
         dv = np.ascontiguousarray(devices, dtype=np.int32)
@@ -215,12 +217,12 @@ class EmOutputs:
 
 
 def em_batch(series, group_series, held, fit_group, theta0, niter=1000, tol=1e-5, n_devices=1,
-             devices=None, chunk_iters=0, poll=None, want_liks=False, want_traj=True, ctx=None):
+             devices=None, chunk_iters=0, poll=None, want_liks=False, want_traj=True, ctx=None, variant=None):
     """ldsr_em_batch with host (numpy) buffers.  Same argument shapes as oracle.em_batch."""
     pb = PackedBatch(series, group_series, held, fit_group, theta0)
     out = EmOutputs(pb, niter, want_liks, want_traj)
     keep = []
-    opt = _options(n_devices, devices, chunk_iters, poll, keep=keep)
+    opt = _options(n_devices, devices, chunk_iters, poll, keep=keep, variant=variant)
     err = C.create_string_buffer(512)
     rc = lib().ldsr_em_batch(ctx.h if isinstance(ctx, Ctx) else ctx, C.byref(pb.c), int(niter), C.c_double(tol),
                              C.byref(opt), C.byref(out.c), err, 512)
@@ -239,9 +241,9 @@ class Plan:
         _check(rc, err)
         self.niter = None
 
-    def em(self, niter=1000, tol=1e-5, chunk_iters=0, stream=None, trace_liks=False, poll=None):
+    def em(self, niter=1000, tol=1e-5, chunk_iters=0, stream=None, trace_liks=False, poll=None, variant=None):
         keep = []
-        opt = _options(chunk_iters=chunk_iters, poll=poll, trace_liks=trace_liks, keep=keep)
+        opt = _options(chunk_iters=chunk_iters, poll=poll, trace_liks=trace_liks, keep=keep, variant=variant)
         stats = (C.c_longlong * 8)()
         err = C.create_string_buffer(512)
         rc = lib().ldsr_plan_em(self.h, int(niter), C.c_double(tol), C.byref(opt),
@@ -249,7 +251,8 @@ class Plan:
         _check(rc, err)
         self.niter = niter
         self.trace = bool(trace_liks)
-        return dict(launches=stats[0], chunks=stats[1], esteps=stats[2], em_kernel_ns=stats[3])
+        return dict(launches=stats[0], chunks=stats[1], esteps=stats[2], em_kernel_ns=stats[3],
+                    kernel="em_split_kernel" if stats[4] else "em_chunk_kernel")
 
     def set_theta0(self, theta0):
         th = np.ascontiguousarray(theta0, dtype=np.float64)

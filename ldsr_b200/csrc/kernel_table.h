@@ -4,6 +4,7 @@
 #pragma once
 #include "aux_kernels.cuh"
 #include "em_kernel.cuh"
+#include "em_split_kernel.cuh"
 
 namespace ldsr {
 
@@ -12,11 +13,28 @@ namespace ldsr {
 #endif
 constexpr int EM_SEG = LDSR_SEG; // steps per checkpoint segment (divides 32)
 constexpr int EM_WARPS = 4; // warps per CTA (one per SM sub-partition)
+// time-split kernel: warps per CTA and the CTAs/SM the register budget is set for
+// (65536 regs / (NW*32*MINB): 4 warps x 3 CTAs -> 170 registers per thread)
+#ifndef LDSR_SPLIT_NW
+#define LDSR_SPLIT_NW 4
+#endif
+constexpr int SPLIT_NW = LDSR_SPLIT_NW;
+constexpr int split_minb_for(int pq) {
+#ifdef LDSR_SPLIT_MINB
+    return LDSR_SPLIT_MINB;
+#else
+    return pq <= 4 ? 3 : (pq <= 8 ? 2 : 1);
+#endif
+}
 
 struct KernelTable {
     int pq;
     cudaError_t (*em_prepare)(size_t smem_bytes); // opt in to > 48 KB dynamic shared memory
     cudaError_t (*em_chunk)(const EmParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
+    // time-split kernel (em_split_kernel.cuh): warps per CTA, CTAs per SM it is compiled for
+    int split_nw, split_minb;
+    cudaError_t (*em_split_prepare)(size_t smem_bytes);
+    cudaError_t (*em_split)(const SplitParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);
     cudaError_t (*mstep)(const MstepParams &, cudaStream_t);
     cudaError_t (*propagate)(const SmootherParams &, cudaStream_t);

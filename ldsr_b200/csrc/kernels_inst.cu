@@ -26,6 +26,15 @@ cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStre
         em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 0><<<n_tasks, EM_WARPS * 32, 0, st>>>(p);
     return cudaGetLastError();
 }
+constexpr int MINB = split_minb_for(PQ);
+cudaError_t em_split_prepare(size_t smem_bytes) {
+    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes);
+}
+cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    em_split_kernel<PQ, SPLIT_NW, MINB><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
+    return cudaGetLastError();
+}
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
     smoother_kernel<PQ><<<(p.n_jobs + 63) / 64, 64, 0, st>>>(p);
     return cudaGetLastError();
@@ -43,7 +52,7 @@ cudaError_t rep(const RepParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-const KernelTable table = {PQ, em_prepare, em_chunk, smoother, mstep, propagate, rep};
+const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, em_split_prepare, em_split, smoother, mstep, propagate, rep};
 
 } // namespace
 

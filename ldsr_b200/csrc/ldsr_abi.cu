@@ -124,6 +124,7 @@ struct ldsr_plan {
     int PQ = 0, TL = 0;
     int n_series = 0, n_groups = 0, n_fits = 0, theta_stride = 0;
     int max_T = 0, max_seg = 0;
+    int max_units = 0; // time-split kernel: upper bound on units per series (em_split_kernel.cuh)
     size_t max_blob_bytes = 0;
     bool blob_in_smem = true;
     int last_niter = 0;
@@ -348,6 +349,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
                 for (int j = 0; j < q; j++) B[S.v_off + (size_t)t * PQ + j] = v[(size_t)t * q + j];
         }
         P->max_T = std::max(P->max_T, T);
+        P->max_units = std::max(P->max_units, split_units_upper_bound(b->y[s], T));
         P->max_blob_bytes = std::max(P->max_blob_bytes, (size_t)S.blob_doubles * 8);
     }
     // fit ranges per series (internal order is series-major)
@@ -417,7 +419,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->dalloc(&P->d_task_off, ns + 1)).ok()) return e;
     if (!(e = P->dalloc(&P->d_counts, 8)).ok()) return e;
     if (!(e = P->dalloc(&P->d_sum, 1)).ok()) return e;
-    P->max_tasks = nf / (32 * EM_WARPS) + ns + 1;
+    P->max_tasks = nf / 32 + ns + 1; // the time-split kernel takes 32 fits per CTA
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
 
@@ -505,7 +507,21 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             smem = blob_sm + ck_sm;
         }
     }
-    CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
+    // time-split kernel (em_split_kernel.cuh): 32 fits per CTA, the warps of the CTA share the time
+    // axis.  Default whenever blob + checkpoints + exchange buffers fit in shared memory.
+    // variant: 0 auto, 1 lane kernel with global checkpoints, 2 lane kernel, 3 time-split kernel
+    const int variant = opt ? opt->variant : 0;
+    const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units);
+    bool use_split = P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
+    if (variant == 3 && !use_split)
+        return fail(LDSR_ERR_UNSUPPORTED, "variant 3 (time-split kernel) needs %zu bytes of shared memory", split_sm);
+    if (use_split) {
+        smem = split_sm;
+        CU(P->kt->em_split_prepare(smem));
+    } else {
+        CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
+    }
+    const int fits_per_cta = use_split ? 32 : 32 * EM_WARPS;
 
     EmParams ep;
     ep.series = P->d_series;
@@ -537,7 +553,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
 
     for (;;) {
         compact_kernel<<<ns, 256, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
-        build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, 32 * EM_WARPS, P->d_tasks, P->d_task_off,
+        build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, fits_per_cta, P->d_tasks, P->d_task_off,
                                               P->d_counts);
         launches += 2;
         CU(cudaMemcpyAsync(P->h_counts, P->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -553,7 +569,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
         if (opt && opt->poll && !abort_flag && opt->poll(opt->poll_arg))
             return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
-        const size_t need = mode == 2 ? 0 : (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
+        const size_t need = (mode == 2 || use_split) ? 0 : (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
         if (P->ckpt_cap < need) {
             Err e = P->dalloc(&P->d_ckpt, need);
             if (!e.ok()) return e;
@@ -561,7 +577,17 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         }
         ep.ckpt = P->d_ckpt;
         if (stats) CU(cudaEventRecord(ev0, st));
-        CU(P->kt->em_chunk(ep, n_tasks, smem, st));
+        if (use_split) {
+            SplitParams sp;
+            sp.em = ep;
+            sp.max_units = P->max_units;
+            sp.blob_smem = (int)blob_sm;
+            sp.cost_u = 32 * 36; // instructions per U word / M segment, measured
+            sp.cost_m = 8 * 185;
+            CU(P->kt->em_split(sp, n_tasks, smem, st));
+        } else {
+            CU(P->kt->em_chunk(ep, n_tasks, smem, st));
+        }
         if (stats) {
             CU(cudaEventRecord(ev1, st));
             ev_pending = true;
@@ -626,7 +652,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         stats[1] = chunks;
         stats[2] = (long long)total;
         stats[3] = (long long)(em_ms * 1e6);
-        stats[4] = stats[5] = stats[6] = stats[7] = 0;
+        stats[4] = use_split ? 1 : 0; // which EM kernel ran
+        stats[5] = stats[6] = stats[7] = 0;
     }
     return Err();
 }

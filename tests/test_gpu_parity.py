@@ -102,7 +102,13 @@ def check_batch(series, group_series, held, fit_group, th0, niter, tol, **kw):
     return g, o
 
 
-def test_em_batch_folds_restarts_np213():
+# both EM kernels must agree with the oracle: 2 = lane-per-fit (em_kernel.cuh), 3 = time-split
+# (em_split_kernel.cuh); 0 = whatever the plan picks
+VARIANTS = [2, 3]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_em_batch_folds_restarts_np213(variant):
     y, u, mu, inst = _np213()
     rng = np.random.default_rng(11)
     n_folds, n_rest = 6, 20
@@ -110,7 +116,7 @@ def test_em_batch_folds_restarts_np213():
     fg = np.repeat(np.arange(n_folds), n_rest)
     th0 = rand_theta0(rng, 3, 3, n_folds * n_rest)
     ser = [dict(y=y, u=u, v=u)]
-    g, o = check_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 300, 1e-5)
+    g, o = check_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 300, 1e-5, variant=variant)
     # winners' smoothed trajectories == oracle E-step with the winner's theta on the fold's y
     for k in range(n_folds):
         b = g["best"][k]
@@ -123,18 +129,20 @@ def test_em_batch_folds_restarts_np213():
         assert np.allclose(g["V"][row], s["V"], rtol=1e-6) and np.allclose(g["J"][row], s["J"], rtol=1e-6)
 
 
-def test_chunking_does_not_change_results():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_chunking_does_not_change_results(variant):
     y, u, mu, inst = _np213()
     rng = np.random.default_rng(5)
     th0 = rand_theta0(rng, 3, 3, 40)
     ser = [dict(y=y, u=u, v=u)]
-    a = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=100)
-    b = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=7)
+    a = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=100, variant=variant)
+    b = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=7, variant=variant)
     for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):
         assert np.array_equal(a[k], b[k]), k
 
 
-def test_sentinels_unequal_dims_and_ensemble():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_sentinels_unequal_dims_and_ensemble(variant):
     # test-LDS-EM.R:58-77, test-ensemble.R:9-18: u=NULL, v=NULL, nrow(u)!=nrow(v), list of u/v
     y, u, mu, inst = _np213()
     rng = np.random.default_rng(3)
@@ -147,9 +155,84 @@ def test_sentinels_unequal_dims_and_ensemble():
             th0.append(np.pad(t, (0, stride - t.size)))
             fg.append(s_i)
     held = [inst[:5], inst[5:9], np.array([], dtype=int), inst[-3:]]
-    g, o = check_batch(series, [0, 1, 2, 3], held, fg, np.stack(th0), 120, 1e-5)
+    g, o = check_batch(series, [0, 1, 2, 3], held, fg, np.stack(th0), 120, 1e-5, variant=variant)
     assert np.all(g["theta"][0:5, 1] == 0)      # B == 0 without u
     assert np.all(g["theta"][5:10, 5] == 0)     # D == 0 without v
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fully_observed_p1_batch(variant):
+    # every step observed (the reference's golden series, p=q=7): no unobserved word anywhere, so the
+    # time-split kernel runs entirely on composed Moebius/affine maps of 8-step segments
+    y, u, th0, kat = data.p1_case()
+    rng = np.random.default_rng(21)
+    th = np.vstack([th0[None], rand_theta0(rng, 7, 7, 37)])
+    held = [np.array([], dtype=int), np.array([0, 1, 2, 40, 84])]
+    fg = np.repeat([0, 1], 19)
+    g, o = check_batch([dict(y=y, u=u, v=u)], [0, 0], held, fg, th, 100, 1e-5, variant=variant)
+    assert g["iters"][0] == 68  # tests/testthat/test-LDS-EM.R:39
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("T", [4, 5, 8, 9, 31, 32, 33, 40, 64, 65, 100, 257])
+def test_ragged_lengths_and_scattered_observations(variant, T):
+    # unit-table edge cases: T below / at / just above the 8-step segment and the 32-step word,
+    # observations scattered so that U words and M segments interleave, first/last step missing
+    rng = np.random.default_rng(100 + T)
+    p, q = (1, 1) if T < 16 else (2, 3)  # a handful of steps cannot identify more inputs
+    niter = 10 if T < 16 else 40
+    u = rng.standard_normal((p, T))
+    v = rng.standard_normal((q, T))
+    x = np.zeros(T)
+    for t in range(1, T):
+        x[t] = 0.7 * x[t - 1] + 0.3 * u[0, t - 1] + 0.5 * rng.standard_normal()
+    y = 0.8 * x + 0.2 * v[-1] + 0.3 * rng.standard_normal(T)
+    ya = y.copy()  # sparse: bursts of observations separated by long gaps
+    keep = np.zeros(T, dtype=bool)
+    for s0 in range(3, T, 70):
+        keep[s0:s0 + 9] = True
+    keep[rng.integers(0, T, 2)] = True
+    ya[~keep] = np.nan
+    if np.isfinite(ya).sum() < 4:
+        ya = y.copy()
+    yb = y.copy()  # dense with random gaps; first and last step missing when long enough
+    yb[rng.uniform(size=T) < 0.3] = np.nan
+    if T > 8:
+        yb[0] = yb[-1] = np.nan
+    if np.isfinite(yb).sum() < 4:
+        yb = y.copy()
+    series = [dict(y=ya, u=u, v=v), dict(y=yb, u=u, v=v)]
+    fg = np.repeat([0, 1], 5)
+    th0 = rand_theta0(rng, p, q, 10)
+    none = np.array([], dtype=int)
+    check_batch(series, [0, 1], [none, none], fg, th0, niter, 1e-7, variant=variant)
+
+
+@pytest.mark.parametrize("variant", VARIANTS + [0])
+def test_cv_np413_sample(variant):
+    # the bench workload in small: NP series T=413 (obs at steps 360..405), folds x restarts, 2 CTAs
+    # of the time-split kernel with several groups per CTA (per-lane masks differ)
+    y, u, mu, inst = data.np_case(401, 1600)
+    assert y.size == 413
+    rng = np.random.default_rng(413)
+    n_folds, n_rest = 8, 6
+    held = [np.sort(rng.choice(inst, 11, replace=False)) for _ in range(n_folds)]
+    fg = np.repeat(np.arange(n_folds), n_rest)
+    th0 = rand_theta0(rng, 3, 3, n_folds * n_rest)
+    check_batch([dict(y=y, u=u, v=u)], np.zeros(n_folds, dtype=int), held, fg, th0, 400, 1e-5, variant=variant)
+
+
+def test_long_series_np813_both_kernels_agree():
+    y, u, mu, inst = data.np_case(1, 1200)
+    rng = np.random.default_rng(813)
+    th0 = rand_theta0(rng, 3, 3, 12)
+    ser = [dict(y=y, u=u, v=u)]
+    fg = np.zeros(12, dtype=int)
+    check_batch(ser, [0], [np.array([], dtype=int)], fg, th0, 150, 1e-5, variant=3)
+    a = _lib.em_batch(ser, [0], None, fg, th0, 150, 1e-5, variant=2)
+    b = _lib.em_batch(ser, [0], None, fg, th0, 150, 1e-5, variant=3)
+    assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["best"], b["best"])
+    assert np.allclose(a["lik"], b["lik"], rtol=LIK_RTOL, atol=0)
 
 
 def test_api_restart_and_cv_shapes():
