@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libldsr_b200.so")
+SO_PATH = os.environ.get("LDSR_SO") or os.path.join(HERE, "libldsr_b200.so")  # LDSR_SO: development builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -43,8 +43,14 @@ def _run(cmd):
 
 def build(force=False, verbose=False, ptxas_info=False):
     """Env (development only): LDSR_PQ_LIST="3,10" builds just those widths; LDSR_SEG=4 overrides
-    the checkpoint segment length; LDSR_NVCC_EXTRA adds nvcc flags."""
-    global PQ_LIST
+    the checkpoint segment length; LDSR_NVCC_EXTRA adds nvcc flags; LDSR_BUILD_TAG=x writes
+    variants/lib_x.so (loaded with LDSR_SO=...) instead of the product library."""
+    global PQ_LIST, OBJ, SO
+    if os.environ.get("LDSR_BUILD_TAG"):  # side-by-side experimental builds: variants/lib_<tag>.so
+        tag = os.environ["LDSR_BUILD_TAG"]
+        OBJ = os.path.join(HERE, "build_" + tag)
+        os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+        SO = os.path.join(HERE, "variants", "lib_%s.so" % tag)
     if os.environ.get("LDSR_PQ_LIST"):
         PQ_LIST = tuple(int(x) for x in os.environ["LDSR_PQ_LIST"].split(","))
     deps = _sources()

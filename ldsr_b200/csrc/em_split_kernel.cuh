@@ -1,5 +1,5 @@
 // em_split_kernel.cuh -- the LDS_EM loop (src/EM.cpp:245-280) with the TIME AXIS SPLIT ACROSS THE
-// WARPS OF A CTA.  lane = fit (32 fits of one series per CTA), warp = a contiguous chunk of time.
+// WARPS OF A CTA.  lane = fit (32 fits of one series per CTA), warp = pieces of the time axis.
 //
 // Why: with one lane per fit and one warp walking all T steps (em_kernel.cuh) a batch of N fits is
 // only N/32 serial instruction streams -- 313 for the 10 000-fit cvLDS job, on a machine with 592
@@ -7,24 +7,29 @@
 // once, so the same batch is NW x more streams, each 1/NW as long.
 //
 // How the recursions are cut (all of it exact algebra on EM.cpp:70-90, 99-104, no approximation):
-//  * The time axis is tiled into UNITS: a 32-step word no fit of the CTA observes (type U), or an
-//    8-step segment (type M).  Warp w owns units [ub[w], ub[w+1]) (cost-balanced at launch).
-//  * P1  each warp composes the VARIANCE map of its chunk.  In 1-D the Riccati step is a Moebius
+//  * The time axis is tiled into UNITS: UW steps no fit of the CTA observes (type U), or MSEG
+//    steps (type M).  The unit list is cut into 2*NW PIECES; warp w owns piece w and piece NW+w
+//    (the cut between the two halves is put where the series changes from mostly-unobserved to
+//    mostly-observed, so every warp gets the same mix of cheap and expensive units and the
+//    forward and the backward phase are both balanced).
+//  * P1  each warp composes the VARIANCE map of its pieces.  In 1-D the Riccati step is a Moebius
 //        map of Vp, i.e. a 2x2 matrix acting on homogeneous coordinates (n,d), Vp = n/d:
 //          observed   [[A^2 R + Q C^2, Q R],[C^2, R]]      unobserved [[A^2, Q],[0, 1]]
-//        (a U word is the closed form [[A^64, Q sum A^2k],[0,1]]).          -> barrier 1
-//        Every warp then applies the maps of the chunks to its left to (V1,1): its incoming Vp.
-//  * P2  forward over the chunk with the true variances.  The MEAN is carried as an affine
+//        (a U unit is the closed form [[A^2UW, Q sum A^2k],[0,1]]).          -> barrier 1
+//        Every warp then applies the maps of the pieces to the left of its own to (V1,1).
+//  * P2  forward over each piece with the true variances.  The MEAN is carried as an affine
 //        function of the (still unknown) incoming mean x_in:  Xp_t = P_t x_in + q_t, so the
 //        innovations are affine and sum delta^2/Sigma is a quadratic (l0,l1,l2) in x_in.  In the
-//        same sweep the chunk's BACKWARD map is composed: the RTS step is affine,
-//        Xs_t = J_t Xs_{t+1} + g_t, Vs_t = J_t^2 Vs_{t+1} + L_t, and over a U word it telescopes
-//        to J = A^32 Vp_first / Vp_last.  Checkpoints (Vp, q, P) per unit.      -> barrier 2
-//        Every warp chains the (P,q) of all chunks -> x_in of every chunk, the likelihood and the
+//        same sweep the piece's BACKWARD map is composed: the RTS step is affine,
+//        Xs_t = J_t Xs_{t+1} + g_t, Vs_t = J_t^2 Vs_{t+1} + L_t, and over a U unit it telescopes
+//        to J = A^UW Vp_first / Vp_last.  Checkpoints (Vp, q, P) per unit.      -> barrier 2
+//        Every warp chains the (P,q) of all pieces -> x_in of every piece, the likelihood and the
 //        stop rule (EM.cpp:272; identical arithmetic in every warp, so no broadcast is needed),
-//        and the backward maps of the chunks to its right -> smoothed state entering its chunk.
-//  * P4  backward over the chunk, unit by unit: M segments are recomputed from their checkpoint
-//        and smoothed as in em_kernel.cuh; U words are STREAMED FORWARD because inside a run of
+//        and the backward maps of the pieces to the right -> smoothed state entering its pieces.
+//        The backward chain starts from the PRIOR of the virtual step T, which makes
+//        Xs_{T-1} = Xu_{T-1} (EM.cpp:94-95) fall out of the ordinary recursion.   -> barrier 2'
+//  * P4  backward over each piece, unit by unit: M units are recomputed from their checkpoint
+//        and smoothed as in em_kernel.cuh; U units are STREAMED FORWARD because inside a run of
 //        unobserved steps  Xs_t = Xp_t + Vp_t A^(r-t) c,  Vs_t = Vp_t + Vp_t^2 A^(2(r-t)) h  with
 //        c = (Xs_r - Xp_r)/Vp_r, h = (Vs_r - Vp_r)/Vp_r^2 taken once at the right end r of the run
 //        -- no reciprocal and no dependency chain per step.  M-step sums in registers.
@@ -37,7 +42,7 @@
 
 namespace ldsr {
 
-constexpr int SPLIT_NCH = 10; // per-chunk values exchanged after P2
+constexpr int SPLIT_NCH = 11; // per-piece values exchanged after P2
 
 // number of M-step partial sums a warp publishes
 template <int PQ> __host__ __device__ constexpr int split_nstat() { return 11 + 3 * PQ; }
@@ -45,29 +50,66 @@ template <int PQ> __host__ __device__ constexpr int split_nstat() { return 11 + 
 // dynamic shared memory of em_split_kernel, in bytes, after the series blob
 __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units) {
     size_t b = 0;
-    b += (size_t)max_units * 3 * 32 * 8;             // checkpoints
-    b += (size_t)nw * 4 * 32 * 8;                    // variance maps
-    b += (size_t)nw * SPLIT_NCH * 32 * 8;            // chunk summaries
-    b += (size_t)nw * (11 + 3 * pq) * 32 * 8;        // partial sums
+    b += (size_t)max_units * 3 * 32 * 8; // checkpoints
+    b += (size_t)2 * nw * 4 * 32 * 8;    // variance maps of the pieces
+    const size_t ch = (size_t)2 * nw * SPLIT_NCH * 32 * 8, st = (size_t)nw * (11 + 3 * pq) * 32 * 8;
+    b += ch > st ? ch : st;                           // piece summaries, later the partial sums
     b += ((size_t)max_units * 4 + 15) & ~size_t(15); // unit table
-    b += 64;                                         // chunk bounds
+    b += 128;                                        // piece bounds
     return b;
 }
 
+// Unit types.  U: UW steps nobody observes.  M: MSEG steps.  M1: a single step -- the tail of the
+// series (everything from the last full M unit to step T-1) is cut into single steps so that the
+// hot M code never sees a partial unit and step T-1 (no transition after it) is a unit of its own.
+constexpr int UNIT_M = 1 << 30, UNIT_M1 = 1 << 29, UNIT_T0 = UNIT_M1 - 1;
+
+// M / M1 units of the non-U window [t0, t0+uw): calls f(t, is_single)
+template <class F> __host__ __device__ inline void split_window_units(int t0, int T, int mseg, int uw, F f) {
+    const int end = T < t0 + uw ? T : t0 + uw;
+    int t = t0;
+    while (t < end) {
+        if (t + mseg <= T - 1 && t + mseg <= end) {
+            f(t, false);
+            t += mseg;
+        } else {
+            f(t, true);
+            t += 1;
+        }
+    }
+}
+
 // upper bound on the number of units of a series from its finite(y) mask (hold-outs only remove
-// observations, and a word with no observation is one unit instead of four)
-inline int split_units_upper_bound(const double *y, int T) {
+// observations, and a window with no observation is one unit instead of several)
+inline int split_units_upper_bound(const double *y, int T, int mseg, int uw) {
     int n = 0;
-    for (int w = 0; w * 32 < T; w++) {
+    for (int t0 = 0; t0 < T; t0 += uw) {
         bool any = false;
-        for (int t = w * 32; t < T && t < w * 32 + 32; t++) any = any || (y[t] == y[t]);
-        const bool inside = 32 * (w + 1) <= T - 1;
+        for (int t = t0; t < T && t < t0 + uw; t++) any = any || (y[t] == y[t]);
+        const bool inside = t0 + uw <= T - 1;
         if (!any && inside)
             n += 1;
         else
-            n += (std::min(T, w * 32 + 32) - w * 32 + 7) / 8;
+            split_window_units(t0, T, mseg, uw, [&](int, bool) { n++; });
     }
     return n;
+}
+
+// N consecutive doubles from shared memory; 16-byte vector loads when N is even (the callers
+// guarantee 16-byte alignment: unit starts are multiples of 4 steps, blob offsets are even)
+template <int N> __device__ __forceinline__ void load_vec(const double *__restrict__ p, double (&dst)[N]) {
+    if constexpr (N % 2 == 0) {
+        const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) {
+            const double2 t = p2[i];
+            dst[2 * i] = t.x;
+            dst[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) dst[i] = p[i];
+    }
 }
 
 __device__ __forceinline__ void rescale4(double &a, double &b, double &c, double &d) {
@@ -80,154 +122,239 @@ __device__ __forceinline__ void rescale4(double &a, double &b, double &c, double
 }
 
 // per-iteration constants of a fit
-template <int PQ> struct SplitConst {
+template <int PQ, int UW> struct SplitConst {
+    static_assert(UW == 16 || UW == 32, "U unit is 16 or 32 steps");
     double A, A2, Q;
-    double Ap[9];            // A^0 .. A^8
-    double A16, A32;         // A^16, A^32
-    double aV32, bV32;       // Vp' = aV32 Vp + bV32 over an unobserved word
+    double Ap[8];      // A^0 .. A^7
+    double A8, A16;    // A^8, A^16
+    double AW;         // A^UW
+    double aVW, bVW;   // Vp' = aVW Vp + bVW over an unobserved unit
     MixedConst<PQ> mc;
     __device__ __forceinline__ void set(const Theta<PQ> &th) {
         A = th.A;
         A2 = A * A;
         Q = th.Q;
+        // powers by squaring: depth 3 instead of a chain of 8 multiplications
+        const double A4 = A2 * A2;
         Ap[0] = 1.0;
-#pragma unroll
-        for (int k = 1; k <= 8; k++) Ap[k] = Ap[k - 1] * A;
-        A16 = Ap[8] * Ap[8];
-        A32 = A16 * A16;
-        aV32 = A32 * A32;
-        double sv = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) sv = fma(sv, A2, 1.0); // sum_{k<8} A2^k
-        // sum_{k<32} A2^k = sv (1 + A2^8)(1 + A2^16),  A2^8 = A^16
-        bV32 = Q * (sv * ((1.0 + A16) * (1.0 + A32)));
+        Ap[1] = A;
+        Ap[2] = A2;
+        Ap[3] = A2 * A;
+        Ap[4] = A4;
+        Ap[5] = A4 * A;
+        Ap[6] = A4 * A2;
+        Ap[7] = A4 * Ap[3];
+        A8 = A4 * A4;
+        A16 = A8 * A8;
+        AW = UW == 32 ? A16 * A16 : A16;
+        aVW = AW * AW;
+        // sum_{k<8} A2^k = (1 + A2)(1 + A2^2)(1 + A2^4)
+        const double sv = ((1.0 + A2) * (1.0 + A4)) * (1.0 + A8);
+        // sum_{k<16} A2^k = sv (1 + A2^8), sum_{k<32} = sv (1 + A2^8)(1 + A2^16);  A2^8 = A^16
+        double s = sv * (1.0 + A16);
+        if (UW == 32) s *= 1.0 + A16 * A16;
+        bVW = Q * s;
         mc.set(th, A2);
     }
 };
 
-// ---- P1: variance map of one M segment, M <- S_j ... S_0 M ----------------------------------
-template <int PQ>
-__device__ __forceinline__ void compose_var_segment(const Theta<PQ> &th, const SplitConst<PQ> &k, unsigned bits,
-                                                    int cnt, double &m11, double &m12, double &m21, double &m22) {
+// ---- P1: variance map of one M unit, M <- S_{N-1} ... S_0 M -----------------------------------
+template <int PQ, int UW, int N>
+__device__ __forceinline__ void compose_var_unit(const Theta<PQ> &th, const SplitConst<PQ, UW> &k, unsigned bits,
+                                                 double &m11, double &m12, double &m21, double &m22) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (j < cnt) {
-            const bool obs = (bits >> j) & 1u;
-            const double s11 = obs ? k.mc.a11 : k.A2, s12 = obs ? k.mc.a12 : k.Q;
-            const double s21 = obs ? k.mc.C2 : 0.0, s22 = obs ? th.R : 1.0;
-            const double n11 = fma(s11, m11, s12 * m21), n12 = fma(s11, m12, s12 * m22);
-            const double n21 = fma(s21, m11, s22 * m21), n22 = fma(s21, m12, s22 * m22);
-            m11 = n11;
-            m12 = n12;
-            m21 = n21;
-            m22 = n22;
-        }
+    for (int j = 0; j < N; j++) {
+        const bool obs = (bits >> j) & 1u;
+        const double s11 = obs ? k.mc.a11 : k.A2, s12 = obs ? k.mc.a12 : k.Q;
+        const double s21 = obs ? k.mc.C2 : 0.0, s22 = obs ? th.R : 1.0;
+        const double n11 = fma(s11, m11, s12 * m21), n12 = fma(s11, m12, s12 * m22);
+        const double n21 = fma(s21, m11, s22 * m21), n22 = fma(s21, m12, s22 * m22);
+        m11 = n11;
+        m12 = n12;
+        m21 = n21;
+        m22 = n22;
     }
     rescale4(m11, m12, m21, m22);
 }
 
-// chunk state carried through P2
-struct ChunkFwd {
+// ---- gains of one M unit -----------------------------------------------------------------------
+// The variance recursion in homogeneous coordinates (see em_kernel.cuh, mixed_forward), written
+// stage by stage: the (n,d) chain first (two multiply-adds per step), then all reciprocals -- they
+// are independent of each other -- then everything that hangs off them.
+template <int N> struct UnitGains {
+    double K[N], rS[N], alpha[N], J[N], L[N];
+    double Vnext; // prior variance of the step after the unit
+    double dend;  // final d: prod_obs Sigma
+};
+template <int PQ, int UW, int N>
+__device__ __forceinline__ void unit_gains(const Theta<PQ> &th, const SplitConst<PQ, UW> &k, unsigned bits, double Vq,
+                                           UnitGains<N> &G) {
+    double nj[N], dj[N], nn[N], dd[N];
+    double n = Vq, d = 1.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const bool obs = (bits >> j) & 1u;
+        const double m11 = obs ? k.mc.a11 : k.A2, m12 = obs ? k.mc.a12 : k.Q;
+        const double m21 = obs ? k.mc.C2 : 0.0, m22 = obs ? th.R : 1.0;
+        nj[j] = n;
+        dj[j] = d;
+        nn[j] = fma(m11, n, m12 * d);
+        dd[j] = fma(m21, n, m22 * d);
+        n = nn[j];
+        d = dd[j];
+    }
+    double rho[N], rn[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        rho[j] = fast_rcp(dd[j]);
+        rn[j] = fast_rcp(nn[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const bool obs = (bits >> j) & 1u;
+        const double K = obs ? th.C * nj[j] * rho[j] : 0.0;
+        const double nu = obs ? th.R * nj[j] : nj[j];
+        const double vu = nu * rho[j];
+        const double J = k.A * nu * rn[j];
+        G.K[j] = K;
+        G.rS[j] = obs ? dj[j] * rho[j] : 0.0; // 1/Sigma
+        G.alpha[j] = fma(-k.mc.AC, K, k.A);
+        G.J[j] = J;
+        G.L[j] = vu * fma(-k.A, J, 1.0); // Vu - J^2 Vp' with J Vp' = A Vu
+    }
+    G.Vnext = nn[N - 1] * rho[N - 1];
+    G.dend = d;
+}
+
+// inputs of one M unit: Bu_j = B u_j, ymd_j = y_j - D v_j (y taken as 0 where unobserved)
+template <int PQ, int N>
+__device__ __forceinline__ void unit_inputs(const Theta<PQ> &th, unsigned bits, const double *__restrict__ yseg,
+                                            const double *__restrict__ useg, const double *__restrict__ vseg,
+                                            double (&Bu)[N], double (&ymd)[N], double (&yo)[N],
+                                            double (&ur)[N * PQ], double (&vr)[N * PQ]) {
+    double yr[N];
+    load_vec<N * PQ>(useg, ur);
+    load_vec<N * PQ>(vseg, vr);
+    load_vec<N>(yseg, yr);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double b = 0.0, dv = 0.0;
+#pragma unroll
+        for (int i = 0; i < PQ; i++) {
+            b = fma(th.B[i], ur[j * PQ + i], b);
+            dv = fma(th.D[i], vr[j * PQ + i], dv);
+        }
+        const bool obs = (bits >> j) & 1u;
+        yo[j] = obs ? yr[j] : 0.0; // y is NaN where missing
+        Bu[j] = b;
+        ymd[j] = yo[j] - dv;
+    }
+}
+
+// piece state carried through P2
+struct PieceFwd {
     double Vq, P, q;            // prior variance; prior mean = P x_in + q
     double l0, l1, l2;          // sum_obs delta^2/Sigma = l0 - 2 C x l1 + C^2 x^2 l2
-    double dprod;               // product of the segments' final d (sum_obs log Sigma = log dprod + shift ln 2)
+    double dprod;               // product of the units' final d (sum_obs log Sigma = log dprod + shift ln 2)
     int shift;
     double PJ, PJ2, G0, GG, Lc; // backward map: Xs_first = PJ Xs_in + G0 + GG x_in, Vs_first = PJ2 Vs_in + Lc
 };
 
-// ---- P2 over one M segment --------------------------------------------------------------------
+// ---- P2 over one M unit -------------------------------------------------------------------------
 // Same recursion as mixed_forward (em_kernel.cuh) with the mean in (P,q) form and the backward map
 // accumulated on the fly.
-template <int PQ, bool GUARDED>
-__device__ __forceinline__ void forward_segment_basis(const Theta<PQ> &th, const SplitConst<PQ> &k, unsigned bits,
-                                                      int cnt, const double *__restrict__ yseg,
-                                                      const double *__restrict__ useg,
-                                                      const double *__restrict__ vseg, ChunkFwd &c) {
-    double n = c.Vq, d = 1.0;
-    int shift = 0;
-    const double A = k.A;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (!GUARDED || j < cnt) {
-            const bool obs = (bits >> j) & 1u;
-            const double m11 = obs ? k.mc.a11 : k.A2, m12 = obs ? k.mc.a12 : k.Q;
-            const double m21 = obs ? k.mc.C2 : 0.0, m22 = obs ? th.R : 1.0;
-            const double nn = fma(m11, n, m12 * d);
-            const double dd = fma(m21, n, m22 * d);
-            const double rho = fast_rcp(dd);
-            const double Bu = dot_row<PQ>(th.B, useg + j * PQ);
-            const double Dv = dot_row<PQ>(th.D, vseg + j * PQ);
-            const double K = obs ? th.C * n * rho : 0.0;
-            const double rS = obs ? d * rho : 0.0; // 1/Sigma
-            const double ymd = (obs ? yseg[j] : 0.0) - Dv;
-            const double d0 = fma(-th.C, c.q, ymd); // innovation for x_in = 0
-            const double w0 = rS * d0;
-            c.l0 = fma(w0, d0, c.l0);
-            c.l1 = fma(w0, c.P, c.l1);
-            c.l2 = fma(rS * c.P, c.P, c.l2);
-            const double alpha = fma(-k.mc.AC, K, A);
-            const double beta = fma(A * K, ymd, Bu);
-            const double xu0 = fma(K, d0, c.q);
-            const double xuP = c.P * fma(-K, th.C, 1.0);
-            const double qn = fma(alpha, c.q, beta);
-            const double Pn = alpha * c.P;
-            const double nu = obs ? th.R * n : n;
-            const double vu = nu * rho;
-            double J, g0, gP, L;
-            if (GUARDED && j == cnt - 1) { // t == T-1: smoothed = filtered (EM.cpp:94-95)
-                J = 0.0;
-                g0 = xu0;
-                gP = xuP;
-                L = vu;
-            } else {
-                J = A * nu * fast_rcp(nn);
-                g0 = fma(-J, qn, xu0);
-                gP = fma(-J, Pn, xuP);
-                L = vu * fma(-A, J, 1.0);
-            }
-            c.G0 = fma(c.PJ, g0, c.G0);
-            c.GG = fma(c.PJ, gP, c.GG);
-            c.Lc = fma(c.PJ2, L, c.Lc);
-            c.PJ *= J;
-            c.PJ2 *= J * J;
-            c.q = qn;
-            c.P = Pn;
-            if (j == (GUARDED ? cnt - 1 : 7)) c.Vq = nn * rho;
-            n = nn;
-            d = dd;
-            if (j == 3) rescale_pow2(n, d, shift);
-        }
+template <int PQ, int UW, int N>
+__device__ __forceinline__ void forward_unit_basis(const Theta<PQ> &th, const SplitConst<PQ, UW> &k, unsigned bits,
+                                                   const double *__restrict__ yseg, const double *__restrict__ useg,
+                                                   const double *__restrict__ vseg, PieceFwd &c) {
+    double Bu[N], ymd[N], yo[N];
+    {
+        double ur[N * PQ], vr[N * PQ];
+        unit_inputs<PQ, N>(th, bits, yseg, useg, vseg, Bu, ymd, yo, ur, vr);
     }
-    c.dprod *= d;
+    UnitGains<N> G;
+    unit_gains<PQ, UW, N>(th, k, bits, c.Vq, G);
+    // mean chain in (P,q) form: one FMA / one MUL per step
+    double q[N + 1], P[N + 1];
+    q[0] = c.q;
+    P[0] = c.P;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double beta = fma(k.A * G.K[j], ymd[j], Bu[j]);
+        q[j + 1] = fma(G.alpha[j], q[j], beta);
+        P[j + 1] = G.alpha[j] * P[j];
+    }
+    // innovations (quadratic in x_in) and the affine backward steps
+    double g0[N], gP[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double d0 = fma(-th.C, q[j], ymd[j]); // innovation for x_in = 0
+        const double w0 = G.rS[j] * d0;
+        c.l0 = fma(w0, d0, c.l0);
+        c.l1 = fma(w0, P[j], c.l1);
+        c.l2 = fma(G.rS[j] * P[j], P[j], c.l2);
+        const double xu0 = fma(G.K[j], d0, q[j]);
+        const double xuP = P[j] * fma(-G.K[j], th.C, 1.0);
+        g0[j] = fma(-G.J[j], q[j + 1], xu0);
+        gP[j] = fma(-G.J[j], P[j + 1], xuP);
+    }
+    // backward map of the piece so far
+    double pj = c.PJ, pj2 = c.PJ2;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        c.G0 = fma(pj, g0[j], c.G0);
+        c.GG = fma(pj, gP[j], c.GG);
+        c.Lc = fma(pj2, G.L[j], c.Lc);
+        pj *= G.J[j];
+        pj2 *= G.J[j] * G.J[j];
+    }
+    c.PJ = pj;
+    c.PJ2 = pj2;
+    c.q = q[N];
+    c.P = P[N];
+    c.Vq = G.Vnext;
+    c.dprod *= G.dend;
     {
         const int e = ((__double2hiint(c.dprod) >> 20) & 0x7ff) - 1023;
         c.dprod *= __hiloint2double((1023 - e) << 20, 0);
-        c.shift += shift + e;
+        c.shift += e;
     }
 }
 
-// ---- P2 over one unobserved 32-step word ------------------------------------------------------
-template <int PQ>
-__device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const SplitConst<PQ> &k,
-                                                   const double *__restrict__ useg, ChunkFwd &c) {
-    double h[4];
+// ---- P2 over one unobserved unit ------------------------------------------------------------------
+template <int PQ, int UW>
+__device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const SplitConst<PQ, UW> &k,
+                                                   const double *__restrict__ useg, PieceFwd &c) {
+    double hh = 0.0;
+#pragma unroll 1
+    for (int b = 0; b < UW / 8; b++) {
+        // the 8 dot products are independent; the Horner sum runs as two chains of four
+        double ur[8 * PQ];
+        load_vec<8 * PQ>(useg + b * 8 * PQ, ur);
+        double Bu[8];
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-        double hb = 0.0;
+        for (int j = 0; j < 8; j++) {
+            double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) hb = fma(k.A, hb, dot_row<PQ>(th.B, useg + (b * 8 + j) * PQ));
-        h[b] = hb;
+            for (int i = 0; i < PQ; i++) acc = fma(th.B[i], ur[j * PQ + i], acc);
+            Bu[j] = acc;
+        }
+        double lo = Bu[0], hi = Bu[4];
+#pragma unroll
+        for (int j = 1; j < 4; j++) {
+            lo = fma(k.A, lo, Bu[j]);
+            hi = fma(k.A, hi, Bu[4 + j]);
+        }
+        hh = fma(hh, k.A8, fma(lo, k.Ap[4], hi));
     }
-    const double A8 = k.Ap[8];
-    const double hh = fma(fma(fma(h[0], A8, h[1]), A8, h[2]), A8, h[3]);
-    const double qn = fma(k.A32, c.q, hh);
-    const double Pn = k.A32 * c.P;
-    const double Vn = fma(k.aV32, c.Vq, k.bV32);
-    // backward map of the word: J = prod J_t = A^32 Vp_first / Vp_last  (EM.cpp:100 telescoped)
-    const double Jc = k.A32 * c.Vq * fast_rcp(Vn);
+    const double qn = fma(k.AW, c.q, hh);
+    const double Pn = k.AW * c.P;
+    const double Vn = fma(k.aVW, c.Vq, k.bVW);
+    // backward map of the unit: J = prod J_t = A^UW Vp_first / Vp_last  (EM.cpp:100 telescoped)
+    const double Jc = k.AW * c.Vq * fast_rcp(Vn);
     const double g0 = fma(-Jc, qn, c.q);
     const double gP = fma(-Jc, Pn, c.P);
-    const double L = c.Vq * fma(-k.A32, Jc, 1.0);
+    const double L = c.Vq * fma(-k.AW, Jc, 1.0);
     c.G0 = fma(c.PJ, g0, c.G0);
     c.GG = fma(c.PJ, gP, c.GG);
     c.Lc = fma(c.PJ2, L, c.Lc);
@@ -238,62 +365,150 @@ __device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const Sp
     c.Vq = Vn;
 }
 
-// ---- P4 over one unobserved 32-step word ------------------------------------------------------
-// (Xq,Vq): prior at the first step of the word.  (cG,cH): the run constants AT THE RIGHT END of the
-// word; on return they are the constants at its left end (= right end of the word before it).
-template <int PQ>
-__device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitConst<PQ> &k,
+// ---- P4 over one M unit -------------------------------------------------------------------------
+// The filter is recomputed from the checkpoint (Xq,Vq), then the backward recursion
+// Xs = J Xs1 + g, Vs = J^2 Vs1 + L runs over it and feeds the sums of EM.cpp:151-161, 180-193.
+// `last` (N = 1 only): the unit is step T-1, which has no transition after it.
+template <int PQ, int UW, int N>
+__device__ __forceinline__ void smooth_unit(const Theta<PQ> &th, const SplitConst<PQ, UW> &k, unsigned bits, bool last,
+                                            const double *__restrict__ yseg, const double *__restrict__ useg,
+                                            const double *__restrict__ vseg, double Xq, double Vq, double &Xs1,
+                                            double &Vs1, Stats<PQ> &st) {
+    constexpr bool KEEP_ROWS = N * PQ <= 16; // keep u, v rows in registers for the sums, else reload
+    double Bu[N], ymd[N], yo[N];
+    double ur[N * PQ], vr[N * PQ];
+    unit_inputs<PQ, N>(th, bits, yseg, useg, vseg, Bu, ymd, yo, ur, vr);
+    UnitGains<N> G;
+    unit_gains<PQ, UW, N>(th, k, bits, Vq, G);
+    double xq[N + 1], g[N];
+    xq[0] = Xq;
+#pragma unroll
+    for (int j = 0; j < N; j++) xq[j + 1] = fma(G.alpha[j], xq[j], fma(k.A * G.K[j], ymd[j], Bu[j]));
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double delta = fma(-th.C, xq[j], ymd[j]);
+        const double xu = fma(G.K[j], delta, xq[j]);
+        g[j] = fma(-G.J[j], xq[j + 1], xu);
+    }
+    double Xs[N + 1], Vs[N + 1];
+    Xs[N] = Xs1;
+    Vs[N] = Vs1;
+#pragma unroll
+    for (int j = N - 1; j >= 0; j--) {
+        Xs[j] = fma(G.J[j], Xs[j + 1], g[j]);
+        Vs[j] = fma(G.J[j] * G.J[j], Vs[j + 1], G.L[j]);
+    }
+    if (!KEEP_ROWS) {
+        load_vec<N * PQ>(useg, ur);
+        load_vec<N * PQ>(vseg, vr);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (N == 1 && last) {
+            st.XT = Xs[j];
+            st.VT = Vs[j];
+        } else {
+            st.Tx1x = fma(Xs[j + 1], Xs[j], st.Tx1x);
+            st.Tx1xv = fma(Vs[j + 1], G.J[j], st.Tx1xv);
+            st.Txx = fma(Xs[j], Xs[j], st.Txx);
+            st.Txxv += Vs[j];
+#pragma unroll
+            for (int i = 0; i < PQ; i++) {
+                st.Tx1u[i] = fma(Xs[j + 1], ur[j * PQ + i], st.Tx1u[i]);
+                st.Tux[i] = fma(ur[j * PQ + i], Xs[j], st.Tux[i]);
+            }
+        }
+        const bool obs = (bits >> j) & 1u;
+        const double xo = obs ? Xs[j] : 0.0;
+        st.Syx = fma(yo[j], xo, st.Syx);
+        st.Sxx = fma(xo, xo, st.Sxx);
+        st.Sxxv += obs ? Vs[j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < PQ; i++) st.Sxv[i] = fma(xo, vr[j * PQ + i], st.Sxv[i]);
+    }
+    Xs1 = Xs[0];
+    Vs1 = Vs[0];
+}
+
+// ---- P4 over one unobserved unit ------------------------------------------------------------------
+// (Xq,Vq): prior at the first step of the unit.  (cG,cH): the run constants AT THE RIGHT END of the
+// unit; on return they are the constants at its left end (= right end of the unit before it).
+template <int PQ, int UW>
+__device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitConst<PQ, UW> &k,
                                             const double *__restrict__ useg, double Xq, double Vq, double &cG,
                                             double &cH, double &Xs1, double &Vs1, Stats<PQ> &st) {
-    const double A8 = k.Ap[8];
-    double Gb[4], Hb[4]; // constants at the right end of each 8-step block
-    Gb[3] = cG;
-    Gb[2] = A8 * cG;
-    Gb[1] = k.A16 * cG;
-    Gb[0] = A8 * Gb[1];
-    Hb[3] = cH;
-    Hb[2] = k.A16 * cH;
-    Hb[1] = k.A32 * cH;
-    Hb[0] = k.A16 * Hb[1];
-    const double G0 = A8 * Gb[0], H0 = k.A16 * Hb[0];
+    constexpr int NB = UW / 8;
+    // constants at the right end of each 8-step block, last block first
+    const double g1 = k.A8 * cG, g2 = k.A16 * cG, g3 = k.A8 * g2;
+    const double A32 = k.A16 * k.A16;
+    const double h1 = k.A16 * cH, h2 = A32 * cH, h3 = k.A16 * h2;
+    const double G0 = NB == 4 ? k.A8 * g3 : k.A8 * g1;
+    const double H0 = NB == 4 ? k.A16 * h3 : k.A16 * h1;
     double xp = Xq, vp = Vq;
     double Xs = fma(vp, G0, xp);
     double Vs = fma(vp, vp * H0, vp);
     const double Xfirst = Xs, Vfirst = Vs;
     double tv = 0.0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
+#pragma unroll 1
+    for (int b = 0; b < NB; b++) {
+        const int r = NB - 1 - b; // blocks to the right of this one
+        const double Gb = r == 0 ? cG : (r == 1 ? g1 : (r == 2 ? g2 : g3));
+        const double Hb = r == 0 ? cH : (r == 1 ? h1 : (r == 2 ? h2 : h3));
+        const double *__restrict__ blk = useg + b * 8 * PQ;
+        // The block is written stage by stage so that every stage is a batch of independent
+        // operations (the only serial chains are one FMA per step on xp and on vp):
+        // 1. inputs of the 8 steps
+        constexpr bool KEEP_U = PQ <= 4; // keep the rows in registers for stage 4, else reload them
+        double uk[8 * PQ];
+        load_vec<8 * PQ>(blk, uk);
+        double Bu[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double *__restrict__ row = useg + (b * 8 + j) * PQ;
-            double uk[PQ];
+            double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < PQ; i++) uk[i] = row[i];
-            double Bu = 0.0;
+            for (int i = 0; i < PQ; i++) acc = fma(th.B[i], uk[j * PQ + i], acc);
+            Bu[j] = acc;
+        }
+        // 2. prediction (EM.cpp:72-76 without a measurement)
+        double xs[9], vs[9];
+        xs[0] = xp;
+        vs[0] = vp;
 #pragma unroll
-            for (int i = 0; i < PQ; i++) Bu = fma(th.B[i], uk[i], Bu);
-            const double xpn = fma(k.A, xp, Bu);
-            const double vpn = fma(k.A2, vp, k.Q);
+        for (int j = 0; j < 8; j++) {
+            xs[j + 1] = fma(k.A, xs[j], Bu[j]);
+            vs[j + 1] = fma(k.A2, vs[j], k.Q);
+        }
+        // 3. smoothed moments of steps 1..8 of the block
+        double Xn[9], Vn[9], t1[8];
+        Xn[0] = Xs;
+        Vn[0] = Vs;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
             const double pw = k.Ap[7 - j];
-            const double Gn = pw * Gb[b];
-            const double Hn = (pw * pw) * Hb[b];
-            const double Xsn = fma(vpn, Gn, xpn);
-            const double t1 = vpn * Hn;
-            const double Vsn = fma(vpn, t1, vpn);
-            st.Tx1x = fma(Xsn, Xs, st.Tx1x);
-            st.Txx = fma(Xs, Xs, st.Txx);
-            st.Txxv += Vs;
-            tv = fma(vp, 1.0 + t1, tv); // V_{t+1} J_t = A Vp_t (1 + Vp_{t+1} H_{t+1})
+            const double Gn = pw * Gb;
+            const double Hn = (pw * pw) * Hb;
+            Xn[j + 1] = fma(vs[j + 1], Gn, xs[j + 1]);
+            t1[j] = vs[j + 1] * Hn;
+            Vn[j + 1] = fma(vs[j + 1], t1[j], vs[j + 1]);
+        }
+        // 4. the sums of EM.cpp:180-193
+        if (!KEEP_U) load_vec<8 * PQ>(blk, uk);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            st.Tx1x = fma(Xn[j + 1], Xn[j], st.Tx1x);
+            st.Txx = fma(Xn[j], Xn[j], st.Txx);
+            st.Txxv += Vn[j];
+            tv = fma(vs[j], 1.0 + t1[j], tv); // V_{t+1} J_t = A Vp_t (1 + Vp_{t+1} H_{t+1})
 #pragma unroll
             for (int i = 0; i < PQ; i++) {
-                st.Tx1u[i] = fma(Xsn, uk[i], st.Tx1u[i]);
-                st.Tux[i] = fma(uk[i], Xs, st.Tux[i]);
+                st.Tx1u[i] = fma(Xn[j + 1], uk[j * PQ + i], st.Tx1u[i]);
+                st.Tux[i] = fma(uk[j * PQ + i], Xn[j], st.Tux[i]);
             }
-            xp = xpn;
-            vp = vpn;
-            Xs = Xsn;
-            Vs = Vsn;
         }
+        xp = xs[8];
+        vp = vs[8];
+        Xs = Xn[8];
+        Vs = Vn[8];
     }
     st.Tx1xv = fma(k.A, tv, st.Tx1xv);
     Xs1 = Xfirst;
@@ -304,19 +519,44 @@ __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitCons
 
 struct SplitParams {
     EmParams em;
-    int max_units;   // capacity of the unit table / checkpoint area
-    int blob_smem;   // bytes reserved for the series blob at the start of dynamic shared memory
-    int cost_u, cost_m; // relative cost of a U word and an M segment (chunk balancing)
+    int max_units;      // capacity of the unit table / checkpoint area
+    int blob_smem;      // bytes reserved for the series blob at the start of dynamic shared memory
+    int cost_u, cost_m; // relative cost of a U unit and an M unit (piece balancing)
 };
 
-constexpr int UNIT_M = 1 << 30;
+// cut units [a,b) into NW pieces of about equal cost: bounds[0..NW]
+__device__ __forceinline__ int unit_cost(int u, int cost_u, int cost_m, int mseg) {
+    return (u & UNIT_M) ? cost_m : ((u & UNIT_M1) ? (3 * cost_m) / (2 * mseg) : cost_u);
+}
+template <int NW>
+__device__ inline void split_range(const int *units, int a, int b, int cost_u, int cost_m, int mseg, int *bounds) {
+    long long total = 0;
+    for (int i = a; i < b; ++i) total += unit_cost(units[i], cost_u, cost_m, mseg);
+    bounds[0] = a;
+    long long acc = 0;
+    int kq = a;
+    for (int w = 1; w < NW; ++w) {
+        const long long target = (total * w + NW / 2) / NW;
+        while (kq < b) {
+            const int cu = unit_cost(units[kq], cost_u, cost_m, mseg);
+            if (acc + cu / 2 >= target) break;
+            acc += cu;
+            kq++;
+        }
+        bounds[w] = kq;
+    }
+    bounds[NW] = b;
+}
 
-template <int PQ, int NW, int MINB>
+template <int PQ, int NW, int MINB, int MSEG, int UW>
 __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitParams SP) {
+    static_assert(MSEG == 4 || MSEG == 8, "M unit is 4 or 8 steps");
     const EmParams &P = SP.em;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     constexpr int NST = split_nstat<PQ>();
+    constexpr int NP = 2 * NW; // pieces
+    constexpr size_t CH_DOUBLES = (size_t)NP * SPLIT_NCH * 32, ST_DOUBLES = (size_t)NW * NST * 32;
 
     const int4 task = P.tasks[blockIdx.x];
     const SeriesDev S = P.series[task.x];
@@ -335,12 +575,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     const double *__restrict__ us = ser + S.u_off;
     const double *__restrict__ vs = ser + S.v_off;
     // shared-memory carve-up after the blob; every per-lane array is [..][32] doubles
-    double *const ck = reinterpret_cast<double *>(smem_raw + SP.blob_smem) + lane;   // [unit][3]
-    double *const MC = ck - lane + (size_t)SP.max_units * 96 + lane;                  // [NW][4]
-    double *const CH = MC - lane + (size_t)NW * 4 * 32 + lane;                        // [NW][SPLIT_NCH]
-    double *const ST = CH - lane + (size_t)NW * SPLIT_NCH * 32 + lane;                // [NW][NST]
-    int *const units = reinterpret_cast<int *>(ST - lane + (size_t)NW * NST * 32);    // [max_units]
-    int *const ubound = units + ((SP.max_units + 3) & ~3);                            // [NW+1]
+    double *const ck = reinterpret_cast<double *>(smem_raw + SP.blob_smem) + lane; // [unit][3]
+    double *const MC = ck + (size_t)SP.max_units * 96;                             // [NP][4]
+    double *const CH = MC + (size_t)NP * 4 * 32;                                   // [NP][SPLIT_NCH]
+    double *const ST = CH; // [NW][NST]: the piece summaries are dead after barrier 2'
+    int *const units =
+        reinterpret_cast<int *>(CH - lane + (CH_DOUBLES > ST_DOUBLES ? CH_DOUBLES : ST_DOUBLES)); // [max_units]
+    int *const pbound = units + ((SP.max_units + 3) & ~3);                                        // [NP+1]
 
     // ---- per-lane fit state: every warp holds the same 32 fits
     const bool valid = lane < task.z;
@@ -361,115 +602,127 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         lik = __longlong_as_double(0x7ff8000000000000ULL);
     }
 
-    // ---- unit table and chunk bounds (warp 0; the vote is over the CTA's 32 fits)
+    // ---- unit table and piece bounds (warp 0; the vote is over the CTA's 32 fits)
     if (warp == 0) {
-        int nu = 0, cost = 0;
-        for (int w = 0; w * 32 < T; ++w) {
-            const bool any = __any_sync(FULL, mw[w] != 0u);
-            const bool inside = 32 * (w + 1) <= T - 1;
+        int nu = 0;
+        for (int t0 = 0; t0 < T; t0 += UW) {
+            const bool any = __any_sync(FULL, seg_bits(mw, t0, UW) != 0u);
+            const bool inside = t0 + UW <= T - 1;
             if (!any && inside) {
-                if (lane == 0) units[nu] = w * 32;
+                if (lane == 0) units[nu] = t0;
                 nu++;
-                cost += SP.cost_u;
             } else {
-                for (int t0 = w * 32; t0 < T && t0 < w * 32 + 32; t0 += 8) {
-                    if (lane == 0) units[nu] = t0 | UNIT_M;
+                split_window_units(t0, T, MSEG, UW, [&](int t, bool single) {
+                    if (lane == 0) units[nu] = t | (single ? UNIT_M1 : UNIT_M);
                     nu++;
-                    cost += SP.cost_m;
-                }
+                });
             }
         }
         __syncwarp();
         if (lane == 0) {
-            ubound[0] = 0;
-            int acc = 0, kq = 0;
-            for (int w = 1; w < NW; ++w) {
-                const int target = (int)(((long long)cost * w + NW / 2) / NW);
-                while (kq < nu) {
-                    const int cu = (units[kq] & UNIT_M) ? SP.cost_m : SP.cost_u;
-                    if (acc + cu / 2 >= target) break;
-                    acc += cu;
-                    kq++;
+            // cut between the halves: where "U before, M after" (or the reverse) fits best; ties go
+            // to the cut closest to the middle
+            int nM = 0;
+            for (int i = 0; i < nu; ++i) nM += (units[i] & (UNIT_M | UNIT_M1)) ? 1 : 0;
+            int best = nu / 2, best_mis = 1 << 30, mb = 0;
+            for (int s = 0; s <= nu; ++s) { // mb = M units before s
+                const int ub = s - mb, ma = nM - mb, uaft = (nu - s) - ma;
+                int mis = min(mb + uaft, ub + ma);
+                if (s == 0 || s == nu) mis = 1 << 29; // both halves must exist when possible
+                if (mis < best_mis || (mis == best_mis && abs(2 * s - nu) < abs(2 * best - nu))) {
+                    best_mis = mis;
+                    best = s;
                 }
-                ubound[w] = kq;
+                if (s < nu && (units[s] & (UNIT_M | UNIT_M1))) mb++;
             }
-            ubound[NW] = nu;
+            split_range<NW>(units, 0, best, SP.cost_u, SP.cost_m, MSEG, pbound);
+            split_range<NW>(units, best, nu, SP.cost_u, SP.cost_m, MSEG, pbound + NW);
         }
     }
     mbar_wait(&bar, 0);
     __syncthreads();
-    const int ua = ubound[warp], ue = ubound[warp + 1];
 
     for (int it = 0; it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
-        SplitConst<PQ> k;
+        SplitConst<PQ, UW> k;
         k.set(th);
 
-        // ================= P1: variance map of the chunk =================
-        if (warp < NW - 1) { // nobody is to the right of the last chunk
+        // ================= P1: variance maps of my pieces =================
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int pj = h * NW + warp;
+            if (pj == NP - 1) break; // nothing is to the right of the last piece
             double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;
+            const int ua = pbound[pj], ue = pbound[pj + 1];
             for (int un = ua; un < ue; ++un) {
                 const int u0 = units[un];
+                const int t0 = u0 & UNIT_T0;
                 if (u0 & UNIT_M) {
-                    const int t0 = u0 & (UNIT_M - 1);
-                    compose_var_segment<PQ>(th, k, seg_bits(mw, t0, 8), min(8, T - t0), m11, m12, m21, m22);
+                    compose_var_unit<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), m11, m12, m21, m22);
+                } else if (u0 & UNIT_M1) {
+                    compose_var_unit<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), m11, m12, m21, m22);
                 } else {
-                    m11 = fma(k.aV32, m11, k.bV32 * m21);
-                    m12 = fma(k.aV32, m12, k.bV32 * m22);
+                    m11 = fma(k.aVW, m11, k.bVW * m21);
+                    m12 = fma(k.aVW, m12, k.bVW * m22);
                 }
             }
-            MC[(warp * 4 + 0) * 32] = m11;
-            MC[(warp * 4 + 1) * 32] = m12;
-            MC[(warp * 4 + 2) * 32] = m21;
-            MC[(warp * 4 + 3) * 32] = m22;
+            MC[(pj * 4 + 0) * 32] = m11;
+            MC[(pj * 4 + 1) * 32] = m12;
+            MC[(pj * 4 + 2) * 32] = m21;
+            MC[(pj * 4 + 3) * 32] = m22;
         }
         __syncthreads();
-        ChunkFwd c;
+        double VinA = th.V1, VinB = th.V1; // prior variance entering piece warp / piece NW+warp
         {
             double n = th.V1, d = 1.0;
-            for (int w = 0; w < warp; ++w) {
-                const double m11 = MC[(w * 4 + 0) * 32], m12 = MC[(w * 4 + 1) * 32];
-                const double m21 = MC[(w * 4 + 2) * 32], m22 = MC[(w * 4 + 3) * 32];
+#pragma unroll
+            for (int pj = 0; pj < NP - 1; ++pj) {
+                const double m11 = MC[(pj * 4 + 0) * 32], m12 = MC[(pj * 4 + 1) * 32];
+                const double m21 = MC[(pj * 4 + 2) * 32], m22 = MC[(pj * 4 + 3) * 32];
+                // every map was normalised to entries summing to [1,2): the chain cannot overflow
                 const double nn = fma(m11, n, m12 * d), dd = fma(m21, n, m22 * d);
                 n = nn;
                 d = dd;
-                int sh = 0;
-                rescale_pow2(n, d, sh);
+                if (pj + 1 == warp) VinA = n * fast_rcp(d);
+                if (pj + 1 == NW + warp) VinB = n * fast_rcp(d);
             }
-            c.Vq = warp == 0 ? th.V1 : n * fast_rcp(d);
         }
 
-        // ================= P2: forward over the chunk =================
-        c.P = 1.0;
-        c.q = 0.0;
-        c.l0 = c.l1 = c.l2 = 0.0;
-        c.dprod = 1.0;
-        c.shift = 0;
-        c.PJ = c.PJ2 = 1.0;
-        c.G0 = c.GG = c.Lc = 0.0;
-        bool any_m = false;
-        for (int un = ua; un < ue; ++un) {
-            const int u0 = units[un];
-            const int t0 = u0 & (UNIT_M - 1);
-            ck[(un * 3 + 0) * 32] = c.Vq;
-            ck[(un * 3 + 1) * 32] = c.q;
-            ck[(un * 3 + 2) * 32] = c.P;
-            if (u0 & UNIT_M) {
-                any_m = true;
-                if (t0 + 8 >= T)
-                    forward_segment_basis<PQ, true>(th, k, seg_bits(mw, t0, 8), T - t0, ys + t0, us + t0 * PQ,
-                                                    vs + t0 * PQ, c);
-                else
-                    forward_segment_basis<PQ, false>(th, k, seg_bits(mw, t0, 8), 8, ys + t0, us + t0 * PQ,
+        // ================= P2: forward over my pieces =================
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int pj = h * NW + warp;
+            const int ua = pbound[pj], ue = pbound[pj + 1];
+            PieceFwd c;
+            c.Vq = h ? VinB : VinA;
+            c.P = 1.0;
+            c.q = 0.0;
+            c.l0 = c.l1 = c.l2 = 0.0;
+            c.dprod = 1.0;
+            c.shift = 0;
+            c.PJ = c.PJ2 = 1.0;
+            c.G0 = c.GG = c.Lc = 0.0;
+            bool any_m = false;
+            for (int un = ua; un < ue; ++un) {
+                const int u0 = units[un];
+                const int t0 = u0 & UNIT_T0;
+                ck[(un * 3 + 0) * 32] = c.Vq;
+                ck[(un * 3 + 1) * 32] = c.q;
+                ck[(un * 3 + 2) * 32] = c.P;
+                if (u0 & UNIT_M) {
+                    any_m = true;
+                    forward_unit_basis<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), ys + t0, us + t0 * PQ,
                                                      vs + t0 * PQ, c);
-            } else {
-                forward_word_basis<PQ>(th, k, us + t0 * PQ, c);
+                } else if (u0 & UNIT_M1) {
+                    any_m = true;
+                    forward_unit_basis<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), ys + t0, us + t0 * PQ, vs + t0 * PQ, c);
+                } else {
+                    forward_word_basis<PQ, UW>(th, k, us + t0 * PQ, c);
+                }
             }
-        }
-        {
             double ld = 0.0;
             if (any_m) ld = fma((double)c.shift, 0.693147180559945309417, log(c.dprod));
-            double *o = CH + (size_t)warp * SPLIT_NCH * 32;
+            double *o = CH + (size_t)pj * SPLIT_NCH * 32;
             o[0 * 32] = c.P;
             o[1 * 32] = c.q;
             o[2 * 32] = c.l0;
@@ -480,21 +733,36 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             o[7 * 32] = c.G0;
             o[8 * 32] = c.GG;
             o[9 * 32] = c.Lc;
+            o[10 * 32] = c.Vq;
         }
         __syncthreads();
 
-        // ---- chain the chunks: x_in of every chunk, likelihood (identical in every warp)
-        double xk[NW];
+        // ---- chain the pieces: x_in of every piece, likelihood (identical in every warp)
+        double gk[NP];                   // full backward offset of each piece
+        double xinA = 0.0, xinB = 0.0;   // prior mean entering my pieces
+        double XrA = 0.0, XrB = 0.0, VrA = 0.0, VrB = 0.0; // prior right of my pieces
         double acc = 0.0;
+        double x = th.mu1; // prior of step 0 (EM.cpp:48)
+        double vend = th.V1;
         {
-            double x = th.mu1; // prior of step 0 (EM.cpp:48)
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const double *o = CH + (size_t)w * SPLIT_NCH * 32;
-                xk[w] = x;
+            for (int pj = 0; pj < NP; ++pj) {
+                const double *o = CH + (size_t)pj * SPLIT_NCH * 32;
+                if (pj == warp) xinA = x;
+                if (pj == NW + warp) xinB = x;
+                gk[pj] = fma(o[8 * 32], x, o[7 * 32]);
                 const double tC = th.C * x;
                 acc += fma(tC, fma(tC, o[4 * 32], -2.0 * o[3 * 32]), o[2 * 32]) + o[5 * 32];
                 x = fma(o[0 * 32], x, o[1 * 32]);
+                vend = o[10 * 32];
+                if (pj == warp) {
+                    XrA = x;
+                    VrA = vend;
+                }
+                if (pj == NW + warp) {
+                    XrB = x;
+                    VrB = vend;
+                }
             }
         }
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs; // EM.cpp:122-124
@@ -509,38 +777,53 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         }
         if (!__any_sync(FULL, live)) break;
 
-        // ---- smoothed state entering the chunk from the right
-        double xin = 0.0, Xs1 = 0.0, Vs1 = 0.0;
+        // ---- smoothed state entering my pieces from the right.  The chain starts from the prior of
+        //      the virtual step T: Xs_{T-1} = Xu + J (Xp_T - Xp_T) = Xu_{T-1}   (EM.cpp:94-95)
+        double Xs1A = 0.0, Vs1A = 0.0, Xs1B = 0.0, Vs1B = 0.0;
+        {
+            double Xs = x, Vs = vend;
 #pragma unroll
-        for (int w = NW - 1; w >= 0; --w) {
-            if (w == warp) xin = xk[w];
-            if (w > warp) {
-                const double *o = CH + (size_t)w * SPLIT_NCH * 32;
-                const double pj = o[6 * 32];
-                Xs1 = fma(pj, Xs1, fma(o[8 * 32], xk[w], o[7 * 32]));
-                Vs1 = fma(pj * pj, Vs1, o[9 * 32]);
+            for (int pj = NP - 1; pj >= 0; --pj) {
+                if (pj == NW + warp) {
+                    Xs1B = Xs;
+                    Vs1B = Vs;
+                }
+                if (pj == warp) {
+                    Xs1A = Xs;
+                    Vs1A = Vs;
+                }
+                const double *o = CH + (size_t)pj * SPLIT_NCH * 32;
+                const double pjv = o[6 * 32];
+                Xs = fma(pjv, Xs, gk[pj]);
+                Vs = fma(pjv * pjv, Vs, o[9 * 32]);
             }
         }
+        __syncthreads(); // the piece summaries are dead: their space becomes the partial sums
 
-        // ================= P4: backward over the chunk, M-step sums =================
+        // ================= P4: backward over my pieces, M-step sums =================
         Stats<PQ> st;
         st.zero();
-        {
-            double Xr = fma(c.P, xin, c.q), Vr = c.Vq; // prior at the first step right of the chunk
+#pragma unroll 1
+        for (int h = 1; h >= 0; --h) {
+            const int pj = h * NW + warp;
+            const int ua = pbound[pj], ue = pbound[pj + 1];
+            const double xin = h ? xinB : xinA;
+            double Xs1 = h ? Xs1B : Xs1A, Vs1 = h ? Vs1B : Vs1A;
+            double Xr = h ? XrB : XrA, Vr = h ? VrB : VrA; // prior at the first step right of the piece
             double cG = 0.0, cH = 0.0;
             bool in_run = false;
             for (int un = ue - 1; un >= ua; --un) {
                 const int u0 = units[un];
-                const int t0 = u0 & (UNIT_M - 1);
+                const int t0 = u0 & UNIT_T0;
                 const double Vq = ck[(un * 3 + 0) * 32];
                 const double Xq = fma(ck[(un * 3 + 2) * 32], xin, ck[(un * 3 + 1) * 32]);
                 if (u0 & UNIT_M) {
-                    if (t0 + 8 >= T)
-                        smooth_segment<PQ, 8, true, true>(th, k.A, k.A2, k.Q, k.mc, seg_bits(mw, t0, 8), T - t0,
-                                                          ys + t0, us + t0 * PQ, vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
-                    else
-                        smooth_segment<PQ, 8, true, false>(th, k.A, k.A2, k.Q, k.mc, seg_bits(mw, t0, 8), 8, ys + t0,
-                                                           us + t0 * PQ, vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
+                    smooth_unit<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), false, ys + t0, us + t0 * PQ,
+                                              vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
+                    in_run = false;
+                } else if (u0 & UNIT_M1) {
+                    smooth_unit<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), t0 == T - 1, ys + t0, us + t0 * PQ,
+                                           vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
                     in_run = false;
                 } else {
                     if (!in_run) {
@@ -549,7 +832,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                         cH = (Vs1 - Vr) * rv * rv;
                         in_run = true;
                     }
-                    smooth_word<PQ>(th, k, us + t0 * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
+                    smooth_word<PQ, UW>(th, k, us + t0 * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
                 }
                 Xr = Xq;
                 Vr = Vq;

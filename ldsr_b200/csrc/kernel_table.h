@@ -19,11 +19,19 @@ constexpr int EM_WARPS = 4; // warps per CTA (one per SM sub-partition)
 #define LDSR_SPLIT_NW 4
 #endif
 constexpr int SPLIT_NW = LDSR_SPLIT_NW;
+#ifndef LDSR_SPLIT_MSEG
+#define LDSR_SPLIT_MSEG 4
+#endif
+#ifndef LDSR_SPLIT_UW
+#define LDSR_SPLIT_UW 32
+#endif
+constexpr int SPLIT_MSEG = LDSR_SPLIT_MSEG; // steps per M unit (observed somewhere in the CTA)
+constexpr int SPLIT_UW = LDSR_SPLIT_UW;     // steps per U unit (unobserved by every fit of the CTA)
 constexpr int split_minb_for(int pq) {
 #ifdef LDSR_SPLIT_MINB
     return LDSR_SPLIT_MINB;
 #else
-    return pq <= 4 ? 3 : (pq <= 8 ? 2 : 1);
+    return pq <= 4 ? 3 : 2;
 #endif
 }
 
@@ -32,7 +40,7 @@ struct KernelTable {
     cudaError_t (*em_prepare)(size_t smem_bytes); // opt in to > 48 KB dynamic shared memory
     cudaError_t (*em_chunk)(const EmParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     // time-split kernel (em_split_kernel.cuh): warps per CTA, CTAs per SM it is compiled for
-    int split_nw, split_minb;
+    int split_nw, split_minb, split_mseg, split_uw;
     cudaError_t (*em_split_prepare)(size_t smem_bytes);
     cudaError_t (*em_split)(const SplitParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);

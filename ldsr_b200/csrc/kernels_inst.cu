@@ -28,11 +28,11 @@ cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStre
 }
 constexpr int MINB = split_minb_for(PQ);
 cudaError_t em_split_prepare(size_t smem_bytes) {
-    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem_bytes);
 }
 cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
-    em_split_kernel<PQ, SPLIT_NW, MINB><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
+    em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
@@ -52,7 +52,7 @@ cudaError_t rep(const RepParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, em_split_prepare, em_split, smoother, mstep, propagate, rep};
+const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW, em_split_prepare, em_split, smoother, mstep, propagate, rep};
 
 } // namespace
 

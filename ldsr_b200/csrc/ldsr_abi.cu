@@ -349,7 +349,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
                 for (int j = 0; j < q; j++) B[S.v_off + (size_t)t * PQ + j] = v[(size_t)t * q + j];
         }
         P->max_T = std::max(P->max_T, T);
-        P->max_units = std::max(P->max_units, split_units_upper_bound(b->y[s], T));
+        P->max_units = std::max(P->max_units, split_units_upper_bound(b->y[s], T, P->kt->split_mseg, P->kt->split_uw));
         P->max_blob_bytes = std::max(P->max_blob_bytes, (size_t)S.blob_doubles * 8);
     }
     // fit ranges per series (internal order is series-major)
@@ -582,8 +582,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             sp.em = ep;
             sp.max_units = P->max_units;
             sp.blob_smem = (int)blob_sm;
-            sp.cost_u = 32 * 36; // instructions per U word / M segment, measured
-            sp.cost_m = 8 * 185;
+            sp.cost_u = P->kt->split_uw * 33; // instructions per U / M unit, measured
+            sp.cost_m = P->kt->split_mseg * 185;
             CU(P->kt->em_split(sp, n_tasks, smem, st));
         } else {
             CU(P->kt->em_chunk(ep, n_tasks, smem, st));
