@@ -272,8 +272,16 @@ def main():
     em_ns = float(np.mean([s["em_kernel_ns"] for s in stats]))
     chunks = float(np.mean([s["chunks"] for s in stats]))
     achieved = flops / (em_ns * 1e-9) / 1e12
+    traffic = None  # DRAM bytes per launch of the EM kernel, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "em_split_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("kernel") == stats[0].get("kernel") and args.workload == "np_cv":
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "fp64", "kernel": stats[0].get("kernel", "em_chunk_kernel"), "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak, "traffic": None,
+                "frac": achieved / fp64_peak, "traffic": traffic,
                 "peak_source": "DFMA microbenchmark in this run (ldsr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flops_per_launch": flops / chunks, "launch_ms": em_ns * 1e-6 / chunks, "launches_per_step": chunks,
                 "kernel_share_of_step": em_ns * 1e-6 / (tot_ms / K)}

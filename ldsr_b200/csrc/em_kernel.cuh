@@ -41,6 +41,7 @@ struct EmParams {
     const int *f_user;        // internal -> user fit index (for liks rows)
     const int *active;        // compacted live fit ids, grouped by series
     const int4 *tasks;        // per CTA: x = series, y = first index into active, z = count
+    const int *n_tasks;       // device-side task count of this launch: CTAs beyond it exit at once
     double *ckpt;             // checkpoint scratch: [global warp][seg][2][32]
     int max_seg;              // segments per warp slot in ckpt
     int ckpt_smem_off;        // MODE 2: byte offset of the checkpoint area in dynamic shared memory
@@ -251,17 +252,24 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
-    const int4 task = P.tasks[blockIdx.x];
-    const SeriesDev S = P.series[task.x];
-    const int T = S.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
     if (STAGED) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
+    }
+    // The grid is an upper bound on (or, with fewer CTAs than tasks, a divisor of) the task count,
+    // which the launch reads from device memory: CTA b takes tasks b, b + gridDim.x, ...
+    const int n_tasks = *P.n_tasks;
+    unsigned phase = 0;
+    for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x, phase ^= 1u) {
+    if (ti != (int)blockIdx.x) __syncthreads(); // the previous task's shared memory is dead
+    const int4 task = P.tasks[ti];
+    const SeriesDev S = P.series[task.x];
+    const int T = S.T;
+    if (STAGED) {
         if (threadIdx.x == 0) stage_blob(smem_raw, P.blobs + S.blob_off, (unsigned)S.blob_doubles * 8u, &bar);
     }
     const double *__restrict__ ser =
@@ -297,8 +305,8 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     const int nseg = (T + SEG - 1) / SEG;       // the last segment (full or not) holds step T-1
     const int cnt_last = T - (nseg - 1) * SEG;  // 1..SEG valid steps in it
 
-    if (STAGED) mbar_wait(&bar, 0);
-    if (warp * 32 >= task.z) return; // whole warp has no fit
+    if (STAGED) mbar_wait(&bar, phase);
+    const bool warp_has_fits = warp * 32 < task.z; // else the whole warp idles through this task
 
     // Which segments hold an observed step for some lane of this warp: fixed for the whole launch,
     // so the vote is taken once here (bitmap in two registers covers 128 segments = T <= 128*SEG;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         return __any_sync(FULL, seg_bits(mw, sg * SEG, SEG) != 0u);
     };
 
-    for (int it = 0; it < P.chunk; ++it) {
+    for (int it = 0; warp_has_fits && it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
         const double A = th.A, A2 = th.A * th.A, Q = th.Q;
         UnobsConst<SEG> uc;
@@ -400,6 +408,7 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         P.ne[fit] = ne;
         P.done[fit] = live ? 0 : 1;
     }
+    } // task loop
 }
 
 } // namespace ldsr

@@ -558,16 +558,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     constexpr int NP = 2 * NW; // pieces
     constexpr size_t CH_DOUBLES = (size_t)NP * SPLIT_NCH * 32, ST_DOUBLES = (size_t)NW * NST * 32;
 
-    const int4 task = P.tasks[blockIdx.x];
-    const SeriesDev S = P.series[task.x];
-    const int T = S.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    // The grid is an upper bound on (or, with fewer CTAs than tasks, a divisor of) the task count,
+    // which the launch reads from device memory: CTA b takes tasks b, b + gridDim.x, ...
+    const int n_tasks = *P.n_tasks;
+    unsigned phase = 0;
+    for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x, phase ^= 1u) {
+    if (ti != (int)blockIdx.x) __syncthreads(); // the previous task's shared memory is dead
+    const int4 task = P.tasks[ti];
+    const SeriesDev S = P.series[task.x];
+    const int T = S.T;
     if (threadIdx.x == 0) stage_blob(smem_raw, P.blobs + S.blob_off, (unsigned)S.blob_doubles * 8u, &bar);
 
     const double *__restrict__ ser = reinterpret_cast<const double *>(smem_raw);
@@ -639,7 +644,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             split_range<NW>(units, best, nu, SP.cost_u, SP.cost_m, MSEG, pbound + NW);
         }
     }
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar, phase);
     __syncthreads();
 
     for (int it = 0; it < P.chunk; ++it) {
@@ -902,6 +907,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         P.ne[fit] = ne;
         P.done[fit] = live ? 0 : 1;
     }
+    } // task loop
 }
 
 } // namespace ldsr

@@ -117,6 +117,7 @@ struct ldsr_ctx {
 // ---- plan -----------------------------------------------------------------------------------
 struct ldsr_plan {
     int device = 0;
+    int n_sm = 148;
     DevicePool *pool = nullptr;
     std::unique_ptr<DevicePool> own_pool;
     cudaStream_t stream = nullptr;
@@ -148,6 +149,7 @@ struct ldsr_plan {
     double *d_liks = nullptr;
     size_t liks_cap = 0;
     int *d_active = nullptr, *d_task_off = nullptr, *d_n_live = nullptr, *d_counts = nullptr;
+    size_t counts_cap = 8;
     int4 *d_tasks = nullptr;
     int max_tasks = 0;
     unsigned long long *d_sum = nullptr;
@@ -267,6 +269,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     }
     CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CU(cudaMallocHost(&P->h_counts, 8 * sizeof(int)));
+    CU(cudaDeviceGetAttribute(&P->n_sm, cudaDevAttrMultiProcessorCount, device));
 
     const int ns = b->n_series, ng = b->n_groups, nf = b->n_fits;
     P->n_series = ns;
@@ -461,19 +464,6 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     const int chunk = (opt && opt->chunk_iters > 0) ? opt->chunk_iters : 100;
     long long launches = 0, chunks = 0;
     double em_ms = 0.0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (stats) {
-        CU(cudaEventCreate(&ev0));
-        CU(cudaEventCreate(&ev1));
-    }
-    struct EvGuard {
-        cudaEvent_t &a, &b;
-        ~EvGuard() {
-            if (a) cudaEventDestroy(a);
-            if (b) cudaEventDestroy(b);
-        }
-    } ev_guard{ev0, ev1};
-    bool ev_pending = false;
     P->last_niter = niter;
     P->em_done = false;
 
@@ -551,32 +541,68 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     ep.ckpt_smem_off = (int)blob_sm;
     ep.ckpt = nullptr;
 
-    for (;;) {
+    // Chunk loop.  Every chunk is compact -> build task list -> EM kernel.  The number of chunks is
+    // bounded by ceil(niter/chunk), and the task count can only shrink, so without a poll callback
+    // the whole sequence is enqueued at once: each EM launch uses the first chunk's grid and reads
+    // its actual task count from device memory (CTAs beyond it exit immediately).  With a poll
+    // callback the host synchronises after every chunk, as the reference polls for interrupts
+    // every 100 iterations (EM.cpp:261).
+    const int max_chunks = (niter + chunk - 1) / chunk;
+    const bool sync_each = (opt && opt->poll) || false;
+    int grid0 = 0; // task count of the first chunk: every fit is live
+    for (int s = 0; s < ns; s++)
+        grid0 += (P->h_series[s].fit_end - P->h_series[s].fit_begin + fits_per_cta - 1) / fits_per_cta;
+    if ((int)P->counts_cap < 2 * max_chunks) {
+        Err e = P->dalloc(&P->d_counts, (size_t)2 * max_chunks);
+        if (!e.ok()) return e;
+        P->counts_cap = 2 * max_chunks;
+        if (P->h_counts) cudaFreeHost(P->h_counts);
+        P->h_counts = nullptr;
+        CU(cudaMallocHost(&P->h_counts, (size_t)2 * max_chunks * sizeof(int)));
+    }
+    const size_t ck_need = (mode == 2 || use_split) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
+    if (P->ckpt_cap < ck_need) {
+        Err e = P->dalloc(&P->d_ckpt, ck_need);
+        if (!e.ok()) return e;
+        P->ckpt_cap = ck_need;
+    }
+    ep.ckpt = P->d_ckpt;
+    std::vector<cudaEvent_t> evs;
+    struct EvVecGuard {
+        std::vector<cudaEvent_t> &v;
+        ~EvVecGuard() {
+            for (cudaEvent_t e : v) cudaEventDestroy(e);
+        }
+    } evs_guard{evs};
+    int enq = 0;
+    for (int c = 0; c < max_chunks; ++c) {
+        int *cnt = P->d_counts + 2 * c;
         compact_kernel<<<ns, 256, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
         build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, fits_per_cta, P->d_tasks, P->d_task_off,
-                                              P->d_counts);
+                                              cnt);
         launches += 2;
-        CU(cudaMemcpyAsync(P->h_counts, P->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (ev_pending) {
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, ev0, ev1));
-            em_ms += ms;
-            ev_pending = false;
+        // Later chunks have at most grid0 tasks.  For a batch that fits the machine in one wave the
+        // grid is capped at two CTAs per SM: CTAs are dealt to SMs in launch order, so idle CTAs
+        // ahead of live ones would push three live CTAs onto some SMs while others hold one
+        // (measured: 2.48 ms instead of 1.83 ms per chunk on the 10 000-fit job).
+        int grid = (c == 0 || grid0 > 3 * P->n_sm) ? grid0 : std::min(grid0, 2 * P->n_sm);
+        if (sync_each) {
+            CU(cudaMemcpyAsync(P->h_counts + 2 * c, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            grid = std::max(1, P->h_counts[2 * c]);
+            if (P->h_counts[2 * c + 1] == 0) break;
+            if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
+            if (opt->poll(opt->poll_arg)) return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
         }
-        const int n_tasks = P->h_counts[0], n_live = P->h_counts[1];
-        if (n_live == 0) break;
-        if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
-        if (opt && opt->poll && !abort_flag && opt->poll(opt->poll_arg))
-            return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
-        const size_t need = (mode == 2 || use_split) ? 0 : (size_t)n_tasks * EM_WARPS * P->max_seg * 64;
-        if (P->ckpt_cap < need) {
-            Err e = P->dalloc(&P->d_ckpt, need);
-            if (!e.ok()) return e;
-            P->ckpt_cap = need;
+        ep.n_tasks = cnt;
+        if (stats) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CU(cudaEventCreate(&a));
+            evs.push_back(a);
+            CU(cudaEventCreate(&b));
+            evs.push_back(b);
+            CU(cudaEventRecord(a, st));
         }
-        ep.ckpt = P->d_ckpt;
-        if (stats) CU(cudaEventRecord(ev0, st));
         if (use_split) {
             SplitParams sp;
             sp.em = ep;
@@ -584,16 +610,28 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             sp.blob_smem = (int)blob_sm;
             sp.cost_u = P->kt->split_uw * 33; // instructions per U / M unit, measured
             sp.cost_m = P->kt->split_mseg * 185;
-            CU(P->kt->em_split(sp, n_tasks, smem, st));
+            CU(P->kt->em_split(sp, grid, smem, st));
         } else {
-            CU(P->kt->em_chunk(ep, n_tasks, smem, st));
+            CU(P->kt->em_chunk(ep, grid, smem, st));
         }
-        if (stats) {
-            CU(cudaEventRecord(ev1, st));
-            ev_pending = true;
-        }
+        if (stats) CU(cudaEventRecord(evs.back(), st));
         launches++;
-        chunks++;
+        enq++;
+    }
+    if (!sync_each) {
+        CU(cudaMemcpyAsync(P->h_counts, P->d_counts, (size_t)2 * max_chunks * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
+    } else {
+        CU(cudaStreamSynchronize(st));
+    }
+    for (int c = 0; c < enq; ++c) {
+        if (P->h_counts[2 * c + 1] > 0) chunks++; // launches that had live fits
+        if (stats) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, evs[2 * c], evs[2 * c + 1]));
+            if (P->h_counts[2 * c + 1] > 0) em_ms += ms;
+        }
     }
     // ---- selection + the winners' smoothed trajectories
     select_kernel<<<(ng + 127) / 128, 128, 0, st>>>(ng, P->d_g_fit_ptr, P->d_theta, P->TL, 1 + P->PQ, P->d_lik,
