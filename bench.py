@@ -123,6 +123,15 @@ def cpu_sample_groups(w, seconds, cores):
     return max(1, min(g, len(w["group_series"])))
 
 
+def host_cores():
+    """Host threads the CPU arm may use: the process's CPU affinity, not OMP_NUM_THREADS (torchrun sets
+    that to 1 for every rank; the reference arm runs on rank 0 alone and takes the whole box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_oracle(sample, args, threads):
     from oracle import oracle as O
     t0 = time.perf_counter()
@@ -136,8 +145,7 @@ def reference_arm(args, rank, world):
     The real Rcpp/Armadillo build cannot run here (no R): see DESIGN.md."""
     if rank != 0:
         return
-    from oracle import oracle as O
-    cores = O.max_threads()
+    cores = host_cores()
     w = build_workload(args.workload, 0)
     K, Wm = args.steps, args.warmup
     g = cpu_sample_groups(w, min(args.cpu_seconds, 150.0 / max(1, K + Wm)), cores)
@@ -289,8 +297,7 @@ def main():
     # ---------------- CPU baseline (oracle port of src/EM.cpp), bounded sample ----------------
     cpu = None
     if not args.no_cpu and world == 1:
-        from oracle import oracle as O
-        cores = O.max_threads()
+        cores = host_cores()
         g = cpu_sample_groups(w, args.cpu_seconds, cores)
         sample = W.subset(w, g)
         dt, ro = run_oracle(sample, args, cores)

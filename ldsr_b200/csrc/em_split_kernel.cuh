@@ -121,33 +121,25 @@ __device__ __forceinline__ void rescale4(double &a, double &b, double &c, double
     d *= sc;
 }
 
-// per-iteration constants of a fit
+// per-iteration constants of a fit.  Kept to the few values every unit needs: ptxas would rather
+// recompute a longer table of powers inside the unit loops than hold it in registers (seen in the
+// SASS: a chain of 4 dependent DMULs at the top of every 8-step block).
 template <int PQ, int UW> struct SplitConst {
     static_assert(UW == 16 || UW == 32, "U unit is 16 or 32 steps");
     double A, A2, Q;
-    double Ap[8];      // A^0 .. A^7
     double A8, A16;    // A^8, A^16
-    double AW;         // A^UW
     double aVW, bVW;   // Vp' = aVW Vp + bVW over an unobserved unit
     MixedConst<PQ> mc;
+    __device__ __forceinline__ double AW() const { return UW == 32 ? A16 * A16 : A16; } // A^UW
     __device__ __forceinline__ void set(const Theta<PQ> &th) {
         A = th.A;
         A2 = A * A;
         Q = th.Q;
-        // powers by squaring: depth 3 instead of a chain of 8 multiplications
         const double A4 = A2 * A2;
-        Ap[0] = 1.0;
-        Ap[1] = A;
-        Ap[2] = A2;
-        Ap[3] = A2 * A;
-        Ap[4] = A4;
-        Ap[5] = A4 * A;
-        Ap[6] = A4 * A2;
-        Ap[7] = A4 * Ap[3];
         A8 = A4 * A4;
         A16 = A8 * A8;
-        AW = UW == 32 ? A16 * A16 : A16;
-        aVW = AW * AW;
+        const double aw = AW();
+        aVW = aw * aw;
         // sum_{k<8} A2^k = (1 + A2)(1 + A2^2)(1 + A2^4)
         const double sv = ((1.0 + A2) * (1.0 + A4)) * (1.0 + A8);
         // sum_{k<16} A2^k = sv (1 + A2^8), sum_{k<32} = sv (1 + A2^8)(1 + A2^16);  A2^8 = A^16
@@ -345,16 +337,17 @@ __device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const Sp
             lo = fma(k.A, lo, Bu[j]);
             hi = fma(k.A, hi, Bu[4 + j]);
         }
-        hh = fma(hh, k.A8, fma(lo, k.Ap[4], hi));
+        hh = fma(hh, k.A8, fma(lo, k.A2 * k.A2, hi));
     }
-    const double qn = fma(k.AW, c.q, hh);
-    const double Pn = k.AW * c.P;
+    const double AW = k.AW();
+    const double qn = fma(AW, c.q, hh);
+    const double Pn = AW * c.P;
     const double Vn = fma(k.aVW, c.Vq, k.bVW);
     // backward map of the unit: J = prod J_t = A^UW Vp_first / Vp_last  (EM.cpp:100 telescoped)
-    const double Jc = k.AW * c.Vq * fast_rcp(Vn);
+    const double Jc = AW * c.Vq * fast_rcp(Vn);
     const double g0 = fma(-Jc, qn, c.q);
     const double gP = fma(-Jc, Pn, c.P);
-    const double L = c.Vq * fma(-k.AW, Jc, 1.0);
+    const double L = c.Vq * fma(-AW, Jc, 1.0);
     c.G0 = fma(c.PJ, g0, c.G0);
     c.GG = fma(c.PJ, gP, c.GG);
     c.Lc = fma(c.PJ2, L, c.Lc);
@@ -478,17 +471,23 @@ __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitCons
             xs[j + 1] = fma(k.A, xs[j], Bu[j]);
             vs[j + 1] = fma(k.A2, vs[j], k.Q);
         }
-        // 3. smoothed moments of steps 1..8 of the block
+        // 3. smoothed moments of steps 1..8 of the block.  G and H at those steps come from the
+        //    block's right end by two short multiplication chains (off the critical path)
+        double Gs[8], Hs[8];
+        Gs[7] = Gb;
+        Hs[7] = Hb;
+#pragma unroll
+        for (int j = 6; j >= 0; j--) {
+            Gs[j] = k.A * Gs[j + 1];
+            Hs[j] = k.A2 * Hs[j + 1];
+        }
         double Xn[9], Vn[9], t1[8];
         Xn[0] = Xs;
         Vn[0] = Vs;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double pw = k.Ap[7 - j];
-            const double Gn = pw * Gb;
-            const double Hn = (pw * pw) * Hb;
-            Xn[j + 1] = fma(vs[j + 1], Gn, xs[j + 1]);
-            t1[j] = vs[j + 1] * Hn;
+            Xn[j + 1] = fma(vs[j + 1], Gs[j], xs[j + 1]);
+            t1[j] = vs[j + 1] * Hs[j];
             Vn[j + 1] = fma(vs[j + 1], t1[j], vs[j + 1]);
         }
         // 4. the sums of EM.cpp:180-193

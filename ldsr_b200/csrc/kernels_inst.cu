@@ -27,9 +27,17 @@ cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStre
     return cudaGetLastError();
 }
 constexpr int MINB = split_minb_for(PQ);
+constexpr int MINB_WIDE = 2;
 cudaError_t em_split_prepare(size_t smem_bytes) {
-    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess || MINB == MINB_WIDE) return e;
+    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
+    return cudaGetLastError();
 }
 cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
@@ -52,7 +60,7 @@ cudaError_t rep(const RepParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW, em_split_prepare, em_split, smoother, mstep, propagate, rep};
+const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW, em_split_prepare, em_split, em_split_wide, smoother, mstep, propagate, rep};
 
 } // namespace
 

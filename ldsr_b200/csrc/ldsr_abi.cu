@@ -610,7 +610,11 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             sp.blob_smem = (int)blob_sm;
             sp.cost_u = P->kt->split_uw * 33; // instructions per U / M unit, measured
             sp.cost_m = P->kt->split_mseg * 185;
-            CU(P->kt->em_split(sp, grid, smem, st));
+            // one wave of at most two CTAs per SM: the 255-register build of the kernel
+            if (grid <= 2 * P->n_sm)
+                CU(P->kt->em_split_wide(sp, grid, smem, st));
+            else
+                CU(P->kt->em_split(sp, grid, smem, st));
         } else {
             CU(P->kt->em_chunk(ep, grid, smem, st));
         }
