@@ -62,6 +62,7 @@ extern "C" {
 #define LDSR_FIT_NONFINITE 2 /* final log-likelihood is NaN/Inf (fit ran to niter) */
 
 #define LDSR_MAX_PQ 32 /* largest supported nrow(u), nrow(v) */
+#define LDSR_MAX_STATE_DIM 4 /* ldsr_smoother_d_batch: largest state dimension */
 
 /* ---- problem description (all HOST pointers) --------------------------------------------- */
 typedef struct {
@@ -177,6 +178,24 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
  * All fits of a group stay on one device, so restart selection is device-local and the host only
  * concatenates results -- there is no collective on the data path. */
 int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, char *errbuf, int errlen);
+
+/* ---- general state dimension, long series (beyond the reference) ----------------------------
+ * The reference is scalar-state only (src/EM.cpp:20 "matrix inversion is treated as /").
+ * BASELINE.json's config 5 (d = 4, 20 proxies, T = 100 000) asks for the E-step of a d-dimensional
+ * state, sequentially and as an associative scan over time.  Conventions are those of
+ * Kalman_smoother (src/EM.cpp:22-131): (mu1,V1) is the predicted law of x_0, u enters with one step
+ * of lag, v without, NaN in y = missing, innovations-form likelihood (divided by n_obs when stdlik).
+ *   theta  [n_fits][theta_stride]: A d*d row-major | B d*p | C d | D q | Q d*d | R | mu1 d | V1 d*d
+ *   u      [T][p] (an R p x T matrix, column-major) or NULL;  v [T][q] or NULL;  y [T]
+ *   method 0 = sequential recursion (one thread per fit), 1 = associative scan (time cut into
+ *            chunks of `chunk` steps, 0 = automatic)
+ *   X [n_fits][T][d], V [n_fits][T][d][d], Y [n_fits][T] may be NULL (not copied back); lik [n_fits]
+ *   kernel_ms (optional): device time of the kernels, CUDA events
+ * One device; no CPU fallback (LDSR_ERR_CUDA without a device). */
+int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *y, const double *u, const double *v,
+                          int n_fits, const double *theta, int theta_stride, int stdlik, int method, int chunk,
+                          double *X, double *V, double *Y, double *lik, double *kernel_ms, char *errbuf,
+                          int errlen);
 
 /* ---- measurement helper -------------------------------------------------------------------
  * FP64 roofline denominator: runs a register-resident DFMA kernel (8 independent chains per

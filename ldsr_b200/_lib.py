@@ -18,7 +18,8 @@ FIT_OK, FIT_SINGULAR, FIT_NONFINITE = 0, 1, 2
 EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy",
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
-           "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak")
+           "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
+           "ldsr_smoother_d_batch")
 
 
 class LdsrError(RuntimeError):
@@ -355,3 +356,28 @@ def shard_groups(series, group_series, held, fit_group, theta0, n_shards):
     err = C.create_string_buffer(512)
     _check(lib().ldsr_shard_groups(C.byref(pb.c), int(n_shards), _i(out), err, 512), err)
     return out
+
+
+def smoother_d(d, y, u, v, theta, stdlik=True, method=1, chunk=0, device=0, want=("X", "V", "Y")):
+    """ldsr_smoother_d_batch: Kalman/RTS smoother for state dimension d (1..4), sequential
+    (method=0) or associative scan over time (method=1).  y [T]; u [p,T] | None; v [q,T] | None;
+    theta [n_fits, len] flat (A d*d | B d*p | C d | D q | Q d*d | R | mu1 d | V1 d*d)."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    T = y.size
+    uf = None if u is None else np.ascontiguousarray(np.asarray(u, dtype=np.float64).T)
+    vf = None if v is None else np.ascontiguousarray(np.asarray(v, dtype=np.float64).T)
+    p = 0 if uf is None else uf.shape[1]
+    q = 0 if vf is None else vf.shape[1]
+    th = np.atleast_2d(np.ascontiguousarray(theta, dtype=np.float64))
+    nf = th.shape[0]
+    X = np.empty((nf, T, d)) if "X" in want else None
+    V = np.empty((nf, T, d, d)) if "V" in want else None
+    Y = np.empty((nf, T)) if "Y" in want else None
+    lik = np.empty(nf)
+    ms = C.c_double()
+    err = C.create_string_buffer(512)
+    rc = lib().ldsr_smoother_d_batch(int(device), int(d), T, p, q, _d(y), _d(uf), _d(vf), nf, _d(th), th.shape[1],
+                                     int(bool(stdlik)), int(method), int(chunk), _d(X), _d(V), _d(Y), _d(lik),
+                                     C.byref(ms), err, 512)
+    _check(rc, err)
+    return dict(X=X, V=V, Y=Y, lik=lik, kernel_ms=ms.value)

@@ -56,6 +56,13 @@ def build(force=False, verbose=False, ptxas_info=False):
     deps = _sources()
     if not force and not _stale(SO, deps):
         return SO
+    # per-object dependencies, so that touching the ABI or the scan kernels does not recompile the
+    # thirteen per-width EM translation units (minutes)
+    c = lambda *names: [os.path.join(CSRC, n) for n in names]
+    em_deps = c("kernels_inst.cu", "kernel_table.h", "em_kernel.cuh", "em_split_kernel.cuh", "aux_kernels.cuh",
+                "lds_math.cuh", "common.cuh")
+    scan_deps = c("scan_inst.cu", "scan_kernels.cuh", "common.cuh")
+    obj_deps = {}
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
     extra = ["-Xptxas", "-v"] if ptxas_info else []
@@ -65,9 +72,13 @@ def build(force=False, verbose=False, ptxas_info=False):
     for pq in PQ_LIST:
         o = os.path.join(OBJ, "kernels_pq%d.o" % pq)
         jobs.append((o, [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))
+        obj_deps[o] = em_deps
+    o_scan = os.path.join(OBJ, "scan_inst.o")
+    jobs.append((o_scan, [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, "scan_inst.cu"), "-o", o_scan]))
+    obj_deps[o_scan] = scan_deps
     o_abi = os.path.join(OBJ, "ldsr_abi.o")
     jobs.append((o_abi, [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, "ldsr_abi.cu"), "-o", o_abi]))
-    todo = [(o, c) for o, c in jobs if force or _stale(o, deps)]
+    todo = [(o, cmd) for o, cmd in jobs if force or _stale(o, obj_deps.get(o, deps))]
     logs = []
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         for out in ex.map(lambda j: _run(j[1]), todo):

@@ -3,6 +3,7 @@
 #include "../../include/ldsr_b200.h"
 #include "generic_kernels.cuh"
 #include "kernel_table.h"
+#include "scan_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1261,6 +1262,114 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
     if (e.ok() && (n_shards < 1 || !group_shard)) e = fail(LDSR_ERR_ARG, "n_shards < 1 or group_shard is NULL");
     if (e.ok()) shard_groups(batch, n_shards, group_shard);
     return report(e, errbuf, errlen);
+}
+
+int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *y, const double *u, const double *v,
+                          int n_fits, const double *theta, int theta_stride, int stdlik, int method, int chunk,
+                          double *X, double *V, double *Y, double *lik, double *kernel_ms, char *errbuf,
+                          int errlen) {
+    auto run = [&]() -> Err {
+        if (d < 1 || d > LDSR_MAX_STATE_DIM)
+            return fail(LDSR_ERR_UNSUPPORTED, "state dimension %d outside 1..%d", d, LDSR_MAX_STATE_DIM);
+        if (T < 2 || p < 0 || q < 0 || n_fits < 1) return fail(LDSR_ERR_ARG, "need T >= 2, p,q >= 0, n_fits >= 1");
+        if (!y || !theta || !lik) return fail(LDSR_ERR_ARG, "y, theta and lik are required");
+        if ((u && p < 1) || (v && q < 1)) return fail(LDSR_ERR_ARG, "u/v given with p/q = 0");
+        const int tl = 2 * d * d + d * p + d + q + 1 + d + d * d;
+        if (theta_stride < tl) return fail(LDSR_ERR_ARG, "theta_stride=%d < %d", theta_stride, tl);
+        if (method != 0 && method != 1) return fail(LDSR_ERR_ARG, "method must be 0 (sequential) or 1 (scan)");
+        for (int t = 0; t < T; t++)
+            if (std::isinf(y[t])) return fail(LDSR_ERR_ARG, "y[%d] is +-Inf", t);
+        if (ldsr_device_count() < 1) return fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+        CU(cudaSetDevice(device));
+        ScanParams P;
+        std::memset(&P, 0, sizeof P);
+        P.n_fits = n_fits;
+        P.T = T;
+        P.p = p;
+        P.q = q;
+        P.stdlik = stdlik;
+        P.theta_len = tl;
+        if (method == 0) {
+            P.L = T; // one chunk: the "down" kernels are the sequential recursion
+        } else if (chunk > 0) {
+            P.L = std::min(chunk, T);
+        } else { // thread phase ~L combines, warp phase ~T/(16 L): balance, power of two in 8..256
+            int L = 8;
+            while (L < 256 && (long long)L * L * 32 < T) L *= 2;
+            P.L = L;
+        }
+        P.n_chunks = (T + P.L - 1) / P.L;
+        std::vector<void *> bufs;
+        struct Guard {
+            std::vector<void *> &b;
+            ~Guard() {
+                for (void *p : b) cudaFree(p);
+            }
+        } guard{bufs};
+        auto dalloc = [&](double **out, size_t n) -> cudaError_t {
+            void *ptr = nullptr;
+            cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(double));
+            if (e == cudaSuccess) {
+                bufs.push_back(ptr);
+                *out = static_cast<double *>(ptr);
+            }
+            return e;
+        };
+        const size_t nT = (size_t)n_fits * T, D = d, nC = (size_t)n_fits * P.n_chunks;
+        double *dy = nullptr, *du = nullptr, *dv_in = nullptr, *dth = nullptr;
+        CU(dalloc(&dy, T));
+        CU(cudaMemcpy(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice));
+        if (u) {
+            CU(dalloc(&du, (size_t)T * p));
+            CU(cudaMemcpy(du, u, sizeof(double) * (size_t)T * p, cudaMemcpyHostToDevice));
+        }
+        if (v) {
+            CU(dalloc(&dv_in, (size_t)T * q));
+            CU(cudaMemcpy(dv_in, v, sizeof(double) * (size_t)T * q, cudaMemcpyHostToDevice));
+        }
+        std::vector<double> th((size_t)n_fits * tl);
+        for (int f = 0; f < n_fits; f++) std::memcpy(&th[(size_t)f * tl], theta + (size_t)f * theta_stride, sizeof(double) * tl);
+        CU(dalloc(&dth, th.size()));
+        CU(cudaMemcpy(dth, th.data(), sizeof(double) * th.size(), cudaMemcpyHostToDevice));
+        P.y = dy;
+        P.u = du;
+        P.v = dv_in;
+        P.theta = dth;
+        CU(dalloc(&P.c, nT * D));
+        CU(dalloc(&P.dv, nT));
+        CU(dalloc(&P.Xu, nT * D));
+        CU(dalloc(&P.Vu, nT * D * D));
+        CU(dalloc(&P.fagg, nC * (3 * D * D + 2 * D)));
+        CU(dalloc(&P.sagg, nC * (2 * D * D + D)));
+        CU(dalloc(&P.pre, nC * (D + D * D)));
+        CU(dalloc(&P.suf, nC * (D + D * D)));
+        CU(dalloc(&P.likp, nC * 2));
+        CU(dalloc(&P.X, nT * D));
+        CU(dalloc(&P.V, nT * D * D));
+        CU(dalloc(&P.Y, nT));
+        CU(dalloc(&P.lik, n_fits));
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        CU(cudaEventRecord(a, nullptr));
+        cudaError_t le = scan_smoother_launch(d, P, nullptr);
+        cudaEventRecord(b, nullptr);
+        cudaError_t se = cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        CU(le);
+        CU(se);
+        CU(cudaGetLastError());
+        if (kernel_ms) *kernel_ms = ms;
+        CU(cudaMemcpy(lik, P.lik, sizeof(double) * n_fits, cudaMemcpyDeviceToHost));
+        if (X) CU(cudaMemcpy(X, P.X, sizeof(double) * nT * D, cudaMemcpyDeviceToHost));
+        if (V) CU(cudaMemcpy(V, P.V, sizeof(double) * nT * D * D, cudaMemcpyDeviceToHost));
+        if (Y) CU(cudaMemcpy(Y, P.Y, sizeof(double) * nT, cudaMemcpyDeviceToHost));
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
 }
 
 int ldsr_measure_fp64_peak(int device, double *tflops, char *errbuf, int errlen) {

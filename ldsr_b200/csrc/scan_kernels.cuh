@@ -1,0 +1,749 @@
+// scan_kernels.cuh -- Kalman filter / RTS smoother for state dimension D > 1 and long series,
+// sequential or as an ASSOCIATIVE SCAN over time (BASELINE.json config 5: d = 4, 20 proxies,
+// T = 100 000).  Beyond the reference, which is scalar-state only (src/EM.cpp:20); conventions are
+// the reference's (src/EM.cpp:43-124): (mu1,V1) is the predicted law of x_0, u enters with one
+// step of lag, v without, NaN = missing, scalar y.  Formulas: SURVEY.md Appendix D (Saerkkae &
+// Garcia-Fernandez, "Temporal parallelization of Bayesian smoothers", IEEE TAC 2021).
+//
+// Time is cut into chunks of L steps, one THREAD per (fit, chunk):
+//   prep        c_t = B u_{t-1}, dv_t = D v_t for every t (one thread per step, coalesced rows)
+//   filt_agg    each chunk's filtering element a = (A,b,C,eta,J), combined step by step
+//   filt_scan   one warp per fit: prefix over the chunk elements -> (Xu,Vu) entering every chunk
+//   filt_down   ordinary Kalman filter inside each chunk from that state: Xu_t, Vu_t, lik terms
+//   smth_agg    each chunk's smoothing element (E,g,L) from Xu,Vu
+//   smth_scan   suffix over the chunk elements -> (Xs,Vs) entering every chunk from the right
+//   smth_down   ordinary RTS recursion inside each chunk: X, V, Y
+// With L >= T there is one chunk per fit and the two "down" kernels ARE the sequential recursion
+// (method 0); the scan kernels are skipped.
+#pragma once
+#include "common.cuh"
+
+namespace ldsr {
+
+struct ScanParams {
+    int n_fits, T, p, q, L, n_chunks, stdlik;
+    int theta_len;
+    const double *y;     // [T]
+    const double *u;     // [T][p] or NULL
+    const double *v;     // [T][q] or NULL
+    const double *theta; // [n_fits][theta_len]
+    double *c;           // [n_fits][T][D]   c_t = B u_{t-1} (c_0 = 0)
+    double *dv;          // [n_fits][T]      D v_t
+    double *Xu, *Vu;     // [n_fits][T][D], [n_fits][T][D*D]
+    double *fagg;        // [n_fits][n_chunks][3D^2+2D]
+    double *sagg;        // [n_fits][n_chunks][2D^2+D]
+    double *pre;         // [n_fits][n_chunks][D+D^2]  filtered state entering the chunk
+    double *suf;         // [n_fits][n_chunks][D+D^2]  smoothed state right of the chunk
+    double *likp;        // [n_fits][n_chunks][2]      (sum of terms, n_obs)
+    double *X, *V, *Y;   // outputs [n_fits][T][D], [n_fits][T][D*D], [n_fits][T]
+    double *lik;         // [n_fits]
+};
+
+template <int D> struct ThetaD {
+    const double *A, *B, *C, *Dd, *Q, *mu1, *V1;
+    double R;
+    __device__ __forceinline__ ThetaD(const double *th, int p, int q) {
+        A = th;
+        B = A + D * D;
+        C = B + D * p;
+        Dd = C + D;
+        Q = Dd + q;
+        R = Q[D * D];
+        mu1 = Q + D * D + 1;
+        V1 = mu1 + D;
+    }
+};
+
+// ---- small dense helpers, fully unrolled, everything in registers -----------------------------
+template <int D> __device__ __forceinline__ void mat_load(const double *__restrict__ g, double (&m)[D * D]) {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) m[i] = g[i];
+}
+template <int D> __device__ __forceinline__ void vec_load(const double *__restrict__ g, double (&x)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++) x[i] = g[i];
+}
+template <int D>
+__device__ __forceinline__ void mm(const double (&A)[D * D], const double (&B)[D * D], double (&C)[D * D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) s = fma(A[i * D + k], B[k * D + j], s);
+            C[i * D + j] = s;
+        }
+}
+template <int D> // C = A * B'
+__device__ __forceinline__ void mmt(const double (&A)[D * D], const double (&B)[D * D], double (&C)[D * D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) s = fma(A[i * D + k], B[j * D + k], s);
+            C[i * D + j] = s;
+        }
+}
+template <int D> // C = A' * B
+__device__ __forceinline__ void mtm(const double (&A)[D * D], const double (&B)[D * D], double (&C)[D * D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) s = fma(A[k * D + i], B[k * D + j], s);
+            C[i * D + j] = s;
+        }
+}
+template <int D> __device__ __forceinline__ void mv(const double (&A)[D * D], const double (&x)[D], double (&y)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(A[i * D + k], x[k], s);
+        y[i] = s;
+    }
+}
+template <int D> // y = A' x
+__device__ __forceinline__ void mtv(const double (&A)[D * D], const double (&x)[D], double (&y)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(A[k * D + i], x[k], s);
+        y[i] = s;
+    }
+}
+// inverse by Gauss-Jordan with partial pivoting; rows are swapped with selects so every index is
+// a compile-time constant and the matrix stays in registers
+template <int D> __device__ __forceinline__ void mat_inv(const double (&A)[D * D], double (&R)[D * D]) {
+    double M[D][2 * D];
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            M[i][j] = A[i * D + j];
+            M[i][D + j] = i == j ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+#pragma unroll
+        for (int r = c + 1; r < D; r++) { // bring the largest |entry| of column c up to row c
+            const bool sw = fabs(M[r][c]) > fabs(M[c][c]);
+#pragma unroll
+            for (int j = 0; j < 2 * D; j++) {
+                const double a = M[c][j], b = M[r][j];
+                M[c][j] = sw ? b : a;
+                M[r][j] = sw ? a : b;
+            }
+        }
+        const double rp = 1.0 / M[c][c];
+#pragma unroll
+        for (int j = 0; j < 2 * D; j++) M[c][j] *= rp;
+#pragma unroll
+        for (int i = 0; i < D; i++)
+            if (i != c) {
+                const double f = M[i][c];
+#pragma unroll
+                for (int j = 0; j < 2 * D; j++) M[i][j] = fma(-f, M[c][j], M[i][j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) R[i * D + j] = M[i][D + j];
+}
+
+// ---- filtering element (Appendix D.2) ---------------------------------------------------------
+template <int D> struct FiltElem {
+    double A[D * D], b[D], C[D * D], eta[D], J[D * D];
+    static constexpr int LEN = 3 * D * D + 2 * D;
+    __device__ __forceinline__ void store(double *__restrict__ g) const {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            g[i] = A[i];
+            g[D * D + D + i] = C[i];
+            g[2 * D * D + 2 * D + i] = J[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            g[D * D + i] = b[i];
+            g[2 * D * D + D + i] = eta[i];
+        }
+    }
+    __device__ __forceinline__ void load(const double *__restrict__ g) {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            A[i] = g[i];
+            C[i] = g[D * D + D + i];
+            J[i] = g[2 * D * D + 2 * D + i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            b[i] = g[D * D + i];
+            eta[i] = g[2 * D * D + D + i];
+        }
+    }
+};
+
+// a <- a (earlier) combined with e (later)
+template <int D> __device__ __forceinline__ void filt_combine(FiltElem<D> &a, const FiltElem<D> &e) {
+    double T1[D * D], M[D * D], N[D * D];
+    mm<D>(a.C, e.J, T1); // C_i J_j
+#pragma unroll
+    for (int i = 0; i < D; i++) T1[i * D + i] += 1.0;
+    mat_inv<D>(T1, M); // M = (I + C_i J_j)^-1 ;  N = (I + J_j C_i)^-1 = M'
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) N[i * D + j] = M[j * D + i];
+    double AjM[D * D];
+    mm<D>(e.A, M, AjM);
+    // b = A_j M (b_i + C_i eta_j) + b_j
+    double t[D], t2[D], nb[D];
+    mv<D>(a.C, e.eta, t);
+#pragma unroll
+    for (int i = 0; i < D; i++) t[i] += a.b[i];
+    mv<D>(AjM, t, nb);
+#pragma unroll
+    for (int i = 0; i < D; i++) nb[i] += e.b[i];
+    // eta = A_i' N (eta_j - J_j b_i) + eta_i
+    mv<D>(e.J, a.b, t);
+#pragma unroll
+    for (int i = 0; i < D; i++) t[i] = e.eta[i] - t[i];
+    mv<D>(N, t, t2);
+    double neta[D];
+    mtv<D>(a.A, t2, neta);
+#pragma unroll
+    for (int i = 0; i < D; i++) neta[i] += a.eta[i];
+    // C = A_j M C_i A_j' + C_j
+    double T2[D * D], nC[D * D];
+    mm<D>(AjM, a.C, T2);
+    mmt<D>(T2, e.A, nC);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) nC[i] += e.C[i];
+    // J = A_i' N J_j A_i + J_i
+    double nJ[D * D];
+    mm<D>(N, e.J, T1);
+    mm<D>(T1, a.A, T2);
+    mtm<D>(a.A, T2, nJ);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) nJ[i] += a.J[i];
+    // A = A_j M A_i
+    double nA[D * D];
+    mm<D>(AjM, a.A, nA);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) {
+        a.A[i] = nA[i];
+        a.C[i] = 0.5 * (nC[i] + nC[(i % D) * D + i / D]); // keep the covariances symmetric
+        a.J[i] = 0.5 * (nJ[i] + nJ[(i % D) * D + i / D]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        a.b[i] = nb[i];
+        a.eta[i] = neta[i];
+    }
+}
+
+// measurement update of (x,V) with scalar y (EM.cpp:61-68 generalised); returns the likelihood term
+template <int D>
+__device__ __forceinline__ double meas_update(const double (&Cc)[D], double R, double r, double (&x)[D],
+                                              double (&V)[D * D]) {
+    double vc[D], S = R, yp = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(V[i * D + k], Cc[k], s);
+        vc[i] = s;
+        yp = fma(Cc[i], x[i], yp);
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) S = fma(Cc[k], vc[k], S);
+    const double rS = 1.0 / S, delta = r - yp;
+#pragma unroll
+    for (int i = 0; i < D; i++) x[i] = fma(vc[i] * rS, delta, x[i]);
+    // Vu = Vp - (Vp C')(C Vp)/S ; Vp symmetric so C Vp = (Vp C')'
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) V[i * D + j] = fma(-vc[i] * rS, vc[j], V[i * D + j]);
+    return delta * rS * delta + log(S);
+}
+
+// filtering element of step t > 0
+template <int D>
+__device__ __forceinline__ void filt_element(const double (&F)[D * D], const double (&Q)[D * D], const double (&Cc)[D],
+                                             double R, bool obs, double r, const double (&c)[D], FiltElem<D> &e) {
+    if (!obs) {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            e.A[i] = F[i];
+            e.C[i] = Q[i];
+            e.J[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            e.b[i] = c[i];
+            e.eta[i] = 0.0;
+        }
+        return;
+    }
+    // r = y - D v ; innovation of the zero-state response: r - H c
+    double qh[D], S = R, hc = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(Q[i * D + k], Cc[k], s);
+        qh[i] = s;
+        hc = fma(Cc[i], c[i], hc);
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) S = fma(Cc[k], qh[k], S);
+    const double rS = 1.0 / S, rr = r - hc;
+    double hf[D]; // H F
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(Cc[k], F[k * D + j], s);
+        hf[j] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const double K = qh[i] * rS;
+        e.b[i] = fma(K, rr, c[i]);
+        e.eta[i] = hf[i] * rS * rr;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            e.A[i * D + j] = fma(-K, hf[j], F[i * D + j]); // (I - K H) F
+            e.C[i * D + j] = fma(-K, qh[j], Q[i * D + j]); // (I - K H) Q
+            e.J[i * D + j] = hf[i] * rS * hf[j];
+        }
+    }
+}
+
+// ---- kernels --------------------------------------------------------------------------------
+// c_t = B u_{t-1}, dv_t = D v_t : one thread per (fit, t)
+template <int D> __global__ void scan_prep_kernel(const ScanParams P) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.n_fits * P.T) return;
+    const int f = (int)(gid / P.T), t = (int)(gid % P.T);
+    const ThetaD<D> th(P.theta + (size_t)f * P.theta_len, P.p, P.q);
+    double c[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) c[i] = 0.0;
+    if (P.u && t > 0) {
+        const double *__restrict__ row = P.u + (size_t)(t - 1) * P.p;
+        for (int j = 0; j < P.p; j++) {
+            const double uj = row[j];
+#pragma unroll
+            for (int i = 0; i < D; i++) c[i] = fma(th.B[i * P.p + j], uj, c[i]);
+        }
+    }
+    double dv = 0.0;
+    if (P.v) {
+        const double *__restrict__ row = P.v + (size_t)t * P.q;
+        for (int j = 0; j < P.q; j++) dv = fma(th.Dd[j], row[j], dv);
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) P.c[((size_t)f * P.T + t) * D + i] = c[i];
+    P.dv[(size_t)f * P.T + t] = dv;
+}
+
+// element of a whole chunk: one thread per (fit, chunk)
+template <int D> __global__ void scan_filt_agg_kernel(const ScanParams P) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P.n_fits * P.n_chunks) return;
+    const int f = gid / P.n_chunks, ch = gid % P.n_chunks;
+    const ThetaD<D> th(P.theta + (size_t)f * P.theta_len, P.p, P.q);
+    double F[D * D], Q[D * D], Cc[D];
+    mat_load<D>(th.A, F);
+    mat_load<D>(th.Q, Q);
+    vec_load<D>(th.C, Cc);
+    const int t0 = ch * P.L, t1 = min(P.T, t0 + P.L);
+    FiltElem<D> a;
+    for (int t = t0; t < t1; t++) {
+        const double yt = P.y[t];
+        const bool obs = yt == yt;
+        const double r = obs ? yt - P.dv[(size_t)f * P.T + t] : 0.0;
+        FiltElem<D> e;
+        if (t == 0) { // (0, Xu_0, Vu_0, 0, 0): the ordinary update of the prior
+            vec_load<D>(th.mu1, e.b);
+            mat_load<D>(th.V1, e.C);
+            if (obs) meas_update<D>(Cc, th.R, r, e.b, e.C);
+#pragma unroll
+            for (int i = 0; i < D * D; i++) e.A[i] = e.J[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) e.eta[i] = 0.0;
+        } else {
+            double c[D];
+            vec_load<D>(P.c + ((size_t)f * P.T + t) * D, c);
+            filt_element<D>(F, Q, Cc, th.R, obs, r, c, e);
+        }
+        if (t == t0)
+            a = e;
+        else
+            filt_combine<D>(a, e);
+    }
+    a.store(P.fagg + ((size_t)f * P.n_chunks + ch) * FiltElem<D>::LEN);
+}
+
+// prefix over the chunk elements: one warp per fit, lane l owns a contiguous range of chunks
+template <int D> __global__ void scan_filt_scan_kernel(const ScanParams P) {
+    extern __shared__ double sh[]; // [32][LEN] lane aggregates, then their exclusive prefixes
+    constexpr int LEN = FiltElem<D>::LEN;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int per = (P.n_chunks + 31) / 32;
+    const int k0 = min(P.n_chunks, lane * per), k1 = min(P.n_chunks, k0 + per);
+    const double *__restrict__ agg = P.fagg + (size_t)f * P.n_chunks * LEN;
+    FiltElem<D> a;
+    for (int k = k0; k < k1; k++) {
+        FiltElem<D> e;
+        e.load(agg + (size_t)k * LEN);
+        if (k == k0)
+            a = e;
+        else
+            filt_combine<D>(a, e);
+    }
+    if (k1 > k0) a.store(sh + lane * LEN);
+    __syncwarp();
+    if (lane == 0) { // exclusive prefixes of the lane aggregates, in place (slot l <- prefix before lane l)
+        FiltElem<D> run, nxt;
+        bool have = false;
+        for (int l = 0; l < 32; l++) {
+            const int a0 = min(P.n_chunks, l * per), a1 = min(P.n_chunks, a0 + per);
+            if (a1 <= a0) break;
+            nxt.load(sh + l * LEN);
+            if (have) run.store(sh + l * LEN);
+            if (!have) {
+                run = nxt;
+                have = true;
+            } else {
+                filt_combine<D>(run, nxt);
+            }
+        }
+    }
+    __syncwarp();
+    // walk the range again: the filtered state entering chunk k is (b, C) of the prefix before it
+    double *__restrict__ pre = P.pre + (size_t)f * P.n_chunks * (D + D * D);
+    FiltElem<D> run;
+    bool have = false;
+    if (lane > 0 && k1 > k0) {
+        run.load(sh + lane * LEN);
+        have = true;
+    }
+    for (int k = k0; k < k1; k++) {
+        if (have) {
+#pragma unroll
+            for (int i = 0; i < D; i++) pre[(size_t)k * (D + D * D) + i] = run.b[i];
+#pragma unroll
+            for (int i = 0; i < D * D; i++) pre[(size_t)k * (D + D * D) + D + i] = run.C[i];
+        }
+        FiltElem<D> e;
+        e.load(agg + (size_t)k * LEN);
+        if (have)
+            filt_combine<D>(run, e);
+        else {
+            run = e;
+            have = true;
+        }
+    }
+}
+
+// ordinary Kalman filter inside a chunk (EM.cpp:70-90 generalised)
+template <int D> __global__ void scan_filt_down_kernel(const ScanParams P) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P.n_fits * P.n_chunks) return;
+    const int f = gid / P.n_chunks, ch = gid % P.n_chunks;
+    const ThetaD<D> th(P.theta + (size_t)f * P.theta_len, P.p, P.q);
+    double F[D * D], Q[D * D], Cc[D];
+    mat_load<D>(th.A, F);
+    mat_load<D>(th.Q, Q);
+    vec_load<D>(th.C, Cc);
+    const int t0 = ch * P.L, t1 = min(P.T, t0 + P.L);
+    double x[D], V[D * D];
+    if (ch > 0) {
+        const double *__restrict__ pre = P.pre + ((size_t)f * P.n_chunks + ch) * (D + D * D);
+        vec_load<D>(pre, x);
+        mat_load<D>(pre + D, V);
+    }
+    double acc = 0.0, nobs = 0.0;
+    for (int t = t0; t < t1; t++) {
+        if (t == 0) {
+            vec_load<D>(th.mu1, x);
+            mat_load<D>(th.V1, V);
+        } else { // predict
+            double c[D], xn[D], T1[D * D];
+            vec_load<D>(P.c + ((size_t)f * P.T + t) * D, c);
+            mv<D>(F, x, xn);
+#pragma unroll
+            for (int i = 0; i < D; i++) x[i] = xn[i] + c[i];
+            mm<D>(F, V, T1);
+            mmt<D>(T1, F, V);
+#pragma unroll
+            for (int i = 0; i < D * D; i++) V[i] += Q[i];
+        }
+        const double yt = P.y[t];
+        if (yt == yt) {
+            acc += meas_update<D>(Cc, th.R, yt - P.dv[(size_t)f * P.T + t], x, V);
+            nobs += 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) P.Xu[((size_t)f * P.T + t) * D + i] = x[i];
+#pragma unroll
+        for (int i = 0; i < D * D; i++) P.Vu[((size_t)f * P.T + t) * D * D + i] = V[i];
+    }
+    P.likp[((size_t)f * P.n_chunks + ch) * 2] = acc;
+    P.likp[((size_t)f * P.n_chunks + ch) * 2 + 1] = nobs;
+}
+
+// ---- smoothing element (Appendix D.3) -----------------------------------------------------------
+template <int D> struct SmthElem {
+    double E[D * D], g[D], L[D * D];
+    static constexpr int LEN = 2 * D * D + D;
+    __device__ __forceinline__ void store(double *__restrict__ o) const {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            o[i] = E[i];
+            o[D * D + D + i] = L[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) o[D * D + i] = g[i];
+    }
+    __device__ __forceinline__ void load(const double *__restrict__ o) {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            E[i] = o[i];
+            L[i] = o[D * D + D + i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) g[i] = o[D * D + i];
+    }
+};
+// a (earlier) <- a combined with e (later): E = E_i E_j, g = E_i g_j + g_i, L = E_i L_j E_i' + L_i
+template <int D> __device__ __forceinline__ void smth_combine(SmthElem<D> &a, const SmthElem<D> &e) {
+    double nE[D * D], t[D], T1[D * D], nL[D * D];
+    mm<D>(a.E, e.E, nE);
+    mv<D>(a.E, e.g, t);
+    mm<D>(a.E, e.L, T1);
+    mmt<D>(T1, a.E, nL);
+#pragma unroll
+    for (int i = 0; i < D; i++) a.g[i] += t[i];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) {
+        a.L[i] += 0.5 * (nL[i] + nL[(i % D) * D + i / D]);
+        a.E[i] = nE[i];
+    }
+}
+// RTS gain and predicted moments of step t+1 from the filtered moments of step t
+template <int D>
+__device__ __forceinline__ void rts_gain(const double (&F)[D * D], const double (&Q)[D * D], const double (&xu)[D],
+                                         const double (&Vu)[D * D], const double (&c1)[D], double (&E)[D * D],
+                                         double (&xp1)[D], double (&Vp1)[D * D]) {
+    double T1[D * D], iV[D * D], VFt[D * D];
+    mm<D>(F, Vu, T1);
+    mmt<D>(T1, F, Vp1);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Vp1[i] += Q[i];
+    mat_inv<D>(Vp1, iV);
+    mmt<D>(Vu, F, VFt); // Vu F'
+    mm<D>(VFt, iV, E);  // J_t = Vu_t A' Vp_{t+1}^-1   (EM.cpp:100)
+    mv<D>(F, xu, xp1);
+#pragma unroll
+    for (int i = 0; i < D; i++) xp1[i] += c1[i];
+}
+
+template <int D> __global__ void scan_smth_agg_kernel(const ScanParams P) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P.n_fits * P.n_chunks) return;
+    const int f = gid / P.n_chunks, ch = gid % P.n_chunks;
+    const ThetaD<D> th(P.theta + (size_t)f * P.theta_len, P.p, P.q);
+    double F[D * D], Q[D * D];
+    mat_load<D>(th.A, F);
+    mat_load<D>(th.Q, Q);
+    const int t0 = ch * P.L, t1 = min(P.T, t0 + P.L);
+    SmthElem<D> a;
+    for (int t = t0; t < t1; t++) {
+        double xu[D], Vu[D * D];
+        vec_load<D>(P.Xu + ((size_t)f * P.T + t) * D, xu);
+        mat_load<D>(P.Vu + ((size_t)f * P.T + t) * D * D, Vu);
+        SmthElem<D> e;
+        if (t == P.T - 1) {
+#pragma unroll
+            for (int i = 0; i < D * D; i++) {
+                e.E[i] = 0.0;
+                e.L[i] = Vu[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) e.g[i] = xu[i];
+        } else {
+            double c1[D], xp1[D], Vp1[D * D], tv[D], T1[D * D];
+            vec_load<D>(P.c + ((size_t)f * P.T + t + 1) * D, c1);
+            rts_gain<D>(F, Q, xu, Vu, c1, e.E, xp1, Vp1);
+            mv<D>(e.E, xp1, tv);
+#pragma unroll
+            for (int i = 0; i < D; i++) e.g[i] = xu[i] - tv[i]; // g = Xu - E (F Xu + c)
+            // L = Vu - E Vp1 E'  (= Vu - E F Vu)
+            mm<D>(e.E, Vp1, T1);
+            double T2[D * D];
+            mmt<D>(T1, e.E, T2);
+#pragma unroll
+            for (int i = 0; i < D * D; i++) e.L[i] = Vu[i] - 0.5 * (T2[i] + T2[(i % D) * D + i / D]);
+        }
+        if (t == t0)
+            a = e;
+        else
+            smth_combine<D>(a, e);
+    }
+    a.store(P.sagg + ((size_t)f * P.n_chunks + ch) * SmthElem<D>::LEN);
+}
+
+// suffix over the chunk elements: (g, L) of the suffix right of chunk k = smoothed state of its first step
+template <int D> __global__ void scan_smth_scan_kernel(const ScanParams P) {
+    extern __shared__ double sh[];
+    constexpr int LEN = SmthElem<D>::LEN;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int per = (P.n_chunks + 31) / 32;
+    const int k0 = min(P.n_chunks, lane * per), k1 = min(P.n_chunks, k0 + per);
+    const double *__restrict__ agg = P.sagg + (size_t)f * P.n_chunks * LEN;
+    SmthElem<D> a;
+    for (int k = k1 - 1; k >= k0; k--) { // a = e_k0 * ... * e_{k1-1}, built from the right
+        SmthElem<D> e;
+        e.load(agg + (size_t)k * LEN);
+        if (k == k1 - 1)
+            a = e;
+        else {
+            smth_combine<D>(e, a);
+            a = e;
+        }
+    }
+    if (k1 > k0) a.store(sh + lane * LEN);
+    __syncwarp();
+    if (lane == 0) { // exclusive suffixes of the lane aggregates: slot l <- product of lanes l+1 ..
+        int last = -1;
+        for (int l = 0; l < 32; l++)
+            if (min(P.n_chunks, l * per) < P.n_chunks) last = l;
+        SmthElem<D> run, cur;
+        bool have = false;
+        for (int l = last; l >= 0; l--) {
+            cur.load(sh + l * LEN);
+            if (have) run.store(sh + l * LEN);
+            if (!have) {
+                run = cur;
+                have = true;
+            } else {
+                smth_combine<D>(cur, run);
+                run = cur;
+            }
+        }
+        if (last >= 0) sh[32 * LEN] = (double)last;
+    }
+    __syncwarp();
+    const int last = (int)sh[32 * LEN];
+    double *__restrict__ suf = P.suf + (size_t)f * P.n_chunks * (D + D * D);
+    SmthElem<D> run;
+    bool have = false;
+    if (lane < last && k1 > k0) {
+        run.load(sh + lane * LEN);
+        have = true;
+    }
+    for (int k = k1 - 1; k >= k0; k--) {
+        if (have) {
+#pragma unroll
+            for (int i = 0; i < D; i++) suf[(size_t)k * (D + D * D) + i] = run.g[i];
+#pragma unroll
+            for (int i = 0; i < D * D; i++) suf[(size_t)k * (D + D * D) + D + i] = run.L[i];
+        }
+        SmthElem<D> e;
+        e.load(agg + (size_t)k * LEN);
+        if (have) {
+            smth_combine<D>(e, run);
+            run = e;
+        } else {
+            run = e;
+            have = true;
+        }
+    }
+}
+
+// ordinary RTS recursion inside a chunk (EM.cpp:99-110 generalised)
+template <int D> __global__ void scan_smth_down_kernel(const ScanParams P) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P.n_fits * P.n_chunks) return;
+    const int f = gid / P.n_chunks, ch = gid % P.n_chunks;
+    const ThetaD<D> th(P.theta + (size_t)f * P.theta_len, P.p, P.q);
+    double F[D * D], Q[D * D], Cc[D];
+    mat_load<D>(th.A, F);
+    mat_load<D>(th.Q, Q);
+    vec_load<D>(th.C, Cc);
+    const int t0 = ch * P.L, t1 = min(P.T, t0 + P.L);
+    double xs1[D], Vs1[D * D];
+    if (ch < P.n_chunks - 1) {
+        const double *__restrict__ suf = P.suf + ((size_t)f * P.n_chunks + ch) * (D + D * D);
+        vec_load<D>(suf, xs1);
+        mat_load<D>(suf + D, Vs1);
+    }
+    for (int t = t1 - 1; t >= t0; t--) {
+        double xu[D], Vu[D * D], xs[D], Vs[D * D];
+        vec_load<D>(P.Xu + ((size_t)f * P.T + t) * D, xu);
+        mat_load<D>(P.Vu + ((size_t)f * P.T + t) * D * D, Vu);
+        if (t == P.T - 1) {
+#pragma unroll
+            for (int i = 0; i < D; i++) xs[i] = xu[i];
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Vs[i] = Vu[i];
+        } else {
+            double c1[D], xp1[D], Vp1[D * D], E[D * D], dx[D], T1[D * D], T2[D * D];
+            vec_load<D>(P.c + ((size_t)f * P.T + t + 1) * D, c1);
+            rts_gain<D>(F, Q, xu, Vu, c1, E, xp1, Vp1);
+#pragma unroll
+            for (int i = 0; i < D; i++) dx[i] = xs1[i] - xp1[i];
+            mv<D>(E, dx, xs);
+#pragma unroll
+            for (int i = 0; i < D; i++) xs[i] += xu[i];
+#pragma unroll
+            for (int i = 0; i < D * D; i++) T1[i] = Vs1[i] - Vp1[i];
+            mm<D>(E, T1, T2);
+            mmt<D>(T2, E, T1);
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Vs[i] = Vu[i] + 0.5 * (T1[i] + T1[(i % D) * D + i / D]);
+        }
+        double ys = P.dv[(size_t)f * P.T + t];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            P.X[((size_t)f * P.T + t) * D + i] = xs[i];
+            ys = fma(Cc[i], xs[i], ys);
+            xs1[i] = xs[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            P.V[((size_t)f * P.T + t) * D * D + i] = Vs[i];
+            Vs1[i] = Vs[i];
+        }
+        P.Y[(size_t)f * P.T + t] = ys;
+    }
+}
+
+// likelihood: chunk terms added in order (EM.cpp:115-124)
+template <int D> __global__ void scan_lik_kernel(const ScanParams P) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P.n_fits) return;
+    double acc = 0.0, n = 0.0;
+    for (int k = 0; k < P.n_chunks; k++) {
+        acc += P.likp[((size_t)f * P.n_chunks + k) * 2];
+        n += P.likp[((size_t)f * P.n_chunks + k) * 2 + 1];
+    }
+    double lik = -0.5 * n * LOG_2PI - 0.5 * acc;
+    if (P.stdlik) lik /= n;
+    P.lik[f] = lik;
+}
+
+cudaError_t scan_smoother_launch(int D, const ScanParams &P, cudaStream_t st); // scan_inst.cu
+
+} // namespace ldsr

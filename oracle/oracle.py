@@ -16,8 +16,8 @@ _ip = C.POINTER(C.c_int)
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "ldsr_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ldsr_oracle.c", "ldsr_oracle_d.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -28,11 +28,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()
         _lib = C.CDLL(_SO)
         for name in ("kalman_smoother", "mstep", "em", "select", "em_batch", "propagate", "rep",
-                     "max_threads"):
+                     "max_threads", "smoother_d"):
             getattr(_lib, "ldsr_oracle_" + name).restype = C.c_int
     return _lib
 
@@ -202,3 +201,28 @@ def rep(theta, u, v, n, z, mu=0.0, exp_trans=True, p=None, q=None):
 
 def max_threads():
     return lib().ldsr_oracle_max_threads()
+
+
+def theta_d_flat(A, B, Cc, D, Q, R, mu1, V1):
+    """General-d theta: [A d*d | B d*p | C d | D q | Q d*d | R | mu1 d | V1 d*d] (row-major blocks)."""
+    return np.concatenate([np.ravel(A), np.ravel(B), np.ravel(Cc), np.ravel(D), np.ravel(Q), [R],
+                           np.ravel(mu1), np.ravel(V1)]).astype(np.float64)
+
+
+def smoother_d(d, y, u, v, theta, stdlik=True):
+    """General state dimension d (ldsr_oracle_d.c).  u [p,T] | None, v [q,T] | None."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    T = y.size
+    uf, p = _mat(u)
+    vf, q = _mat(v)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    assert th.size == 2 * d * d + d * p + d + q + 1 + d + d * d, th.size
+    X = np.empty((T, d))
+    V = np.empty((T, d, d))
+    Y = np.empty(T)
+    lik = C.c_double()
+    rc = lib().ldsr_oracle_smoother_d(int(d), T, int(p), int(q), _d(y), _d(uf), _d(vf), _d(th), int(bool(stdlik)),
+                                      _d(X), _d(V), _d(Y), C.byref(lik))
+    if rc != 0:
+        raise RuntimeError("ldsr_oracle_smoother_d failed: %d" % rc)
+    return dict(X=X, V=V, Y=Y, lik=lik.value)

@@ -122,3 +122,25 @@ def test_propagate_and_rep_definitions():
         assert abs(r["simX"][k] - x) <= 1e-12 * max(1, abs(x))
         x = t["A"] * x + t["B"] @ u[:, k] + z[1 + k] * np.sqrt(t["Q"])
     assert np.allclose(r["simQ"], np.exp(r["simY"] + mu))
+
+
+def test_general_d_reduces_to_1d():
+    """oracle/ldsr_oracle_d.c (general state dimension; no reference counterpart, src/EM.cpp:20 is
+    scalar-state) at d = 1 must reproduce the pinned 1-D oracle: on the NPlds fixture (T = 813, 767
+    missing steps) and on the fully observed P1 series."""
+    g = data.load("nplds.json")
+    y, u, mu, inst = data.np_case(1, 1200)
+    th = data.theta_of(g["theta"])
+    cases = [(y, u, u, th, 3, 3)]
+    y1, u1, th1, _ = data.p1_case()
+    cases.append((y1, u1, u1, th1, 7, 7))
+    for yy, uu, vv, t, p, q in cases:
+        o1 = O.kalman_smoother(yy, uu, vv, t)
+        thd = O.theta_d_flat([[t[0]]], [t[1:1 + p]], [t[1 + p]], t[2 + p:2 + p + q], [[t[2 + p + q]]], t[3 + p + q],
+                             [t[4 + p + q]], [[t[5 + p + q]]])
+        od = O.smoother_d(1, yy, uu, vv, thd)
+        assert abs(od["lik"] - o1["lik"]) < 1e-13 * max(1.0, abs(o1["lik"]))
+        assert np.max(np.abs(od["X"][:, 0] - o1["X"])) < 1e-12
+        assert np.max(np.abs(od["V"][:, 0, 0] - o1["V"])) < 1e-12
+        assert np.max(np.abs(od["Y"] - o1["Y"])) < 1e-12
+    assert abs(od["lik"] - (-11.678657)) < 1e-6  # tests/testthat/test-LDS-EM.R:26 through the d = 1 path
