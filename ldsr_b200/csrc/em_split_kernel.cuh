@@ -52,7 +52,8 @@ __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units
     size_t b = 0;
     b += (size_t)max_units * 3 * 32 * 8; // checkpoints
     b += (size_t)2 * nw * 4 * 32 * 8;    // variance maps of the pieces
-    const size_t ch = (size_t)2 * nw * SPLIT_NCH * 32 * 8, st = (size_t)nw * (11 + 3 * pq) * 32 * 8;
+    const bool pair = nw % 2 == 0 && nw * (11 + 3 * pq) > 2 * nw * SPLIT_NCH; // split_pairwise<PQ,NW>()
+    const size_t ch = (size_t)2 * nw * SPLIT_NCH * 32 * 8, st = (size_t)(pair ? nw / 2 : nw) * (11 + 3 * pq) * 32 * 8;
     b += ch > st ? ch : st;                           // piece summaries, later the partial sums
     b += ((size_t)max_units * 4 + 15) & ~size_t(15); // unit table
     b += 128;                                        // piece bounds
@@ -516,6 +517,55 @@ __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitCons
     cH = H0;
 }
 
+// partial M-step sums <-> shared memory ([NST][32] doubles per slot, pointer already offset by lane)
+template <int PQ> __device__ __forceinline__ void stats_store(const Stats<PQ> &st, double *o) {
+    o[0 * 32] = st.Syx;
+    o[1 * 32] = st.Sxx;
+    o[2 * 32] = st.Sxxv;
+    o[3 * 32] = st.Tx1x;
+    o[4 * 32] = st.Tx1xv;
+    o[5 * 32] = st.Txx;
+    o[6 * 32] = st.Txxv;
+    o[7 * 32] = st.X0;
+    o[8 * 32] = st.V0;
+    o[9 * 32] = st.XT;
+    o[10 * 32] = st.VT;
+#pragma unroll
+    for (int i = 0; i < PQ; i++) {
+        o[(11 + i) * 32] = st.Sxv[i];
+        o[(11 + PQ + i) * 32] = st.Tx1u[i];
+        o[(11 + 2 * PQ + i) * 32] = st.Tux[i];
+    }
+}
+template <int PQ> __device__ __forceinline__ void stats_add(Stats<PQ> &st, const double *o) {
+    st.Syx += o[0 * 32];
+    st.Sxx += o[1 * 32];
+    st.Sxxv += o[2 * 32];
+    st.Tx1x += o[3 * 32];
+    st.Tx1xv += o[4 * 32];
+    st.Txx += o[5 * 32];
+    st.Txxv += o[6 * 32];
+    st.X0 += o[7 * 32];
+    st.V0 += o[8 * 32];
+    st.XT += o[9 * 32];
+    st.VT += o[10 * 32];
+#pragma unroll
+    for (int i = 0; i < PQ; i++) {
+        st.Sxv[i] += o[(11 + i) * 32];
+        st.Tx1u[i] += o[(11 + PQ + i) * 32];
+        st.Tux[i] += o[(11 + 2 * PQ + i) * 32];
+    }
+}
+// With many inputs the NW slots of partial sums would be the largest shared-memory consumer
+// (PQ = 10: 42 KB, one CTA per SM).  Then the sums are reduced in two stages through NW/2 slots:
+// the upper half of the warps publish, the lower half add their own and publish, everybody sums.
+template <int PQ, int NW> __host__ __device__ constexpr bool split_pairwise() {
+    return NW % 2 == 0 && NW * (11 + 3 * PQ) > 2 * NW * SPLIT_NCH;
+}
+template <int PQ, int NW> __host__ __device__ constexpr int split_st_slots() {
+    return split_pairwise<PQ, NW>() ? NW / 2 : NW;
+}
+
 struct SplitParams {
     EmParams em;
     int max_units;      // capacity of the unit table / checkpoint area
@@ -555,7 +605,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     __shared__ __align__(8) uint64_t bar;
     constexpr int NST = split_nstat<PQ>();
     constexpr int NP = 2 * NW; // pieces
-    constexpr size_t CH_DOUBLES = (size_t)NP * SPLIT_NCH * 32, ST_DOUBLES = (size_t)NW * NST * 32;
+    constexpr bool PAIR = split_pairwise<PQ, NW>();
+    constexpr int ST_SLOTS = split_st_slots<PQ, NW>();
+    constexpr size_t CH_DOUBLES = (size_t)NP * SPLIT_NCH * 32, ST_DOUBLES = (size_t)ST_SLOTS * NST * 32;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -846,50 +898,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 st.V0 = Vs1;
             }
         }
-        {
-            double *o = ST + (size_t)warp * NST * 32;
-            o[0 * 32] = st.Syx;
-            o[1 * 32] = st.Sxx;
-            o[2 * 32] = st.Sxxv;
-            o[3 * 32] = st.Tx1x;
-            o[4 * 32] = st.Tx1xv;
-            o[5 * 32] = st.Txx;
-            o[6 * 32] = st.Txxv;
-            o[7 * 32] = st.X0;
-            o[8 * 32] = st.V0;
-            o[9 * 32] = st.XT;
-            o[10 * 32] = st.VT;
+        if (!PAIR) {
+            stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
+            __syncthreads();
+            // ============ M-step (EM.cpp:139-229), same arithmetic in every warp ============
+            st.zero();
 #pragma unroll
-            for (int i = 0; i < PQ; i++) {
-                o[(11 + i) * 32] = st.Sxv[i];
-                o[(11 + PQ + i) * 32] = st.Tx1u[i];
-                o[(11 + 2 * PQ + i) * 32] = st.Tux[i];
+            for (int w = 0; w < NW; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
+        } else {
+            if (warp >= NW / 2) stats_store<PQ>(st, ST + (size_t)(warp - NW / 2) * NST * 32);
+            __syncthreads();
+            if (warp < NW / 2) {
+                stats_add<PQ>(st, ST + (size_t)warp * NST * 32);
+                stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
             }
-        }
-        __syncthreads();
-
-        // ================= M-step (EM.cpp:139-229), same arithmetic in every warp =================
-        st.zero();
+            __syncthreads();
+            st.zero();
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const double *o = ST + (size_t)w * NST * 32;
-            st.Syx += o[0 * 32];
-            st.Sxx += o[1 * 32];
-            st.Sxxv += o[2 * 32];
-            st.Tx1x += o[3 * 32];
-            st.Tx1xv += o[4 * 32];
-            st.Txx += o[5 * 32];
-            st.Txxv += o[6 * 32];
-            st.X0 += o[7 * 32];
-            st.V0 += o[8 * 32];
-            st.XT += o[9 * 32];
-            st.VT += o[10 * 32];
-#pragma unroll
-            for (int i = 0; i < PQ; i++) {
-                st.Sxv[i] += o[(11 + i) * 32];
-                st.Tx1u[i] += o[(11 + PQ + i) * 32];
-                st.Tux[i] += o[(11 + 2 * PQ + i) * 32];
-            }
+            for (int w = 0; w < NW / 2; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
         }
         if (live) {
             mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);

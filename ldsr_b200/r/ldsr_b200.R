@@ -112,3 +112,14 @@ LDS_rep <- function(theta, u = NULL, v = NULL, years, num.reps = 100, mu = 0, ex
   data.table::data.table(year = rep(years, num.reps), simX = m[, 1], simY = m[, 2], simQ = m[, 3],
                          rep = rep(seq_len(num.reps), each = n))
 }
+
+
+#' Kalman / RTS smoother for a state of dimension d > 1 (beyond ldsr, whose state is scalar).
+#' theta: list(A d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d x 1, V1 d x d); y 1 x T with NA.
+#' method: 1 = associative scan over time (long series), 0 = sequential recursion.
+#' Returns list(X d x T, Y 1 x T, V (d*d) x T with column t = vec(V_t), lik).
+Kalman_smoother_d <- function(y, u, v, theta, stdlik = TRUE, method = 1L) {
+  if (is.null(u)) u <- matrix(0)
+  if (is.null(v)) v <- matrix(0)
+  .Call(`_ldsr_smoother_d`, y, u, v, theta, stdlik, as.integer(method))
+}

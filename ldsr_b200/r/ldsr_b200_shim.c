@@ -14,6 +14,8 @@
  * and add the batched ones used by the drop-in R wrappers in ldsr_b200.R:
  *     _ldsr_em_batch(series,group_series,held,fit_group,theta0,niter,tol,n_devices)   8
  *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans)                         8
+ *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
+ *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
  *
  * The reference's `matrix(0)` sentinel (a 1x1 matrix, EM.cpp:50,71) is mapped to a NULL u/v
  * pointer here, so callers keep passing what they pass today.
@@ -275,6 +277,52 @@ SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS
 }
 
 /* same shape as src/RcppExports.cpp:132-148 */
+/* General state dimension (beyond the reference): theta holds R matrices, which are column-major;
+ * the ABI wants row-major blocks. */
+static void put_rowmajor(SEXP m, int rows, int cols, double *out) {
+    if (Rf_nrows(m) * Rf_ncols(m) != rows * cols) Rf_error("ldsr: theta block has the wrong size");
+    const double *x = REAL(m);
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++) out[i * cols + j] = x[j * rows + i];
+}
+SEXP _ldsr_smoother_d(SEXP y, SEXP u, SEXP v, SEXP theta, SEXP stdlik, SEXP methodS) {
+    char err[512] = "";
+    const int T = Rf_ncols(y);
+    int p = 0, q = 0;
+    const double *up = input_ptr(u, T, &p), *vp = input_ptr(v, T, &q);
+    if (!up) p = 0;
+    if (!vp) q = 0;
+    const int d = Rf_nrows(list_get(theta, "A"));
+    const int tl = 2 * d * d + d * p + d + q + 1 + d + d * d;
+    double *th = (double *)R_alloc((size_t)tl, sizeof(double)), *o = th;
+    put_rowmajor(list_get(theta, "A"), d, d, o); o += d * d;
+    if (p) { put_rowmajor(list_get(theta, "B"), d, p, o); o += d * p; }
+    put_rowmajor(list_get(theta, "C"), 1, d, o); o += d;
+    if (q) { put_rowmajor(list_get(theta, "D"), 1, q, o); o += q; }
+    put_rowmajor(list_get(theta, "Q"), d, d, o); o += d * d;
+    *o++ = REAL(list_get(theta, "R"))[0];
+    put_rowmajor(list_get(theta, "mu1"), d, 1, o); o += d;
+    put_rowmajor(list_get(theta, "V1"), d, d, o);
+    double *X = (double *)R_alloc((size_t)T * d, sizeof(double));
+    double *V = (double *)R_alloc((size_t)T * d * d, sizeof(double));
+    double *Y = (double *)R_alloc((size_t)T, sizeof(double)), lik;
+    check(ldsr_smoother_d_batch(0, d, T, p, q, REAL(y), up, vp, 1, th, tl, Rf_asLogical(stdlik), Rf_asInteger(methodS), 0,
+                                X, V, Y, &lik, NULL, err, sizeof err),
+          err);
+    const char *nm[] = {"X", "Y", "V", "lik", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    SEXP Xm = PROTECT(Rf_allocMatrix(REALSXP, d, T)); /* d x T: X[t][i] is already column-major */
+    memcpy(REAL(Xm), X, sizeof(double) * (size_t)T * d);
+    SEXP Vm = PROTECT(Rf_allocMatrix(REALSXP, d * d, T)); /* column t = vec(V_t) (symmetric) */
+    memcpy(REAL(Vm), V, sizeof(double) * (size_t)T * d * d);
+    SET_VECTOR_ELT(out, 0, Xm);
+    SET_VECTOR_ELT(out, 1, mat1(Y, T));
+    SET_VECTOR_ELT(out, 2, Vm);
+    SET_VECTOR_ELT(out, 3, Rf_ScalarReal(lik));
+    UNPROTECT(3);
+    return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_Kalman_smoother", (DL_FUNC)&_ldsr_Kalman_smoother, 5},
     {"_ldsr_Mstep", (DL_FUNC)&_ldsr_Mstep, 4},
@@ -282,6 +330,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_propagate", (DL_FUNC)&_ldsr_propagate, 5},
     {"_ldsr_em_batch", (DL_FUNC)&_ldsr_em_batch, 8},
     {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 8},
+    {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
     {NULL, NULL, 0}};
 
 void R_init_ldsr(DllInfo *dll) {
