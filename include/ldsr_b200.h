@@ -179,6 +179,18 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
  * concatenates results -- there is no collective on the data path. */
 int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, char *errbuf, int errlen);
 
+/* ---- cross-validation skill metrics: the step right after the EM hot path in cvLDS -------------
+ * Replaces `mapply(calculate_metrics, sim = Ycv, z = Z, MoreArgs = list(obs = target))`
+ * (R/LDS_reconstruction.R:395) = calculate_metrics (R/utils.R:56-70) over NSE, RE, nRMSE, corr, KGE
+ * of src/utils.cpp:13-97, for all folds in one launch (one warp per fold).
+ *   sim [n_folds][n]: cross-validated output per fold; exp_trans != 0 applies exp() first
+ *                     (transform = 'log', R/LDS_reconstruction.R:385-386)
+ *   obs [n]: target, NaN allowed (dropped from the calibration part)
+ *   z_ptr [n_folds+1], z_idx: CSR of each fold's hold-out indices, 1-BASED as in R
+ *   out [n_folds][5]: R2, RE, CE, nRMSE, KGE (the column order of metrics.dist) */
+int ldsr_cv_metrics_batch(int device, int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
+                          const int *z_idx, int exp_trans, double *out, char *errbuf, int errlen);
+
 /* ---- general state dimension, long series (beyond the reference) ----------------------------
  * The reference is scalar-state only (src/EM.cpp:20 "matrix inversion is treated as /").
  * BASELINE.json's config 5 (d = 4, 20 proxies, T = 100 000) asks for the E-step of a d-dimensional

@@ -19,7 +19,7 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
-           "ldsr_smoother_d_batch")
+           "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch")
 
 
 class LdsrError(RuntimeError):
@@ -381,3 +381,22 @@ def smoother_d(d, y, u, v, theta, stdlik=True, method=1, chunk=0, device=0, want
                                      C.byref(ms), err, 512)
     _check(rc, err)
     return dict(X=X, V=V, Y=Y, lik=lik, kernel_ms=ms.value)
+
+
+METRIC_NAMES = ("R2", "RE", "CE", "nRMSE", "KGE")
+
+
+def cv_metrics(sim, obs, Z, exp_trans=False, device=0):
+    """ldsr_cv_metrics_batch: calculate_metrics (R/utils.R:56-70) for every fold on the device.
+    sim [n_folds, n]; obs [n]; Z: list of 1-based hold-out index vectors.  Returns [n_folds, 5]."""
+    sim = np.ascontiguousarray(sim, dtype=np.float64)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    nf, n = sim.shape
+    zp = np.zeros(nf + 1, dtype=np.int32)
+    zp[1:] = np.cumsum([len(z) for z in Z])
+    zi = np.ascontiguousarray(np.concatenate([np.asarray(z, dtype=np.int32) for z in Z]), dtype=np.int32)
+    out = np.empty((nf, 5))
+    err = C.create_string_buffer(512)
+    _check(lib().ldsr_cv_metrics_batch(int(device), int(n), int(nf), _d(sim), _d(obs), _i(zp), _i(zi),
+                                       int(bool(exp_trans)), _d(out), err, 512), err)
+    return out

@@ -380,9 +380,10 @@ def cvLDS(Qa, u, v, start_year, method="EM", transform="log", num_restarts=50, Z
         target = np.asarray(Qa["Qa"], dtype=float)
     else:
         target = obs
-    dist = [calculate_metrics(sim, target, z) for sim, z in zip(Ycv, Z)]
-    keys = ("R2", "RE", "CE", "nRMSE", "KGE")
-    metrics_dist = {k: np.array([d[k] for d in dist]) for k in keys}
+    # mapply(calculate_metrics, ...) (:395) for all folds in one device call
+    keys = _lib.METRIC_NAMES
+    dist = _lib.cv_metrics(np.stack(Ycv), target, Z)
+    metrics_dist = {k: dist[:, j].copy() for j, k in enumerate(keys)}
     return dict(metrics_dist=metrics_dist, metrics={k: float(np.mean(metrics_dist[k])) for k in keys},
                 target=dict(year=qyears, y=target), Ycv=np.stack(Ycv, axis=1), Z=Z,
                 best=r["best"], lik=r["lik"], iters=r["iters"])
@@ -411,3 +412,23 @@ def one_LDS_rep(rep_num, theta, u=None, v=None, years=None, mu=0.0, exp_trans=Tr
     out = LDS_rep(theta, u, v, years, 1, mu, exp_trans, seed=seed + rep_num, z=None if z is None else z[None, :])
     out["rep"][:] = rep_num
     return out
+
+
+def Kalman_smoother_d(y, u, v, theta, stdlik=True, method=1):
+    """Kalman / RTS smoother for a state of dimension d = nrow(theta$A) in 2..4 (d = 1 works too).
+    No counterpart in the reference, whose state is scalar (src/EM.cpp:20); same conventions as
+    Kalman_smoother (src/EM.cpp:22-131).  theta: dict(A [d,d], B [d,p], C [d], D [q], Q [d,d], R, mu1 [d],
+    V1 [d,d]).  method 1 = associative scan over time, 0 = sequential.  Returns dict(X [d,T], Y [T],
+    V [T,d,d], lik) -- mirrors ldsr_b200.R::Kalman_smoother_d."""
+    A = np.atleast_2d(np.asarray(theta["A"], dtype=float))
+    d = A.shape[0]
+    blocks = [A.ravel()]
+    if u is not None:
+        blocks.append(np.asarray(theta["B"], dtype=float).reshape(d, -1).ravel())
+    blocks.append(np.asarray(theta["C"], dtype=float).ravel())
+    if v is not None:
+        blocks.append(np.asarray(theta["D"], dtype=float).ravel())
+    blocks += [np.asarray(theta["Q"], dtype=float).reshape(d, d).ravel(), [float(np.ravel(theta["R"])[0])],
+               np.asarray(theta["mu1"], dtype=float).ravel(), np.asarray(theta["V1"], dtype=float).reshape(d, d).ravel()]
+    r = _lib.smoother_d(d, np.ravel(y), u, v, np.concatenate(blocks), stdlik=stdlik, method=method)
+    return dict(X=r["X"][0].T, Y=r["Y"][0], V=r["V"][0], lik=float(r["lik"][0]))

@@ -252,6 +252,72 @@ __global__ void build_tasks_kernel(const SeriesDev *series, int n_series, const 
     }
 }
 
+
+// ---- cross-validation skill metrics (the epilogue of cvLDS) --------------------------------------
+// calculate_metrics (R/utils.R:56-70) with the definitions of src/utils.cpp:13-97, one warp per
+// fold: R2 = NSE on the calibration part, RE, CE = NSE on the hold-out, nRMSE (normalised by
+// mean(obs)), KGE.  held [n_folds][n] marks the hold-out points; sim is exp()'d first when exp_trans
+// (cvLDS with transform = 'log', R/LDS_reconstruction.R:385-386).  Two passes (means, then moments
+// about the means) with shuffle reductions.
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__global__ void cv_metrics_kernel(int n, int n_folds, const double *__restrict__ sim, const double *__restrict__ obs,
+                                  const unsigned char *__restrict__ held, int exp_trans, double *__restrict__ out) {
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n_folds) return;
+    const double *__restrict__ s = sim + (size_t)f * n;
+    const unsigned char *__restrict__ h = held + (size_t)f * n;
+    double so = 0, sto = 0, nt = 0, svs = 0, svo = 0, nv = 0, no = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double o = obs[i], x = exp_trans ? exp(s[i]) : s[i];
+        const bool fin = o == o;
+        if (fin) {
+            so += o;
+            no += 1;
+        }
+        if (h[i]) {
+            svs += x;
+            svo += o;
+            nv += 1;
+        } else if (fin) {
+            sto += o;
+            nt += 1;
+        }
+    }
+    so = warp_sum(so), no = warp_sum(no), sto = warp_sum(sto), nt = warp_sum(nt);
+    svs = warp_sum(svs), svo = warp_sum(svo), nv = warp_sum(nv);
+    const double norm = so / no, yc = sto / nt, mvs = svs / nv, mvo = svo / nv;
+    double t_rss = 0, t_tss = 0, v_rss = 0, v_tss = 0, v_tssc = 0, v_ss = 0, v_sc = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double o = obs[i], x = exp_trans ? exp(s[i]) : s[i];
+        if (h[i]) {
+            v_rss = fma(o - x, o - x, v_rss);
+            v_tss = fma(o - mvo, o - mvo, v_tss);
+            v_tssc = fma(o - yc, o - yc, v_tssc);
+            v_ss = fma(x - mvs, x - mvs, v_ss);
+            v_sc = fma(x - mvs, o - mvo, v_sc);
+        } else if (o == o) {
+            t_rss = fma(o - x, o - x, t_rss);
+            t_tss = fma(o - yc, o - yc, t_tss);
+        }
+    }
+    t_rss = warp_sum(t_rss), t_tss = warp_sum(t_tss), v_rss = warp_sum(v_rss), v_tss = warp_sum(v_tss);
+    v_tssc = warp_sum(v_tssc), v_ss = warp_sum(v_ss), v_sc = warp_sum(v_sc);
+    if (lane == 0) {
+        const double sg = sqrt(v_tss / (nv - 1)), sgh = sqrt(v_ss / (nv - 1));
+        const double r = v_sc / (nv - 1) / (sg * sgh), a = sgh / sg, b = mvs / mvo;
+        double *o5 = out + (size_t)f * 5;
+        o5[0] = 1.0 - t_rss / t_tss;
+        o5[1] = 1.0 - v_rss / v_tssc;
+        o5[2] = 1.0 - v_rss / v_tss;
+        o5[3] = sqrt(v_rss / nv) / norm;
+        o5[4] = 1.0 - sqrt((r - 1) * (r - 1) + (a - 1) * (a - 1) + (b - 1) * (b - 1));
+    }
+}
+
 // [rows][cols] -> [cols][rows] through a padded shared-memory tile.
 __global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int cols) {
     __shared__ double tile[32][33];

@@ -1264,6 +1264,49 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
     return report(e, errbuf, errlen);
 }
 
+int ldsr_cv_metrics_batch(int device, int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
+                          const int *z_idx, int exp_trans, double *out, char *errbuf, int errlen) {
+    auto run = [&]() -> Err {
+        if (n < 2 || n_folds < 1) return fail(LDSR_ERR_ARG, "need n >= 2 and n_folds >= 1");
+        if (!sim || !obs || !z_ptr || !z_idx || !out) return fail(LDSR_ERR_ARG, "a required pointer is NULL");
+        std::vector<unsigned char> held((size_t)n_folds * n, 0);
+        for (int f = 0; f < n_folds; f++) {
+            if (z_ptr[f + 1] < z_ptr[f]) return fail(LDSR_ERR_ARG, "z_ptr not monotone at fold %d", f);
+            for (int k = z_ptr[f]; k < z_ptr[f + 1]; k++) {
+                const int i = z_idx[k] - 1; // R indices are 1-based
+                if (i < 0 || i >= n) return fail(LDSR_ERR_ARG, "fold %d: hold-out index %d outside 1..%d", f, z_idx[k], n);
+                held[(size_t)f * n + i] = 1;
+            }
+        }
+        if (ldsr_device_count() < 1) return fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+        CU(cudaSetDevice(device));
+        double *d_sim = nullptr, *d_obs = nullptr, *d_out = nullptr;
+        unsigned char *d_held = nullptr;
+        struct Guard {
+            double *&a, *&b, *&c;
+            unsigned char *&h;
+            ~Guard() {
+                cudaFree(a);
+                cudaFree(b);
+                cudaFree(c);
+                cudaFree(h);
+            }
+        } guard{d_sim, d_obs, d_out, d_held};
+        CU(cudaMalloc(&d_sim, sizeof(double) * (size_t)n_folds * n));
+        CU(cudaMalloc(&d_obs, sizeof(double) * n));
+        CU(cudaMalloc(&d_out, sizeof(double) * (size_t)n_folds * 5));
+        CU(cudaMalloc(&d_held, held.size()));
+        CU(cudaMemcpy(d_sim, sim, sizeof(double) * (size_t)n_folds * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_obs, obs, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_held, held.data(), held.size(), cudaMemcpyHostToDevice));
+        cv_metrics_kernel<<<(n_folds + 3) / 4, 128>>>(n, n_folds, d_sim, d_obs, d_held, exp_trans, d_out);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out, d_out, sizeof(double) * (size_t)n_folds * 5, cudaMemcpyDeviceToHost));
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
+}
+
 int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *y, const double *u, const double *v,
                           int n_fits, const double *theta, int theta_stride, int stdlik, int method, int chunk,
                           double *X, double *V, double *Y, double *lik, double *kernel_ms, char *errbuf,

@@ -123,3 +123,14 @@ Kalman_smoother_d <- function(y, u, v, theta, stdlik = TRUE, method = 1L) {
   if (is.null(v)) v <- matrix(0)
   .Call(`_ldsr_smoother_d`, y, u, v, theta, stdlik, as.integer(method))
 }
+
+
+#' All folds' skill metrics in one device call; replaces
+#' `mapply(calculate_metrics, sim = Ycv, z = Z, MoreArgs = list(obs = target))` in cvLDS
+#' (R/LDS_reconstruction.R:395).  Ycv: list of per-fold vectors (or an n x n_folds matrix).
+cv_metrics_batched <- function(Ycv, Z, target, exp_trans = FALSE) {
+  if (is.list(Ycv)) Ycv <- do.call(cbind, Ycv)
+  m <- .Call(`_ldsr_cv_metrics`, Ycv, as.numeric(target), lapply(Z, as.integer), exp_trans)
+  rownames(m) <- c("R2", "RE", "CE", "nRMSE", "KGE")
+  m
+}

@@ -14,6 +14,7 @@
  * and add the batched ones used by the drop-in R wrappers in ldsr_b200.R:
  *     _ldsr_em_batch(series,group_series,held,fit_group,theta0,niter,tol,n_devices)   8
  *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans)                         8
+ *     _ldsr_cv_metrics(Ycv,target,Z,exp_trans)                                        4
  *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
  *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
  *
@@ -277,6 +278,29 @@ SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS
 }
 
 /* same shape as src/RcppExports.cpp:132-148 */
+/* mapply(calculate_metrics, sim = Ycv, z = Z, MoreArgs = list(obs = target)) in one call
+ * (R/LDS_reconstruction.R:395): Ycv is an n x n_folds matrix, Z a list of integer vectors. */
+SEXP _ldsr_cv_metrics(SEXP Ycv, SEXP target, SEXP Z, SEXP expS) {
+    char err[512] = "";
+    const int n = Rf_nrows(Ycv), nf = Rf_ncols(Ycv);
+    if ((int)XLENGTH(Z) != nf) Rf_error("ldsr: one fold per column of Ycv");
+    int *zp = (int *)R_alloc((size_t)nf + 1, sizeof(int)), tot = 0;
+    zp[0] = 0;
+    for (int f = 0; f < nf; f++) {
+        tot += (int)XLENGTH(VECTOR_ELT(Z, f));
+        zp[f + 1] = tot;
+    }
+    int *zi = (int *)R_alloc((size_t)(tot > 0 ? tot : 1), sizeof(int));
+    for (int f = 0; f < nf; f++)
+        memcpy(zi + zp[f], INTEGER(VECTOR_ELT(Z, f)), sizeof(int) * (size_t)(zp[f + 1] - zp[f]));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 5, nf)); /* 5 x n_folds, like mapply's result */
+    check(ldsr_cv_metrics_batch(0, n, nf, REAL(Ycv), REAL(target), zp, zi, Rf_asLogical(expS), REAL(out), err,
+                                sizeof err),
+          err);
+    UNPROTECT(1);
+    return out;
+}
+
 /* General state dimension (beyond the reference): theta holds R matrices, which are column-major;
  * the ABI wants row-major blocks. */
 static void put_rowmajor(SEXP m, int rows, int cols, double *out) {
@@ -331,6 +355,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_em_batch", (DL_FUNC)&_ldsr_em_batch, 8},
     {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 8},
     {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
+    {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
     {NULL, NULL, 0}};
 
 void R_init_ldsr(DllInfo *dll) {

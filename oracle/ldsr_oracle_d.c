@@ -177,3 +177,97 @@ int ldsr_oracle_smoother_d(int d, int T, int p, int q, const double *y, const do
     free(Xp); free(Vp); free(Xu); free(Vu);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Cross-validation skill metrics (the step right after the EM hot path in cvLDS).
+ * Restates calculate_metrics (/root/reference/R/utils.R:56-70) with the metric definitions of
+ * /root/reference/src/utils.cpp:13-97 (NSE :13-19, nRMSE :35-38, corr :48-56, KGE :67-77,
+ * RE :93-97).  PINNED: tests/test_oracle_golden.py checks it against the reference's own stored
+ * cvLDS result (R/sysdata.rda::NPcv: Ycv, Z, target -> metrics.dist, 30 folds x 5 metrics).
+ *   sim    [n_folds][n]  model output per fold (already back-transformed if exp_trans == 0)
+ *   obs    [n]           target (NaN allowed: dropped from the calibration part, utils.R:58-59)
+ *   z_ptr/z_idx          CSR of the 1-based hold-out indices of every fold
+ *   out    [n_folds][5]  R2, RE, CE, nRMSE, KGE
+ * exp_trans != 0: sim is exp()'d first (cvLDS with transform = 'log', LDS_reconstruction.R:385-386).
+ * --------------------------------------------------------------------------------------------- */
+static double mean_of(const double *x, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += x[i];
+    return s / n;
+}
+static double sd_of(const double *x, int n) {
+    const double m = mean_of(x, n);
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += (x[i] - m) * (x[i] - m);
+    return sqrt(s / (n - 1));
+}
+static double nse_of(const double *yhat, const double *y, int n) { /* utils.cpp:13-19 */
+    const double ybar = mean_of(y, n);
+    double rss = 0.0, tss = 0.0;
+    for (int i = 0; i < n; i++) {
+        rss += (y[i] - yhat[i]) * (y[i] - yhat[i]);
+        tss += (y[i] - ybar) * (y[i] - ybar);
+    }
+    return 1.0 - rss / tss;
+}
+int ldsr_oracle_cv_metrics(int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
+                           const int *z_idx, int exp_trans, double *out) {
+    double *s = malloc(sizeof(double) * n), *ts = malloc(sizeof(double) * n), *to = malloc(sizeof(double) * n);
+    double *vs = malloc(sizeof(double) * n), *vo = malloc(sizeof(double) * n);
+    char *held = malloc(n);
+    if (!s || !ts || !to || !vs || !vo || !held) return 2;
+    double osum = 0.0;
+    int on = 0;
+    for (int i = 0; i < n; i++)
+        if (!isnan(obs[i])) {
+            osum += obs[i];
+            on++;
+        }
+    const double norm = osum / on; /* norm.fun = mean(obs, na.rm = TRUE), utils.R:67 */
+    for (int f = 0; f < n_folds; f++) {
+        for (int i = 0; i < n; i++) s[i] = exp_trans ? exp(sim[(size_t)f * n + i]) : sim[(size_t)f * n + i];
+        memset(held, 0, n);
+        int nv = 0, nt = 0;
+        for (int k = z_ptr[f]; k < z_ptr[f + 1]; k++) {
+            const int i = z_idx[k] - 1;
+            if (i < 0 || i >= n) { free(s); free(ts); free(to); free(vs); free(vo); free(held); return 1; }
+            held[i] = 1;
+            vs[nv] = s[i];
+            vo[nv] = obs[i];
+            nv++;
+        }
+        for (int i = 0; i < n; i++)
+            if (!held[i] && !isnan(obs[i])) {
+                ts[nt] = s[i];
+                to[nt] = obs[i];
+                nt++;
+            }
+        double *o = out + (size_t)f * 5;
+        o[0] = nse_of(ts, to, nt);                                   /* R2: NSE on the calibration part */
+        {                                                            /* RE, utils.cpp:93-97 */
+            const double yc = mean_of(to, nt);
+            double rss = 0.0, tss = 0.0;
+            for (int i = 0; i < nv; i++) {
+                rss += (vo[i] - vs[i]) * (vo[i] - vs[i]);
+                tss += (vo[i] - yc) * (vo[i] - yc);
+            }
+            o[1] = 1.0 - rss / tss;
+        }
+        o[2] = nse_of(vs, vo, nv);                                   /* CE */
+        {                                                            /* nRMSE, utils.cpp:35-38 */
+            double ss = 0.0;
+            for (int i = 0; i < nv; i++) ss += (vo[i] - vs[i]) * (vo[i] - vs[i]);
+            o[3] = sqrt(ss / nv) / norm;
+        }
+        {                                                            /* KGE, utils.cpp:67-77 with corr :48-56 */
+            const double mu = mean_of(vo, nv), muh = mean_of(vs, nv), sg = sd_of(vo, nv), sgh = sd_of(vs, nv);
+            double r = 0.0;
+            for (int i = 0; i < nv; i++) r += (vs[i] - muh) / sgh * ((vo[i] - mu) / sg);
+            r /= (nv - 1);
+            const double a = sgh / sg, b = muh / mu;
+            o[4] = 1.0 - sqrt((r - 1) * (r - 1) + (a - 1) * (a - 1) + (b - 1) * (b - 1));
+        }
+    }
+    free(s); free(ts); free(to); free(vs); free(vo); free(held);
+    return 0;
+}

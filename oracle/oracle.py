@@ -31,7 +31,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         for name in ("kalman_smoother", "mstep", "em", "select", "em_batch", "propagate", "rep",
-                     "max_threads", "smoother_d"):
+                     "max_threads", "smoother_d", "cv_metrics"):
             getattr(_lib, "ldsr_oracle_" + name).restype = C.c_int
     return _lib
 
@@ -226,3 +226,22 @@ def smoother_d(d, y, u, v, theta, stdlik=True):
     if rc != 0:
         raise RuntimeError("ldsr_oracle_smoother_d failed: %d" % rc)
     return dict(X=X, V=V, Y=Y, lik=lik.value)
+
+
+METRIC_NAMES = ("R2", "RE", "CE", "nRMSE", "KGE")
+
+
+def cv_metrics(sim, obs, Z, exp_trans=False):
+    """calculate_metrics for every fold (R/utils.R:56-70, src/utils.cpp:13-97).  sim [n_folds, n];
+    obs [n]; Z list of 1-based index vectors.  Returns [n_folds, 5] in METRIC_NAMES order."""
+    sim = np.ascontiguousarray(sim, dtype=np.float64)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    nf, n = sim.shape
+    zp = np.zeros(nf + 1, dtype=np.int32)
+    zp[1:] = np.cumsum([len(z) for z in Z])
+    zi = np.concatenate([np.asarray(z, dtype=np.int32) for z in Z]).astype(np.int32)
+    out = np.empty((nf, 5))
+    rc = lib().ldsr_oracle_cv_metrics(int(n), int(nf), _d(sim), _d(obs), _i(zp), _i(zi), int(bool(exp_trans)), _d(out))
+    if rc != 0:
+        raise RuntimeError("ldsr_oracle_cv_metrics failed: %d" % rc)
+    return out

@@ -313,3 +313,26 @@ def test_poll_callback_interrupts():
         _lib.em_batch([dict(y=y, u=u, v=u)], [0], None, np.zeros(8, dtype=int), th0, 1000, 0.0, chunk_iters=10,
                       poll=lambda: calls.append(1) or len(calls) >= 3)
     assert e.value.code == _lib.ERR_INTERRUPTED and len(calls) == 3
+
+
+def test_cv_metrics_kernel_matches_the_stored_cvLDS_result():
+    # R/sysdata.rda::NPcv: Ycv, Z, target -> metrics.dist (30 folds x 5), the reference's own numbers
+    g = data.load("npcv.json")
+    n = len(g["target"]["y"])
+    Y = np.array(g["Ycv"]["Y"]).reshape(-1, n)
+    obs = np.array(g["target"]["y"])
+    m = _lib.cv_metrics(Y, obs, g["Z"])
+    for j, name in enumerate(_lib.METRIC_NAMES):
+        assert np.allclose(m[:, j], np.array(g["metrics_dist"][name]), rtol=1e-10, atol=1e-12), name
+    assert np.allclose(_lib.cv_metrics(np.log(Y), obs, g["Z"], exp_trans=True), m, rtol=1e-12)
+    # against the oracle on ragged folds, NaN in obs, n not a multiple of 32
+    rng = np.random.default_rng(8)
+    n2, nf = 211, 37
+    obs2 = np.exp(rng.standard_normal(n2))
+    obs2[rng.choice(n2, 9, replace=False)] = np.nan
+    ok = np.nonzero(~np.isnan(obs2))[0] + 1
+    Z = [np.sort(rng.choice(ok, rng.integers(3, 40), replace=False)) for _ in range(nf)]
+    sim = np.exp(np.log(np.nan_to_num(obs2, nan=1.0)) + 0.3 * rng.standard_normal((nf, n2)))
+    assert np.allclose(_lib.cv_metrics(sim, obs2, Z), O.cv_metrics(sim, obs2, Z), rtol=1e-11, atol=1e-13)
+    with pytest.raises(_lib.LdsrError):
+        _lib.cv_metrics(sim, obs2, [np.array([0])] * nf)  # R indices are 1-based

@@ -117,3 +117,21 @@ def test_argument_errors():
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(_lib.LdsrError):
         _lib.smoother_d(2, y, None, None, np.zeros(3))  # theta too short
+
+
+def test_api_mirror_kalman_smoother_d():
+    import ldsr_b200 as L
+    rng = np.random.default_rng(3)
+    d, p, q, T = 2, 3, 2, 120
+    y, u, v, th = random_model(rng, d, p, q, T)
+    o = O.smoother_d(d, y, u, v, th)
+    k = 0
+    blocks = {}
+    for name, shape in (("A", (d, d)), ("B", (d, p)), ("C", (d,)), ("D", (q,)), ("Q", (d, d)), ("R", (1,)),
+                        ("mu1", (d,)), ("V1", (d, d))):
+        n = int(np.prod(shape))
+        blocks[name] = th[k:k + n].reshape(shape)
+        k += n
+    g = L.Kalman_smoother_d(y, u, v, blocks)
+    assert g["X"].shape == (d, T) and np.max(np.abs(g["X"].T - o["X"])) < 1e-9
+    assert abs(g["lik"] - o["lik"]) < 1e-10 * max(1.0, abs(o["lik"]))

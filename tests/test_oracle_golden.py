@@ -144,3 +144,20 @@ def test_general_d_reduces_to_1d():
         assert np.max(np.abs(od["V"][:, 0, 0] - o1["V"])) < 1e-12
         assert np.max(np.abs(od["Y"] - o1["Y"])) < 1e-12
     assert abs(od["lik"] - (-11.678657)) < 1e-6  # tests/testthat/test-LDS-EM.R:26 through the d = 1 path
+
+
+def test_cv_metrics_match_the_stored_cvLDS_result():
+    """The reference's own stored cvLDS output (R/sysdata.rda::NPcv) holds, for 30 folds of 12 points,
+    the cross-validated flows Ycv, the folds Z and the five skill metrics of every fold: a golden
+    vector for calculate_metrics (R/utils.R:56-70) + src/utils.cpp:13-97."""
+    g = data.load("npcv.json")
+    n = len(g["target"]["y"])
+    Y = np.array(g["Ycv"]["Y"]).reshape(-1, n)
+    assert Y.shape[0] == len(g["Z"]) == 30
+    m = O.cv_metrics(Y, np.array(g["target"]["y"]), g["Z"])
+    for j, name in enumerate(O.METRIC_NAMES):
+        want = np.array(g["metrics_dist"][name])
+        assert np.allclose(m[:, j], want, rtol=1e-10, atol=1e-12), (name, np.max(np.abs(m[:, j] - want)))
+    # exp_trans path: log-space input gives the same numbers
+    m2 = O.cv_metrics(np.log(Y), np.array(g["target"]["y"]), g["Z"], exp_trans=True)
+    assert np.allclose(m2, m, rtol=1e-12)
