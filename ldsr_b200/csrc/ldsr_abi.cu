@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -67,6 +68,44 @@ class DevicePool {
     ~DevicePool() {
         cudaSetDevice(device_);
         for (auto &b : blocks_) cudaFree(b.ptr);
+        for (auto &b : pinned_) cudaFreeHost(b.ptr);
+        for (cudaStream_t s : streams_) cudaStreamDestroy(s);
+    }
+    // pinned host blocks and streams are cached the same way: a host-buffer call (ldsr_em_batch)
+    // creates and destroys a plan every time, and cudaMallocHost / cudaStreamCreate are not cheap
+    cudaError_t alloc_pinned(size_t bytes, void **out) {
+        bytes = std::max<size_t>((bytes + 255) & ~size_t(255), 256);
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &b : pinned_)
+            if (!b.used && b.size >= bytes) {
+                b.used = true;
+                *out = b.ptr;
+                return cudaSuccess;
+            }
+        void *p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) return e;
+        pinned_.push_back({p, bytes, true});
+        *out = p;
+        return cudaSuccess;
+    }
+    void release_pinned(void *p) {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &b : pinned_)
+            if (b.ptr == p) b.used = false;
+    }
+    cudaError_t get_stream(cudaStream_t *out) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!streams_.empty()) {
+            *out = streams_.back();
+            streams_.pop_back();
+            return cudaSuccess;
+        }
+        return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+    }
+    void put_stream(cudaStream_t s) {
+        std::lock_guard<std::mutex> lk(mu_);
+        streams_.push_back(s);
     }
     cudaError_t alloc(size_t bytes, void **out) {
         bytes = std::max<size_t>((bytes + 255) & ~size_t(255), 256);
@@ -103,7 +142,8 @@ class DevicePool {
     };
     int device_;
     std::mutex mu_;
-    std::vector<Block> blocks_;
+    std::vector<Block> blocks_, pinned_;
+    std::vector<cudaStream_t> streams_;
 };
 
 } // namespace ldsr
@@ -116,6 +156,7 @@ struct ldsr_ctx {
 };
 
 // ---- plan -----------------------------------------------------------------------------------
+constexpr size_t COUNTS_CAP = 256; // (tasks, live fits) per chunk: room for 128 chunks without regrowing
 struct ldsr_plan {
     int device = 0;
     int n_sm = 148;
@@ -150,7 +191,7 @@ struct ldsr_plan {
     double *d_liks = nullptr;
     size_t liks_cap = 0;
     int *d_active = nullptr, *d_task_off = nullptr, *d_n_live = nullptr, *d_counts = nullptr;
-    size_t counts_cap = 8;
+    size_t counts_cap = COUNTS_CAP;
     int4 *d_tasks = nullptr;
     int max_tasks = 0;
     unsigned long long *d_sum = nullptr;
@@ -183,8 +224,8 @@ struct ldsr_plan {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         for (void *p : allocs) pool->release(p);
-        if (h_counts) cudaFreeHost(h_counts);
-        if (stream) cudaStreamDestroy(stream);
+        if (h_counts) pool->release_pinned(h_counts);
+        if (stream) pool->put_stream(stream);
     }
 };
 
@@ -268,8 +309,12 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
         P->own_pool.reset(new DevicePool(device));
         P->pool = P->own_pool.get();
     }
-    CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
-    CU(cudaMallocHost(&P->h_counts, 8 * sizeof(int)));
+    CU(P->pool->get_stream(&P->stream));
+    {
+        void *hp = nullptr;
+        CU(P->pool->alloc_pinned(COUNTS_CAP * sizeof(int), &hp));
+        P->h_counts = static_cast<int *>(hp);
+    }
     CU(cudaDeviceGetAttribute(&P->n_sm, cudaDevAttrMultiProcessorCount, device));
 
     const int ns = b->n_series, ng = b->n_groups, nf = b->n_fits;
@@ -421,7 +466,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->dalloc(&P->d_active, nf)).ok()) return e;
     if (!(e = P->dalloc(&P->d_n_live, ns)).ok()) return e;
     if (!(e = P->dalloc(&P->d_task_off, ns + 1)).ok()) return e;
-    if (!(e = P->dalloc(&P->d_counts, 8)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_counts, COUNTS_CAP)).ok()) return e;
     if (!(e = P->dalloc(&P->d_sum, 1)).ok()) return e;
     P->max_tasks = nf / 32 + ns + 1; // the time-split kernel takes 32 fits per CTA
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
@@ -449,7 +494,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     merge_status_kernel<<<(ng + 127) / 128, 128, 0, P->stream>>>(P->d_series, P->d_sconst, P->d_g_series, ng, PQ,
                                                                  P->d_g_status);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(P->stream)); // host vectors above go out of scope
+    // No synchronisation here: cudaMemcpyAsync from pageable memory returns once the source has
+    // been staged, so the host vectors above may go out of scope; errors surface at the first sync.
     *out = P.release();
     return Err();
 }
@@ -557,9 +603,11 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         Err e = P->dalloc(&P->d_counts, (size_t)2 * max_chunks);
         if (!e.ok()) return e;
         P->counts_cap = 2 * max_chunks;
-        if (P->h_counts) cudaFreeHost(P->h_counts);
+        if (P->h_counts) P->pool->release_pinned(P->h_counts);
         P->h_counts = nullptr;
-        CU(cudaMallocHost(&P->h_counts, (size_t)2 * max_chunks * sizeof(int)));
+        void *hp = nullptr;
+        CU(P->pool->alloc_pinned((size_t)2 * max_chunks * sizeof(int), &hp));
+        P->h_counts = static_cast<int *>(hp);
     }
     const size_t ck_need = (mode == 2 || use_split) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
     if (P->ckpt_cap < ck_need) {
@@ -660,7 +708,6 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         if (!(e = P->upload(&P->d_job_group, jg)).ok()) return e;
         if (!(e = P->upload(&P->d_job_row, jr)).ok()) return e;
         P->stream = keep;
-        CU(cudaStreamSynchronize(st));
     }
     SmootherParams sp;
     sp.series = P->d_series;
@@ -831,13 +878,30 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
 
     // single device, whole batch: no sub-batch copies
     if (nd == 1) {
+        // LDSR_TIMING=1 (development): wall-clock split of the host-buffer call on stderr
+        static const bool timing = std::getenv("LDSR_TIMING") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) {
+            return std::chrono::duration<double, std::milli>(c - a).count();
+        };
+        const auto t0 = now();
         ldsr_plan *P = nullptr;
         e = plan_build(b, ctx->devices[0], ctx->pools[0].get(), &P);
         if (!e.ok()) return e;
-        std::unique_ptr<ldsr_plan> guard(P);
-        e = plan_em(P, niter, tol, opt, nullptr, want_liks, nullptr, nullptr);
-        if (!e.ok()) return e;
-        return plan_fetch(P, out);
+        const auto t1 = now();
+        {
+            std::unique_ptr<ldsr_plan> guard(P);
+            e = plan_em(P, niter, tol, opt, nullptr, want_liks, nullptr, nullptr);
+            if (!e.ok()) return e;
+            const auto t2 = now();
+            e = plan_fetch(P, out);
+            const auto t3 = now();
+            guard.reset();
+            if (timing)
+                std::fprintf(stderr, "ldsr_em_batch: build %.3f ms, em %.3f ms, fetch %.3f ms, destroy %.3f ms\n",
+                             ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
+        }
+        return e;
     }
 
     // ---- shard groups over devices (no data-path collective: a group's restarts stay together)
