@@ -13,7 +13,7 @@
  *     _ldsr_propagate(theta,u,v,y,stdlik)         5
  * and add the batched ones used by the drop-in R wrappers in ldsr_b200.R:
  *     _ldsr_em_batch(series,group_series,held,fit_group,theta0,niter,tol,n_devices)   8
- *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans)                         8
+ *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans,z)                       9
  *     _ldsr_cv_metrics(Ycv,target,Z,exp_trans)                                        4
  *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
  *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
@@ -255,7 +255,7 @@ SEXP _ldsr_em_batch(SEXP series, SEXP group_series, SEXP held, SEXP fit_group, S
 
 /* LDS_rep (R/stochastics.R:58-63) on the device generator.  Returns a 3-column matrix
  * (simX, simY, simQ), rows replicate-major like rbindlist(lapply(...)). */
-SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS, SEXP muS, SEXP expS) {
+SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS, SEXP muS, SEXP expS, SEXP zS) {
     const int n = Rf_asInteger(nS), reps = Rf_asInteger(repsS);
     int p = 0, q = 0;
     const double *up = Rf_isNull(u) ? NULL : input_ptr(u, n, &p), *vp = Rf_isNull(u) || Rf_isNull(v) ? NULL : input_ptr(v, n, &q);
@@ -271,7 +271,10 @@ SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n * reps, 3));
     double *o = REAL(out);
     char err[512] = "";
-    check(ldsr_rep_batch(NULL, th, up, vp, n, p, q, reps, NULL, (unsigned long long)Rf_asReal(seedS), Rf_asReal(muS),
+    /* z: num_reps*(1+2n) standard normals drawn by R in one_LDS_rep's order (R/stochastics.R:23-26), or NULL */
+    const double *z = Rf_isNull(zS) ? NULL : REAL(zS);
+    if (z && XLENGTH(zS) != (R_xlen_t)reps * (1 + 2 * (R_xlen_t)n)) Rf_error("ldsr: z must hold num.reps*(1+2n) draws");
+    check(ldsr_rep_batch(NULL, th, up, vp, n, p, q, reps, z, (unsigned long long)Rf_asReal(seedS), Rf_asReal(muS),
                          Rf_asLogical(expS), o, o + (size_t)n * reps, o + 2 * (size_t)n * reps, err, sizeof err), err);
     UNPROTECT(1);
     return out;
@@ -353,7 +356,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_LDS_EM", (DL_FUNC)&_ldsr_LDS_EM, 6},
     {"_ldsr_propagate", (DL_FUNC)&_ldsr_propagate, 5},
     {"_ldsr_em_batch", (DL_FUNC)&_ldsr_em_batch, 8},
-    {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 8},
+    {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 9},
     {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
     {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
     {NULL, NULL, 0}};
