@@ -21,7 +21,8 @@ struct SeriesDev {
     long long blob_off;  // offset of the blob in the blob arena, in doubles (even)
     long long sconst_off; // -> TuuInv[PQ*PQ] in the constants arena
     int fit_begin, fit_end; // this series' contiguous range in the (internally sorted) fit table
-    int n_seg_pad;       // unused padding
+    int uwin_off;        // -> this series' window Gram blocks sum_{t in window} u_t u_t' in the uwin arena
+                         //    ([window][PQ*PQ] doubles, windows of SPLIT_UW steps; em_split_kernel.cuh)
 };
 
 // per-group constants (theta-independent M-step blocks, EM.cpp:158,161 restricted to the group's

@@ -26,6 +26,7 @@ struct EmParams {
     const SeriesDev *series;
     const double *blobs;
     const double *sconst;     // per series TuuInv
+    const double *uwin;       // per series, per window of SPLIT_UW steps: sum u u' (time-split kernel)
     const int *g_series;
     const unsigned *masks;    // per group observed-bit words
     const long long *g_mask_off;

@@ -42,13 +42,18 @@
 
 namespace ldsr {
 
-constexpr int SPLIT_NCH = 11; // per-piece values exchanged after P2
+constexpr int SPLIT_NCH = 10; // per-piece values exchanged after P2
 
 // number of M-step partial sums a warp publishes
 template <int PQ> __host__ __device__ constexpr int split_nstat() { return 11 + 3 * PQ; }
 
 // dynamic shared memory of em_split_kernel, in bytes, after the series blob
-__host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units) {
+// The Tx1u identity of smooth_word needs the unit's Horner vector W from P2, kept per U unit in
+// shared memory.  Narrow inputs only: at PQ = 10 it was measured slower (a PQ x PQ product per unit,
+// more spills; W would not fit shared memory and went through an L2-resident scratch): 1.38 -> 1.44 s
+// on the 480 000-fit job.
+__host__ __device__ constexpr bool split_w_in_smem(int pq) { return pq <= 4; }
+__host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units, int max_uunits) {
     size_t b = 0;
     b += (size_t)max_units * 3 * 32 * 8; // checkpoints
     b += (size_t)2 * nw * 4 * 32 * 8;    // variance maps of the pieces
@@ -57,6 +62,8 @@ __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units
     b += ch > st ? ch : st;                           // piece summaries, later the partial sums
     b += ((size_t)max_units * 4 + 15) & ~size_t(15); // unit table
     b += 128;                                        // piece bounds
+    b += (size_t)8 * 32 * 8;                         // closed-form variance-sum coefficients
+    if (split_w_in_smem(pq)) b += (size_t)max_uunits * pq * 32 * 8; // W of every U unit
     return b;
 }
 
@@ -317,28 +324,58 @@ __device__ __forceinline__ void forward_unit_basis(const Theta<PQ> &th, const Sp
 // ---- P2 over one unobserved unit ------------------------------------------------------------------
 template <int PQ, int UW>
 __device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const SplitConst<PQ, UW> &k,
-                                                   const double *__restrict__ useg, PieceFwd &c) {
+                                                   const double *__restrict__ useg, double *__restrict__ wk,
+                                                   PieceFwd &c) {
+    // zero-state response of the unit, sum_t A^(r-1-t) B u_t.  With KEEP_W it is formed as B . W with
+    // the Horner VECTOR W = sum_t A^(r-1-t) u_t, which P4 needs again (smooth_word) and costs one FMA
+    // per step less than dot-then-Horner.
+    constexpr bool KEEP_W = split_w_in_smem(PQ);
+    const double A4 = k.A2 * k.A2;
     double hh = 0.0;
+    double W[KEEP_W ? PQ : 1];
+    if (KEEP_W) {
+#pragma unroll
+        for (int i = 0; i < PQ; i++) W[i] = 0.0;
+    }
 #pragma unroll 1
     for (int b = 0; b < UW / 8; b++) {
-        // the 8 dot products are independent; the Horner sum runs as two chains of four
         double ur[8 * PQ];
         load_vec<8 * PQ>(useg + b * 8 * PQ, ur);
-        double Bu[8];
+        if (KEEP_W) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            double acc = 0.0;
+            for (int i = 0; i < PQ; i++) { // per component: two Horner chains of four steps
+                double lo = ur[i], hi = ur[4 * PQ + i];
 #pragma unroll
-            for (int i = 0; i < PQ; i++) acc = fma(th.B[i], ur[j * PQ + i], acc);
-            Bu[j] = acc;
+                for (int j = 1; j < 4; j++) {
+                    lo = fma(k.A, lo, ur[j * PQ + i]);
+                    hi = fma(k.A, hi, ur[(4 + j) * PQ + i]);
+                }
+                W[i] = fma(W[i], k.A8, fma(lo, A4, hi));
+            }
+        } else {
+            double Bu[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < PQ; i++) acc = fma(th.B[i], ur[j * PQ + i], acc);
+                Bu[j] = acc;
+            }
+            double lo = Bu[0], hi = Bu[4];
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                lo = fma(k.A, lo, Bu[j]);
+                hi = fma(k.A, hi, Bu[4 + j]);
+            }
+            hh = fma(hh, k.A8, fma(lo, A4, hi));
         }
-        double lo = Bu[0], hi = Bu[4];
+    }
+    if (KEEP_W) {
 #pragma unroll
-        for (int j = 1; j < 4; j++) {
-            lo = fma(k.A, lo, Bu[j]);
-            hi = fma(k.A, hi, Bu[4 + j]);
+        for (int i = 0; i < PQ; i++) {
+            hh = fma(th.B[i], W[i], hh);
+            wk[i * 32] = W[i];
         }
-        hh = fma(hh, k.A8, fma(lo, k.A2 * k.A2, hi));
     }
     const double AW = k.AW();
     const double qn = fma(AW, c.q, hh);
@@ -424,93 +461,124 @@ __device__ __forceinline__ void smooth_unit(const Theta<PQ> &th, const SplitCons
     Vs1 = Vs[0];
 }
 
+// ---- variance sums of an unobserved unit in closed form ------------------------------------------
+// Inside a U unit of n = UW steps that starts with prior variance v0 and whose right end carries
+// H = hR:   Vp_s = a^s v0 + Q sig_s  (a = A^2, sig_s = 1 + a + ... + a^(s-1)),   H_s = a^(n-s) hR,
+//   sum_s Vs_s                    = sum Vp_s + hR sum Vp_s^2 a^(n-s)          (-> Txx's variance part)
+//   sum_s Vp_s (1 + Vp_{s+1} H_{s+1}) = sum Vp_s + hR sum Vp_s Vp_{s+1} a^(n-1-s)  (-> Tx1x's, times A)
+// are quadratics in v0 whose seven coefficients depend on (A, Q) only -- the same for every U unit of
+// the iteration.  They are built once per iteration by exact recurrences (no 1/(1-a): nothing
+// degenerates as A -> 1) by a warp that has no P1 work, and shared through shared memory.
+constexpr int SPLIT_NUV = 7;
+template <int UW> __device__ __forceinline__ void uvar_constants(double a, double Q, double aW, double *o) {
+    double sig = 0.0, b1 = 0.0, W = 0.0, Z = 0.0, pw = 1.0, pw_prev = 1.0;
+#pragma unroll 4
+    for (int s = 0; s < UW; s++) {
+        const double sn = fma(a, sig, 1.0); // sig_{s+1}
+        b1 += sig;
+        W = fma(a, W, sig * sig);           // sum_{k<=s} sig_k^2 a^(s-k)
+        Z = fma(a, Z, sig * sn);            // sum_{k<=s} sig_k sig_{k+1} a^(s-k)
+        sig = sn;
+        pw_prev = pw;
+        pw *= a;
+    }
+    const double Q2 = Q * Q;
+    o[0 * 32] = sig;                                         // sum Vp = K0 v0 + K1
+    o[1 * 32] = Q * b1;
+    o[2 * 32] = aW * sig;                                    // v0^2 coefficient of both quadratics
+    o[3 * 32] = 2.0 * Q * aW * b1;                           // sum Vp^2 a^(n-s): v0 coefficient
+    o[4 * 32] = Q2 * (a * W);                                //                   constant
+    o[5 * 32] = Q * fma(pw_prev, b1 + sig, aW * b1);         // sum Vp Vp' a^(n-1-s): v0 coefficient
+    o[6 * 32] = Q2 * Z;                                      //                       constant
+}
+
 // ---- P4 over one unobserved unit ------------------------------------------------------------------
 // (Xq,Vq): prior at the first step of the unit.  (cG,cH): the run constants AT THE RIGHT END of the
 // unit; on return they are the constants at its left end (= right end of the unit before it).
 template <int PQ, int UW>
 __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitConst<PQ, UW> &k,
-                                            const double *__restrict__ useg, double Xq, double Vq, double &cG,
-                                            double &cH, double &Xs1, double &Vs1, Stats<PQ> &st) {
+                                            const double *__restrict__ useg, const double *__restrict__ uv,
+                                            const double *__restrict__ wk, const double *__restrict__ tuu_w,
+                                            double Xq, double Vq, double &cG, double &cH, double &Xs1, double &Vs1,
+                                            Stats<PQ> &st) {
     constexpr int NB = UW / 8;
-    // constants at the right end of each 8-step block, last block first
-    const double g1 = k.A8 * cG, g2 = k.A16 * cG, g3 = k.A8 * g2;
-    const double A32 = k.A16 * k.A16;
-    const double h1 = k.A16 * cH, h2 = A32 * cH, h3 = k.A16 * h2;
-    const double G0 = NB == 4 ? k.A8 * g3 : k.A8 * g1;
-    const double H0 = NB == 4 ? k.A16 * h3 : k.A16 * h1;
-    double xp = Xq, vp = Vq;
-    double Xs = fma(vp, G0, xp);
-    double Vs = fma(vp, vp * H0, vp);
-    const double Xfirst = Xs, Vfirst = Vs;
-    double tv = 0.0;
+    constexpr bool KEEP_W = split_w_in_smem(PQ);
+    // Q G at the right end of each 8-step block, last block first
+    const double qg0 = k.Q * cG;
+    const double g1 = k.A8 * qg0, g2 = k.A16 * qg0, g3 = k.A8 * g2;
+    const double G0 = (NB == 4 ? k.A8 * k.A16 * k.A8 : k.A16) * cG; // G at the left end: A^UW cG
+    const double H0 = k.aVW * cH;                                    // A^(2 UW) hR
+    const double Xfirst = fma(Vq, G0, Xq), Vfirst = fma(Vq, Vq * H0, Vq);
+    { // the variance sums of the whole unit, closed form (uvar_constants)
+        const double sumVp = fma(uv[0 * 32], Vq, uv[1 * 32]);
+        const double qa = uv[2 * 32] * Vq;
+        st.Txxv += fma(cH, fma(Vq, qa + uv[3 * 32], uv[4 * 32]), sumVp);
+        st.Tx1xv = fma(k.A, fma(cH, fma(Vq, qa + uv[5 * 32], uv[6 * 32]), sumVp), st.Tx1xv);
+    }
+    // Inside the run the smoothed mean obeys its own forward recursion,
+    //     Xs_{t+1} = A Xs_t + B u_t + Q G_{t+1}
+    // (from Xs = Xp + Vp G, G_t = A G_{t+1}, Vp_{t+1} = A^2 Vp_t + Q), so neither Xp nor Vp is needed
+    // per step.
+    double Xs = Xfirst;
+    double tux[KEEP_W ? PQ : 1]; // this unit's sum u_t Xs_t (for the Tx1u identity below)
+    if (KEEP_W) {
+#pragma unroll
+        for (int i = 0; i < PQ; i++) tux[i] = 0.0;
+    }
 #pragma unroll 1
     for (int b = 0; b < NB; b++) {
         const int r = NB - 1 - b; // blocks to the right of this one
-        const double Gb = r == 0 ? cG : (r == 1 ? g1 : (r == 2 ? g2 : g3));
-        const double Hb = r == 0 ? cH : (r == 1 ? h1 : (r == 2 ? h2 : h3));
+        const double Gb = r == 0 ? qg0 : (r == 1 ? g1 : (r == 2 ? g2 : g3));
         const double *__restrict__ blk = useg + b * 8 * PQ;
-        // The block is written stage by stage so that every stage is a batch of independent
-        // operations (the only serial chains are one FMA per step on xp and on vp):
-        // 1. inputs of the 8 steps
-        constexpr bool KEEP_U = PQ <= 4; // keep the rows in registers for stage 4, else reload them
+        // stage by stage: every stage is a batch of independent operations except the Xs chain
+        constexpr bool KEEP_U = PQ <= 4; // keep the rows in registers for the sums, else reload them
         double uk[8 * PQ];
         load_vec<8 * PQ>(blk, uk);
-        double Bu[8];
+        double Gs[8];
+        Gs[7] = Gb;
+#pragma unroll
+        for (int j = 6; j >= 0; j--) Gs[j] = k.A * Gs[j + 1];
+        double inp[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            double acc = 0.0;
+            double acc = Gs[j]; // Q G_{t+1}
 #pragma unroll
             for (int i = 0; i < PQ; i++) acc = fma(th.B[i], uk[j * PQ + i], acc);
-            Bu[j] = acc;
+            inp[j] = acc;
         }
-        // 2. prediction (EM.cpp:72-76 without a measurement)
-        double xs[9], vs[9];
-        xs[0] = xp;
-        vs[0] = vp;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            xs[j + 1] = fma(k.A, xs[j], Bu[j]);
-            vs[j + 1] = fma(k.A2, vs[j], k.Q);
-        }
-        // 3. smoothed moments of steps 1..8 of the block.  G and H at those steps come from the
-        //    block's right end by two short multiplication chains (off the critical path)
-        double Gs[8], Hs[8];
-        Gs[7] = Gb;
-        Hs[7] = Hb;
-#pragma unroll
-        for (int j = 6; j >= 0; j--) {
-            Gs[j] = k.A * Gs[j + 1];
-            Hs[j] = k.A2 * Hs[j + 1];
-        }
-        double Xn[9], Vn[9], t1[8];
+        double Xn[9];
         Xn[0] = Xs;
-        Vn[0] = Vs;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            Xn[j + 1] = fma(vs[j + 1], Gs[j], xs[j + 1]);
-            t1[j] = vs[j + 1] * Hs[j];
-            Vn[j + 1] = fma(vs[j + 1], t1[j], vs[j + 1]);
-        }
-        // 4. the sums of EM.cpp:180-193
+        for (int j = 0; j < 8; j++) Xn[j + 1] = fma(k.A, Xn[j], inp[j]);
+        // the sums of EM.cpp:180-193
         if (!KEEP_U) load_vec<8 * PQ>(blk, uk);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             st.Tx1x = fma(Xn[j + 1], Xn[j], st.Tx1x);
             st.Txx = fma(Xn[j], Xn[j], st.Txx);
-            st.Txxv += Vn[j];
-            tv = fma(vs[j], 1.0 + t1[j], tv); // V_{t+1} J_t = A Vp_t (1 + Vp_{t+1} H_{t+1})
 #pragma unroll
             for (int i = 0; i < PQ; i++) {
-                st.Tx1u[i] = fma(Xn[j + 1], uk[j * PQ + i], st.Tx1u[i]);
-                st.Tux[i] = fma(uk[j * PQ + i], Xn[j], st.Tux[i]);
+                if (KEEP_W) {
+                    tux[i] = fma(uk[j * PQ + i], Xn[j], tux[i]);
+                } else {
+                    st.Tx1u[i] = fma(Xn[j + 1], uk[j * PQ + i], st.Tx1u[i]);
+                    st.Tux[i] = fma(uk[j * PQ + i], Xn[j], st.Tux[i]);
+                }
             }
         }
-        xp = xs[8];
-        vp = vs[8];
         Xs = Xn[8];
-        Vs = Vn[8];
     }
-    st.Tx1xv = fma(k.A, tv, st.Tx1xv);
+    if (KEEP_W) {
+        // sum_t Xs_{t+1} u_t' = A sum_t Xs_t u_t' + B sum_t u_t u_t' + Q cG W'   (the recursion above times u_t')
+#pragma unroll
+        for (int i = 0; i < PQ; i++) {
+            double acc = fma(qg0, wk[i * 32], k.A * tux[i]);
+#pragma unroll
+            for (int j = 0; j < PQ; j++) acc = fma(th.B[j], tuu_w[j * PQ + i], acc);
+            st.Tx1u[i] += acc;
+            st.Tux[i] += tux[i];
+        }
+    }
     Xs1 = Xfirst;
     Vs1 = Vfirst;
     cG = G0;
@@ -569,6 +637,7 @@ template <int PQ, int NW> __host__ __device__ constexpr int split_st_slots() {
 struct SplitParams {
     EmParams em;
     int max_units;      // capacity of the unit table / checkpoint area
+    int max_uunits;     // number of UW-step windows of the longest series
     int blob_smem;      // bytes reserved for the series blob at the start of dynamic shared memory
     int cost_u, cost_m; // relative cost of a U unit and an M unit (piece balancing)
 };
@@ -638,6 +707,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     int *const units =
         reinterpret_cast<int *>(CH - lane + (CH_DOUBLES > ST_DOUBLES ? CH_DOUBLES : ST_DOUBLES)); // [max_units]
     int *const pbound = units + ((SP.max_units + 3) & ~3);                                        // [NP+1]
+    double *const UV = reinterpret_cast<double *>(pbound + 32) + lane;                            // [SPLIT_NUV][32]
+    double *const WK = UV + 8 * 32; // [window][PQ][32]: Horner vectors of the U units (split_w_in_smem)
 
     // ---- per-lane fit state: every warp holds the same 32 fits
     const bool valid = lane < task.z;
@@ -704,6 +775,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         k.set(th);
 
         // ================= P1: variance maps of my pieces =================
+        if (warp == NW - 1) uvar_constants<UW>(k.A2, k.Q, k.aVW, UV); // this warp has no second map to build
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int pj = h * NW + warp;
@@ -773,7 +845,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                     any_m = true;
                     forward_unit_basis<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), ys + t0, us + t0 * PQ, vs + t0 * PQ, c);
                 } else {
-                    forward_word_basis<PQ, UW>(th, k, us + t0 * PQ, c);
+                    forward_word_basis<PQ, UW>(th, k, us + t0 * PQ, WK + (size_t)(t0 / UW) * PQ * 32, c);
                 }
             }
             double ld = 0.0;
@@ -781,15 +853,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             double *o = CH + (size_t)pj * SPLIT_NCH * 32;
             o[0 * 32] = c.P;
             o[1 * 32] = c.q;
-            o[2 * 32] = c.l0;
+            o[2 * 32] = c.l0 + ld; // x_in-independent part of sum_obs (delta^2/Sigma + log Sigma)
             o[3 * 32] = c.l1;
             o[4 * 32] = c.l2;
-            o[5 * 32] = ld;
-            o[6 * 32] = c.PJ;
-            o[7 * 32] = c.G0;
-            o[8 * 32] = c.GG;
-            o[9 * 32] = c.Lc;
-            o[10 * 32] = c.Vq;
+            o[5 * 32] = c.PJ;
+            o[6 * 32] = c.G0;
+            o[7 * 32] = c.GG;
+            o[8 * 32] = c.Lc;
+            o[9 * 32] = c.Vq;
         }
         __syncthreads();
 
@@ -806,11 +877,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 const double *o = CH + (size_t)pj * SPLIT_NCH * 32;
                 if (pj == warp) xinA = x;
                 if (pj == NW + warp) xinB = x;
-                gk[pj] = fma(o[8 * 32], x, o[7 * 32]);
+                gk[pj] = fma(o[7 * 32], x, o[6 * 32]);
                 const double tC = th.C * x;
-                acc += fma(tC, fma(tC, o[4 * 32], -2.0 * o[3 * 32]), o[2 * 32]) + o[5 * 32];
+                acc += fma(tC, fma(tC, o[4 * 32], -2.0 * o[3 * 32]), o[2 * 32]);
                 x = fma(o[0 * 32], x, o[1 * 32]);
-                vend = o[10 * 32];
+                vend = o[9 * 32];
                 if (pj == warp) {
                     XrA = x;
                     VrA = vend;
@@ -849,9 +920,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                     Vs1A = Vs;
                 }
                 const double *o = CH + (size_t)pj * SPLIT_NCH * 32;
-                const double pjv = o[6 * 32];
+                const double pjv = o[5 * 32];
                 Xs = fma(pjv, Xs, gk[pj]);
-                Vs = fma(pjv * pjv, Vs, o[9 * 32]);
+                Vs = fma(pjv * pjv, Vs, o[8 * 32]);
             }
         }
         __syncthreads(); // the piece summaries are dead: their space becomes the partial sums
@@ -888,7 +959,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                         cH = (Vs1 - Vr) * rv * rv;
                         in_run = true;
                     }
-                    smooth_word<PQ, UW>(th, k, us + t0 * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
+                    smooth_word<PQ, UW>(th, k, us + t0 * PQ, UV, WK + (size_t)(t0 / UW) * PQ * 32,
+                                        P.uwin + S.uwin_off + (size_t)(t0 / UW) * PQ * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
                 }
                 Xr = Xq;
                 Vr = Vq;

@@ -180,7 +180,7 @@ struct ldsr_plan {
     std::vector<void *> allocs;
     // device
     SeriesDev *d_series = nullptr;
-    double *d_blobs = nullptr, *d_sconst = nullptr, *d_gconst = nullptr;
+    double *d_blobs = nullptr, *d_sconst = nullptr, *d_gconst = nullptr, *d_uwin = nullptr;
     int *d_g_series = nullptr, *d_g_status = nullptr, *d_g_nobs = nullptr, *d_g_fit_ptr = nullptr;
     int *d_held_ptr = nullptr, *d_held_idx = nullptr;
     unsigned *d_masks = nullptr;
@@ -365,7 +365,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
 
     // ---- series blobs
     P->h_series.resize(ns);
-    std::vector<double> blobs;
+    std::vector<double> blobs, uwin;
     long long sconst_off = 0;
     for (int s = 0; s < ns; s++) {
         SeriesDev &S = P->h_series[s];
@@ -399,6 +399,17 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
         }
         P->max_T = std::max(P->max_T, T);
         P->max_units = std::max(P->max_units, split_units_upper_bound(b->y[s], T, P->kt->split_mseg, P->kt->split_uw));
+        { // window Gram blocks of u for the time-split kernel's unobserved units (theta-independent)
+            const int UWn = P->kt->split_uw, nwin = (T + UWn - 1) / UWn;
+            S.uwin_off = (int)uwin.size();
+            uwin.resize(uwin.size() + (size_t)nwin * PQ * PQ, 0.0);
+            if (u)
+                for (int t = 0; t < T; t++) {
+                    double *G = uwin.data() + S.uwin_off + (size_t)(t / UWn) * PQ * PQ;
+                    for (int a = 0; a < p; a++)
+                        for (int c = 0; c < p; c++) G[a * PQ + c] += u[(size_t)t * p + a] * u[(size_t)t * p + c];
+                }
+        }
         P->max_blob_bytes = std::max(P->max_blob_bytes, (size_t)S.blob_doubles * 8);
     }
     // fit ranges per series (internal order is series-major)
@@ -442,6 +453,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     // ---- upload
     if (!(e = P->upload(&P->d_series, P->h_series)).ok()) return e;
     if (!(e = P->upload(&P->d_blobs, blobs)).ok()) return e;
+    if (uwin.empty()) uwin.push_back(0.0);
+    if (!(e = P->upload(&P->d_uwin, uwin)).ok()) return e;
     if (!(e = P->upload(&P->d_g_series, P->h_g_series)).ok()) return e;
     if (!(e = P->upload(&P->d_g_fit_ptr, P->h_g_fit_ptr)).ok()) return e;
     if (!(e = P->upload(&P->d_g_mask_off, mask_off)).ok()) return e;
@@ -548,7 +561,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // axis.  Default whenever blob + checkpoints + exchange buffers fit in shared memory.
     // variant: 0 auto, 1 lane kernel with global checkpoints, 2 lane kernel, 3 time-split kernel
     const int variant = opt ? opt->variant : 0;
-    const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units);
+    const int max_uunits = (P->max_T + P->kt->split_uw - 1) / P->kt->split_uw;
+    const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units, max_uunits);
     bool use_split = P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
     if (variant == 3 && !use_split)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 3 (time-split kernel) needs %zu bytes of shared memory", split_sm);
@@ -564,6 +578,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     ep.series = P->d_series;
     ep.blobs = P->d_blobs;
     ep.sconst = P->d_sconst;
+    ep.uwin = P->d_uwin;
     ep.g_series = P->d_g_series;
     ep.masks = P->d_masks;
     ep.g_mask_off = P->d_g_mask_off;
@@ -656,6 +671,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             SplitParams sp;
             sp.em = ep;
             sp.max_units = P->max_units;
+            sp.max_uunits = max_uunits;
             sp.blob_smem = (int)blob_sm;
             sp.cost_u = P->kt->split_uw * 33; // instructions per U / M unit, measured
             sp.cost_m = P->kt->split_mseg * 185;

@@ -336,3 +336,20 @@ def test_cv_metrics_kernel_matches_the_stored_cvLDS_result():
     assert np.allclose(_lib.cv_metrics(sim, obs2, Z), O.cv_metrics(sim, obs2, Z), rtol=1e-11, atol=1e-13)
     with pytest.raises(_lib.LdsrError):
         _lib.cv_metrics(sim, obs2, [np.array([0])] * nf)  # R indices are 1-based
+
+
+def test_em_batch_across_two_devices_matches_single_device():
+    # ldsr_em_batch shards groups over devices (no collective); results must not depend on the split
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    y, u, mu, inst = _np213()
+    rng = np.random.default_rng(12)
+    n_folds, n_rest = 7, 9
+    held = [np.sort(rng.choice(inst, 11, replace=False)) for _ in range(n_folds)]
+    fg = np.repeat(np.arange(n_folds), n_rest)
+    th0 = rand_theta0(rng, 3, 3, n_folds * n_rest)
+    ser = [dict(y=y, u=u, v=u)]
+    a = _lib.em_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 200, 1e-5, n_devices=1)
+    b = _lib.em_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 200, 1e-5, n_devices=2)
+    for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
