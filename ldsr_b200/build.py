@@ -15,6 +15,7 @@ OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libldsr_b200.so")
 PQ_LIST = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 32)  # keep in sync with LDSR_PQ_LIST in ldsr_abi.cu
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SPLIT_TU_FROM_PQ = 12  # widths from here on are compiled as 5 translation units each
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
 
@@ -69,10 +70,15 @@ def build(force=False, verbose=False, ptxas_info=False):
     if os.environ.get("LDSR_SEG"):
         extra += ["-DLDSR_SEG=" + os.environ["LDSR_SEG"]]
     extra += os.environ.get("LDSR_NVCC_EXTRA", "").split()
-    for pq in PQ_LIST:
-        o = os.path.join(OBJ, "kernels_pq%d.o" % pq)
-        jobs.append((o, [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))
-        obj_deps[o] = em_deps
+    # widest first (longest jobs first); a wide PQ is cut into 5 parts (see kernels_inst.cu) so that no
+    # single nvcc process is the critical path of the build
+    for pq in sorted(PQ_LIST, reverse=True):
+        parts = [None] if pq < SPLIT_TU_FROM_PQ else [1, 2, 3, 4, 0]
+        for part in parts:
+            o = os.path.join(OBJ, "kernels_pq%d%s.o" % (pq, "" if part is None else "_part%d" % part))
+            cmd = [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq] + ([] if part is None else ["-DLDSR_PART=%d" % part])
+            jobs.append((o, cmd + ["-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))
+            obj_deps[o] = em_deps
     o_scan = os.path.join(OBJ, "scan_inst.o")
     jobs.append((o_scan, [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, "scan_inst.cu"), "-o", o_scan]))
     obj_deps[o_scan] = scan_deps

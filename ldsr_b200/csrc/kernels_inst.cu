@@ -1,47 +1,103 @@
 // kernels_inst.cu -- compiled once per supported padded width: nvcc -DLDSR_PQ=<n>.
+// A wide PQ takes minutes to compile (fully unrolled PQ x PQ bodies), so the build may cut the
+// translation unit into parts, one nvcc process each: -DLDSR_PART=0 (table + single-step kernels),
+// 1, 2, 3 (lane-per-fit EM kernel, MODE 0 / 1 / 2), 4 (time-split EM kernel).  Without LDSR_PART
+// everything is in one unit.
 #include "kernel_table.h"
 
 #ifndef LDSR_PQ
 #error "compile with -DLDSR_PQ=<n>"
 #endif
+#ifdef LDSR_PART
+#define LDSR_HAS_PART(k) (LDSR_PART == (k))
+#else
+#define LDSR_HAS_PART(k) 1
+#endif
 
 namespace ldsr {
-namespace {
 
 constexpr int PQ = LDSR_PQ;
-
-cudaError_t em_prepare(size_t smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem_bytes);
-}
-cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
-    if (p.mode == 2)
-        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 2><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
-    else if (p.mode == 1)
-        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 1><<<n_tasks, EM_WARPS * 32, smem_bytes, st>>>(p);
-    else
-        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, 0><<<n_tasks, EM_WARPS * 32, 0, st>>>(p);
-    return cudaGetLastError();
-}
 constexpr int MINB = split_minb_for(PQ);
 constexpr int MINB_WIDE = 2;
-cudaError_t em_split_prepare(size_t smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess || MINB == MINB_WIDE) return e;
+
+// launchers: explicit specialisations, defined in the part that owns the kernel
+template <int PQV, int MODE> cudaError_t chunk_prepare(size_t smem_bytes);
+template <int PQV, int MODE> cudaError_t chunk_launch(const EmParams &, int, size_t, cudaStream_t);
+template <int PQV, int WIDE> cudaError_t split_prepare(size_t smem_bytes);
+template <int PQV, int WIDE> cudaError_t split_launch(const SplitParams &, int, size_t, cudaStream_t);
+#define LDSR_DECLARE_CHUNK(M)                                                                      \
+    template <> cudaError_t chunk_prepare<PQ, M>(size_t);                                          \
+    template <> cudaError_t chunk_launch<PQ, M>(const EmParams &, int, size_t, cudaStream_t);
+LDSR_DECLARE_CHUNK(0)
+LDSR_DECLARE_CHUNK(1)
+LDSR_DECLARE_CHUNK(2)
+template <> cudaError_t split_prepare<PQ, 0>(size_t);
+template <> cudaError_t split_prepare<PQ, 1>(size_t);
+template <> cudaError_t split_launch<PQ, 0>(const SplitParams &, int, size_t, cudaStream_t);
+template <> cudaError_t split_launch<PQ, 1>(const SplitParams &, int, size_t, cudaStream_t);
+
+#define LDSR_DEFINE_CHUNK(M)                                                                       \
+    template <> cudaError_t chunk_prepare<PQ, M>(size_t smem_bytes) {                              \
+        if (M == 0) return cudaSuccess;                                                            \
+        return cudaFuncSetAttribute(em_chunk_kernel<PQ, EM_SEG, EM_WARPS, M>,                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); \
+    }                                                                                              \
+    template <> cudaError_t chunk_launch<PQ, M>(const EmParams &p, int n_tasks, size_t smem_bytes, \
+                                                cudaStream_t st) {                                 \
+        em_chunk_kernel<PQ, EM_SEG, EM_WARPS, M><<<n_tasks, EM_WARPS * 32, M == 0 ? 0 : smem_bytes, st>>>(p); \
+        return cudaGetLastError();                                                                 \
+    }
+#if LDSR_HAS_PART(1)
+LDSR_DEFINE_CHUNK(0)
+#endif
+#if LDSR_HAS_PART(2)
+LDSR_DEFINE_CHUNK(1)
+#endif
+#if LDSR_HAS_PART(3)
+LDSR_DEFINE_CHUNK(2)
+#endif
+
+#if LDSR_HAS_PART(4)
+template <> cudaError_t split_prepare<PQ, 0>(size_t smem_bytes) {
+    return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+template <> cudaError_t split_launch<PQ, 0>(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
+    return cudaGetLastError();
+}
+// the same kernel compiled for two CTAs per SM (255 registers); identical when MINB is already 2
+template <> cudaError_t split_prepare<PQ, 1>(size_t smem_bytes) {
     return cudaFuncSetAttribute(em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
-cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+template <> cudaError_t split_launch<PQ, 1>(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
+#endif
+
+#if LDSR_HAS_PART(0)
+namespace {
+
+cudaError_t em_prepare(size_t smem_bytes) {
+    cudaError_t e = chunk_prepare<PQ, 1>(smem_bytes);
+    return e != cudaSuccess ? e : chunk_prepare<PQ, 2>(smem_bytes);
+}
+cudaError_t em_chunk(const EmParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    if (p.mode == 2) return chunk_launch<PQ, 2>(p, n_tasks, smem_bytes, st);
+    if (p.mode == 1) return chunk_launch<PQ, 1>(p, n_tasks, smem_bytes, st);
+    return chunk_launch<PQ, 0>(p, n_tasks, smem_bytes, st);
+}
+cudaError_t em_split_prepare(size_t smem_bytes) {
+    cudaError_t e = split_prepare<PQ, 0>(smem_bytes);
+    return e != cudaSuccess ? e : split_prepare<PQ, 1>(smem_bytes);
+}
 cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
-    em_split_kernel<PQ, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
-    return cudaGetLastError();
+    return split_launch<PQ, 0>(p, n_tasks, smem_bytes, st);
+}
+cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    return split_launch<PQ, 1>(p, n_tasks, smem_bytes, st);
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
     smoother_kernel<PQ><<<(p.n_jobs + 63) / 64, 64, 0, st>>>(p);
@@ -60,12 +116,14 @@ cudaError_t rep(const RepParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-const KernelTable table = {PQ, em_prepare, em_chunk, SPLIT_NW, MINB, SPLIT_MSEG, SPLIT_UW, em_split_prepare, em_split, em_split_wide, smoother, mstep, propagate, rep};
+const KernelTable table = {PQ,    em_prepare,       em_chunk, SPLIT_NW,      MINB,     SPLIT_MSEG, SPLIT_UW,
+                           em_split_prepare, em_split, em_split_wide, smoother, mstep,      propagate, rep};
 
 } // namespace
 
 #define LDSR_CAT2(a, b) a##b
 #define LDSR_CAT(a, b) LDSR_CAT2(a, b)
 const KernelTable *LDSR_CAT(kernel_table_pq, LDSR_PQ)() { return &table; }
+#endif
 
 } // namespace ldsr

@@ -353,3 +353,23 @@ def test_em_batch_across_two_devices_matches_single_device():
     b = _lib.em_batch(ser, np.zeros(n_folds, dtype=int), held, fg, th0, 200, 1e-5, n_devices=2)
     for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("p,q", [(10, 10), (18, 20), (32, 29)])
+def test_wide_inputs(variant, p, q):
+    # the padded widths 10 / 24 / 32 (the last two are built as several translation units)
+    rng = np.random.default_rng(p * 100 + q)
+    T = 150
+    u = rng.standard_normal((p, T))
+    v = rng.standard_normal((q, T)) if p != q else u
+    x = np.zeros(T)
+    for t in range(1, T):
+        x[t] = 0.6 * x[t - 1] + 0.1 * u[0, t - 1] + 0.5 * rng.standard_normal()
+    y = 0.8 * x + 0.05 * v[0] + 0.3 * rng.standard_normal(T)
+    y[:60] = np.nan  # instrumental period = the last 90 steps
+    th0 = rand_theta0(rng, p, q, 6)
+    th0[:, 1:1 + p] *= 0.1
+    th0[:, 2 + p:2 + p + q] *= 0.1
+    held = [np.array([], dtype=int), np.arange(70, 90)]
+    check_batch([dict(y=y, u=u, v=v)], [0, 0], held, np.repeat([0, 1], 3), th0, 25, 1e-6, variant=variant)
