@@ -20,7 +20,7 @@ template <int D> cudaError_t run(const ScanParams &P, cudaStream_t st) {
         scan_smth_scan_kernel<D><<<P.n_fits, 32, (32 * SmthElem<D>::LEN + 1) * sizeof(double), st>>>(P);
     }
     scan_smth_down_kernel<D><<<gb, TB, 0, st>>>(P);
-    scan_lik_kernel<D><<<(P.n_fits + 63) / 64, 64, 0, st>>>(P);
+    scan_lik_kernel<D><<<P.n_fits, 32, 0, st>>>(P);
     return cudaGetLastError();
 }
 

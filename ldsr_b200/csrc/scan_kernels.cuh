@@ -730,18 +730,25 @@ template <int D> __global__ void scan_smth_down_kernel(const ScanParams P) {
     }
 }
 
-// likelihood: chunk terms added in order (EM.cpp:115-124)
+// likelihood: the chunk terms of a fit are added by one warp, lane-strided then a shuffle tree --
+// a fixed order, so the result does not depend on the launch (EM.cpp:115-124)
 template <int D> __global__ void scan_lik_kernel(const ScanParams P) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= P.n_fits) return;
+    const int f = blockIdx.x, lane = threadIdx.x;
     double acc = 0.0, n = 0.0;
-    for (int k = 0; k < P.n_chunks; k++) {
+    for (int k = lane; k < P.n_chunks; k += 32) {
         acc += P.likp[((size_t)f * P.n_chunks + k) * 2];
         n += P.likp[((size_t)f * P.n_chunks + k) * 2 + 1];
     }
-    double lik = -0.5 * n * LOG_2PI - 0.5 * acc;
-    if (P.stdlik) lik /= n;
-    P.lik[f] = lik;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, o);
+        n += __shfl_xor_sync(FULL, n, o);
+    }
+    if (lane == 0) {
+        double lik = -0.5 * n * LOG_2PI - 0.5 * acc;
+        if (P.stdlik) lik /= n;
+        P.lik[f] = lik;
+    }
 }
 
 cudaError_t scan_smoother_launch(int D, const ScanParams &P, cudaStream_t st); // scan_inst.cu
