@@ -69,3 +69,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c", ".R")):
                 txt = open(os.path.join(root, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "ldsr_oracle" not in txt, f
+
+
+def test_argument_validation_runs_on_the_host():
+    """Argument errors are reported (code LDSR_ERR_ARG / UNSUPPORTED) before any device is touched,
+    so these hold with or without a GPU; with valid arguments and no device the new entry points
+    refuse with LDSR_ERR_CUDA like the rest (no CPU fallback)."""
+    y = np.zeros(12)
+    with pytest.raises(_lib.LdsrError) as e:  # state dimension beyond LDSR_MAX_STATE_DIM
+        _lib.smoother_d(5, y, None, None, np.zeros(2 * 25 + 5 + 1 + 5 + 25))
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    with pytest.raises(_lib.LdsrError) as e:  # theta shorter than the layout needs
+        _lib.smoother_d(2, y, None, None, np.zeros(5))
+    assert e.value.code == _lib.ERR_ARG
+    yy = y.copy()
+    yy[3] = np.inf
+    with pytest.raises(_lib.LdsrError) as e:
+        _lib.smoother_d(1, yy, None, None, np.array([0.5, 1.0, 1.0, 1.0, 0.0, 1.0]))
+    assert e.value.code == _lib.ERR_ARG
+    sim = np.ones((2, 12))
+    with pytest.raises(_lib.LdsrError) as e:  # R indices are 1-based: 0 is out of range
+        _lib.cv_metrics(sim, y + 1.0, [np.array([0, 1]), np.array([2, 3])])
+    assert e.value.code == _lib.ERR_ARG
+    with pytest.raises(_lib.LdsrError) as e:
+        _lib.cv_metrics(sim, y + 1.0, [np.array([1, 13]), np.array([2, 3])])
+    assert e.value.code == _lib.ERR_ARG
+    if _lib.device_count() == 0:
+        with pytest.raises(_lib.LdsrError) as e:
+            _lib.smoother_d(1, y, None, None, np.array([0.5, 1.0, 1.0, 1.0, 0.0, 1.0]))
+        assert e.value.code == _lib.ERR_CUDA
+        with pytest.raises(_lib.LdsrError) as e:
+            _lib.cv_metrics(sim, y + 1.0, [np.array([1, 2]), np.array([2, 3])])
+        assert e.value.code == _lib.ERR_CUDA
