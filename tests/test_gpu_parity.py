@@ -373,3 +373,63 @@ def test_wide_inputs(variant, p, q):
     th0[:, 2 + p:2 + p + q] *= 0.1
     held = [np.array([], dtype=int), np.arange(70, 90)]
     check_batch([dict(y=y, u=u, v=v)], [0, 0], held, np.repeat([0, 1], 3), th0, 25, 1e-6, variant=variant)
+
+
+def test_full_size_cvlds_job_properties():
+    """BASELINE config 2 at full size (10 000 fits: 100 folds x 100 restarts on NP-413), where the
+    oracle would take minutes: size-independent properties instead.
+      * EM never decreases the likelihood (trace of every fit, the E-step likelihood of each iteration);
+      * the result of a fit does not depend on which other fits share its CTA / launch: reversing the
+        order of the groups and changing the chunk length give bit-identical results;
+      * the selected restart is the first maximum of lik among restarts with C > 0
+        (R/LDS_reconstruction.R:50-58);
+      * iteration counts respect the stop rule (EM.cpp:272): 3 <= iters <= niter."""
+    from ldsr_b200 import workloads as W
+    w = W.np_cv(100, 100)
+    a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 1000, 1e-5,
+                      want_liks=True, want_traj=False)
+    it = a["iters"]
+    assert it.min() >= 3 and it.max() <= 1000 and np.all(a["status"] == 0)
+    liks = a["liks"]
+    d = np.diff(liks, axis=1)
+    valid = np.arange(999)[None, :] < (it[:, None] - 1)
+    assert np.all(np.isfinite(liks[np.arange(1000)[None, :] < it[:, None]]))
+    assert d[valid].min() > -1e-11, d[valid].min()  # monotone up to rounding
+    assert np.allclose(liks[np.arange(it.size), it - 1], a["lik"], rtol=0, atol=0)
+    # selection
+    ng = len(w["group_series"])
+    C = a["theta"][:, 1 + 3]
+    for g in range(ng):
+        idx = np.nonzero(w["fit_group"] == g)[0]
+        pos = idx[C[idx] > 0]
+        cand = pos if pos.size else idx
+        assert a["best"][g] == cand[np.argmax(a["lik"][cand])]
+    # order / chunking invariance (bitwise)
+    perm_g = np.arange(ng)[::-1]
+    fg_new, th_new, src = [], [], []
+    for k, g in enumerate(perm_g):
+        idx = np.nonzero(w["fit_group"] == g)[0]
+        fg_new += [k] * idx.size
+        src.append(idx)
+    src = np.concatenate(src)
+    b = _lib.em_batch(w["series"], [w["group_series"][g] for g in perm_g], [w["held"][g] for g in perm_g],
+                      np.array(fg_new), w["theta0"][src], 1000, 1e-5, chunk_iters=250, want_traj=False)
+    assert np.array_equal(b["iters"], it[src])
+    assert np.array_equal(b["lik"], a["lik"][src])
+    assert np.array_equal(b["theta"], a["theta"][src], equal_nan=True)
+
+
+def test_task_loop_when_later_chunks_have_more_tasks_than_ctas():
+    """A batch between two and three CTAs per SM: later chunks are launched with two CTAs per SM while
+    more tasks are still live, so some CTAs take a second task (the task loop of both kernels).  The
+    results must equal the single-launch run bit for bit."""
+    from ldsr_b200 import workloads as W
+    w = W.np_cv(120, 100)  # 12 000 fits = 375 tasks of 32
+    for variant in VARIANTS:
+        a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 60, 1e-5,
+                          chunk_iters=60, want_traj=False, variant=variant)
+        b = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 60, 1e-5,
+                          chunk_iters=7, want_traj=False, variant=variant)
+        for k in ("iters", "lik", "best"):
+            assert np.array_equal(a[k], b[k]), (variant, k)
+        assert np.array_equal(a["theta"], b["theta"], equal_nan=True)
