@@ -191,6 +191,18 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
 int ldsr_cv_metrics_batch(int device, int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
                           const int *z_idx, int exp_trans, double *out, char *errbuf, int errlen);
 
+/* ---- construct_rec: the step right after restart selection in LDS_reconstruction -------------
+ * Replaces construct_rec (R/LDS_reconstruction.R:190-212; exp_ci and inv_boxcox of
+ * R/utils.R:112-125) for all ensemble members at once, and the year-wise ensemble mean of X and Q
+ * (R/LDS_reconstruction.R:247-248).
+ *   X, V, Y [n][T]: smoothed state, its variance, smoothed output of every member (fit$X, fit$V, fit$Y)
+ *   C, R [n]: each member's theta$C and theta$R;  mu: mean of the transformed observations
+ *   transform 0 = none, 1 = log, 2 = boxcox with `lambda`
+ *   out [n][6][T]: X, Xl, Xu, Q, Ql, Qu (the columns of `rec`);  mean [2][T] (may be NULL): mean X, mean Q */
+int ldsr_construct_rec_batch(int device, int n, int T, const double *X, const double *V, const double *Y,
+                             const double *C, const double *R, double mu, int transform, double lambda, double *out,
+                             double *mean, char *errbuf, int errlen);
+
 /* ---- general state dimension, long series (beyond the reference) ----------------------------
  * The reference is scalar-state only (src/EM.cpp:20 "matrix inversion is treated as /").
  * BASELINE.json's config 5 (d = 4, 20 proxies, T = 100 000) asks for the E-step of a d-dimensional

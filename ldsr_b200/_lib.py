@@ -19,7 +19,7 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
-           "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch")
+           "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch")
 
 
 class LdsrError(RuntimeError):
@@ -400,3 +400,23 @@ def cv_metrics(sim, obs, Z, exp_trans=False, device=0):
     _check(lib().ldsr_cv_metrics_batch(int(device), int(n), int(nf), _d(sim), _d(obs), _i(zp), _i(zi),
                                        int(bool(exp_trans)), _d(out), err, 512), err)
     return out
+
+
+REC_COLUMNS = ("X", "Xl", "Xu", "Q", "Ql", "Qu")
+TRANSFORMS = {"none": 0, "log": 1, "boxcox": 2}
+
+
+def construct_rec(X, V, Y, C_, R_, mu, transform="log", lam=0.0, device=0):
+    """ldsr_construct_rec_batch: construct_rec (R/LDS_reconstruction.R:190-212) for every ensemble member
+    and the ensemble mean of X and Q.  X, V, Y: [n, T]; C_, R_: [n].  Returns (out [n, 6, T], mean [2, T])."""
+    X, V, Y = (np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in (X, V, Y))
+    n, T = X.shape
+    Cv = np.ascontiguousarray(np.broadcast_to(np.asarray(C_, dtype=np.float64).ravel(), (n,)))
+    Rv = np.ascontiguousarray(np.broadcast_to(np.asarray(R_, dtype=np.float64).ravel(), (n,)))
+    out = np.empty((n, 6, T))
+    mean = np.empty((2, T))
+    err = C.create_string_buffer(512)
+    _check(lib().ldsr_construct_rec_batch(int(device), int(n), int(T), _d(X), _d(V), _d(Y), _d(Cv), _d(Rv),
+                                          C.c_double(mu), int(TRANSFORMS[transform]), C.c_double(lam), _d(out),
+                                          _d(mean), err, 512), err)
+    return out, mean

@@ -219,19 +219,11 @@ def _make_y(years_Qa, obs, start_year, N):
 
 
 def _construct_rec(fit, theta, mu, transform, lam, years):
-    """R/LDS_reconstruction.R:190-212 (host-side post-processing, O(T))."""
-    X, V, Y = fit["X"], fit["V"], fit["Y"] + mu
-    Cc = theta["C"]
-    ciX = 1.96 * np.sqrt(V)
-    sdY = np.sqrt(Cc * V * Cc + theta["R"])
-    rec = dict(year=years, X=X, Xl=X - ciX, Xu=X + ciX)
-    if transform == "log" or (transform == "boxcox" and lam == 0):
-        # exp_ci: qlnorm(c(.05,.95), m, s)  (R/utils.R:122-125)
-        rec.update(Q=np.exp(Y), Ql=np.exp(Y - _Z05 * sdY), Qu=np.exp(Y + _Z05 * sdY))
-    elif transform == "none":
-        rec.update(Q=Y, Ql=Y - 1.96 * sdY, Qu=Y + 1.96 * sdY)
-    else:
-        rec.update(Q=inv_boxcox(Y, lam), Ql=inv_boxcox(Y - 1.96 * sdY, lam), Qu=inv_boxcox(Y + 1.96 * sdY, lam))
+    """R/LDS_reconstruction.R:190-212 through ldsr_construct_rec_batch (one member)."""
+    out, _ = _lib.construct_rec(fit["X"], fit["V"], fit["Y"], float(np.ravel(theta["C"])[0]),
+                                float(np.ravel(theta["R"])[0]), mu, transform, 0.0 if lam is None else float(lam))
+    rec = dict(year=years)
+    rec.update({k: out[0, j] for j, k in enumerate(_lib.REC_COLUMNS)})
     return rec
 
 

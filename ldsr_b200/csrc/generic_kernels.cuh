@@ -318,6 +318,51 @@ __global__ void cv_metrics_kernel(int n, int n_folds, const double *__restrict__
     }
 }
 
+
+// ---- construct_rec + ensemble mean (the step after restart selection in LDS_reconstruction) --------
+// R/LDS_reconstruction.R:190-212 with exp_ci / inv_boxcox of R/utils.R:112-125; one thread per year:
+// it walks the members in order, so the ensemble mean (:247-248) is a fixed-order sum.
+//   X,V,Y [n][T]; Cm,Rm [n]; out [n][6][T] = X, Xl, Xu, Q, Ql, Qu; mean [2][T] = mean X, mean Q.
+__global__ void construct_rec_kernel(int n, int T, const double *__restrict__ X, const double *__restrict__ V,
+                                     const double *__restrict__ Y, const double *__restrict__ Cm,
+                                     const double *__restrict__ Rm, double mu, int transform, double lambda,
+                                     double *__restrict__ out, double *__restrict__ mean) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double QNORM_05 = -1.6448536269514722; // qnorm(0.05): qlnorm(p, m, s) = exp(m + s qnorm(p))
+    double sx = 0.0, sq = 0.0;
+    for (int m = 0; m < n; m++) {
+        const double x = X[(size_t)m * T + t], v = V[(size_t)m * T + t], y = Y[(size_t)m * T + t] + mu;
+        const double ciX = 1.96 * sqrt(v), sdY = sqrt(Cm[m] * v * Cm[m] + Rm[m]), ciY = 1.96 * sdY;
+        double q, ql, qu;
+        if (transform == 1 || (transform == 2 && lambda == 0.0)) {
+            q = exp(y);
+            ql = exp(y + sdY * QNORM_05);
+            qu = exp(y - sdY * QNORM_05);
+        } else if (transform == 0) {
+            q = y;
+            ql = y - ciY;
+            qu = y + ciY;
+        } else {
+            const double il = 1.0 / lambda;
+            q = pow(y * lambda + 1.0, il);
+            ql = pow((y - ciY) * lambda + 1.0, il);
+            qu = pow((y + ciY) * lambda + 1.0, il);
+        }
+        double *o = out + (size_t)m * 6 * T;
+        o[t] = x;
+        o[T + t] = x - ciX;
+        o[2 * T + t] = x + ciX;
+        o[3 * T + t] = q;
+        o[4 * T + t] = ql;
+        o[5 * T + t] = qu;
+        sx += x;
+        sq += q;
+    }
+    mean[t] = sx / n;
+    mean[T + t] = sq / n;
+}
+
 // [rows][cols] -> [cols][rows] through a padded shared-memory tile.
 __global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int cols) {
     __shared__ double tile[32][33];

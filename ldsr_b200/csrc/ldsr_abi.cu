@@ -1344,6 +1344,38 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
     return report(e, errbuf, errlen);
 }
 
+int ldsr_construct_rec_batch(int device, int n, int T, const double *X, const double *V, const double *Y,
+                             const double *C, const double *R, double mu, int transform, double lambda, double *out,
+                             double *mean, char *errbuf, int errlen) {
+    auto run = [&]() -> Err {
+        if (n < 1 || T < 1) return fail(LDSR_ERR_ARG, "need n >= 1 and T >= 1");
+        if (!X || !V || !Y || !C || !R || !out) return fail(LDSR_ERR_ARG, "a required pointer is NULL");
+        if (transform < 0 || transform > 2) return fail(LDSR_ERR_ARG, "transform must be 0 (none), 1 (log) or 2 (boxcox)");
+        if (ldsr_device_count() < 1) return fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+        CU(cudaSetDevice(device));
+        const size_t nT = (size_t)n * T;
+        double *d = nullptr;
+        struct Guard {
+            double *&p;
+            ~Guard() { cudaFree(p); }
+        } guard{d};
+        // one arena: X V Y | C R | out | mean
+        CU(cudaMalloc(&d, sizeof(double) * (3 * nT + 2 * (size_t)n + 6 * nT + 2 * (size_t)T)));
+        double *dX = d, *dV = dX + nT, *dY = dV + nT, *dC = dY + nT, *dR = dC + n, *dO = dR + n, *dM = dO + 6 * nT;
+        CU(cudaMemcpy(dX, X, sizeof(double) * nT, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dV, V, sizeof(double) * nT, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dY, Y, sizeof(double) * nT, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dC, C, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dR, R, sizeof(double) * n, cudaMemcpyHostToDevice));
+        construct_rec_kernel<<<(T + 127) / 128, 128>>>(n, T, dX, dV, dY, dC, dR, mu, transform, lambda, dO, dM);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out, dO, sizeof(double) * 6 * nT, cudaMemcpyDeviceToHost));
+        if (mean) CU(cudaMemcpy(mean, dM, sizeof(double) * 2 * T, cudaMemcpyDeviceToHost));
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
+}
+
 int ldsr_cv_metrics_batch(int device, int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
                           const int *z_idx, int exp_trans, double *out, char *errbuf, int errlen) {
     auto run = [&]() -> Err {

@@ -141,3 +141,21 @@ cv_metrics_batched <- function(Ycv, Z, target, exp_trans = FALSE) {
   rownames(m) <- c("R2", "RE", "CE", "nRMSE", "KGE")
   m
 }
+
+
+#' construct_rec for all ensemble members in one device call (R/LDS_reconstruction.R:190-212) and the
+#' year-wise ensemble mean of X and Q (:247-248).  fits: list of fit lists (X, V, Y as 1 x T matrices),
+#' thetas: the matching theta lists.  Returns list(members = list of data.tables, mean = data.table).
+construct_rec_batched <- function(fits, thetas, mu, transform, years, lambda = 0) {
+  X <- sapply(fits, function(f) c(f$X)); V <- sapply(fits, function(f) c(f$V)); Y <- sapply(fits, function(f) c(f$Y))
+  C <- sapply(thetas, function(t) c(t$C)); R <- sapply(thetas, function(t) c(t$R))
+  tr <- match(transform, c("none", "log", "boxcox")) - 1L
+  r <- .Call(`_ldsr_construct_rec`, as.matrix(X), as.matrix(V), as.matrix(Y), as.numeric(C), as.numeric(R),
+             as.numeric(mu), as.integer(tr), as.numeric(lambda))
+  a <- array(r$rec, dim = c(length(years), 6L, length(fits)))
+  members <- lapply(seq_along(fits), function(i) {
+    dt <- data.table::as.data.table(a[, , i]); data.table::setnames(dt, c("X", "Xl", "Xu", "Q", "Ql", "Qu"))
+    cbind(data.table::data.table(year = years), dt)
+  })
+  list(members = members, mean = data.table::data.table(year = years, X = r$mean[, 1], Q = r$mean[, 2]))
+}

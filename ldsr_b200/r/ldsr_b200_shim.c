@@ -15,6 +15,7 @@
  *     _ldsr_em_batch(series,group_series,held,fit_group,theta0,niter,tol,n_devices)   8
  *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans,z)                       9
  *     _ldsr_cv_metrics(Ycv,target,Z,exp_trans)                                        4
+ *     _ldsr_construct_rec(X,V,Y,C,R,mu,transform,lambda)                              8
  *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
  *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
  *
@@ -304,6 +305,24 @@ SEXP _ldsr_cv_metrics(SEXP Ycv, SEXP target, SEXP Z, SEXP expS) {
     return out;
 }
 
+/* construct_rec for all ensemble members + the ensemble mean (R/LDS_reconstruction.R:190-212, 247-248).
+ * X, V, Y: T x n matrices (one column per member).  Returns list(rec = T x 6 x n array, mean = T x 2). */
+SEXP _ldsr_construct_rec(SEXP X, SEXP V, SEXP Y, SEXP C, SEXP R, SEXP muS, SEXP trS, SEXP lamS) {
+    char err[512] = "";
+    const int T = Rf_nrows(X), n = Rf_ncols(X);
+    const char *nm[] = {"rec", "mean", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    SEXP rec = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)T * 6 * n)); /* [member][column][year], year fastest */
+    SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, T, 2));
+    check(ldsr_construct_rec_batch(0, n, T, REAL(X), REAL(V), REAL(Y), REAL(C), REAL(R), Rf_asReal(muS),
+                                   Rf_asInteger(trS), Rf_asReal(lamS), REAL(rec), REAL(mean), err, sizeof err),
+          err);
+    SET_VECTOR_ELT(out, 0, rec);
+    SET_VECTOR_ELT(out, 1, mean);
+    UNPROTECT(3);
+    return out;
+}
+
 /* General state dimension (beyond the reference): theta holds R matrices, which are column-major;
  * the ABI wants row-major blocks. */
 static void put_rowmajor(SEXP m, int rows, int cols, double *out) {
@@ -359,6 +378,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 9},
     {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
     {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
+    {"_ldsr_construct_rec", (DL_FUNC)&_ldsr_construct_rec, 8},
     {NULL, NULL, 0}};
 
 void R_init_ldsr(DllInfo *dll) {

@@ -271,3 +271,52 @@ int ldsr_oracle_cv_metrics(int n, int n_folds, const double *sim, const double *
     free(s); free(ts); free(to); free(vs); free(vo); free(held);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * construct_rec + ensemble averaging (the step right after restart selection in
+ * LDS_reconstruction).  Restates /root/reference/R/LDS_reconstruction.R:190-212 (construct_rec),
+ * /root/reference/R/utils.R:112-125 (inv_boxcox, exp_ci = qlnorm(c(.05,.95), m, s)) and the
+ * year-wise ensemble mean of X and Q (:247-248).  PINNED: tests/test_oracle_golden.py rebuilds all
+ * six columns of the reference's stored reconstruction (R/sysdata.rda::NPlds$rec, T = 813).
+ *   X, V, Y  [n][T]  smoothed state, its variance, smoothed output (before + mu) of every member
+ *   C, R     [n]     each member's theta$C, theta$R
+ *   transform 0 = none, 1 = log, 2 = boxcox (lambda)
+ *   out      [n][6][T]: X, Xl, Xu, Q, Ql, Qu;   mean [2][T]: ensemble mean of X and of Q
+ * --------------------------------------------------------------------------------------------- */
+#define QNORM_05 (-1.6448536269514722) /* qnorm(0.05); qlnorm(p, m, s) = exp(m + s qnorm(p)) */
+static double inv_boxcox_c(double x, double lambda) { return lambda == 0.0 ? exp(x) : pow(x * lambda + 1.0, 1.0 / lambda); }
+int ldsr_oracle_construct_rec(int n, int T, const double *X, const double *V, const double *Y, const double *C,
+                              const double *R, double mu, int transform, double lambda, double *out, double *mean) {
+    for (int t = 0; t < T; t++) mean[t] = mean[T + t] = 0.0;
+    for (int m = 0; m < n; m++) {
+        double *o = out + (size_t)m * 6 * T;
+        for (int t = 0; t < T; t++) {
+            const double x = X[(size_t)m * T + t], v = V[(size_t)m * T + t], y = Y[(size_t)m * T + t] + mu;
+            const double ciX = 1.96 * sqrt(v), sdY = sqrt(C[m] * v * C[m] + R[m]), ciY = 1.96 * sdY;
+            double q, ql, qu;
+            if (transform == 1 || (transform == 2 && lambda == 0.0)) { /* exp_ci */
+                q = exp(y);
+                ql = exp(y + sdY * QNORM_05);
+                qu = exp(y - sdY * QNORM_05);
+            } else if (transform == 0) {
+                q = y;
+                ql = y - ciY;
+                qu = y + ciY;
+            } else {
+                q = inv_boxcox_c(y, lambda);
+                ql = inv_boxcox_c(y - ciY, lambda);
+                qu = inv_boxcox_c(y + ciY, lambda);
+            }
+            o[t] = x;
+            o[T + t] = x - ciX;
+            o[2 * T + t] = x + ciX;
+            o[3 * T + t] = q;
+            o[4 * T + t] = ql;
+            o[5 * T + t] = qu;
+            mean[t] += x;
+            mean[T + t] += q;
+        }
+    }
+    for (int t = 0; t < 2 * T; t++) mean[t] /= n;
+    return 0;
+}

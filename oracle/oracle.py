@@ -31,7 +31,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         for name in ("kalman_smoother", "mstep", "em", "select", "em_batch", "propagate", "rep",
-                     "max_threads", "smoother_d", "cv_metrics"):
+                     "max_threads", "smoother_d", "cv_metrics", "construct_rec"):
             getattr(_lib, "ldsr_oracle_" + name).restype = C.c_int
     return _lib
 
@@ -245,3 +245,24 @@ def cv_metrics(sim, obs, Z, exp_trans=False):
     if rc != 0:
         raise RuntimeError("ldsr_oracle_cv_metrics failed: %d" % rc)
     return out
+
+
+REC_COLUMNS = ("X", "Xl", "Xu", "Q", "Ql", "Qu")
+TRANSFORMS = {"none": 0, "log": 1, "boxcox": 2}
+
+
+def construct_rec(X, V, Y, C_, R_, mu, transform="log", lam=0.0):
+    """construct_rec for every ensemble member + the year-wise ensemble mean of X and Q
+    (R/LDS_reconstruction.R:190-212, 247-248).  X, V, Y: [n, T]; C_, R_: [n].  Returns
+    (out [n, 6, T] in REC_COLUMNS order, mean [2, T])."""
+    X, V, Y = (np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in (X, V, Y))
+    n, T = X.shape
+    Cv = np.ascontiguousarray(np.broadcast_to(np.asarray(C_, dtype=np.float64).ravel(), (n,)))
+    Rv = np.ascontiguousarray(np.broadcast_to(np.asarray(R_, dtype=np.float64).ravel(), (n,)))
+    out = np.empty((n, 6, T))
+    mean = np.empty((2, T))
+    rc = lib().ldsr_oracle_construct_rec(int(n), int(T), _d(X), _d(V), _d(Y), _d(Cv), _d(Rv), C.c_double(mu),
+                                         int(TRANSFORMS[transform]), C.c_double(lam), _d(out), _d(mean))
+    if rc != 0:
+        raise RuntimeError("ldsr_oracle_construct_rec failed: %d" % rc)
+    return out, mean

@@ -433,3 +433,24 @@ def test_task_loop_when_later_chunks_have_more_tasks_than_ctas():
         for k in ("iters", "lik", "best"):
             assert np.array_equal(a[k], b[k]), (variant, k)
         assert np.array_equal(a["theta"], b["theta"], equal_nan=True)
+
+
+def test_construct_rec_kernel_reproduces_the_stored_reconstruction():
+    # R/sysdata.rda::NPlds$rec (X, Xl, Xu, Q, Ql, Qu, T = 813) from the GPU E-step with the stored theta
+    g = data.load("nplds.json")
+    y, u, mu, inst = data.np_case(1, 1200)
+    th = data.theta_of(g["theta"])
+    s = L.Kalman_smoother(y, u, u, L.vec_to_theta(th, 3, 3))
+    out, mean = _lib.construct_rec(s["X"], s["V"], s["Y"], th[4], th[9], mu, "log")
+    for j, name in enumerate(_lib.REC_COLUMNS):
+        assert np.allclose(out[0, j], np.array(g["rec"][name]), rtol=1e-10, atol=1e-11), name
+    # ensemble of 3 members, all three transforms, against the oracle
+    rng = np.random.default_rng(4)
+    n, T = 3, 97
+    X, Y = rng.standard_normal((n, T)), 0.3 * rng.standard_normal((n, T)) + 1.0
+    V = rng.uniform(0.1, 2.0, (n, T))
+    Cm, Rm = rng.uniform(0.1, 1.0, n), rng.uniform(0.01, 0.2, n)
+    for tr, lam in (("log", 0.0), ("none", 0.0), ("boxcox", 0.3), ("boxcox", 0.0)):
+        a, am = _lib.construct_rec(X, V, Y, Cm, Rm, 0.7, tr, lam)
+        b, bm = O.construct_rec(X, V, Y, Cm, Rm, 0.7, tr, lam)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-13) and np.allclose(am, bm, rtol=1e-12, atol=1e-13), tr

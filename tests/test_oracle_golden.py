@@ -161,3 +161,18 @@ def test_cv_metrics_match_the_stored_cvLDS_result():
     # exp_trans path: log-space input gives the same numbers
     m2 = O.cv_metrics(np.log(Y), np.array(g["target"]["y"]), g["Z"], exp_trans=True)
     assert np.allclose(m2, m, rtol=1e-12)
+
+
+def test_construct_rec_reproduces_the_stored_reconstruction():
+    """All six columns of the reference's stored LDS_reconstruction result (R/sysdata.rda::NPlds$rec:
+    X, Xl, Xu, Q, Ql, Qu over T = 813) from the E-step with the stored theta: pins construct_rec
+    (R/LDS_reconstruction.R:190-212) incl. exp_ci's qlnorm quantiles (R/utils.R:122-125)."""
+    g = data.load("nplds.json")
+    y, u, mu, inst = data.np_case(1, 1200)
+    th = data.theta_of(g["theta"])
+    s = O.kalman_smoother(y, u, u, th)
+    out, mean = O.construct_rec(s["X"], s["V"], s["Y"], th[4], th[9], mu, "log")
+    for j, name in enumerate(O.REC_COLUMNS):
+        want = np.array(g["rec"][name])
+        assert np.allclose(out[0, j], want, rtol=1e-11, atol=1e-12), (name, np.max(np.abs(out[0, j] - want)))
+    assert np.allclose(mean[0], out[0, 0]) and np.allclose(mean[1], out[0, 3])
