@@ -641,7 +641,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     int enq = 0;
     for (int c = 0; c < max_chunks; ++c) {
         int *cnt = P->d_counts + 2 * c;
-        compact_kernel<<<ns, 256, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
+        compact_kernel<<<ns, 1024, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
         build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, fits_per_cta, P->d_tasks, P->d_task_off,
                                               cnt);
         launches += 2;
