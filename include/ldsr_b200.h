@@ -191,6 +191,16 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
 int ldsr_cv_metrics_batch(int device, int n, int n_folds, const double *sim, const double *obs, const int *z_ptr,
                           const int *z_idx, int exp_trans, double *out, char *errbuf, int errlen);
 
+/* ---- objectives of the experimental learners, for a whole population of parameter vectors ------
+ * One value per fit (= per theta0 row of the batch, on its group's y with its hold-outs removed):
+ *   kind 0  penalized_likelihood (R/LDS_GA.R:28-44): Kalman_smoother(stdlik = FALSE)$lik
+ *           - lambda * sum_t (X_{t+1} - A X_t - B u_t)^2          -- the GA fitness of LDS_GA
+ *   kind 1  negLogLik (R/LDS_GA.R:136-141): -propagate(theta,u,v,y)$lik   -- LDS_BFGS objective
+ *   kind 2  ssqTrain  (R/LDS_GA.R:143-147): sum((y - propagate(...)$Y)^2, na.rm = TRUE)
+ * The reference calls these once per candidate from GA::gaisl / optim; here a generation is one call. */
+int ldsr_objective_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int kind, double lambda, double *values,
+                         char *errbuf, int errlen);
+
 /* ---- construct_rec: the step right after restart selection in LDS_reconstruction -------------
  * Replaces construct_rec (R/LDS_reconstruction.R:190-212; exp_ci and inv_boxcox of
  * R/utils.R:112-125) for all ensemble members at once, and the year-wise ensemble mean of X and Q

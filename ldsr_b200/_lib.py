@@ -19,7 +19,8 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
-           "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch")
+           "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch",
+           "ldsr_objective_batch")
 
 
 class LdsrError(RuntimeError):
@@ -420,3 +421,17 @@ def construct_rec(X, V, Y, C_, R_, mu, transform="log", lam=0.0, device=0):
                                           C.c_double(mu), int(TRANSFORMS[transform]), C.c_double(lam), _d(out),
                                           _d(mean), err, 512), err)
     return out, mean
+
+
+OBJECTIVES = {"penalized_likelihood": 0, "negLogLik": 1, "ssqTrain": 2}
+
+
+def objective_batch(series, group_series, held, fit_group, theta, kind, lam=1.0, ctx=None):
+    """ldsr_objective_batch: the objective functions of the reference's experimental learners
+    (R/LDS_GA.R:28-44, 136-147) for a whole population of parameter vectors in one call."""
+    pb = PackedBatch(series, group_series, held, fit_group, theta)
+    out = np.empty(pb.c.n_fits)
+    err = C.create_string_buffer(512)
+    _check(lib().ldsr_objective_batch(ctx.h if isinstance(ctx, Ctx) else ctx, C.byref(pb.c), int(OBJECTIVES[kind]),
+                                      C.c_double(lam), _d(out), err, 512), err)
+    return out

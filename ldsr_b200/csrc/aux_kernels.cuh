@@ -25,6 +25,9 @@ struct SmootherParams {
     const double *theta;      // padded thetas
     double *X, *Y, *V, *J, *lik;
     int stdlik;
+    // optional per-job scalar for the experimental learners' objectives (R/LDS_GA.R:28-44,136-147):
+    // smoother: sum_t (X_{t+1} - A X_t - B u_t)^2 ; propagate: sum over observed t of (y_t - Y_t)^2
+    double *aux;
 };
 
 template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
@@ -77,9 +80,11 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
         Y[T - 1] = fma(th.C, X[T - 1], dot_row<PQ>(th.D, vs + (size_t)(T - 1) * PQ));
     }
     double Xs1 = X[T - 1], Vs1 = V[T - 1];
+    double ssq = 0.0;
     for (int t = T - 2; t >= 0; t--) {
         const double Xu = X[t], Vu = V[t];
-        const double Xp1 = fma(A, Xu, dot_row<PQ>(th.B, us + (size_t)t * PQ));
+        const double Bu = dot_row<PQ>(th.B, us + (size_t)t * PQ);
+        const double Xp1 = fma(A, Xu, Bu);
         const double Vp1 = fma(A2, Vu, Q);
         const double Jt = Vu * A * (1.0 / Vp1);
         const double Xs = fma(Jt, Xs1 - Xp1, Xu);
@@ -88,9 +93,12 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
         V[t] = Vs;
         if (J) J[t] = Jt;
         Y[t] = fma(th.C, Xs, dot_row<PQ>(th.D, vs + (size_t)t * PQ));
+        const double res = Xs1 - fma(A, Xs, Bu); // X_{t+1} - A X_t - B u_t   (R/LDS_GA.R:38)
+        ssq = fma(res, res, ssq);
         Xs1 = Xs;
         Vs1 = Vs;
     }
+    if (P.aux) P.aux[job] = ssq;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -175,7 +183,7 @@ template <int PQ> __global__ void propagate_kernel(const SmootherParams P) {
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta + (size_t)P.job_theta[job] * theta_pad_len<PQ>());
     const double A2 = th.A * th.A;
-    double Xp = th.mu1, Vp = th.V1, acc = 0.0;
+    double Xp = th.mu1, Vp = th.V1, acc = 0.0, ssq = 0.0;
     for (int t = 0; t < T; t++) {
         const double Yp = fma(th.C, Xp, dot_row<PQ>(th.D, vs + (size_t)t * PQ));
         X[t] = Xp;
@@ -184,6 +192,7 @@ template <int PQ> __global__ void propagate_kernel(const SmootherParams P) {
         if ((mw[t >> 5] >> (t & 31)) & 1u) {
             const double delta = ys[t] - Yp, Sg = fma(th.C * Vp, th.C, th.R);
             acc += delta / Sg * delta + log(Sg);
+            ssq = fma(delta, delta, ssq); // ssqTrain (R/LDS_GA.R:143-147)
         }
         Xp = fma(th.A, Xp, dot_row<PQ>(th.B, us + (size_t)t * PQ));
         Vp = fma(A2, Vp, th.Q);
@@ -191,6 +200,7 @@ template <int PQ> __global__ void propagate_kernel(const SmootherParams P) {
     const double n = (double)P.g_nobs[grp];
     double l = -0.5 * n * LOG_2PI - 0.5 * acc;
     P.lik[job] = P.stdlik ? l / n : l;
+    if (P.aux) P.aux[job] = ssq;
 }
 
 // ------------------------------------------------------------------------------------------

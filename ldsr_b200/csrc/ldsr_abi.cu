@@ -743,6 +743,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     sp.J = P->d_J;
     sp.lik = nullptr;
     sp.stdlik = 1;
+    sp.aux = nullptr;
     CU(P->kt->smoother(sp, st));
     launches++;
     CU(cudaMemsetAsync(P->d_sum, 0, sizeof(unsigned long long), st));
@@ -1024,7 +1025,7 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
 enum class StepKind { Smoother, Propagate };
 
 static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int stdlik, double *X, double *Y, double *V,
-                      double *J, double *lik) {
+                      double *J, double *lik, double *aux = nullptr, bool rows_to_host = true) {
     std::unique_ptr<ldsr_ctx> tmp_ctx;
     if (!ctx) {
         ldsr_ctx *c = nullptr;
@@ -1034,7 +1035,7 @@ static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int std
         tmp_ctx.reset(c);
         ctx = c;
     }
-    if (!X || !Y || !V) return fail(LDSR_ERR_ARG, "X, Y and V outputs are required");
+    if (rows_to_host && (!X || !Y || !V)) return fail(LDSR_ERR_ARG, "X, Y and V outputs are required");
     ldsr_plan *P = nullptr;
     Err e = plan_build(b, ctx->devices[0], ctx->pools[0].get(), &P);
     if (!e.ok()) return e;
@@ -1050,7 +1051,7 @@ static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int std
         jt[fi] = fi;
     }
     const size_t tot = (size_t)row_user[nf];
-    double *dX, *dY, *dV, *dJ = nullptr, *dlik;
+    double *dX, *dY, *dV, *dJ = nullptr, *dlik, *daux = nullptr;
     int *d_jt;
     long long *d_jr;
     if (!(e = P->dalloc(&dX, tot)).ok()) return e;
@@ -1058,6 +1059,7 @@ static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int std
     if (!(e = P->dalloc(&dV, tot)).ok()) return e;
     if (J && !(e = P->dalloc(&dJ, tot)).ok()) return e;
     if (!(e = P->dalloc(&dlik, nf)).ok()) return e;
+    if (aux && !(e = P->dalloc(&daux, nf)).ok()) return e;
     if (!(e = P->upload(&d_jt, jt)).ok()) return e;
     if (!(e = P->upload(&d_jr, jr)).ok()) return e;
     SmootherParams sp;
@@ -1078,12 +1080,20 @@ static Err step_batch(ldsr_ctx *ctx, const ldsr_batch *b, StepKind kind, int std
     sp.J = dJ;
     sp.lik = dlik;
     sp.stdlik = stdlik;
+    sp.aux = daux;
     CU(kind == StepKind::Smoother ? P->kt->smoother(sp, P->stream) : P->kt->propagate(sp, P->stream));
     CU(cudaStreamSynchronize(P->stream));
-    CU(cudaMemcpy(X, dX, tot * sizeof(double), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(Y, dY, tot * sizeof(double), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(V, dV, tot * sizeof(double), cudaMemcpyDeviceToHost));
-    if (J) CU(cudaMemcpy(J, dJ, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    if (rows_to_host) {
+        CU(cudaMemcpy(X, dX, tot * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(Y, dY, tot * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(V, dV, tot * sizeof(double), cudaMemcpyDeviceToHost));
+        if (J) CU(cudaMemcpy(J, dJ, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (aux) {
+        std::vector<double> a(nf);
+        CU(cudaMemcpy(a.data(), daux, nf * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int fi = 0; fi < nf; fi++) aux[P->f_user[fi]] = a[fi];
+    }
     if (lik) {
         std::vector<double> l(nf);
         CU(cudaMemcpy(l.data(), dlik, nf * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1342,6 +1352,24 @@ int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, c
     if (e.ok() && (n_shards < 1 || !group_shard)) e = fail(LDSR_ERR_ARG, "n_shards < 1 or group_shard is NULL");
     if (e.ok()) shard_groups(batch, n_shards, group_shard);
     return report(e, errbuf, errlen);
+}
+
+int ldsr_objective_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int kind, double lambda, double *values, char *errbuf,
+                         int errlen) {
+    auto run = [&]() -> Err {
+        if (!values) return fail(LDSR_ERR_ARG, "values is NULL");
+        if (kind < 0 || kind > 2) return fail(LDSR_ERR_ARG, "kind must be 0 (penalized_likelihood), 1 (negLogLik) or 2 (ssqTrain)");
+        if (!batch) return fail(LDSR_ERR_ARG, "batch is NULL");
+        const int nf = batch->n_fits;
+        std::vector<double> lik(std::max(nf, 1)), aux(std::max(nf, 1));
+        Err e = step_batch(ctx, batch, kind == 0 ? StepKind::Smoother : StepKind::Propagate, kind == 0 ? 0 : 1, nullptr,
+                           nullptr, nullptr, nullptr, lik.data(), aux.data(), false);
+        if (!e.ok()) return e;
+        for (int f = 0; f < nf; f++)
+            values[f] = kind == 0 ? lik[f] - lambda * aux[f] : (kind == 1 ? -lik[f] : aux[f]);
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
 }
 
 int ldsr_construct_rec_batch(int device, int n, int T, const double *X, const double *V, const double *Y,

@@ -159,3 +159,13 @@ construct_rec_batched <- function(fits, thetas, mu, transform, years, lambda = 0
   })
   list(members = members, mean = data.table::data.table(year = years, X = r$mean[, 1], Q = r$mean[, 2]))
 }
+
+
+#' Objective of the experimental learners for a whole population (R/LDS_GA.R:28-44, 136-147):
+#' `thetas` is a (2d+6) x n matrix of candidate vectors; kind is "penalized_likelihood", "negLogLik" or
+#' "ssqTrain".  GA::gaisl / optim call the scalar versions once per candidate; with a vectorised fitness
+#' (e.g. GA's `parallel` hook or a custom generation loop) one generation is one device call.
+objective_batched <- function(y, u, v, thetas, kind = "penalized_likelihood", lambda = 1) {
+  k <- match(kind, c("penalized_likelihood", "negLogLik", "ssqTrain")) - 1L
+  .Call(`_ldsr_objective`, y, u, v, thetas, as.integer(k), as.numeric(lambda))
+}

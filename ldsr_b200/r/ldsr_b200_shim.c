@@ -16,6 +16,7 @@
  *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans,z)                       9
  *     _ldsr_cv_metrics(Ycv,target,Z,exp_trans)                                        4
  *     _ldsr_construct_rec(X,V,Y,C,R,mu,transform,lambda)                              8
+ *     _ldsr_objective(y,u,v,thetas,kind,lambda)   thetas: (2d+6) x n matrix, one column per candidate   6
  *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
  *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
  *
@@ -323,6 +324,27 @@ SEXP _ldsr_construct_rec(SEXP X, SEXP V, SEXP Y, SEXP C, SEXP R, SEXP muS, SEXP 
     return out;
 }
 
+/* penalized_likelihood / negLogLik / ssqTrain (R/LDS_GA.R:28-44, 136-147) for a population of
+ * parameter vectors (the columns of `thetas`, in vec_to_list order, R/LDS_GA.R:6-16) in one call. */
+SEXP _ldsr_objective(SEXP y, SEXP u, SEXP v, SEXP thetas, SEXP kindS, SEXP lamS) {
+    char err[512] = "";
+    const int T = Rf_ncols(y), n = Rf_ncols(thetas), stride = Rf_nrows(thetas);
+    int p = 0, q = 0;
+    const double *up = input_ptr(u, T, &p), *vp = input_ptr(v, T, &q);
+    const double *yp = REAL(y);
+    int Ts = T, zero = 0, *fg = (int *)R_alloc((size_t)n, sizeof(int));
+    for (int i = 0; i < n; i++) fg[i] = 0;
+    ldsr_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_series = 1; b.n_groups = 1; b.n_fits = n; b.theta_stride = stride;
+    b.T = &Ts; b.p = &p; b.q = &q; b.y = &yp; b.u = &up; b.v = &vp;
+    b.group_series = &zero; b.fit_group = fg; b.theta0 = REAL(thetas);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+    check(ldsr_objective_batch(NULL, &b, Rf_asInteger(kindS), Rf_asReal(lamS), REAL(out), err, sizeof err), err);
+    UNPROTECT(1);
+    return out;
+}
+
 /* General state dimension (beyond the reference): theta holds R matrices, which are column-major;
  * the ABI wants row-major blocks. */
 static void put_rowmajor(SEXP m, int rows, int cols, double *out) {
@@ -379,6 +401,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
     {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
     {"_ldsr_construct_rec", (DL_FUNC)&_ldsr_construct_rec, 8},
+    {"_ldsr_objective", (DL_FUNC)&_ldsr_objective, 6},
     {NULL, NULL, 0}};
 
 void R_init_ldsr(DllInfo *dll) {

@@ -454,3 +454,19 @@ def test_construct_rec_kernel_reproduces_the_stored_reconstruction():
         a, am = _lib.construct_rec(X, V, Y, Cm, Rm, 0.7, tr, lam)
         b, bm = O.construct_rec(X, V, Y, Cm, Rm, 0.7, tr, lam)
         assert np.allclose(a, b, rtol=1e-12, atol=1e-13) and np.allclose(am, bm, rtol=1e-12, atol=1e-13), tr
+
+
+def test_objectives_of_the_experimental_learners():
+    # penalized_likelihood / negLogLik / ssqTrain (R/LDS_GA.R:28-44, 136-147) for a population of thetas
+    y, u, mu, inst = _np213()
+    rng = np.random.default_rng(17)
+    n = 40
+    th = rand_theta0(rng, 3, 3, n)
+    th[:, 8] = rng.uniform(0.2, 2.0, n)   # Q
+    th[:, 9] = rng.uniform(0.05, 1.0, n)  # R
+    ser = [dict(y=y, u=u, v=u)]
+    none = [np.array([], dtype=int)]
+    for kind, lam in (("penalized_likelihood", 1.0), ("penalized_likelihood", 0.25), ("negLogLik", 0.0), ("ssqTrain", 0.0)):
+        g = _lib.objective_batch(ser, [0], none, np.zeros(n, dtype=int), th, kind, lam)
+        o = np.array([O.objective(y, u, u, th[i], kind, lam) for i in range(n)])
+        assert np.allclose(g, o, rtol=1e-9, atol=1e-12), (kind, np.max(np.abs(g - o)))
