@@ -318,8 +318,24 @@ def calculate_metrics(sim, obs, z):
                 KGE=1 - np.sqrt((r - 1) ** 2 + (alpha - 1) ** 2 + (beta - 1) ** 2))
 
 
+def tbrm(x, C=9.0):
+    """Tukey's biweight robust mean, one step from the median, as dplR::tbrm (the reference's default
+    aggregator of metrics.dist, R/LDS_reconstruction.R:397-398).  dplR is not part of the reference tree
+    and is not installed here: this follows its published definition (Mosteller & Tukey 1977; weights
+    (1 - u^2)^2 with u = (x - median)/(C * MAD + 1e-6), |u| < 1) -- unpinned.  The reference's stored NPcv
+    result was aggregated with the plain mean (its `metrics` equal colMeans(metrics.dist))."""
+    x = np.asarray(x, dtype=float)
+    x = x[~np.isnan(x)]
+    if x.size == 0:
+        return float("nan")
+    m = np.median(x)
+    u = (x - m) / (C * np.median(np.abs(x - m)) + 1e-6)
+    w = np.where(np.abs(u) < 1, (1 - u * u) ** 2, 0.0)
+    return float(np.sum(w * x) / np.sum(w))
+
+
 def cvLDS(Qa, u, v, start_year, method="EM", transform="log", num_restarts=50, Z=None, metric_space="original",
-          use_raw=False, niter=1000, tol=1e-5, rng=None, n_devices=1):
+          use_raw=False, niter=1000, tol=1e-5, rng=None, n_devices=1, use_robust_mean=True):
     """R/LDS_reconstruction.R:308-409.  All folds x members x restarts run as ONE batch; initial
     values are drawn fold-major exactly as `foreach(z = Z) ... one_lds_cv` would under
     registerDoSEQ (:373-381, :275)."""
@@ -376,7 +392,8 @@ def cvLDS(Qa, u, v, start_year, method="EM", transform="log", num_restarts=50, Z
     keys = _lib.METRIC_NAMES
     dist = _lib.cv_metrics(np.stack(Ycv), target, Z)
     metrics_dist = {k: dist[:, j].copy() for j, k in enumerate(keys)}
-    return dict(metrics_dist=metrics_dist, metrics={k: float(np.mean(metrics_dist[k])) for k in keys},
+    mean_func = tbrm if use_robust_mean else np.mean  # R/LDS_reconstruction.R:397
+    return dict(metrics_dist=metrics_dist, metrics={k: float(mean_func(metrics_dist[k])) for k in keys},
                 target=dict(year=qyears, y=target), Ycv=np.stack(Ycv, axis=1), Z=Z,
                 best=r["best"], lik=r["lik"], iters=r["iters"])
 

@@ -88,3 +88,20 @@ def test_reference_arm_runs_on_rank0_only():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_tbrm_and_stored_cv_aggregate():
+    """The stored cvLDS result aggregates metrics.dist with the plain mean (R/sysdata.rda::NPcv);
+    api.tbrm (dplR's robust mean, unpinned) is at least a robust location: it ignores a gross outlier
+    and equals the mean on symmetric data."""
+    import json
+    import os
+    import numpy as np
+    from ldsr_b200 import api
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "npcv.json")))
+    for k in ("R2", "RE", "CE", "nRMSE", "KGE"):
+        assert abs(np.mean(g["metrics_dist"][k]) - g["metrics"][k][0]) < 1e-12
+    x = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    assert abs(api.tbrm(x) - 3.0) < 1e-12
+    assert abs(api.tbrm(np.append(x, 1e6)) - api.tbrm(np.append(x, 3.5))) < 0.5
+    assert np.isnan(api.tbrm([np.nan]))
