@@ -2,7 +2,9 @@
 """Per-source-line view of an ncu capture without the GUI: joins the SASS page of a .ncu-rep
 (instructions executed + warp-stall samples per instruction) with nvdisasm's line table of the
 object file the kernel was built from.
-    python tools/ncu_lines.py gpurun_out/em.ncu-rep ldsr_b200/build/kernels_pq3.o em_split_kernel [top]
+    python tools/ncu_lines.py gpurun_out/em.ncu-rep ldsr_b200/build/kernels_pq3.o em_split_kernelILi3ELi4ELi2E [top]
+The kernel pattern must select ONE instantiation (give enough of the mangled name): offsets of several
+functions would overwrite each other in the line table.
 Prints the hottest source lines (by stall samples) and totals per source function region."""
 import collections
 import csv
