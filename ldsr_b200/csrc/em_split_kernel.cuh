@@ -70,7 +70,9 @@ __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units
 // Unit types.  U: UW steps nobody observes.  M: MSEG steps.  M1: a single step -- the tail of the
 // series (everything from the last full M unit to step T-1) is cut into single steps so that the
 // hot M code never sees a partial unit and step T-1 (no transition after it) is a unit of its own.
-constexpr int UNIT_M = 1 << 30, UNIT_M1 = 1 << 29, UNIT_T0 = UNIT_M1 - 1;
+// US: MSEG steps inside a mixed window that no fit of the CTA observes (NP: 352..359 before the first
+// observation, 408..411 after the last): handled like a short U unit, about 6x cheaper than an M unit.
+constexpr int UNIT_M = 1 << 30, UNIT_M1 = 1 << 29, UNIT_US = 1 << 28, UNIT_T0 = UNIT_US - 1;
 
 // M / M1 units of the non-U window [t0, t0+uw): calls f(t, is_single)
 template <class F> __host__ __device__ inline void split_window_units(int t0, int T, int mseg, int uw, F f) {
@@ -461,6 +463,88 @@ __device__ __forceinline__ void smooth_unit(const Theta<PQ> &th, const SplitCons
     Vs1 = Vs[0];
 }
 
+// ---- short unobserved units (UNIT_US): N steps nobody observes, inside a mixed window ------------
+template <int N> struct ShortConst {
+    double AN, aV, bV; // A^N ; Vp' = aV Vp + bV over the unit
+    __device__ __forceinline__ ShortConst(double A, double A2, double Q) {
+        double an = 1.0, av = 1.0, sv = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            an *= A;
+            sv = fma(sv, A2, 1.0);
+            av *= A2;
+        }
+        AN = an;
+        aV = av;
+        bV = Q * sv;
+    }
+};
+// P2: the unit as one affine step of the mean and of the variance, and its backward map (telescoped)
+template <int PQ, int N>
+__device__ __forceinline__ void forward_short_basis(const Theta<PQ> &th, double A, double A2, double Q,
+                                                    const double *__restrict__ useg, PieceFwd &c) {
+    const ShortConst<N> sc(A, A2, Q);
+    double hh = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) hh = fma(A, hh, dot_row<PQ>(th.B, useg + j * PQ));
+    const double qn = fma(sc.AN, c.q, hh), Pn = sc.AN * c.P, Vn = fma(sc.aV, c.Vq, sc.bV);
+    const double Jc = sc.AN * c.Vq * fast_rcp(Vn);
+    const double g0 = fma(-Jc, qn, c.q), gP = fma(-Jc, Pn, c.P), L = c.Vq * fma(-sc.AN, Jc, 1.0);
+    c.G0 = fma(c.PJ, g0, c.G0);
+    c.GG = fma(c.PJ, gP, c.GG);
+    c.Lc = fma(c.PJ2, L, c.Lc);
+    c.PJ *= Jc;
+    c.PJ2 *= Jc * Jc;
+    c.q = qn;
+    c.P = Pn;
+    c.Vq = Vn;
+}
+// P4: streamed forward like smooth_word (same run constants cG, cH at the right end), sums taken per step
+template <int PQ, int N>
+__device__ __forceinline__ void smooth_short(const Theta<PQ> &th, double A, double A2, double Q,
+                                             const double *__restrict__ useg, double Xq, double Vq, double &cG,
+                                             double &cH, double &Xs1, double &Vs1, Stats<PQ> &st) {
+    double Gs[N], Hs[N]; // Q G and H at steps 1..N of the unit
+    Gs[N - 1] = Q * cG;
+    Hs[N - 1] = cH;
+#pragma unroll
+    for (int j = N - 2; j >= 0; j--) {
+        Gs[j] = A * Gs[j + 1];
+        Hs[j] = A2 * Hs[j + 1];
+    }
+    const ShortConst<N> sc(A, A2, Q);
+    const double G0 = sc.AN * cG, H0 = sc.aV * cH;
+    double Xn[N + 1], vp[N + 1], Vn[N + 1];
+    Xn[0] = fma(Vq, G0, Xq);
+    vp[0] = Vq;
+    Vn[0] = fma(Vq, Vq * H0, Vq);
+    double tv = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double inp = Gs[j];
+#pragma unroll
+        for (int i = 0; i < PQ; i++) inp = fma(th.B[i], useg[j * PQ + i], inp);
+        Xn[j + 1] = fma(A, Xn[j], inp); // Xs_{t+1} = A Xs_t + B u_t + Q G_{t+1}
+        vp[j + 1] = fma(A2, vp[j], Q);
+        const double t1 = vp[j + 1] * Hs[j];
+        Vn[j + 1] = fma(vp[j + 1], t1, vp[j + 1]);
+        st.Tx1x = fma(Xn[j + 1], Xn[j], st.Tx1x);
+        st.Txx = fma(Xn[j], Xn[j], st.Txx);
+        st.Txxv += Vn[j];
+        tv = fma(vp[j], 1.0 + t1, tv); // V_{t+1} J_t = A Vp_t (1 + Vp_{t+1} H_{t+1})
+#pragma unroll
+        for (int i = 0; i < PQ; i++) {
+            st.Tx1u[i] = fma(Xn[j + 1], useg[j * PQ + i], st.Tx1u[i]);
+            st.Tux[i] = fma(useg[j * PQ + i], Xn[j], st.Tux[i]);
+        }
+    }
+    st.Tx1xv = fma(A, tv, st.Tx1xv);
+    Xs1 = Xn[0];
+    Vs1 = Vn[0];
+    cG = G0;
+    cH = H0;
+}
+
 // ---- variance sums of an unobserved unit in closed form ------------------------------------------
 // Inside a U unit of n = UW steps that starts with prior variance v0 and whose right end carries
 // H = hR:   Vp_s = a^s v0 + Q sig_s  (a = A^2, sig_s = 1 + a + ... + a^(s-1)),   H_s = a^(n-s) hR,
@@ -644,6 +728,7 @@ struct SplitParams {
 
 // cut units [a,b) into NW pieces of about equal cost: bounds[0..NW]
 __device__ __forceinline__ int unit_cost(int u, int cost_u, int cost_m, int mseg) {
+    if (u & UNIT_US) return cost_m / 5;
     return (u & UNIT_M) ? cost_m : ((u & UNIT_M1) ? (3 * cost_m) / (2 * mseg) : cost_u);
 }
 template <int NW>
@@ -729,18 +814,31 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         lik = __longlong_as_double(0x7ff8000000000000ULL);
     }
 
-    // ---- unit table and piece bounds (warp 0; the vote is over the CTA's 32 fits)
+    // ---- unit table and piece bounds (warp 0).  Units are classified from the SERIES (is y finite?),
+    //      not from the hold-out masks of the fits that happen to share the CTA: which code path a fit
+    //      takes must not depend on its neighbours, or its result would change in the last bits with
+    //      the order of the batch and with the compaction between launches.
     if (warp == 0) {
+        mbar_wait(&bar, phase); // y is needed
+        auto any_finite = [&](int t0, int n) -> bool { // some y_t, t0 <= t < t0+n (n <= 32), is observed
+            const int t = t0 + lane;
+            const double yt = (lane < n && t < T) ? ys[t] : __longlong_as_double(0x7ff8000000000000ULL);
+            return __any_sync(FULL, yt == yt);
+        };
         int nu = 0;
         for (int t0 = 0; t0 < T; t0 += UW) {
-            const bool any = __any_sync(FULL, seg_bits(mw, t0, UW) != 0u);
+            const bool any = any_finite(t0, UW);
             const bool inside = t0 + UW <= T - 1;
             if (!any && inside) {
                 if (lane == 0) units[nu] = t0;
                 nu++;
             } else {
                 split_window_units(t0, T, MSEG, UW, [&](int t, bool single) {
-                    if (lane == 0) units[nu] = t | (single ? UNIT_M1 : UNIT_M);
+                    int type = single ? UNIT_M1 : UNIT_M;
+#ifndef LDSR_NO_US
+                    if (!single && !any_finite(t, MSEG)) type = UNIT_US;
+#endif
+                    if (lane == 0) units[nu] = t | type;
                     nu++;
                 });
             }
@@ -789,6 +887,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                     compose_var_unit<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), m11, m12, m21, m22);
                 } else if (u0 & UNIT_M1) {
                     compose_var_unit<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), m11, m12, m21, m22);
+                } else if (u0 & UNIT_US) {
+                    const ShortConst<MSEG> sc(k.A, k.A2, k.Q);
+                    m11 = fma(sc.aV, m11, sc.bV * m21);
+                    m12 = fma(sc.aV, m12, sc.bV * m22);
                 } else {
                     m11 = fma(k.aVW, m11, k.bVW * m21);
                     m12 = fma(k.aVW, m12, k.bVW * m22);
@@ -844,6 +946,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 } else if (u0 & UNIT_M1) {
                     any_m = true;
                     forward_unit_basis<PQ, UW, 1>(th, k, seg_bits(mw, t0, 1), ys + t0, us + t0 * PQ, vs + t0 * PQ, c);
+                } else if (u0 & UNIT_US) {
+                    forward_short_basis<PQ, MSEG>(th, k.A, k.A2, k.Q, us + t0 * PQ, c);
                 } else {
                     forward_word_basis<PQ, UW>(th, k, us + t0 * PQ, WK + (size_t)(t0 / UW) * PQ * 32, c);
                 }
@@ -959,6 +1063,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                         cH = (Vs1 - Vr) * rv * rv;
                         in_run = true;
                     }
+                    if (u0 & UNIT_US)
+                        smooth_short<PQ, MSEG>(th, k.A, k.A2, k.Q, us + t0 * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
+                    else
                     smooth_word<PQ, UW>(th, k, us + t0 * PQ, UV, WK + (size_t)(t0 / UW) * PQ * 32,
                                         P.uwin + S.uwin_off + (size_t)(t0 / UW) * PQ * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
                 }

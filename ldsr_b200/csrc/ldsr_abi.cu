@@ -673,8 +673,10 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             sp.max_units = P->max_units;
             sp.max_uunits = max_uunits;
             sp.blob_smem = (int)blob_sm;
-            sp.cost_u = P->kt->split_uw * 33; // instructions per U / M unit, measured
-            sp.cost_m = P->kt->split_mseg * 185;
+            // instructions per step of a U / M unit, measured at PQ = 3 (profiles/em_r01_split3_lines.txt);
+            // scaling them with the input width was tried and balanced the PQ = 10 job worse (46.2 vs 45.0 ms)
+            sp.cost_u = P->kt->split_uw * 22;
+            sp.cost_m = P->kt->split_mseg * 168;
             // one wave of at most two CTAs per SM: the 255-register build of the kernel
             if (grid <= 2 * P->n_sm)
                 CU(P->kt->em_split_wide(sp, grid, smem, st));
