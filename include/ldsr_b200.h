@@ -126,6 +126,10 @@ typedef struct {
 typedef struct ldsr_ctx ldsr_ctx;
 int ldsr_ctx_create(int n_devices, const int *devices, ldsr_ctx **out, char *errbuf, int errlen);
 void ldsr_ctx_destroy(ldsr_ctx *ctx);
+/* The arenas are caches: blocks are kept for reuse between calls and handed back to the driver only
+   when an allocation fails, on ldsr_ctx_destroy, or here.  Returns the device bytes released (blocks
+   in use by a live plan are kept); cached_bytes, if not NULL, receives what the context still holds. */
+long long ldsr_ctx_trim(ldsr_ctx *ctx, long long *cached_bytes);
 int ldsr_device_count(void); /* 0 when there is no usable CUDA device */
 int ldsr_abi_version(void);
 

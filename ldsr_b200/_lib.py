@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_INTERRUPTED, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 FIT_OK, FIT_SINGULAR, FIT_NONFINITE = 0, 1, 2
 
 # every symbol include/ldsr_b200.h declares (checked by tests/test_abi_symbols.py)
-EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy",
+EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx_destroy", "ldsr_ctx_trim",
            "ldsr_em_batch", "ldsr_plan_create", "ldsr_plan_em", "ldsr_plan_set_theta0",
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
@@ -64,6 +64,7 @@ def lib():
         for name in EXPORTS:
             getattr(L, name).restype = C.c_int
         L.ldsr_ctx_destroy.restype = None
+        L.ldsr_ctx_trim.restype = C.c_longlong
         L.ldsr_plan_destroy.restype = None
         _lib = L
     return _lib
@@ -178,6 +179,12 @@ class Ctx:
         err = C.create_string_buffer(512)
         rc = lib().ldsr_ctx_create(int(dv.size if dv is not None else n_devices), _i(dv), C.byref(self.h), err, 512)
         _check(rc, err)
+
+    def trim(self):
+        """Hand the cached device blocks back to the driver: (bytes released, bytes still held)."""
+        kept = C.c_longlong(0)
+        freed = lib().ldsr_ctx_trim(self.h, C.byref(kept))
+        return int(freed), int(kept.value)
 
     def close(self):
         if self.h:

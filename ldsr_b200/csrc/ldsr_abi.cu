@@ -122,6 +122,12 @@ class DevicePool {
         }
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation) {
+            // the cache may be holding blocks of other sizes: give them back and try once more
+            cudaGetLastError();
+            trim_locked();
+            e = cudaMalloc(&p, bytes);
+        }
         if (e != cudaSuccess) return e;
         blocks_.push_back({p, bytes, true});
         *out = p;
@@ -132,6 +138,17 @@ class DevicePool {
         for (auto &b : blocks_)
             if (b.ptr == p) b.used = false;
     }
+    // frees every cached block that is not in use; returns the device bytes given back
+    size_t trim() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return trim_locked();
+    }
+    size_t cached_bytes() {
+        std::lock_guard<std::mutex> lk(mu_);
+        size_t n = 0;
+        for (auto &b : blocks_) n += b.size;
+        return n;
+    }
     int device() const { return device_; }
 
   private:
@@ -140,6 +157,32 @@ class DevicePool {
         size_t size;
         bool used;
     };
+    size_t trim_locked() {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device_);
+        size_t freed = 0;
+        auto drop = [&](std::vector<Block> &v, bool pinned) {
+            size_t keep = 0;
+            for (auto &b : v) {
+                if (b.used) {
+                    v[keep++] = b;
+                    continue;
+                }
+                if (pinned)
+                    cudaFreeHost(b.ptr);
+                else {
+                    cudaFree(b.ptr);
+                    freed += b.size;
+                }
+            }
+            v.resize(keep);
+        };
+        drop(blocks_, false);
+        drop(pinned_, true);
+        if (prev >= 0) cudaSetDevice(prev);
+        return freed;
+    }
     int device_;
     std::mutex mu_;
     std::vector<Block> blocks_, pinned_;
@@ -696,12 +739,16 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     } else {
         CU(cudaStreamSynchronize(st));
     }
+    static const bool trace_chunks = std::getenv("LDSR_TIMING") != nullptr;
     for (int c = 0; c < enq; ++c) {
         if (P->h_counts[2 * c + 1] > 0) chunks++; // launches that had live fits
         if (stats) {
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, evs[2 * c], evs[2 * c + 1]));
             if (P->h_counts[2 * c + 1] > 0) em_ms += ms;
+            if (trace_chunks)
+                std::fprintf(stderr, "[ldsr] chunk %d: %d tasks, %d live fits, %.3f ms\n", c, P->h_counts[2 * c],
+                             P->h_counts[2 * c + 1], ms);
         }
     }
     // ---- selection + the winners' smoothed trajectories
@@ -1288,6 +1335,17 @@ int ldsr_ctx_create(int n_devices, const int *devices, ldsr_ctx **out, char *err
 }
 
 void ldsr_ctx_destroy(ldsr_ctx *ctx) { delete ctx; }
+
+long long ldsr_ctx_trim(ldsr_ctx *ctx, long long *cached_bytes) {
+    long long freed = 0, kept = 0;
+    if (ctx)
+        for (auto &p : ctx->pools) {
+            freed += (long long)p->trim();
+            kept += (long long)p->cached_bytes();
+        }
+    if (cached_bytes) *cached_bytes = kept;
+    return freed;
+}
 
 int ldsr_em_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int niter, double tol, const ldsr_options *opt,
                   ldsr_em_result *out, char *errbuf, int errlen) {

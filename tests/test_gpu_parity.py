@@ -470,3 +470,66 @@ def test_objectives_of_the_experimental_learners():
         g = _lib.objective_batch(ser, [0], none, np.zeros(n, dtype=int), th, kind, lam)
         o = np.array([O.objective(y, u, u, th[i], kind, lam) for i in range(n)])
         assert np.allclose(g, o, rtol=1e-9, atol=1e-12), (kind, np.max(np.abs(g - o)))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_unusual_initial_values(variant):
+    # initial values outside make_init's ranges: negative / explosive A, negative C, tiny and large noise
+    # variances.  The unobserved-unit shortcuts use powers of A and A^2 up to A^64: they must agree with
+    # the step-by-step oracle for every sign and for |A| > 1 as well.
+    y, u, mu, inst = data.np_case(401, 1600)  # T = 413, 360 unobserved steps before the first record
+    base = np.array([0.5, 0.3, -0.2, 0.1, 0.5, 0.05, -0.1, 0.2, 1.0, 1.0, 0.0, 1.0])
+    th = []
+    for A in (-0.9, -0.3, 1e-3, 0.999, 1.02):
+        for C in (0.7, -0.4):
+            for Q, R in ((1.0, 1.0), (1e-3, 10.0), (25.0, 1e-3)):
+                t = base.copy()
+                t[0], t[4], t[8], t[9] = A, C, Q, R
+                th.append(t)
+    th = np.stack(th)
+    fg = np.zeros(len(th), dtype=int)
+    none = [np.array([], dtype=int)]
+    g = _lib.em_batch([dict(y=y, u=u, v=u)], [0], none, fg, th, 4, 0.0, want_liks=True, variant=variant)
+    o = O.em_batch([dict(y=y, u=u, v=u)], [0], none, fg, th, 4, 0.0)
+    assert np.array_equal(g["iters"], o["iters"])
+    # a stable start is held to the usual bars; an explosive one (A = 1.02: the predicted variance reaches
+    # 1e7 Q before the first record, so the update (1 - K C) P cancels ~11 digits against R = 1e-3) is
+    # ill-conditioned in the reference's own arithmetic and is held to the digits that survive
+    stable = np.abs(th[:, 0]) < 1.0
+    assert np.allclose(g["lik"][stable], o["lik"][stable], rtol=1e-9, atol=0)
+    assert_theta_close(g["theta"][stable], o["theta"][stable], 1e-6)
+    assert np.allclose(g["lik"][~stable], o["lik"][~stable], rtol=1e-6, atol=0)
+    assert_theta_close(g["theta"][~stable], o["theta"][~stable], 1e-5)
+
+
+def test_repeated_calls_reuse_the_context_arenas_and_trim_releases_them():
+    # a long R session calls the library thousands of times with batches of varying size: the
+    # context's cache must stop growing once it has seen the largest call, repeated calls must give
+    # identical results, and ldsr_ctx_trim must hand the cached blocks back
+    import torch
+
+    torch.cuda.init()
+    y, u, mu, inst = _np213()
+    ser = [dict(y=y, u=u, v=u)]
+    none = [np.array([], dtype=int)]
+    ctx = _lib.Ctx(devices=[0])
+    sizes = [64, 7, 300, 33, 128, 300, 5, 64, 300, 17, 300, 64]
+    first, free = {}, []
+    for n in sizes:
+        th = rand_theta0(np.random.default_rng(1000), 3, 3, 300)[:n]
+        r = _lib.em_batch(ser, [0], none, np.zeros(n, dtype=int), th, 30, 1e-5, ctx=ctx, want_traj=False)
+        key = n
+        if key in first:
+            assert np.array_equal(first[key]["theta"], r["theta"], equal_nan=True)
+            assert np.array_equal(first[key]["lik"], r["lik"])
+        first[key] = r
+        free.append(torch.cuda.mem_get_info(0)[0])
+    assert free[-1] == free[5], (free[5], free[-1])  # no growth after the largest batch has been seen twice
+    freed, kept = ctx.trim()
+    assert freed > 0 and kept == 0
+    assert torch.cuda.mem_get_info(0)[0] >= free[-1] + freed - (1 << 20)
+    r = _lib.em_batch(ser, [0], none, np.zeros(64, dtype=int),
+                      rand_theta0(np.random.default_rng(1000), 3, 3, 300)[:64],
+                      30, 1e-5, ctx=ctx, want_traj=False)
+    assert np.array_equal(first[64]["lik"], r["lik"])
+    ctx.close()
