@@ -169,3 +169,9 @@ objective_batched <- function(y, u, v, thetas, kind = "penalized_likelihood", la
   k <- match(kind, c("penalized_likelihood", "negLogLik", "ssqTrain")) - 1L
   .Call(`_ldsr_objective`, y, u, v, thetas, as.integer(k), as.numeric(lambda))
 }
+
+
+#' The shim keeps one device context per R session; its device and pinned buffers are cached between
+#' calls.  This hands the cached device memory back to the driver (bytes released, invisibly); the next
+#' call simply allocates again.  Unloading the package (R_unload_ldsr) releases everything.
+ldsr_gpu_trim <- function() invisible(.Call(`_ldsr_trim`))

@@ -18,6 +18,7 @@
  *     _ldsr_construct_rec(X,V,Y,C,R,mu,transform,lambda)                              8
  *     _ldsr_objective(y,u,v,thetas,kind,lambda)   thetas: (2d+6) x n matrix, one column per candidate   6
  *     _ldsr_smoother_d(y,u,v,theta,stdlik,method)                                     6
+ *     _ldsr_trim()                                release the session's cached device memory  0
  *       (state dimension d > 1: theta$A is d x d, B d x p, C 1 x d, D 1 x q, Q d x d, R, mu1 d, V1 d x d)
  *
  * The reference's `matrix(0)` sentinel (a 1x1 matrix, EM.cpp:50,71) is mapped to a NULL u/v
@@ -29,6 +30,18 @@
 #include <string.h>
 
 #include "ldsr_b200.h"
+
+/* One context per R session: its device and pinned arenas are reused by every call (a context per
+ * call would pay cudaMalloc / cudaMallocHost each time).  Created on first use, released by
+ * R_unload_ldsr or by ldsr_gpu_trim() from R. */
+static ldsr_ctx *session_ctx = NULL;
+static ldsr_ctx *ctx(void) {
+    if (!session_ctx) {
+        char err[256] = "";
+        if (ldsr_ctx_create(0, NULL, &session_ctx, err, sizeof err) != LDSR_OK) Rf_error("ldsr_b200: %s", err);
+    }
+    return session_ctx;
+}
 
 static const char *TH_NAMES[] = {"A", "B", "C", "D", "Q", "R", "mu1", "V1", ""};
 
@@ -123,7 +136,7 @@ SEXP _ldsr_Kalman_smoother(SEXP y, SEXP u, SEXP v, SEXP theta, SEXP stdlik) {
     one_fit f; char err[512] = "";
     one_fit_init(&f, y, u, v, theta);
     double *buf = (double *)R_alloc(4 * (size_t)f.T, sizeof(double)), lik;
-    check(ldsr_smoother_batch(NULL, &f.b, Rf_asLogical(stdlik), buf, buf + f.T, buf + 2 * f.T, buf + 3 * f.T, &lik,
+    check(ldsr_smoother_batch(ctx(), &f.b, Rf_asLogical(stdlik), buf, buf + f.T, buf + 2 * f.T, buf + 3 * f.T, &lik,
                               err, sizeof err), err);
     return fit_list(buf, buf + f.T, buf + 2 * f.T, buf + 3 * f.T, lik, f.T);
 }
@@ -134,7 +147,7 @@ SEXP _ldsr_Mstep(SEXP y, SEXP u, SEXP v, SEXP fit) {
     one_fit_init(&f, y, u, v, R_NilValue);
     int status = 0;
     double *th = (double *)R_alloc(f.p + f.q + 6, sizeof(double));
-    check(ldsr_mstep_batch(NULL, &f.b, REAL(list_get(fit, "X")), REAL(list_get(fit, "V")), REAL(list_get(fit, "J")),
+    check(ldsr_mstep_batch(ctx(), &f.b, REAL(list_get(fit, "X")), REAL(list_get(fit, "V")), REAL(list_get(fit, "J")),
                            th, &status, err, sizeof err), err);
     if (status == LDSR_FIT_SINGULAR) Rf_error("inv(): matrix is singular");
     SEXP out = PROTECT(flat_to_theta(th, f.p, f.q));
@@ -155,7 +168,7 @@ SEXP _ldsr_LDS_EM(SEXP y, SEXP u, SEXP v, SEXP theta0, SEXP niterS, SEXP tolS) {
     r.X = buf; r.Y = buf + f.T; r.V = buf + 2 * f.T; r.J = buf + 3 * f.T;
     ldsr_options opt; memset(&opt, 0, sizeof opt);
     opt.n_devices = 1; opt.poll = poll_interrupt;
-    check(ldsr_em_batch(NULL, &f.b, niter, Rf_asReal(tolS), &opt, &r, err, sizeof err), err);
+    check(ldsr_em_batch(ctx(), &f.b, niter, Rf_asReal(tolS), &opt, &r, err, sizeof err), err);
     if (status == LDSR_FIT_SINGULAR) Rf_error("inv(): matrix is singular");
     const char *nm[] = {"theta", "fit", "liks", "lik", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
@@ -174,7 +187,7 @@ SEXP _ldsr_propagate(SEXP theta, SEXP u, SEXP v, SEXP y, SEXP stdlik) {
     one_fit f; char err[512] = "";
     one_fit_init(&f, y, u, v, theta);
     double *buf = (double *)R_alloc(3 * (size_t)f.T, sizeof(double)), lik;
-    check(ldsr_propagate_batch(NULL, &f.b, Rf_asLogical(stdlik), buf, buf + f.T, buf + 2 * f.T, &lik, err, sizeof err),
+    check(ldsr_propagate_batch(ctx(), &f.b, Rf_asLogical(stdlik), buf, buf + f.T, buf + 2 * f.T, &lik, err, sizeof err),
           err);
     const char *nm[] = {"X", "Y", "V", "lik", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
@@ -241,7 +254,7 @@ SEXP _ldsr_em_batch(SEXP series, SEXP group_series, SEXP held, SEXP fit_group, S
     ldsr_options opt; memset(&opt, 0, sizeof opt);
     opt.n_devices = Rf_asInteger(ndevS); opt.poll = poll_interrupt;
     char err[512] = "";
-    check(ldsr_em_batch(NULL, &b, Rf_asInteger(niterS), Rf_asReal(tolS), &opt, &r, err, sizeof err), err);
+    check(ldsr_em_batch(ctx(), &b, Rf_asInteger(niterS), Rf_asReal(tolS), &opt, &r, err, sizeof err), err);
     for (int g = 0; g < ng; g++) INTEGER(best)[g] = INTEGER(best)[g] < 0 ? NA_INTEGER : INTEGER(best)[g] + 1;
     SET_VECTOR_ELT(out, 0, th); SET_VECTOR_ELT(out, 1, lik); SET_VECTOR_ELT(out, 2, it);
     SET_VECTOR_ELT(out, 3, st); SET_VECTOR_ELT(out, 4, best);
@@ -276,7 +289,7 @@ SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS
     /* z: num_reps*(1+2n) standard normals drawn by R in one_LDS_rep's order (R/stochastics.R:23-26), or NULL */
     const double *z = Rf_isNull(zS) ? NULL : REAL(zS);
     if (z && XLENGTH(zS) != (R_xlen_t)reps * (1 + 2 * (R_xlen_t)n)) Rf_error("ldsr: z must hold num.reps*(1+2n) draws");
-    check(ldsr_rep_batch(NULL, th, up, vp, n, p, q, reps, z, (unsigned long long)Rf_asReal(seedS), Rf_asReal(muS),
+    check(ldsr_rep_batch(ctx(), th, up, vp, n, p, q, reps, z, (unsigned long long)Rf_asReal(seedS), Rf_asReal(muS),
                          Rf_asLogical(expS), o, o + (size_t)n * reps, o + 2 * (size_t)n * reps, err, sizeof err), err);
     UNPROTECT(1);
     return out;
@@ -340,7 +353,7 @@ SEXP _ldsr_objective(SEXP y, SEXP u, SEXP v, SEXP thetas, SEXP kindS, SEXP lamS)
     b.T = &Ts; b.p = &p; b.q = &q; b.y = &yp; b.u = &up; b.v = &vp;
     b.group_series = &zero; b.fit_group = fg; b.theta0 = REAL(thetas);
     SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
-    check(ldsr_objective_batch(NULL, &b, Rf_asInteger(kindS), Rf_asReal(lamS), REAL(out), err, sizeof err), err);
+    check(ldsr_objective_batch(ctx(), &b, Rf_asInteger(kindS), Rf_asReal(lamS), REAL(out), err, sizeof err), err);
     UNPROTECT(1);
     return out;
 }
@@ -391,6 +404,9 @@ SEXP _ldsr_smoother_d(SEXP y, SEXP u, SEXP v, SEXP theta, SEXP stdlik, SEXP meth
     return out;
 }
 
+/* bytes of cached device memory handed back to the driver */
+SEXP _ldsr_trim(void) { return Rf_ScalarReal(session_ctx ? (double)ldsr_ctx_trim(session_ctx, NULL) : 0.0); }
+
 static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_Kalman_smoother", (DL_FUNC)&_ldsr_Kalman_smoother, 5},
     {"_ldsr_Mstep", (DL_FUNC)&_ldsr_Mstep, 4},
@@ -402,9 +418,16 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
     {"_ldsr_construct_rec", (DL_FUNC)&_ldsr_construct_rec, 8},
     {"_ldsr_objective", (DL_FUNC)&_ldsr_objective, 6},
+    {"_ldsr_trim", (DL_FUNC)&_ldsr_trim, 0},
     {NULL, NULL, 0}};
 
 void R_init_ldsr(DllInfo *dll) {
     R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
     R_useDynamicSymbols(dll, FALSE);
+}
+
+void R_unload_ldsr(DllInfo *dll) {
+    (void)dll;
+    if (session_ctx) ldsr_ctx_destroy(session_ctx);
+    session_ctx = NULL;
 }
