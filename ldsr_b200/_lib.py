@@ -203,15 +203,16 @@ class EmOutputs:
 
     def __init__(self, pb, niter, want_liks=False, want_traj=True):
         nf, ng = pb.n_fits, pb.n_groups
+        # the library writes every element of every output except the tail of a theta row beyond
+        # its series' p + q + 6 (kept NaN here)
         self.theta = np.full((nf, pb.stride), np.nan)
-        self.lik = np.full(nf, np.nan)
-        self.iters = np.zeros(nf, dtype=np.int32)
-        self.status = np.zeros(nf, dtype=np.int32)
-        self.best = np.full(ng, -1, dtype=np.int32)
-        self.liks = np.full((nf, niter), np.nan) if want_liks else None
+        self.lik = np.empty(nf)
+        self.iters = np.empty(nf, dtype=np.int32)
+        self.status = np.empty(nf, dtype=np.int32)
+        self.best = np.empty(ng, dtype=np.int32)
+        self.liks = np.empty((nf, niter)) if want_liks else None
         tot = int(pb.traj_ptr[-1])
-        self.X, self.Y, self.V, self.J = ((np.full(tot, np.nan) for _ in range(4)) if want_traj
-                                          else (None,) * 4)
+        self.X, self.Y, self.V, self.J = ((np.empty(tot) for _ in range(4)) if want_traj else (None,) * 4)
         self.c = EmResult(_d(self.theta), _d(self.lik), _i(self.iters), _i(self.status),
                           _d(self.liks), _i(self.best), _d(self.X), _d(self.Y), _d(self.V), _d(self.J))
 

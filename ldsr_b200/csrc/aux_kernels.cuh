@@ -40,8 +40,10 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
     const double *__restrict__ us = P.blobs + S.blob_off + S.u_off;
     const double *__restrict__ vs = P.blobs + S.blob_off + S.v_off;
     const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
-    double *X = P.X + P.job_row[job], *Y = P.Y + P.job_row[job], *V = P.V + P.job_row[job],
-           *J = P.J ? P.J + P.job_row[job] : nullptr;
+    // the four output rows of a job never overlap each other or the inputs
+    double *__restrict__ X = P.X + P.job_row[job], *__restrict__ Y = P.Y + P.job_row[job],
+                        *__restrict__ V = P.V + P.job_row[job],
+                        *__restrict__ J = P.J ? P.J + P.job_row[job] : nullptr;
     if (P.job_theta[job] < 0) {
         const double nan = __longlong_as_double(0x7ff8000000000000ULL);
         for (int t = 0; t < T; t++) {
@@ -81,8 +83,18 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
     }
     double Xs1 = X[T - 1], Vs1 = V[T - 1];
     double ssq = 0.0;
+    // The filtered rows come back from L2 (hundreds of cycles); nothing in the recursion depends on
+    // the address, so the loads run two steps ahead of their use.
+    double Xn0 = X[T - 2], Vn0 = V[T - 2];
+    double Xn1 = T > 2 ? X[T - 3] : 0.0, Vn1 = T > 2 ? V[T - 3] : 0.0;
     for (int t = T - 2; t >= 0; t--) {
-        const double Xu = X[t], Vu = V[t];
+        const double Xu = Xn0, Vu = Vn0;
+        Xn0 = Xn1;
+        Vn0 = Vn1;
+        if (t >= 2) {
+            Xn1 = X[t - 2];
+            Vn1 = V[t - 2];
+        }
         const double Bu = dot_row<PQ>(th.B, us + (size_t)t * PQ);
         const double Xp1 = fma(A, Xu, Bu);
         const double Vp1 = fma(A2, Vu, Q);

@@ -169,89 +169,144 @@ __global__ void merge_status_kernel(const SeriesDev *series, const double *scons
 }
 
 // ------------------------------------------------------------------------------------------
-// Restart selection, one thread per group (R/LDS_reconstruction.R:50-58): among fits with C > 0
+// Restart selection, one warp per group (R/LDS_reconstruction.R:50-58): among fits with C > 0
 // the first with the largest non-NaN lik; if no fit has C > 0, the first largest non-NaN lik.
-// Also writes the per-fit status.
+// Also writes the per-fit status.  Lanes stride over the group's fits; "first" is kept by breaking
+// likelihood ties towards the lower fit index in the lane merge.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void select_merge(double &l, int &f, double lo, int fo) {
+    // (lo, fo) replaces (l, f) when it is a valid candidate that is larger, or equal and earlier
+    if (fo >= 0 && (f < 0 || lo > l || (lo == l && fo < f))) {
+        l = lo;
+        f = fo;
+    }
+}
 __global__ void select_kernel(int n_groups, const int *g_fit_ptr, const double *theta, int theta_len, int c_index,
                               const double *lik, const int *g_status, int *best, int *f_status) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_groups) return; // whole warps leave together
+    const int gs = g_status[g];
+    double lpos = 0.0, lall = 0.0;
     int bpos = -1, ball = -1;
     bool any_pos = false;
-    for (int f = g_fit_ptr[g]; f < g_fit_ptr[g + 1]; f++) {
+    for (int f = g_fit_ptr[g] + lane; f < g_fit_ptr[g + 1]; f += 32) {
         const double l = lik[f], c = theta[(size_t)f * theta_len + c_index];
-        f_status[f] = g_status[g] ? 1 : (isfinite(l) ? 0 : 2);
+        f_status[f] = gs ? 1 : (isfinite(l) ? 0 : 2);
+        // posC is decided on C alone, NaN liks included (which(allC > 0))
+        if (c > 0.0) any_pos = true;
         if (l != l) continue;
-        if (c > 0.0) {
-            any_pos = true;
-            if (bpos < 0 || l > lik[bpos]) bpos = f;
+        if (c > 0.0 && (bpos < 0 || l > lpos)) {
+            lpos = l;
+            bpos = f;
         }
-        if (ball < 0 || l > lik[ball]) ball = f;
+        if (ball < 0 || l > lall) {
+            lall = l;
+            ball = f;
+        }
     }
-    // posC is decided on C alone, NaN liks included (which(allC > 0))
-    if (!any_pos)
-        for (int f = g_fit_ptr[g]; f < g_fit_ptr[g + 1]; f++)
-            if (theta[(size_t)f * theta_len + c_index] > 0.0) any_pos = true;
-    best[g] = any_pos ? bpos : ball;
+    for (int o = 16; o > 0; o >>= 1) {
+        select_merge(lpos, bpos, __shfl_xor_sync(FULL, lpos, o), __shfl_xor_sync(FULL, bpos, o));
+        select_merge(lall, ball, __shfl_xor_sync(FULL, lall, o), __shfl_xor_sync(FULL, ball, o));
+    }
+    any_pos = __any_sync(FULL, any_pos);
+    if (lane == 0) best[g] = any_pos ? bpos : ball;
 }
 
 // ---- compaction of live fits, per series (fits of a series are contiguous) --------------------
-// One block per series: writes the ids of its live fits to active[fit_begin ..) and the count to
-// n_live[series].
-__global__ void compact_kernel(const SeriesDev *series, const int *done, int *active, int *n_live) {
+// One block per series: writes the ids of its live fits to active[fit_begin ..) in order and the
+// count to n_live[series].  Each thread owns a contiguous run of fits (count, block scan, write).
+// The last block to finish turns the per-series counts into the CTA task list:
+// counts[0] = number of CTA tasks, counts[1] = number of live fits; *ticket is left at 0 again.
+__global__ void compact_kernel(const SeriesDev *series, int n_series, const int *done, int *active, int *n_live,
+                               int fits_per_cta, int4 *tasks, int *task_off, int *counts, unsigned *ticket) {
     __shared__ int warp_sums[32];
-    __shared__ int base;
+    __shared__ bool last;
     const SeriesDev S = series[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    for (int f0 = S.fit_begin; f0 < S.fit_end; f0 += blockDim.x) {
-        const int f = f0 + threadIdx.x;
-        const bool lv = f < S.fit_end && done[f] == 0;
-        const unsigned bal = __ballot_sync(FULL, lv);
-        if (lane == 0) warp_sums[warp] = __popc(bal);
-        __syncthreads();
-        int off = base;
-        for (int w = 0; w < warp; w++) off += warp_sums[w];
-        if (lv) active[S.fit_begin + off + __popc(bal & ((1u << lane) - 1u))] = f;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < nw; w++) tot += warp_sums[w];
-            base += tot;
-        }
-        __syncthreads();
+    const int n = S.fit_end - S.fit_begin, per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = S.fit_begin + min(n, (int)threadIdx.x * per), hi = S.fit_begin + min(n, ((int)threadIdx.x + 1) * per);
+    int mine = 0;
+    for (int f = lo; f < hi; f++) mine += done[f] == 0;
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
     }
-    if (threadIdx.x == 0) n_live[blockIdx.x] = base;
-}
-
-// Single block: turns the per-series live counts into the CTA task list.
-// counts[0] = number of CTA tasks, counts[1] = number of live fits.
-__global__ void build_tasks_kernel(const SeriesDev *series, int n_series, const int *n_live, int fits_per_cta,
-                                   int4 *tasks, int *task_off, int *counts) {
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int off = incl - mine, total = 0;
+    for (int w = 0; w < nw; w++) {
+        if (w < warp) off += warp_sums[w];
+        total += warp_sums[w];
+    }
+    for (int f = lo; f < hi; f++)
+        if (done[f] == 0) active[S.fit_begin + off++] = f;
+    if (threadIdx.x == 0) {
+        n_live[blockIdx.x] = total;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     if (threadIdx.x == 0) {
         int nt = 0, nl = 0;
         for (int s = 0; s < n_series; s++) {
+            const int live = ((volatile int *)n_live)[s];
             task_off[s] = nt;
-            nt += (n_live[s] + fits_per_cta - 1) / fits_per_cta;
-            nl += n_live[s];
+            nt += (live + fits_per_cta - 1) / fits_per_cta;
+            nl += live;
         }
         task_off[n_series] = nt;
         counts[0] = nt;
         counts[1] = nl;
+        *ticket = 0;
     }
     __syncthreads();
     for (int s = 0; s < n_series; s++) {
-        const int n = task_off[s + 1] - task_off[s];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int live = ((volatile int *)n_live)[s], t0 = task_off[s], nt = task_off[s + 1] - t0;
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
             const int first = i * fits_per_cta;
-            const int cnt = min(fits_per_cta, n_live[s] - first);
-            tasks[task_off[s] + i] = make_int4(s, series[s].fit_begin + first, cnt, 0);
+            tasks[t0 + i] = make_int4(s, series[s].fit_begin + first, min(fits_per_cta, live - first), 0);
         }
     }
 }
 
+
+// ---- results in the caller's order and layout, ready for one device-to-host copy ---------------
+// theta rows are unpadded to the caller's (p, q) (B / D come back as zeros when the series has no
+// u / v, EM.cpp:186,154); fit-indexed outputs move from internal to caller order; best[] is mapped
+// to caller fit ids.  One thread per fit, the first n_groups threads also do a group.
+struct PackParams {
+    int n_fits, n_groups, theta_len, pq, stride; // theta_len = 2 pq + 6 (device), stride = caller's row length
+    const SeriesDev *series;
+    const int *g_series, *f_group, *f_user, *g_user;
+    const double *theta, *lik;
+    const int *iters, *status, *best;
+    double *theta_u, *lik_u;
+    int *iters_u, *status_u, *best_u;
+};
+__global__ void pack_results_kernel(const PackParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_fits) {
+        const SeriesDev S = P.series[P.g_series[P.f_group[i]]];
+        const int fu = P.f_user[i];
+        const double *src = P.theta + (size_t)i * P.theta_len;
+        double *dst = P.theta_u + (size_t)fu * P.stride;
+        dst[0] = src[0];
+        for (int j = 0; j < S.p; j++) dst[1 + j] = S.has_u ? src[1 + j] : 0.0;
+        dst[1 + S.p] = src[1 + P.pq];
+        for (int j = 0; j < S.q; j++) dst[2 + S.p + j] = S.has_v ? src[2 + P.pq + j] : 0.0;
+        for (int k = 0; k < 4; k++) dst[2 + S.p + S.q + k] = src[2 + 2 * P.pq + k];
+        P.lik_u[fu] = P.lik[i];
+        P.iters_u[fu] = P.iters[i];
+        P.status_u[fu] = P.status[i];
+    }
+    if (i < P.n_groups) {
+        const int b = P.best[i];
+        P.best_u[P.g_user[i]] = b < 0 ? -1 : P.f_user[b];
+    }
+}
 
 // ---- cross-validation skill metrics (the epilogue of cvLDS) --------------------------------------
 // calculate_metrics (R/utils.R:56-70) with the definitions of src/utils.cpp:13-97, one warp per

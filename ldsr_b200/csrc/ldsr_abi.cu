@@ -238,11 +238,18 @@ struct ldsr_plan {
     int4 *d_tasks = nullptr;
     int max_tasks = 0;
     unsigned long long *d_sum = nullptr;
+    unsigned *d_ticket = nullptr; // compact_kernel's last-block counter (0 between launches)
     double *d_ckpt = nullptr;
     size_t ckpt_cap = 0;
     int *d_best = nullptr;
     // winners' trajectories (internal group order rows)
     double *d_X = nullptr, *d_Y = nullptr, *d_V = nullptr, *d_J = nullptr;
+    // results block in the caller's order (pack_results_kernel), fetched with one copy:
+    // [theta nf x stride | lik nf | iters nf, status nf, best ng (int) | X | Y | V | J]
+    double *d_res = nullptr, *h_res = nullptr; // h_res pinned
+    size_t res_head = 0, res_total = 0;        // doubles: everything before X, everything
+    int *d_g_user = nullptr;
+    bool same_width = true; // every series has p + q + 6 == theta_stride
     int *d_job_group = nullptr, *d_job_theta = nullptr;
     long long *d_job_row = nullptr;
     int *h_counts = nullptr; // pinned
@@ -268,6 +275,7 @@ struct ldsr_plan {
         if (stream) cudaStreamSynchronize(stream);
         for (void *p : allocs) pool->release(p);
         if (h_counts) pool->release_pinned(h_counts);
+        if (h_res) pool->release_pinned(h_res);
         if (stream) pool->put_stream(stream);
     }
 };
@@ -506,6 +514,11 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->upload(&P->d_held_idx, held_idx)).ok()) return e;
     if (!(e = P->upload(&P->d_f_group, P->h_f_group)).ok()) return e;
     if (!(e = P->upload(&P->d_f_user, P->f_user)).ok()) return e;
+    if (!(e = P->upload(&P->d_g_user, P->g_user)).ok()) return e;
+    for (int s = 0; s < ns; s++) P->same_width = P->same_width && b->p[s] + b->q[s] + 6 == b->theta_stride;
+    P->res_head = (size_t)nf * b->theta_stride + nf + ((size_t)2 * nf + ng + 1) / 2;
+    P->res_total = P->res_head + 4 * (size_t)P->traj_total;
+    if (!(e = P->dalloc(&P->d_res, P->res_total)).ok()) return e;
     if (!(e = P->upload(&P->d_theta0, th0)).ok()) return e;
     if (!(e = P->dalloc(&P->d_masks, (size_t)nwords)).ok()) return e;
     if (!(e = P->dalloc(&P->d_sconst, (size_t)sconst_off)).ok()) return e;
@@ -524,6 +537,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->dalloc(&P->d_task_off, ns + 1)).ok()) return e;
     if (!(e = P->dalloc(&P->d_counts, COUNTS_CAP)).ok()) return e;
     if (!(e = P->dalloc(&P->d_sum, 1)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_ticket, 1)).ok()) return e;
+    CU(cudaMemsetAsync(P->d_ticket, 0, sizeof(unsigned), P->stream));
     P->max_tasks = nf / 32 + ns + 1; // the time-split kernel takes 32 fits per CTA
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
@@ -563,6 +578,15 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     if (!(tol == tol)) return fail(LDSR_ERR_ARG, "tol is NaN");
     CU(cudaSetDevice(P->device));
     if (!st) st = P->stream;
+    if (st != P->stream) {
+        // the plan's uploads and set-up kernels were enqueued on its own stream: order the caller's after them
+        cudaEvent_t ready = nullptr;
+        CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ready, P->stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(st, ready, 0);
+        cudaEventDestroy(ready);
+        CU(e1);
+    }
     const int nf = P->n_fits, ns = P->n_series, ng = P->n_groups;
     const int chunk = (opt && opt->chunk_iters > 0) ? opt->chunk_iters : 100;
     long long launches = 0, chunks = 0;
@@ -684,10 +708,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     int enq = 0;
     for (int c = 0; c < max_chunks; ++c) {
         int *cnt = P->d_counts + 2 * c;
-        compact_kernel<<<ns, 1024, 0, st>>>(P->d_series, P->d_done, P->d_active, P->d_n_live);
-        build_tasks_kernel<<<1, 256, 0, st>>>(P->d_series, ns, P->d_n_live, fits_per_cta, P->d_tasks, P->d_task_off,
-                                              cnt);
-        launches += 2;
+        compact_kernel<<<ns, 1024, 0, st>>>(P->d_series, ns, P->d_done, P->d_active, P->d_n_live, fits_per_cta,
+                                            P->d_tasks, P->d_task_off, cnt, P->d_ticket);
+        launches++;
         // Later chunks have at most grid0 tasks.  For a batch that fits the machine in one wave the
         // grid is capped at two CTAs per SM: CTAs are dealt to SMs in launch order, so idle CTAs
         // ahead of live ones would push three live CTAs onto some SMs while others hold one
@@ -752,16 +775,16 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         }
     }
     // ---- selection + the winners' smoothed trajectories
-    select_kernel<<<(ng + 127) / 128, 128, 0, st>>>(ng, P->d_g_fit_ptr, P->d_theta, P->TL, 1 + P->PQ, P->d_lik,
+    select_kernel<<<(ng + 3) / 4, 128, 0, st>>>(ng, P->d_g_fit_ptr, P->d_theta, P->TL, 1 + P->PQ, P->d_lik,
                                                     P->d_g_status, P->d_best, P->d_status);
     CU(cudaGetLastError());
     launches++;
     if (!P->d_X) {
         Err e;
-        if (!(e = P->dalloc(&P->d_X, (size_t)P->traj_total)).ok()) return e;
-        if (!(e = P->dalloc(&P->d_Y, (size_t)P->traj_total)).ok()) return e;
-        if (!(e = P->dalloc(&P->d_V, (size_t)P->traj_total)).ok()) return e;
-        if (!(e = P->dalloc(&P->d_J, (size_t)P->traj_total)).ok()) return e;
+        P->d_X = P->d_res + P->res_head;
+        P->d_Y = P->d_X + P->traj_total;
+        P->d_V = P->d_Y + P->traj_total;
+        P->d_J = P->d_V + P->traj_total;
         std::vector<int> jg(ng);
         std::vector<long long> jr(ng);
         for (int gi = 0; gi < ng; gi++) {
@@ -818,47 +841,70 @@ static Err plan_fetch(ldsr_plan *P, ldsr_em_result *out) {
     if (!P->em_done) return fail(LDSR_ERR_ARG, "ldsr_plan_fetch before a successful ldsr_plan_em");
     if (!out) return fail(LDSR_ERR_ARG, "result struct is NULL");
     CU(cudaSetDevice(P->device));
-    const int nf = P->n_fits, ng = P->n_groups, TL = P->TL;
-    std::vector<double> th, lik;
-    std::vector<int> tmp;
-    if (out->theta) {
-        th.resize((size_t)nf * TL);
-        CU(cudaMemcpy(th.data(), P->d_theta, th.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int fi = 0; fi < nf; fi++) {
-            const int s = P->h_g_series[P->h_f_group[fi]];
-            unpad_theta(&th[(size_t)fi * TL], P->s_p[s], P->s_q[s], P->h_series[s].has_u != 0,
-                        P->h_series[s].has_v != 0, P->PQ, out->theta + (size_t)P->f_user[fi] * P->theta_stride);
-        }
+    const int nf = P->n_fits, ng = P->n_groups, stride = P->theta_stride;
+    cudaStream_t st = P->stream;
+    // pack on the device (caller's order and layout), one copy into pinned memory, then plain memcpys
+    double *d_theta_u = P->d_res, *d_lik_u = d_theta_u + (size_t)nf * stride;
+    int *d_int = reinterpret_cast<int *>(d_lik_u + nf);
+    PackParams pk;
+    pk.n_fits = nf;
+    pk.n_groups = ng;
+    pk.theta_len = P->TL;
+    pk.pq = P->PQ;
+    pk.stride = stride;
+    pk.series = P->d_series;
+    pk.g_series = P->d_g_series;
+    pk.f_group = P->d_f_group;
+    pk.f_user = P->d_f_user;
+    pk.g_user = P->d_g_user;
+    pk.theta = P->d_theta;
+    pk.lik = P->d_lik;
+    pk.iters = P->d_ne;
+    pk.status = P->d_status;
+    pk.best = P->d_best;
+    pk.theta_u = d_theta_u;
+    pk.lik_u = d_lik_u;
+    pk.iters_u = d_int;
+    pk.status_u = d_int + nf;
+    pk.best_u = d_int + 2 * (size_t)nf;
+    pack_results_kernel<<<(std::max(nf, ng) + 255) / 256, 256, 0, st>>>(pk);
+    CU(cudaGetLastError());
+    if (!P->h_res) {
+        void *hp = nullptr;
+        CU(P->pool->alloc_pinned(P->res_total * sizeof(double), &hp));
+        P->h_res = static_cast<double *>(hp);
     }
-    if (out->lik) {
-        lik.resize(nf);
-        CU(cudaMemcpy(lik.data(), P->d_lik, nf * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int fi = 0; fi < nf; fi++) out->lik[P->f_user[fi]] = lik[fi];
-    }
-    if (out->iters) {
-        tmp.resize(nf);
-        CU(cudaMemcpy(tmp.data(), P->d_ne, nf * sizeof(int), cudaMemcpyDeviceToHost));
-        for (int fi = 0; fi < nf; fi++) out->iters[P->f_user[fi]] = tmp[fi];
-    }
-    if (out->status) {
-        tmp.resize(nf);
-        CU(cudaMemcpy(tmp.data(), P->d_status, nf * sizeof(int), cudaMemcpyDeviceToHost));
-        for (int fi = 0; fi < nf; fi++) out->status[P->f_user[fi]] = tmp[fi];
-    }
+    const bool traj = out->X || out->Y || out->V || out->J;
+    CU(cudaMemcpyAsync(P->h_res, P->d_res, (traj ? P->res_total : P->res_head) * sizeof(double),
+                       cudaMemcpyDeviceToHost, st));
     if (out->liks) {
         if (!P->d_liks) return fail(LDSR_ERR_ARG, "liks requested at fetch but not at ldsr_plan_em time");
-        CU(cudaMemcpy(out->liks, P->d_liks, (size_t)nf * P->last_niter * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(out->liks, P->d_liks, (size_t)nf * P->last_niter * sizeof(double), cudaMemcpyDeviceToHost,
+                           st));
     }
-    if (out->best) {
-        tmp.resize(ng);
-        CU(cudaMemcpy(tmp.data(), P->d_best, ng * sizeof(int), cudaMemcpyDeviceToHost));
-        for (int gi = 0; gi < ng; gi++) out->best[P->g_user[gi]] = tmp[gi] < 0 ? -1 : P->f_user[tmp[gi]];
+    CU(cudaStreamSynchronize(st));
+    const double *h_theta = P->h_res, *h_lik = h_theta + (size_t)nf * stride;
+    const int *h_int = reinterpret_cast<const int *>(h_lik + nf);
+    if (out->theta) {
+        if (P->same_width)
+            std::memcpy(out->theta, h_theta, sizeof(double) * (size_t)nf * stride);
+        else // the tail of a caller row beyond its series' p + q + 6 is left as the caller set it
+            for (int fi = 0; fi < nf; fi++) {
+                const int s = P->h_g_series[P->h_f_group[fi]];
+                const size_t row = (size_t)P->f_user[fi] * stride;
+                std::memcpy(out->theta + row, h_theta + row, sizeof(double) * (P->s_p[s] + P->s_q[s] + 6));
+            }
     }
-    const size_t tb = (size_t)P->traj_total * sizeof(double);
-    if (out->X) CU(cudaMemcpy(out->X, P->d_X, tb, cudaMemcpyDeviceToHost));
-    if (out->Y) CU(cudaMemcpy(out->Y, P->d_Y, tb, cudaMemcpyDeviceToHost));
-    if (out->V) CU(cudaMemcpy(out->V, P->d_V, tb, cudaMemcpyDeviceToHost));
-    if (out->J) CU(cudaMemcpy(out->J, P->d_J, tb, cudaMemcpyDeviceToHost));
+    if (out->lik) std::memcpy(out->lik, h_lik, sizeof(double) * nf);
+    if (out->iters) std::memcpy(out->iters, h_int, sizeof(int) * nf);
+    if (out->status) std::memcpy(out->status, h_int + nf, sizeof(int) * nf);
+    if (out->best) std::memcpy(out->best, h_int + 2 * (size_t)nf, sizeof(int) * ng);
+    const size_t tt = (size_t)P->traj_total, tb = tt * sizeof(double);
+    const double *h_traj = P->h_res + P->res_head;
+    if (out->X) std::memcpy(out->X, h_traj, tb);
+    if (out->Y) std::memcpy(out->Y, h_traj + tt, tb);
+    if (out->V) std::memcpy(out->V, h_traj + 2 * tt, tb);
+    if (out->J) std::memcpy(out->J, h_traj + 3 * tt, tb);
     return Err();
 }
 
