@@ -30,6 +30,23 @@ struct SmootherParams {
     double *aux;
 };
 
+// Input rows of a block of BK consecutive steps starting at t0, in registers (zeros past the end).
+// Every lane of a warp reads the same addresses, so these are L1 broadcasts; issuing a block at a
+// time, one block ahead of its use, keeps the L1/L2 latency out of the recursion.
+template <int PQ, int BK>
+__device__ __forceinline__ void load_rows(const double *__restrict__ rows, int t0, int T, double (&dst)[BK * PQ]) {
+#pragma unroll
+    for (int k = 0; k < BK; k++)
+#pragma unroll
+        for (int j = 0; j < PQ; j++) dst[k * PQ + j] = t0 + k >= 0 && t0 + k < T ? rows[(size_t)(t0 + k) * PQ + j] : 0.0;
+}
+template <int PQ> __device__ __forceinline__ double dot_regs(const double (&w)[PQ], const double *row) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < PQ; j++) s = fma(w[j], row[j], s);
+    return s;
+}
+
 template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
     const int job = blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= P.n_jobs) return;
@@ -56,26 +73,48 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta + (size_t)P.job_theta[job] * theta_pad_len<PQ>());
     const double A = th.A, A2 = th.A * th.A, Q = th.Q;
+    // steps per block: about 24 input values in flight, always a divisor of the 32-step mask word
+    constexpr int BK = PQ <= 3 ? 8 : (PQ <= 6 ? 4 : (PQ <= 12 ? 2 : 1));
+    const bool same_uv = S.same_uv != 0;
+
+    // ---- forward (EM.cpp:43-90); Xu, Vu are parked in the X, V rows
     double Xp = th.mu1, Vp = th.V1, acc = 0.0;
-    for (int t = 0; t < T; t++) {
-        const bool obs = (mw[t >> 5] >> (t & 31)) & 1u;
-        double Xu = Xp, Vu = Vp;
-        if (obs) {
-            double dq, Sg;
-            measurement_update<PQ>(th, true, ys[t], vs + (size_t)t * PQ, Xp, Vp, Xu, Vu, dq, Sg);
-            acc += dq + log(Sg);
+    {
+        double ub[BK * PQ], un[BK * PQ];
+        load_rows<PQ, BK>(us, 0, T, ub);
+        for (int t0 = 0; t0 < T; t0 += BK) {
+            load_rows<PQ, BK>(us, t0 + BK, T, un);
+            const unsigned bits = mw[t0 >> 5] >> (t0 & 31);
+#pragma unroll
+            for (int k = 0; k < BK; k++) {
+                const int t = t0 + k;
+                if (t >= T) break;
+                double Xu = Xp, Vu = Vp;
+                if ((bits >> k) & 1u) { // EM.cpp:61-68, 82-89
+                    const double Dv = same_uv ? dot_regs<PQ>(th.D, &ub[k * PQ]) : dot_row<PQ>(th.D, vs + (size_t)t * PQ);
+                    const double Sg = fma(th.C * Vp, th.C, th.R);
+                    const double rS = 1.0 / Sg;
+                    const double K = Vp * th.C * rS;
+                    const double delta = ys[t] - fma(th.C, Xp, Dv);
+                    Xu = fma(K, delta, Xp);
+                    Vu = (1.0 - K * th.C) * Vp;
+                    acc += delta * rS * delta + log(Sg);
+                }
+                X[t] = Xu;
+                V[t] = Vu;
+                Xp = fma(A, Xu, dot_regs<PQ>(th.B, &ub[k * PQ]));
+                Vp = fma(A2, Vu, Q);
+            }
+#pragma unroll
+            for (int i = 0; i < BK * PQ; i++) ub[i] = un[i];
         }
-        X[t] = Xu;
-        V[t] = Vu;
-        Xp = fma(A, Xu, dot_row<PQ>(th.B, us + (size_t)t * PQ));
-        Vp = fma(A2, Vu, Q);
     }
     if (P.lik) {
         const double n = (double)P.g_nobs[grp];
         double l = -0.5 * n * LOG_2PI - 0.5 * acc;
         P.lik[job] = P.stdlik ? l / n : l;
     }
-    // backward (EM.cpp:94-110)
+    // ---- backward (EM.cpp:94-110)
     {
         const double VuT = V[T - 1];
         if (J) J[T - 1] = VuT * A * (1.0 / fma(A2, VuT, Q)); // EM.cpp:98
@@ -83,32 +122,54 @@ template <int PQ> __global__ void smoother_kernel(const SmootherParams P) {
     }
     double Xs1 = X[T - 1], Vs1 = V[T - 1];
     double ssq = 0.0;
-    // The filtered rows come back from L2 (hundreds of cycles); nothing in the recursion depends on
-    // the address, so the loads run two steps ahead of their use.
-    double Xn0 = X[T - 2], Vn0 = V[T - 2];
-    double Xn1 = T > 2 ? X[T - 3] : 0.0, Vn1 = T > 2 ? V[T - 3] : 0.0;
-    for (int t = T - 2; t >= 0; t--) {
-        const double Xu = Xn0, Vu = Vn0;
-        Xn0 = Xn1;
-        Vn0 = Vn1;
-        if (t >= 2) {
-            Xn1 = X[t - 2];
-            Vn1 = V[t - 2];
+    // The filtered rows come back from L2 (several hundred cycles per access): they are read a
+    // block at a time as well, one block ahead of the arithmetic.  Blocks are [lo, lo + BK), walked
+    // downwards from the block that holds T - 2; step k of a block is lo + k.
+    {
+        double xb[BK], vb[BK], xn[BK], vn[BK], ub[BK * PQ], un[BK * PQ];
+        int lo = ((T - 2) / BK) * BK;
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            xb[k] = lo + k <= T - 2 ? X[lo + k] : 0.0;
+            vb[k] = lo + k <= T - 2 ? V[lo + k] : 0.0;
         }
-        const double Bu = dot_row<PQ>(th.B, us + (size_t)t * PQ);
-        const double Xp1 = fma(A, Xu, Bu);
-        const double Vp1 = fma(A2, Vu, Q);
-        const double Jt = Vu * A * (1.0 / Vp1);
-        const double Xs = fma(Jt, Xs1 - Xp1, Xu);
-        const double Vs = fma(Jt * (Vs1 - Vp1), Jt, Vu);
-        X[t] = Xs;
-        V[t] = Vs;
-        if (J) J[t] = Jt;
-        Y[t] = fma(th.C, Xs, dot_row<PQ>(th.D, vs + (size_t)t * PQ));
-        const double res = Xs1 - fma(A, Xs, Bu); // X_{t+1} - A X_t - B u_t   (R/LDS_GA.R:38)
-        ssq = fma(res, res, ssq);
-        Xs1 = Xs;
-        Vs1 = Vs;
+        load_rows<PQ, BK>(us, lo, T, ub);
+        for (; lo >= 0; lo -= BK) {
+#pragma unroll
+            for (int k = 0; k < BK; k++) {
+                xn[k] = lo - BK + k >= 0 ? X[lo - BK + k] : 0.0;
+                vn[k] = lo - BK + k >= 0 ? V[lo - BK + k] : 0.0;
+            }
+            load_rows<PQ, BK>(us, lo - BK, T, un);
+#pragma unroll
+            for (int k = BK - 1; k >= 0; k--) {
+                const int t = lo + k;
+                if (t > T - 2) continue;
+                const double Xu = xb[k], Vu = vb[k];
+                const double Bu = dot_regs<PQ>(th.B, &ub[k * PQ]);
+                const double Xp1 = fma(A, Xu, Bu);
+                const double Vp1 = fma(A2, Vu, Q);
+                const double Jt = Vu * A * fast_rcp(Vp1); // off the loop-carried chain: overlaps across the block
+                const double Xs = fma(Jt, Xs1 - Xp1, Xu);
+                const double Vs = fma(Jt * (Vs1 - Vp1), Jt, Vu);
+                X[t] = Xs;
+                V[t] = Vs;
+                if (J) J[t] = Jt;
+                // v differs from u only for callers that pass two input sets: read in place then
+                Y[t] = fma(th.C, Xs, same_uv ? dot_regs<PQ>(th.D, &ub[k * PQ]) : dot_row<PQ>(th.D, vs + (size_t)t * PQ));
+                const double res = Xs1 - fma(A, Xs, Bu); // X_{t+1} - A X_t - B u_t   (R/LDS_GA.R:38)
+                ssq = fma(res, res, ssq);
+                Xs1 = Xs;
+                Vs1 = Vs;
+            }
+#pragma unroll
+            for (int k = 0; k < BK; k++) {
+                xb[k] = xn[k];
+                vb[k] = vn[k];
+            }
+#pragma unroll
+            for (int i = 0; i < BK * PQ; i++) ub[i] = un[i];
+        }
     }
     if (P.aux) P.aux[job] = ssq;
 }

@@ -775,6 +775,12 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         }
     }
     // ---- selection + the winners' smoothed trajectories
+    cudaEvent_t tail_a = nullptr, tail_b = nullptr;
+    if (trace_chunks && stats) {
+        cudaEventCreate(&tail_a);
+        cudaEventCreate(&tail_b);
+        cudaEventRecord(tail_a, st);
+    }
     select_kernel<<<(ng + 3) / 4, 128, 0, st>>>(ng, P->d_g_fit_ptr, P->d_theta, P->TL, 1 + P->PQ, P->d_lik,
                                                     P->d_g_status, P->d_best, P->d_status);
     CU(cudaGetLastError());
@@ -818,6 +824,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     sp.aux = nullptr;
     CU(P->kt->smoother(sp, st));
     launches++;
+    if (tail_a) cudaEventRecord(tail_b, st);
     CU(cudaMemsetAsync(P->d_sum, 0, sizeof(unsigned long long), st));
     sum_int_kernel<<<64, 256, 0, st>>>(P->d_ne, nf, P->d_sum);
     launches++;
@@ -826,6 +833,14 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     P->em_done = true;
+    if (tail_a) {
+        float ms = 0.f, all = 0.f;
+        cudaEventElapsedTime(&ms, tail_a, tail_b);
+        if (!evs.empty()) cudaEventElapsedTime(&all, evs.front(), tail_b);
+        std::fprintf(stderr, "[ldsr] selection + winners' smoother %.3f ms; first chunk start -> end %.3f ms\n", ms, all);
+        cudaEventDestroy(tail_a);
+        cudaEventDestroy(tail_b);
+    }
     if (stats) {
         stats[0] = launches;
         stats[1] = chunks;
