@@ -724,7 +724,30 @@ struct SplitParams {
     int max_uunits;     // number of UW-step windows of the longest series
     int blob_smem;      // bytes reserved for the series blob at the start of dynamic shared memory
     int cost_u, cost_m; // relative cost of a U unit and an M unit (piece balancing)
+#ifdef LDSR_PHASE_CLOCKS
+    long long *clk; // development build: [CTA][NW][21] cycles per phase / unit type of the iteration loop
+#endif
 };
+#ifdef LDSR_PHASE_CLOCKS
+#define LDSR_PHASE_MARK(kk)                       \
+    do {                                          \
+        const long long c_ = clock64();           \
+        pc[kk] += c_ - tprev;                     \
+        tprev = c_;                               \
+    } while (0)
+#define LDSR_UNIT_BEGIN() const long long ub_ = clock64()
+#define LDSR_UNIT_END(base, u0) pc[(base) + (((u0) & UNIT_M) ? 1 : ((u0) & UNIT_M1) ? 2 : ((u0) & UNIT_US) ? 3 : 0)] += clock64() - ub_
+#else
+#define LDSR_PHASE_MARK(kk) \
+    do {                    \
+    } while (0)
+#define LDSR_UNIT_BEGIN() \
+    do {                  \
+    } while (0)
+#define LDSR_UNIT_END(base, u0) \
+    do {                        \
+    } while (0)
+#endif
 
 // cut units [a,b) into NW pieces of about equal cost: bounds[0..NW]
 __device__ __forceinline__ int unit_cost(int u, int cost_u, int cost_m, int mseg) {
@@ -867,6 +890,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     mbar_wait(&bar, phase);
     __syncthreads();
 
+#ifdef LDSR_PHASE_CLOCKS
+    long long pc[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
     for (int it = 0; it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
         SplitConst<PQ, UW> k;
@@ -874,6 +900,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
 
         // ================= P1: variance maps of my pieces =================
         if (warp == NW - 1) uvar_constants<UW>(k.A2, k.Q, k.aVW, UV); // this warp has no second map to build
+        LDSR_PHASE_MARK(9);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int pj = h * NW + warp;
@@ -901,7 +928,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             MC[(pj * 4 + 2) * 32] = m21;
             MC[(pj * 4 + 3) * 32] = m22;
         }
+        LDSR_PHASE_MARK(0);
         __syncthreads();
+        LDSR_PHASE_MARK(1);
         double VinA = th.V1, VinB = th.V1; // prior variance entering piece warp / piece NW+warp
         {
             double n = th.V1, d = 1.0;
@@ -918,6 +947,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             }
         }
 
+        LDSR_PHASE_MARK(10);
         // ================= P2: forward over my pieces =================
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -939,6 +969,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 ck[(un * 3 + 0) * 32] = c.Vq;
                 ck[(un * 3 + 1) * 32] = c.q;
                 ck[(un * 3 + 2) * 32] = c.P;
+                LDSR_UNIT_BEGIN();
                 if (u0 & UNIT_M) {
                     any_m = true;
                     forward_unit_basis<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), ys + t0, us + t0 * PQ,
@@ -951,6 +982,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 } else {
                     forward_word_basis<PQ, UW>(th, k, us + t0 * PQ, WK + (size_t)(t0 / UW) * PQ * 32, c);
                 }
+                LDSR_UNIT_END(13, u0);
             }
             double ld = 0.0;
             if (any_m) ld = fma((double)c.shift, 0.693147180559945309417, log(c.dprod));
@@ -966,7 +998,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             o[8 * 32] = c.Lc;
             o[9 * 32] = c.Vq;
         }
+        LDSR_PHASE_MARK(2);
         __syncthreads();
+        LDSR_PHASE_MARK(3);
 
         // ---- chain the pieces: x_in of every piece, likelihood (identical in every warp)
         double gk[NP];                   // full backward offset of each piece
@@ -1029,7 +1063,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 Vs = fma(pjv * pjv, Vs, o[8 * 32]);
             }
         }
+        LDSR_PHASE_MARK(4);
         __syncthreads(); // the piece summaries are dead: their space becomes the partial sums
+        LDSR_PHASE_MARK(5);
 
         // ================= P4: backward over my pieces, M-step sums =================
         Stats<PQ> st;
@@ -1048,6 +1084,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 const int t0 = u0 & UNIT_T0;
                 const double Vq = ck[(un * 3 + 0) * 32];
                 const double Xq = fma(ck[(un * 3 + 2) * 32], xin, ck[(un * 3 + 1) * 32]);
+                LDSR_UNIT_BEGIN();
                 if (u0 & UNIT_M) {
                     smooth_unit<PQ, UW, MSEG>(th, k, seg_bits(mw, t0, MSEG), false, ys + t0, us + t0 * PQ,
                                               vs + t0 * PQ, Xq, Vq, Xs1, Vs1, st);
@@ -1069,6 +1106,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                     smooth_word<PQ, UW>(th, k, us + t0 * PQ, UV, WK + (size_t)(t0 / UW) * PQ * 32,
                                         P.uwin + S.uwin_off + (size_t)(t0 / UW) * PQ * PQ, Xq, Vq, cG, cH, Xs1, Vs1, st);
                 }
+                LDSR_UNIT_END(17, u0);
                 Xr = Xq;
                 Vr = Vq;
             }
@@ -1077,9 +1115,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 st.V0 = Vs1;
             }
         }
+        LDSR_PHASE_MARK(6);
         if (!PAIR) {
             stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
             __syncthreads();
+            LDSR_PHASE_MARK(7);
             // ============ M-step (EM.cpp:139-229), same arithmetic in every warp ============
             st.zero();
 #pragma unroll
@@ -1096,12 +1136,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
 #pragma unroll
             for (int w = 0; w < NW / 2; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
         }
+        LDSR_PHASE_MARK(11);
         if (live) {
             mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
             l2 = l1;
             l1 = lik;
         }
+        LDSR_PHASE_MARK(8);
     }
+#ifdef LDSR_PHASE_CLOCKS
+    if (lane == 0 && SP.clk)
+        for (int i = 0; i < 21; i++) SP.clk[((size_t)blockIdx.x * NW + warp) * 21 + i] = pc[i];
+#endif
 
     if (warp == 0 && valid) {
         store_theta<PQ>(th, P.theta + (size_t)fit * TL);

@@ -572,6 +572,9 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
 }
 
 // ---- the EM driver ---------------------------------------------------------------------------
+#ifdef LDSR_PHASE_CLOCKS
+static long long *sp_clk_last = nullptr; // development build only
+#endif
 static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt, cudaStream_t st, bool want_liks,
                    std::atomic<int> *abort_flag, long long *stats) {
     if (niter < 2) return fail(LDSR_ERR_ARG, "niter=%d: the reference requires niter >= 2 (EM.cpp:247,256)", niter);
@@ -743,6 +746,10 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             // scaling them with the input width was tried and balanced the PQ = 10 job worse (46.2 vs 45.0 ms)
             sp.cost_u = P->kt->split_uw * 22;
             sp.cost_m = P->kt->split_mseg * 168;
+#ifdef LDSR_PHASE_CLOCKS
+            if (!sp_clk_last) cudaMalloc(&sp_clk_last, sizeof(long long) * 4096 * 21 * 8);
+            sp.clk = (c == 1 && grid <= 4096) ? sp_clk_last : nullptr; // the second launch: a two-per-SM wave
+#endif
             // one wave of at most two CTAs per SM: the 255-register build of the kernel
             if (grid <= 2 * P->n_sm)
                 CU(P->kt->em_split_wide(sp, grid, smem, st));
@@ -752,6 +759,28 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             CU(P->kt->em_chunk(ep, grid, smem, st));
         }
         if (stats) CU(cudaEventRecord(evs.back(), st));
+#ifdef LDSR_PHASE_CLOCKS
+        if (use_split && c == 1 && grid <= 4096) {
+            const int nw = P->kt->split_nw;
+            std::vector<long long> h((size_t)grid * nw * 21);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h.data(), sp_clk_last, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            static const char *names[21] = {"P1 loops", "B1 wait", "P2", "B2 wait", "chain+stop", "B2' wait",
+                                            "P4", "B3 wait", "M-step", "constants", "prefix", "reduce",
+                                            "-", "P2 U words", "P2 M units", "P2 M1 units",
+                                            "P2 US units", "P4 U words", "P4 M units", "P4 M1 units", "P4 US units"};
+            std::fprintf(stderr, "[ldsr] phase clocks of launch 1 (cycles per iteration, mean over %d CTAs), per warp:\n", grid);
+            for (int i = 0; i < 21; i++) {
+                std::fprintf(stderr, "[ldsr]   %-14s", names[i]);
+                for (int w = 0; w < nw; w++) {
+                    double sum = 0;
+                    for (int b = 0; b < grid; b++) sum += (double)h[((size_t)b * nw + w) * 21 + i];
+                    std::fprintf(stderr, " %9.0f", sum / grid / chunk);
+                }
+                std::fprintf(stderr, "\n");
+            }
+        }
+#endif
         launches++;
         enq++;
     }
