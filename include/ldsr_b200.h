@@ -177,6 +177,28 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    int exp_trans, double *simX, double *simY, double *simQ, char *errbuf,
                    int errlen);
 
+/* The same, with the noise the reference itself would draw: equal to `set.seed(r_seed);
+ * LDS_rep(theta, u, v, years, num.reps = n_reps, mu, exp.trans)` under R's default generators
+ * (Mersenne-Twister + Inversion, one stream across the replicates, R/stochastics.R:23-26,60-61).
+ * The n_reps*(1+2n) normals are generated on the device (r_rng.cuh) and never cross PCIe. */
+int ldsr_rep_batch_r(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n,
+                     int p, int q, int n_reps, unsigned int r_seed, double mu, int exp_trans,
+                     double *simX, double *simY, double *simQ, char *errbuf, int errlen);
+
+/* ---- the reference's random numbers (R's default generators after set.seed) ---------------
+ * The reference draws its restarts' initial values with runif (make_init, R/LDS_reconstruction.R:
+ * 14-30) and its replicates with rnorm; a caller outside R reproduces a seeded reference run by
+ * drawing from this generator instead.  ldsr_r_rng_* is a sequential host generator (initial values
+ * are a few thousand draws; no device needed): create = set.seed(seed), unif = runif(n, a, b),
+ * norm = rnorm(n); the state advances across calls exactly as R's does.  ldsr_r_rnorm_device is
+ * `set.seed(seed); rnorm(n)` generated on the GPU into a host buffer (bulk draws). */
+typedef struct ldsr_r_rng ldsr_r_rng;
+int ldsr_r_rng_create(unsigned int seed, ldsr_r_rng **out, char *errbuf, int errlen);
+int ldsr_r_rng_unif(ldsr_r_rng *rng, int n, double a, double b, double *out, char *errbuf, int errlen);
+int ldsr_r_rng_norm(ldsr_r_rng *rng, int n, double *out, char *errbuf, int errlen);
+void ldsr_r_rng_destroy(ldsr_r_rng *rng);
+int ldsr_r_rnorm_device(int device, unsigned int seed, long long n, double *out, char *errbuf, int errlen);
+
 /* ---- multi-GPU sharding (pure host logic, no device needed) ------------------------------
  * The partition ldsr_em_batch uses: group g goes to shard group_shard[g] in 0..n_shards-1.
  * All fits of a group stay on one device, so restart selection is device-local and the host only

@@ -20,7 +20,8 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_plan_fetch", "ldsr_plan_destroy", "ldsr_smoother_batch", "ldsr_mstep_batch",
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
            "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch",
-           "ldsr_objective_batch")
+           "ldsr_objective_batch", "ldsr_rep_batch_r", "ldsr_r_rng_create", "ldsr_r_rng_unif", "ldsr_r_rng_norm",
+           "ldsr_r_rng_destroy", "ldsr_r_rnorm_device")
 
 
 class LdsrError(RuntimeError):
@@ -65,6 +66,7 @@ def lib():
             getattr(L, name).restype = C.c_int
         L.ldsr_ctx_destroy.restype = None
         L.ldsr_ctx_trim.restype = C.c_longlong
+        L.ldsr_r_rng_destroy.restype = None
         L.ldsr_plan_destroy.restype = None
         _lib = L
     return _lib
@@ -330,7 +332,8 @@ def propagate_batch(series, group_series, held, fit_group, theta, stdlik=True, c
 
 
 def rep_batch(theta, u, v, n, n_reps, z=None, seed=0, mu=0.0, exp_trans=True, p=None, q=None,
-              want=("simX", "simY", "simQ"), ctx=None):
+              want=("simX", "simY", "simQ"), ctx=None, r_seed=None):
+    """ldsr_rep_batch; with r_seed the noise is what R draws after set.seed(r_seed) (ldsr_rep_batch_r)."""
     uf, pu = _colmajor(u)
     vf, qv = _colmajor(v)
     p = pu if p is None else p
@@ -343,11 +346,65 @@ def rep_batch(theta, u, v, n, n_reps, z=None, seed=0, mu=0.0, exp_trans=True, p=
         assert zz.size == n_reps * (1 + 2 * n)
     outs = {k: (np.empty((n_reps, n)) if k in want else None) for k in ("simX", "simY", "simQ")}
     err = C.create_string_buffer(512)
-    rc = lib().ldsr_rep_batch(ctx, _d(theta), _d(uf), _d(vf), int(n), int(p), int(q), int(n_reps), _d(zz),
-                              C.c_ulonglong(seed), C.c_double(mu), int(exp_trans), _d(outs["simX"]),
-                              _d(outs["simY"]), _d(outs["simQ"]), err, 512)
+    if r_seed is not None and z is None:
+        rc = lib().ldsr_rep_batch_r(ctx, _d(theta), _d(uf), _d(vf), int(n), int(p), int(q), int(n_reps),
+                                    C.c_uint(int(r_seed) & 0xFFFFFFFF), C.c_double(mu), int(exp_trans),
+                                    _d(outs["simX"]), _d(outs["simY"]), _d(outs["simQ"]), err, 512)
+    else:
+        rc = lib().ldsr_rep_batch(ctx, _d(theta), _d(uf), _d(vf), int(n), int(p), int(q), int(n_reps), _d(zz),
+                                  C.c_ulonglong(seed), C.c_double(mu), int(exp_trans), _d(outs["simX"]),
+                                  _d(outs["simY"]), _d(outs["simQ"]), err, 512)
     _check(rc, err)
     return {k: v for k, v in outs.items() if v is not None}
+
+
+class RRandom:
+    """R's default generators after set.seed(seed) (ldsr_r_rng_*): runif / rnorm with R's state
+    semantics, so that a seeded reference run (make_init, R/LDS_reconstruction.R:14-30) can be
+    reproduced from outside R.  Host-side and sequential: meant for initial values, not bulk noise."""
+
+    def __init__(self, seed):
+        self.h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        _check(lib().ldsr_r_rng_create(C.c_uint(int(seed) & 0xFFFFFFFF), C.byref(self.h), err, 256), err)
+
+    def runif(self, n=1, a=0.0, b=1.0):
+        out = np.empty(int(n))
+        err = C.create_string_buffer(256)
+        _check(lib().ldsr_r_rng_unif(self.h, int(n), C.c_double(a), C.c_double(b), _d(out), err, 256), err)
+        return out
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        """numpy-Generator spelling of runif, so that api.make_init(p, q, n, RRandom(seed)) draws what
+        `set.seed(seed); replicate(n, make_init(p, q))` draws."""
+        r = self.runif(1 if size is None else size, low, high)
+        return float(r[0]) if size is None else r
+
+    def rnorm(self, n=1, mean=0.0, sd=1.0):
+        out = np.empty(int(n))
+        err = C.create_string_buffer(256)
+        _check(lib().ldsr_r_rng_norm(self.h, int(n), _d(out), err, 256), err)
+        return mean + sd * out  # rnorm.c: mu + sigma * norm_rand()
+
+    def close(self):
+        if self.h:
+            lib().ldsr_r_rng_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def r_rnorm_device(seed, n, device=0):
+    """set.seed(seed); rnorm(n), generated on the GPU."""
+    out = np.empty(int(n))
+    err = C.create_string_buffer(256)
+    _check(lib().ldsr_r_rnorm_device(int(device), C.c_uint(int(seed) & 0xFFFFFFFF), C.c_longlong(int(n)), _d(out),
+                                     err, 256), err)
+    return out
 
 
 def measure_fp64_peak(device=0):

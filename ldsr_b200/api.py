@@ -401,17 +401,18 @@ def cvLDS(Qa, u, v, start_year, method="EM", transform="log", num_restarts=50, Z
 # ---------------------------------------------------------------------------------------------
 # Stochastic replicates (R/stochastics.R)
 # ---------------------------------------------------------------------------------------------
-def LDS_rep(theta, u=None, v=None, years=None, num_reps=100, mu=0.0, exp_trans=True, seed=0, z=None):
+def LDS_rep(theta, u=None, v=None, years=None, num_reps=100, mu=0.0, exp_trans=True, seed=0, z=None, r_seed=None):
     """R/stochastics.R:58-63.  Returns long-format columns like the reference's data.table
-    (year, simX, simY, simQ, rep).  z (optional): [num_reps, 1+2n] standard normals in the
-    reference's draw order for exact replay; otherwise the device generator keyed by `seed`."""
+    (year, simX, simY, simQ, rep).  Noise: r_seed = s gives the replicates of `set.seed(s); LDS_rep(...)`
+    in R (R's own stream, generated on the device); z (optional): [num_reps, 1+2n] standard normals in
+    the reference's draw order; otherwise the counter-based device generator keyed by `seed`."""
     n = len(years)
     if u is None:  # is.null(u): both input terms are dropped (stochastics.R:28-32)
         v = None
     p, q = (0 if u is None else np.atleast_2d(u).shape[0]), (0 if v is None else np.atleast_2d(v).shape[0])
     th = np.concatenate([[theta["A"]], np.ravel(theta["B"])[:p], [theta["C"]], np.ravel(theta["D"])[:q],
                          [theta["Q"], theta["R"], theta["mu1"], theta["V1"]]]).astype(float)
-    r = _lib.rep_batch(th, u, v, n, num_reps, z=z, seed=seed, mu=mu, exp_trans=exp_trans, p=p, q=q)
+    r = _lib.rep_batch(th, u, v, n, num_reps, z=z, seed=seed, mu=mu, exp_trans=exp_trans, p=p, q=q, r_seed=r_seed)
     return dict(year=np.tile(np.asarray(years), num_reps), simX=r["simX"].ravel(), simY=r["simY"].ravel(),
                 simQ=r["simQ"].ravel(), rep=np.repeat(np.arange(1, num_reps + 1), n))
 

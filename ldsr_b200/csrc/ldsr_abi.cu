@@ -3,6 +3,7 @@
 #include "../../include/ldsr_b200.h"
 #include "generic_kernels.cuh"
 #include "kernel_table.h"
+#include "r_rng.cuh"
 #include "scan_kernels.cuh"
 
 #include <algorithm>
@@ -1309,7 +1310,7 @@ static Err mstep_batch(ldsr_ctx *ctx, const ldsr_batch *b, const double *X, cons
 
 static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n, int p, int q,
                      int n_reps, const double *z, unsigned long long seed, double mu, int exp_trans, double *simX,
-                     double *simY, double *simQ) {
+                     double *simY, double *simQ, const unsigned *r_seed = nullptr) {
     if (!theta || n < 1 || n_reps < 1 || p < 0 || q < 0) return fail(LDSR_ERR_ARG, "bad theta/n/n_reps/p/q");
     if (p > LDSR_MAX_PQ || q > LDSR_MAX_PQ) return fail(LDSR_ERR_UNSUPPORTED, "p or q exceeds LDSR_MAX_PQ");
     std::unique_ptr<ldsr_ctx> tmp_ctx;
@@ -1361,6 +1362,11 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     if (z) {
         CU(dal((size_t)n_reps * (1 + 2 * (size_t)n) * 8, (void **)&dz));
         CU(cudaMemcpy(dz, z, (size_t)n_reps * (1 + 2 * (size_t)n) * 8, cudaMemcpyHostToDevice));
+    } else if (r_seed) { // the reference's own stream: set.seed(*r_seed); rnorm(...) in replicate order
+        const long long nz = (long long)n_reps * (1 + 2 * (long long)n);
+        CU(dal((size_t)nz * 8, (void **)&dz));
+        r_rnorm_kernel<<<1, 256>>>(*r_seed, nz, dz);
+        CU(cudaGetLastError());
     }
     // one pass per requested output keeps the staging footprint at 2 arrays
     double *outs[3] = {simX, simY, simQ};
@@ -1495,6 +1501,55 @@ int ldsr_rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const do
                    double *simY, double *simQ, char *errbuf, int errlen) {
     return report(rep_batch(ctx, theta, u, v, n, p, q, n_reps, z, seed, mu, exp_trans, simX, simY, simQ), errbuf,
                   errlen);
+}
+
+int ldsr_rep_batch_r(ldsr_ctx *ctx, const double *theta, const double *u, const double *v, int n, int p, int q,
+                     int n_reps, unsigned int r_seed, double mu, int exp_trans, double *simX, double *simY,
+                     double *simQ, char *errbuf, int errlen) {
+    return report(rep_batch(ctx, theta, u, v, n, p, q, n_reps, nullptr, 0ull, mu, exp_trans, simX, simY, simQ, &r_seed),
+                  errbuf, errlen);
+}
+
+struct ldsr_r_rng {
+    ldsr::RMersenne g;
+    explicit ldsr_r_rng(unsigned seed) : g(seed) {}
+};
+
+int ldsr_r_rng_create(unsigned int seed, ldsr_r_rng **out, char *errbuf, int errlen) {
+    if (!out) return report(fail(LDSR_ERR_ARG, "out is NULL"), errbuf, errlen);
+    *out = new (std::nothrow) ldsr_r_rng(seed);
+    if (!*out) return report(fail(LDSR_ERR_ARG, "out of memory"), errbuf, errlen);
+    return LDSR_OK;
+}
+int ldsr_r_rng_unif(ldsr_r_rng *rng, int n, double a, double b, double *out, char *errbuf, int errlen) {
+    if (!rng || n < 0 || (n > 0 && !out)) return report(fail(LDSR_ERR_ARG, "rng / out is NULL or n < 0"), errbuf, errlen);
+    for (int i = 0; i < n; i++) out[i] = a + (b - a) * rng->g.unif(); // runif.c
+    return LDSR_OK;
+}
+int ldsr_r_rng_norm(ldsr_r_rng *rng, int n, double *out, char *errbuf, int errlen) {
+    if (!rng || n < 0 || (n > 0 && !out)) return report(fail(LDSR_ERR_ARG, "rng / out is NULL or n < 0"), errbuf, errlen);
+    for (int i = 0; i < n; i++) out[i] = rng->g.norm();
+    return LDSR_OK;
+}
+void ldsr_r_rng_destroy(ldsr_r_rng *rng) { delete rng; }
+
+int ldsr_r_rnorm_device(int device, unsigned int seed, long long n, double *out, char *errbuf, int errlen) {
+    auto run = [&]() -> Err {
+        if (n < 1 || !out) return fail(LDSR_ERR_ARG, "need n >= 1 and out");
+        if (ldsr_device_count() < 1) return fail(LDSR_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+        CU(cudaSetDevice(device));
+        double *d = nullptr;
+        struct Guard {
+            double *&p;
+            ~Guard() { cudaFree(p); }
+        } guard{d};
+        CU(cudaMalloc(&d, sizeof(double) * (size_t)n));
+        r_rnorm_kernel<<<1, 256>>>(seed, n, d);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+        return Err();
+    };
+    return report(run(), errbuf, errlen);
 }
 
 int ldsr_shard_groups(const ldsr_batch *batch, int n_shards, int *group_shard, char *errbuf, int errlen) {

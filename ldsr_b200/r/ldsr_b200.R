@@ -108,14 +108,18 @@ reconstruct_members_batched <- function(y, u, v, init, niter, tol, return.init, 
 # order one_LDS_rep draws it -- per replicate rnorm(1) for x1, rnorm(n) for the state, rnorm(n) for the
 # observations (R/stochastics.R:23-26); one rnorm() call of the total length yields the same stream as
 # those calls in sequence, and rnorm(k, 0, s) is s * N(0,1) -- so set.seed() reproduces the
-# reference's replicates.  exact.rng = FALSE uses the device generator keyed by `seed` (no 1.3 GB of
-# host noise for 100 000 replicates; statistically, not bitwise, equal).
+# reference's replicates.  r.seed = s: the same replicates as `set.seed(s); LDS_rep(...)` with R's
+# default generators, but the stream (Mersenne-Twister + inversion) is generated on the device: no
+# 1.3 GB of host noise for 100 000 replicates and no time in rnorm; R's own RNG state is left alone.
+# exact.rng = FALSE uses the counter-based device generator keyed by `seed` (statistically, not
+# bitwise, equal).
 LDS_rep <- function(theta, u = NULL, v = NULL, years, num.reps = 100, mu = 0, exp.trans = TRUE,
-                    exact.rng = TRUE, seed = 0) {
+                    exact.rng = TRUE, seed = 0, r.seed = NULL) {
   n <- length(years)
-  z <- if (exact.rng) stats::rnorm(num.reps * (1 + 2 * n)) else NULL
+  z <- if (exact.rng && is.null(r.seed)) stats::rnorm(num.reps * (1 + 2 * n)) else NULL
   m <- .Call('_ldsr_rep_batch', theta, u, v, as.integer(n), as.integer(num.reps), as.numeric(seed),
-             as.numeric(mu), as.logical(exp.trans), z, PACKAGE = 'ldsr')
+             as.numeric(mu), as.logical(exp.trans), z, if (is.null(r.seed)) NULL else as.integer(r.seed),
+             PACKAGE = 'ldsr')
   data.table::data.table(year = rep(years, num.reps), simX = m[, 1], simY = m[, 2], simQ = m[, 3],
                          rep = rep(seq_len(num.reps), each = n))
 }

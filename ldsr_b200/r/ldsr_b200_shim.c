@@ -13,7 +13,7 @@
  *     _ldsr_propagate(theta,u,v,y,stdlik)         5
  * and add the batched ones used by the drop-in R wrappers in ldsr_b200.R:
  *     _ldsr_em_batch(series,group_series,held,fit_group,theta0,niter,tol,n_devices)   8
- *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans,z)                       9
+ *     _ldsr_rep_batch(theta,u,v,n,num_reps,seed,mu,exp_trans,z,r_seed)               10
  *     _ldsr_cv_metrics(Ycv,target,Z,exp_trans)                                        4
  *     _ldsr_construct_rec(X,V,Y,C,R,mu,transform,lambda)                              8
  *     _ldsr_objective(y,u,v,thetas,kind,lambda)   thetas: (2d+6) x n matrix, one column per candidate   6
@@ -270,7 +270,8 @@ SEXP _ldsr_em_batch(SEXP series, SEXP group_series, SEXP held, SEXP fit_group, S
 
 /* LDS_rep (R/stochastics.R:58-63) on the device generator.  Returns a 3-column matrix
  * (simX, simY, simQ), rows replicate-major like rbindlist(lapply(...)). */
-SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS, SEXP muS, SEXP expS, SEXP zS) {
+SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS, SEXP muS, SEXP expS, SEXP zS,
+                     SEXP rseedS) {
     const int n = Rf_asInteger(nS), reps = Rf_asInteger(repsS);
     int p = 0, q = 0;
     const double *up = Rf_isNull(u) ? NULL : input_ptr(u, n, &p), *vp = Rf_isNull(u) || Rf_isNull(v) ? NULL : input_ptr(v, n, &q);
@@ -289,6 +290,11 @@ SEXP _ldsr_rep_batch(SEXP theta, SEXP u, SEXP v, SEXP nS, SEXP repsS, SEXP seedS
     /* z: num_reps*(1+2n) standard normals drawn by R in one_LDS_rep's order (R/stochastics.R:23-26), or NULL */
     const double *z = Rf_isNull(zS) ? NULL : REAL(zS);
     if (z && XLENGTH(zS) != (R_xlen_t)reps * (1 + 2 * (R_xlen_t)n)) Rf_error("ldsr: z must hold num.reps*(1+2n) draws");
+    if (!z && !Rf_isNull(rseedS)) /* the stream of set.seed(r_seed), generated on the device (r_rng.cuh) */
+        check(ldsr_rep_batch_r(ctx(), th, up, vp, n, p, q, reps, (unsigned int)Rf_asInteger(rseedS), Rf_asReal(muS),
+                               Rf_asLogical(expS), o, o + (size_t)n * reps, o + 2 * (size_t)n * reps, err, sizeof err),
+              err);
+    else
     check(ldsr_rep_batch(ctx(), th, up, vp, n, p, q, reps, z, (unsigned long long)Rf_asReal(seedS), Rf_asReal(muS),
                          Rf_asLogical(expS), o, o + (size_t)n * reps, o + 2 * (size_t)n * reps, err, sizeof err), err);
     UNPROTECT(1);
@@ -413,7 +419,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_ldsr_LDS_EM", (DL_FUNC)&_ldsr_LDS_EM, 6},
     {"_ldsr_propagate", (DL_FUNC)&_ldsr_propagate, 5},
     {"_ldsr_em_batch", (DL_FUNC)&_ldsr_em_batch, 8},
-    {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 9},
+    {"_ldsr_rep_batch", (DL_FUNC)&_ldsr_rep_batch, 10},
     {"_ldsr_smoother_d", (DL_FUNC)&_ldsr_smoother_d, 6},
     {"_ldsr_cv_metrics", (DL_FUNC)&_ldsr_cv_metrics, 4},
     {"_ldsr_construct_rec", (DL_FUNC)&_ldsr_construct_rec, 8},
