@@ -1365,8 +1365,7 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     } else if (r_seed) { // the reference's own stream: set.seed(*r_seed); rnorm(...) in replicate order
         const long long nz = (long long)n_reps * (1 + 2 * (long long)n);
         CU(dal((size_t)nz * 8, (void **)&dz));
-        r_rnorm_kernel<<<1, 256>>>(*r_seed, nz, dz);
-        CU(cudaGetLastError());
+        CU(r_rnorm_device(*r_seed, nz, dz, 0));
     }
     // one pass per requested output keeps the staging footprint at 2 arrays
     double *outs[3] = {simX, simY, simQ};
@@ -1544,8 +1543,7 @@ int ldsr_r_rnorm_device(int device, unsigned int seed, long long n, double *out,
             ~Guard() { cudaFree(p); }
         } guard{d};
         CU(cudaMalloc(&d, sizeof(double) * (size_t)n));
-        r_rnorm_kernel<<<1, 256>>>(seed, n, d);
-        CU(cudaGetLastError());
+        CU(r_rnorm_device(seed, n, d, 0));
         CU(cudaMemcpy(out, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
         return Err();
     };

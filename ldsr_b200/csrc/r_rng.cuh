@@ -16,9 +16,8 @@
 // and AS 241 to scipy's ndtri over the whole range (1e-15).
 //
 // Host: RMersenne, a plain sequential generator (initial values: a few thousand draws).
-// Device: r_rnorm_kernel, one CTA that regenerates the 624-word state in three dependency phases
-// and turns each batch of 624 outputs into 312 normals; MT19937 is one sequential stream, so the
-// parallelism is inside a regeneration.  163 M normals (100 000 replicates x 1627) take ~0.3 s.
+// Device: r_rnorm_device -- one CTA walks the twister (one sequential stream: the parallelism is
+// inside a regeneration of the 624 words), the whole grid then turns output pairs into normals.
 // The arithmetic of qnorm is written with the non-contracting intrinsics (__dmul_rn, __dadd_rn,
 // __ddiv_rn, __dsqrt_rn) so that it rounds like R's compiled C does on x86-64; log() is CUDA's
 // (<= 1 ulp), so tail draws (|p - 0.5| > 0.425, 15 % of them) may differ from R's in the last bit.
@@ -175,47 +174,48 @@ struct RMersenne {
 
 #ifdef __CUDACC__
 // ---- device: set.seed(seed); rnorm(n) ----------------------------------------------------------
-// One CTA of 256 threads.  A regeneration of the 624 words has three phases (words 0..226 need only
-// old words, 227..453 need the new 0..226, 454..623 the new 227..396 and, for the last one, the new
-// word 0); inside a phase every word is independent.  Each phase reads its inputs into registers,
-// synchronises, then writes (word k reads the old word k+1 that a neighbour is about to replace).
-// The 624 tempered outputs of a regeneration are 312 pairs = 312 normals, written in order.
-__global__ void __launch_bounds__(256) r_rnorm_kernel(uint32_t seed, long long n, double *__restrict__ out) {
-    __shared__ uint32_t mt[R_MT_N];
+// Two kernels.  r_mt_stream_kernel: ONE CTA walks the twister (it is a single sequential stream) and
+// writes the tempered 32-bit outputs, two per normal, into the 8 bytes the normal will occupy.  A
+// regeneration of the 624 words has three phases (words 0..226 need only old words, 227..453 need
+// the new 0..226, 454..623 the new 227..396 and, for the last one, the new word 0); inside a phase
+// every word is independent, and with the state double-buffered (read old, write new) a phase is one
+// barrier.  r_norm_from_words_kernel: every pair of outputs becomes a normal, in place, over the
+// whole grid (unif_rand scaling and fixup, the 2^27 splice, AS 241).
+__global__ void __launch_bounds__(256) r_mt_stream_kernel(uint32_t seed, long long n_words, uint32_t *__restrict__ out) {
+    __shared__ uint32_t st[2][R_MT_N];
     const int tid = threadIdx.x;
-    if (tid == 0) r_mt_seed(seed, mt);
+    if (tid == 0) r_mt_seed(seed, st[0]);
     __syncthreads();
-    for (long long base = 0; base < n; base += R_MT_N / 2) {
-        // phase A: words 0..226
-        uint32_t nv = 0;
-        if (tid < 227) nv = r_mt_twist(mt[tid], mt[tid + 1], mt[tid + R_MT_M]);
+    int cur = 0;
+    for (long long base = 0; base < n_words; base += R_MT_N, cur ^= 1) {
+        const uint32_t *__restrict__ o = st[cur];
+        uint32_t *__restrict__ nw = st[cur ^ 1];
+        if (tid < 227) nw[tid] = r_mt_twist(o[tid], o[tid + 1], o[tid + R_MT_M]);
         __syncthreads();
-        if (tid < 227) mt[tid] = nv;
+        if (tid < 227) nw[227 + tid] = r_mt_twist(o[227 + tid], o[228 + tid], nw[tid]);
         __syncthreads();
-        // phase B: words 227..453
-        if (tid < 227) nv = r_mt_twist(mt[227 + tid], mt[228 + tid], mt[tid]);
-        __syncthreads();
-        if (tid < 227) mt[227 + tid] = nv;
-        __syncthreads();
-        // phase C: words 454..623
         if (tid < 170) {
             const int k = 454 + tid;
-            nv = r_mt_twist(mt[k], k == R_MT_N - 1 ? mt[0] : mt[k + 1], mt[k - 227]);
+            nw[k] = r_mt_twist(o[k], k == R_MT_N - 1 ? nw[0] : o[k + 1], nw[k - 227]);
         }
         __syncthreads();
-        if (tid < 170) mt[454 + tid] = nv;
-        __syncthreads();
-        // 312 normals from the 624 outputs
-        for (int j = tid; j < R_MT_N / 2; j += 256) {
-            const long long i = base + j;
-            if (i < n) {
-                const double u1 = r_unif_from_u32(r_mt_temper(mt[2 * j]));
-                const double u2 = r_unif_from_u32(r_mt_temper(mt[2 * j + 1]));
-                out[i] = r_norm_from_unifs(u1, u2);
-            }
-        }
-        // the next phase A only writes after its own barrier, which every thread reaches after these reads
+        for (int j = tid; j < R_MT_N; j += 256)
+            if (base + j < n_words) out[base + j] = r_mt_temper(nw[j]);
+        // the next regeneration writes st[cur] only after its first barrier... which no thread passes
+        // before every thread has left this loop: st[cur] (the old state) is not read here
     }
+}
+__global__ void r_norm_from_words_kernel(long long n, double *__restrict__ inout) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 w = reinterpret_cast<const uint2 *>(inout)[i];
+    inout[i] = r_norm_from_unifs(r_unif_from_u32(w.x), r_unif_from_u32(w.y));
+}
+// set.seed(seed); rnorm(n) into d_out (device), on stream st
+inline cudaError_t r_rnorm_device(uint32_t seed, long long n, double *d_out, cudaStream_t st) {
+    r_mt_stream_kernel<<<1, 256, 0, st>>>(seed, 2 * n, reinterpret_cast<uint32_t *>(d_out));
+    r_norm_from_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_out);
+    return cudaGetLastError();
 }
 #endif
 
