@@ -190,12 +190,15 @@ int ldsr_rep_batch_r(ldsr_ctx *ctx, const double *theta, const double *u, const 
  * 14-30) and its replicates with rnorm; a caller outside R reproduces a seeded reference run by
  * drawing from this generator instead.  ldsr_r_rng_* is a sequential host generator (initial values
  * are a few thousand draws; no device needed): create = set.seed(seed), unif = runif(n, a, b),
- * norm = rnorm(n); the state advances across calls exactly as R's does.  ldsr_r_rnorm_device is
+ * norm = rnorm(n), sample = sample.int(n, k); the state advances across calls exactly as R's does.  ldsr_r_rnorm_device is
  * `set.seed(seed); rnorm(n)` generated on the GPU into a host buffer (bulk draws). */
 typedef struct ldsr_r_rng ldsr_r_rng;
 int ldsr_r_rng_create(unsigned int seed, ldsr_r_rng **out, char *errbuf, int errlen);
 int ldsr_r_rng_unif(ldsr_r_rng *rng, int n, double a, double b, double *out, char *errbuf, int errlen);
 int ldsr_r_rng_norm(ldsr_r_rng *rng, int n, double *out, char *errbuf, int errlen);
+/* sample.int(n, k) without replacement, 1-based (the folds of make_Z, R/utils.R:83-101; R >= 3.6
+ * "Rejection" sampling) */
+int ldsr_r_rng_sample(ldsr_r_rng *rng, int n, int k, int *out, char *errbuf, int errlen);
 void ldsr_r_rng_destroy(ldsr_r_rng *rng);
 int ldsr_r_rnorm_device(int device, unsigned int seed, long long n, double *out, char *errbuf, int errlen);
 

@@ -21,7 +21,7 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
            "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch",
            "ldsr_objective_batch", "ldsr_rep_batch_r", "ldsr_r_rng_create", "ldsr_r_rng_unif", "ldsr_r_rng_norm",
-           "ldsr_r_rng_destroy", "ldsr_r_rnorm_device")
+           "ldsr_r_rng_sample", "ldsr_r_rng_destroy", "ldsr_r_rnorm_device")
 
 
 class LdsrError(RuntimeError):
@@ -379,6 +379,24 @@ class RRandom:
         `set.seed(seed); replicate(n, make_init(p, q))` draws."""
         r = self.runif(1 if size is None else size, low, high)
         return float(r[0]) if size is None else r
+
+    def sample_int(self, n, size=None):
+        """sample.int(n, size) without replacement (1-based)."""
+        size = n if size is None else size
+        out = np.empty(int(size), dtype=np.int32)
+        err = C.create_string_buffer(256)
+        _check(lib().ldsr_r_rng_sample(self.h, int(n), int(size), _i(out), err, 256), err)
+        return out
+
+    def choice(self, a, size, replace=False):
+        """numpy-Generator spelling of R's sample(a, size): api.make_Z(obs, ..., rng=RRandom(seed)) makes the
+        folds `set.seed(seed); make_Z(obs, ...)` makes.  Like R, a single number a >= 1 means 1:a."""
+        if replace:
+            raise ValueError("only sampling without replacement is needed by the reference (R/utils.R:96,98)")
+        a = np.atleast_1d(np.asarray(a))
+        if a.size == 1 and a[0] >= 1:
+            return self.sample_int(int(a[0]), size)
+        return a[self.sample_int(a.size, size) - 1]
 
     def rnorm(self, n=1, mean=0.0, sd=1.0):
         out = np.empty(int(n))

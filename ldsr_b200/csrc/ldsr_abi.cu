@@ -1530,6 +1530,12 @@ int ldsr_r_rng_norm(ldsr_r_rng *rng, int n, double *out, char *errbuf, int errle
     for (int i = 0; i < n; i++) out[i] = rng->g.norm();
     return LDSR_OK;
 }
+int ldsr_r_rng_sample(ldsr_r_rng *rng, int n, int k, int *out, char *errbuf, int errlen) {
+    if (!rng || n < 1 || k < 0 || k > n || (k > 0 && !out))
+        return report(fail(LDSR_ERR_ARG, "need rng, 0 <= k <= n, n >= 1 and out"), errbuf, errlen);
+    rng->g.sample_int(n, k, out);
+    return LDSR_OK;
+}
 void ldsr_r_rng_destroy(ldsr_r_rng *rng) { delete rng; }
 
 int ldsr_r_rnorm_device(int device, unsigned int seed, long long n, double *out, char *errbuf, int errlen) {

@@ -24,6 +24,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <vector>
 
 namespace ldsr {
 
@@ -169,6 +170,28 @@ struct RMersenne {
         const double u1 = unif();
         const double u2 = unif();
         return r_norm_from_unifs(u1, u2);
+    }
+    // R_unif_index (RNG.c), sample.kind "Rejection" (default since R 3.6.0): an integer below dn
+    // from ceil(log2(dn)) random bits, 16 per unif_rand(), redrawn until it is below dn
+    long long unif_index(double dn) {
+        if (dn <= 0) return 0;
+        const int bits = (int)std::ceil(std::log2(dn));
+        for (;;) {
+            long long v = 0;
+            for (int n = 0; n <= bits; n += 16) v = 65536 * v + (long long)std::floor(unif() * 65536);
+            if (bits < 64) v &= (1LL << bits) - 1;
+            if ((double)v < dn) return v;
+        }
+    }
+    // sample.int(n, k) without replacement (do_sample): partial Fisher-Yates, 1-based results
+    void sample_int(int n, int k, int *out) {
+        std::vector<int> x(n);
+        for (int i = 0; i < n; i++) x[i] = i;
+        for (int i = 0; i < k; i++) {
+            const int j = (int)unif_index(n);
+            out[i] = x[j] + 1;
+            x[j] = x[--n];
+        }
     }
 };
 

@@ -82,3 +82,32 @@ def qnorm(p):
                  + .59983220655588793769) * r + 1.)
     return -val if q < 0 else val
 
+
+
+def unif_index(g, dn):
+    """R_unif_index (RNG.c), sample.kind = "Rejection" (the default since R 3.6.0)."""
+    if dn <= 0:
+        return 0
+    bits = int(math.ceil(math.log2(dn)))
+    while True:
+        v = 0
+        n = 0
+        while n <= bits:
+            v = 65536 * v + int(math.floor(g.unif() * 65536))
+            n += 16
+        if bits < 64:
+            v &= (1 << bits) - 1
+        if v < dn:
+            return v
+
+
+def sample_int(g, n, k):
+    """sample.int(n, k) without replacement (do_sample, unique.c / random.c): partial Fisher-Yates."""
+    x = list(range(n))
+    out = []
+    for _ in range(k):
+        j = unif_index(g, n)
+        out.append(x[j] + 1)
+        n -= 1
+        x[j] = x[n]
+    return out

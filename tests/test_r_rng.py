@@ -68,6 +68,26 @@ def test_make_init_with_r_generator_draws_in_the_reference_order():
         assert np.array_equal(th["D"], [-1 + 2 * o.unif() for _ in range(2)])
 
 
+def test_sample_reproduces_known_r_output_and_make_Z_uses_it():
+    # R >= 3.6.0 (sample.kind = "Rejection")
+    known = [(42, 10, 10, [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]), (123, 10, 10, [3, 10, 2, 8, 6, 9, 1, 7, 5, 4]),
+             (1, 10, 10, [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]), (123, 100, 5, [31, 79, 51, 14, 67])]
+    for seed, n, k, vals in known:
+        assert RO.sample_int(RO.RMT(seed), n, k) == vals
+        assert list(_lib.RRandom(seed).sample_int(n, k)) == vals
+    # make_Z (R/utils.R:83-101): contiguous = sort(sample(1:maxInd, nRuns)) then obsInd[x:(x+k)];
+    # scattered = replicate(nRuns, sort(sample(obsInd, k)))
+    obs = np.r_[np.full(5, np.nan), np.arange(46.0)]
+    Z = L.make_Z(obs, nRuns=4, frac=0.25, contiguous=True, rng=L.RRandom(9))
+    o = RO.RMT(9)
+    starts = sorted(RO.sample_int(o, 46 - 11, 4))
+    assert [list(z) for z in Z] == [list(range(5 + x, 5 + x + 12)) for x in starts]
+    Z = L.make_Z(obs, nRuns=3, frac=0.25, contiguous=False, rng=L.RRandom(9))
+    o = RO.RMT(9)
+    for z in Z:
+        assert list(z) == sorted(5 + i for i in RO.sample_int(o, 46, 11))
+
+
 @pytest.mark.gpu
 def test_device_stream_equals_the_host_generator():
     n = 5 * 312 + 17  # several regenerations and a ragged tail
