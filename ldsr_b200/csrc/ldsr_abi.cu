@@ -518,8 +518,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->upload(&P->d_g_user, P->g_user)).ok()) return e;
     for (int s = 0; s < ns; s++) P->same_width = P->same_width && b->p[s] + b->q[s] + 6 == b->theta_stride;
     P->res_head = (size_t)nf * b->theta_stride + nf + ((size_t)2 * nf + ng + 1) / 2;
-    P->res_total = P->res_head + 4 * (size_t)P->traj_total;
-    if (!(e = P->dalloc(&P->d_res, P->res_total)).ok()) return e;
+    P->res_total = P->res_head + 4 * (size_t)P->traj_total; // allocated by the first ldsr_plan_em
     if (!(e = P->upload(&P->d_theta0, th0)).ok()) return e;
     if (!(e = P->dalloc(&P->d_masks, (size_t)nwords)).ok()) return e;
     if (!(e = P->dalloc(&P->d_sconst, (size_t)sconst_off)).ok()) return e;
@@ -817,6 +816,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     launches++;
     if (!P->d_X) {
         Err e;
+        if (!(e = P->dalloc(&P->d_res, P->res_total)).ok()) return e;
         P->d_X = P->d_res + P->res_head;
         P->d_Y = P->d_X + P->traj_total;
         P->d_V = P->d_Y + P->traj_total;
