@@ -254,6 +254,11 @@ def test_api_restart_and_cv_shapes():
     for kw in (dict(u=None, v=pc), dict(u=pc, v=None), dict(u=pc[:2], v=pc)):
         f = L.LDS_reconstruction(Qa, kw["u"], kw["v"], start_year=1800, num_restarts=2, rng=rng, niter=100)
         assert np.isfinite(f["lik"])
+    # test-LDS-EM.R:43-46 "Fixed restart works": init = make_init(nrow(u), nrow(v), 2), here drawn from R's
+    # own stream (set.seed(5)) so that the run is the one a seeded R session would make; repeatable
+    fa = L.LDS_reconstruction(Qa, pc, pc, start_year=1800, init=L.make_init(3, 3, 2, L.RRandom(5)), niter=150)
+    fb = L.LDS_reconstruction(Qa, pc, pc, start_year=1800, init=L.make_init(3, 3, 2, L.RRandom(5)), niter=150)
+    assert np.isfinite(fa["lik"]) and fa["lik"] == fb["lik"] and np.array_equal(fa["rec"]["Q"], fb["rec"]["Q"])
 
 
 def test_propagate_and_rep_against_oracle():
