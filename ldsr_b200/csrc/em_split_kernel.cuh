@@ -1132,13 +1132,35 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
             }
             __syncthreads();
-            st.zero();
+            if (warp == 0) {
+                st.zero();
 #pragma unroll
-            for (int w = 0; w < NW / 2; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
+                for (int w = 0; w < NW / 2; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
+            }
         }
         LDSR_PHASE_MARK(11);
+        if (!PAIR) {
+            if (live) mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
+        } else {
+            // Wide inputs: the M-step is two (PQ+1)-dimensional solves, thousands of instructions.  Done once,
+            // by warp 0, and published through shared memory (the partial-sum slots are dead once warp 0
+            // has read them): the other warps' issue slots go to the CTA sharing the SM instead of
+            // to three redundant copies.
+            double g[TL];
+            if (warp == 0) {
+                if (live) mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
+                store_theta<PQ>(th, g);
+#pragma unroll
+                for (int i = 0; i < TL; i++) ST[i * 32] = g[i];
+            }
+            __syncthreads();
+            if (warp != 0) {
+#pragma unroll
+                for (int i = 0; i < TL; i++) g[i] = ST[i * 32];
+                load_theta<PQ>(th, g);
+            }
+        }
         if (live) {
-            mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
             l2 = l1;
             l1 = lik;
         }
