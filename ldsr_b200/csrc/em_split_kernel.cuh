@@ -71,7 +71,7 @@ __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units
 // series (everything from the last full M unit to step T-1) is cut into single steps so that the
 // hot M code never sees a partial unit and step T-1 (no transition after it) is a unit of its own.
 // US: MSEG steps inside a mixed window that no fit of the CTA observes (NP: 352..359 before the first
-// observation, 408..411 after the last): handled like a short U unit, about 6x cheaper than an M unit.
+// observation, 408..411 after the last): handled like a short U unit, about half the cycles of an M unit.
 constexpr int UNIT_M = 1 << 30, UNIT_M1 = 1 << 29, UNIT_US = 1 << 28, UNIT_T0 = UNIT_US - 1;
 
 // M / M1 units of the non-U window [t0, t0+uw): calls f(t, is_single)
