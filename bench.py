@@ -293,6 +293,18 @@ def main():
                 "peak_source": "DFMA microbenchmark in this run (ldsr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flops_per_launch": flops / chunks, "launch_ms": em_ns * 1e-6 / chunks, "launches_per_step": chunks,
                 "kernel_share_of_step": em_ns * 1e-6 / (tot_ms / K)}
+    # the same launch against the HBM roofline, to show which bound is the live one: the DRAM traffic of
+    # the committed ncu capture over the launch time, against the driver's measured copy bandwidth
+    if traffic is not None:
+        hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+        hbm_ach = traffic / (em_ns * 1e-9 / chunks) / 1e9
+        roofline["hbm"] = {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                           "peak_source": hbm_src, "note": "not the bound: the working set stays in shared memory"}
 
     # ---------------- CPU baseline (oracle port of src/EM.cpp), bounded sample ----------------
     cpu = None
