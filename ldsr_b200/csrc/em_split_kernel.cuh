@@ -64,6 +64,7 @@ __host__ __device__ inline size_t split_smem_bytes(int pq, int nw, int max_units
     b += 128;                                        // piece bounds
     b += (size_t)8 * 32 * 8;                         // closed-form variance-sum coefficients
     if (split_w_in_smem(pq)) b += (size_t)max_uunits * pq * 32 * 8; // W of every U unit
+    if (theta_bd_in_smem(pq)) b += (size_t)2 * pq * 32 * 8;          // B and D of the CTA's fits
     return b;
 }
 
@@ -243,8 +244,8 @@ __device__ __forceinline__ void unit_inputs(const Theta<PQ> &th, unsigned bits, 
         double b = 0.0, dv = 0.0;
 #pragma unroll
         for (int i = 0; i < PQ; i++) {
-            b = fma(th.B[i], ur[j * PQ + i], b);
-            dv = fma(th.D[i], vr[j * PQ + i], dv);
+            b = fma(th.b(i), ur[j * PQ + i], b);
+            dv = fma(th.d(i), vr[j * PQ + i], dv);
         }
         const bool obs = (bits >> j) & 1u;
         yo[j] = obs ? yr[j] : 0.0; // y is NaN where missing
@@ -360,7 +361,7 @@ __device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const Sp
             for (int j = 0; j < 8; j++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < PQ; i++) acc = fma(th.B[i], ur[j * PQ + i], acc);
+                for (int i = 0; i < PQ; i++) acc = fma(th.b(i), ur[j * PQ + i], acc);
                 Bu[j] = acc;
             }
             double lo = Bu[0], hi = Bu[4];
@@ -375,7 +376,7 @@ __device__ __forceinline__ void forward_word_basis(const Theta<PQ> &th, const Sp
     if (KEEP_W) {
 #pragma unroll
         for (int i = 0; i < PQ; i++) {
-            hh = fma(th.B[i], W[i], hh);
+            hh = fma(th.b(i), W[i], hh);
             wk[i * 32] = W[i];
         }
     }
@@ -486,7 +487,12 @@ __device__ __forceinline__ void forward_short_basis(const Theta<PQ> &th, double 
     const ShortConst<N> sc(A, A2, Q);
     double hh = 0.0;
 #pragma unroll
-    for (int j = 0; j < N; j++) hh = fma(A, hh, dot_row<PQ>(th.B, useg + j * PQ));
+    for (int j = 0; j < N; j++) {
+        double bu = 0.0;
+#pragma unroll
+        for (int i = 0; i < PQ; i++) bu = fma(th.b(i), useg[j * PQ + i], bu);
+        hh = fma(A, hh, bu);
+    }
     const double qn = fma(sc.AN, c.q, hh), Pn = sc.AN * c.P, Vn = fma(sc.aV, c.Vq, sc.bV);
     const double Jc = sc.AN * c.Vq * fast_rcp(Vn);
     const double g0 = fma(-Jc, qn, c.q), gP = fma(-Jc, Pn, c.P), L = c.Vq * fma(-sc.AN, Jc, 1.0);
@@ -523,7 +529,7 @@ __device__ __forceinline__ void smooth_short(const Theta<PQ> &th, double A, doub
     for (int j = 0; j < N; j++) {
         double inp = Gs[j];
 #pragma unroll
-        for (int i = 0; i < PQ; i++) inp = fma(th.B[i], useg[j * PQ + i], inp);
+        for (int i = 0; i < PQ; i++) inp = fma(th.b(i), useg[j * PQ + i], inp);
         Xn[j + 1] = fma(A, Xn[j], inp); // Xs_{t+1} = A Xs_t + B u_t + Q G_{t+1}
         vp[j + 1] = fma(A2, vp[j], Q);
         const double t1 = vp[j + 1] * Hs[j];
@@ -627,7 +633,7 @@ __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitCons
         for (int j = 0; j < 8; j++) {
             double acc = Gs[j]; // Q G_{t+1}
 #pragma unroll
-            for (int i = 0; i < PQ; i++) acc = fma(th.B[i], uk[j * PQ + i], acc);
+            for (int i = 0; i < PQ; i++) acc = fma(th.b(i), uk[j * PQ + i], acc);
             inp[j] = acc;
         }
         double Xn[9];
@@ -658,7 +664,7 @@ __device__ __forceinline__ void smooth_word(const Theta<PQ> &th, const SplitCons
         for (int i = 0; i < PQ; i++) {
             double acc = fma(qg0, wk[i * 32], k.A * tux[i]);
 #pragma unroll
-            for (int j = 0; j < PQ; j++) acc = fma(th.B[j], tuu_w[j * PQ + i], acc);
+            for (int j = 0; j < PQ; j++) acc = fma(th.b(j), tuu_w[j * PQ + i], acc);
             st.Tx1u[i] += acc;
             st.Tux[i] += tux[i];
         }
@@ -817,6 +823,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     int *const pbound = units + ((SP.max_units + 3) & ~3);                                        // [NP+1]
     double *const UV = reinterpret_cast<double *>(pbound + 32) + lane;                            // [SPLIT_NUV][32]
     double *const WK = UV + 8 * 32; // [window][PQ][32]: Horner vectors of the U units (split_w_in_smem)
+    double *const TB = WK + (split_w_in_smem(PQ) ? (size_t)SP.max_uunits * PQ * 32 : 0); // [PQ][32] B, then D
+    double *const TD = TB + PQ * 32;                                                      // (theta_bd_in_smem)
+    constexpr bool BD_SMEM = theta_bd_in_smem(PQ);
 
     // ---- per-lane fit state: every warp holds the same 32 fits
     const bool valid = lane < task.z;
@@ -829,6 +838,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     constexpr int TL = theta_pad_len<PQ>();
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta + (size_t)fit * TL);
+    th.sb = TB;
+    th.sd = TD;
+    if (BD_SMEM && warp == 0) { // visible to the other warps after the barrier that ends the set-up
+#pragma unroll
+        for (int i = 0; i < PQ; i++) {
+            TB[i * 32] = th.B[i];
+            TD[i * 32] = th.D[i];
+        }
+    }
     double l1 = P.l1[fit], l2 = P.l2[fit], lik = P.lik[fit];
     int ne = P.ne[fit];
     bool live = valid && (P.done[fit] == 0);
@@ -1148,7 +1166,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             // to three redundant copies.
             double g[TL];
             if (warp == 0) {
+                if (BD_SMEM) { // B, D live in shared memory between M-steps, not in registers
+#pragma unroll
+                    for (int i = 0; i < PQ; i++) {
+                        th.B[i] = TB[i * 32];
+                        th.D[i] = TD[i * 32];
+                    }
+                }
                 if (live) mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
+                if (BD_SMEM) {
+#pragma unroll
+                    for (int i = 0; i < PQ; i++) {
+                        TB[i * 32] = th.B[i];
+                        TD[i * 32] = th.D[i];
+                    }
+                }
                 store_theta<PQ>(th, g);
 #pragma unroll
                 for (int i = 0; i < TL; i++) ST[i * 32] = g[i];
@@ -1171,6 +1203,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         for (int i = 0; i < 21; i++) SP.clk[((size_t)blockIdx.x * NW + warp) * 21 + i] = pc[i];
 #endif
 
+    if (BD_SMEM && warp == 0) {
+#pragma unroll
+        for (int i = 0; i < PQ; i++) {
+            th.B[i] = TB[i * 32];
+            th.D[i] = TD[i * 32];
+        }
+    }
     if (warp == 0 && valid) {
         store_theta<PQ>(th, P.theta + (size_t)fit * TL);
         P.l1[fit] = l1;

@@ -11,9 +11,22 @@
 
 namespace ldsr {
 
+// Wide inputs: the time-split kernel keeps B and D in shared memory during the unit loops (one copy
+// per CTA, [i][lane]) instead of 2 PQ registers per lane -- at PQ = 10 the kernel needs well over
+// 255 registers and spills (profiles/em_r01_pq10.txt); only that kernel sets sb / sd and calls b() / d().
+__host__ __device__ constexpr bool theta_bd_in_smem(int pq) { return pq >= 8; }
 template <int PQ> struct Theta {
     double A, C, Q, R, mu1, V1;
     double B[PQ], D[PQ];
+    const double *sb, *sd;
+    __device__ __forceinline__ double b(int i) const {
+        if constexpr (theta_bd_in_smem(PQ)) return sb[i * 32];
+        else return B[i];
+    }
+    __device__ __forceinline__ double d(int i) const {
+        if constexpr (theta_bd_in_smem(PQ)) return sd[i * 32];
+        else return D[i];
+    }
 };
 
 // device-side flat layout of a padded theta: [A, B[PQ], C, D[PQ], Q, R, mu1, V1]
