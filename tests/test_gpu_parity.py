@@ -538,3 +538,41 @@ def test_repeated_calls_reuse_the_context_arenas_and_trim_releases_them():
                       30, 1e-5, ctx=ctx, want_traj=False)
     assert np.array_equal(first[64]["lik"], r["lik"])
     ctx.close()
+
+
+def test_wide_multi_station_batch_matches_oracle_and_is_order_invariant():
+    # BASELINE config 3 in miniature: several stations of different length with ten inputs each (the
+    # width at which B and D live in shared memory and one warp does the M-step), two folds per
+    # station, a handful of restarts.  Against the oracle, and bit-identical when the stations are
+    # listed in reverse and the chunk length changes (a CTA then walks different tasks in a different
+    # order through the same shared-memory areas).
+    from ldsr_b200 import workloads as W
+    w = W.synthetic_stations(n_stations=3, T=200, p=10, n_folds=2, n_restarts=5, seed=77)
+    for i, s in enumerate(w["series"]):  # ragged: shorten two of the three stations
+        cut = (0, 37, 90)[i]
+        if cut:
+            s["y"], s["u"], s["v"] = s["y"][cut:], s["u"][:, cut:], s["v"][:, cut:]
+            for g in np.nonzero(w["group_series"] == i)[0]:
+                w["held"][g] = w["held"][g] - cut
+    niter = 40
+    a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], niter, 1e-6,
+                      want_traj=False)
+    o = O.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], niter, 1e-6)
+    assert np.array_equal(a["iters"], o["iters"]) and np.array_equal(a["best"], o["best"])
+    assert np.allclose(a["lik"], o["lik"], rtol=LIK_RTOL, atol=0)
+    assert_theta_close(a["theta"], o["theta"])
+    # reversed station order, different chunking
+    ng = len(w["group_series"])
+    ns = len(w["series"])
+    perm = np.arange(ng)[::-1]
+    fg2, th2, src = [], [], []
+    for gnew, gold in enumerate(perm):
+        idx = np.nonzero(w["fit_group"] == gold)[0]
+        fg2 += [gnew] * idx.size
+        th2.append(w["theta0"][idx])
+        src.append(idx)
+    src = np.concatenate(src)
+    b = _lib.em_batch(w["series"][::-1], (ns - 1 - w["group_series"])[perm], [w["held"][g] for g in perm],
+                      np.array(fg2), np.concatenate(th2), niter, 1e-6, chunk_iters=7, want_traj=False)
+    assert np.array_equal(b["iters"], a["iters"][src]) and np.array_equal(b["lik"], a["lik"][src])
+    assert np.array_equal(b["theta"], a["theta"][src], equal_nan=True)
