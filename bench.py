@@ -10,7 +10,10 @@ fits, niter=1000, tol=1e-5, followed by the per-fold restart selection and the w
 trajectories.  With N>1 (torchrun, one rank per GPU) every rank owns its own such batch
 (different folds / initial values): weak scaling, no data-path collective.
 
-Printed JSON (one line, rank 0): see the task contract; extra keys `roofline`, `cpu_baseline`.
+Printed JSON (one line, rank 0): see the task contract; extra keys `roofline`, `cpu_baseline`, `run`
+(how the line was measured), `strong` (BASELINE config 3 = 480 000 fits SHARED by the N ranks: groups
+dealt by ldsr_shard_groups, slowest rank timed, plus `e2e_sharded`: the one-process host-buffer call
+ldsr_em_batch(n_devices=N) on rank 0) and `configs` (the other BASELINE configurations, one record each).
   value   fits/s, inputs resident in HBM (ldsr_plan_em), device time by CUDA events per step
   e2e     fits/s through the public host-buffer call (ldsr_em_batch): packing, H2D of all inputs,
           EM, D2H of all results inside the timed region (wall clock, synchronised)
@@ -123,6 +126,12 @@ def cpu_sample_groups(w, seconds, cores):
     return max(1, min(g, len(w["group_series"])))
 
 
+def cpu_sample_seconds(args):
+    """Oracle work per step/sample: the same in the cpu_baseline leg and in the reference arm, bounded so
+    that `--impl reference --steps K --warmup W` ends within a few minutes."""
+    return min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
+
+
 def host_cores():
     """Host threads the CPU arm may use: the process's CPU affinity, not OMP_NUM_THREADS (torchrun sets
     that to 1 for every rank; the reference arm runs on rank 0 alone and takes the whole box)."""
@@ -130,6 +139,15 @@ def host_cores():
         return max(1, len(os.sched_getaffinity(0)))
     except Exception:
         return max(1, os.cpu_count() or 1)
+
+
+def matches_oracle(ro, res, ns, g):
+    """The parity gates of BASELINE.json on a sample: identical iteration counts and selected restarts,
+    log-likelihood to 1e-9, theta to 1e-6 (relative)."""
+    th_o, th_g = ro["theta"], res["theta"][:ns, :ro["theta"].shape[1]]
+    return bool(np.array_equal(ro["iters"], res["iters"][:ns]) and np.array_equal(ro["best"], res["best"][:g])
+                and np.allclose(ro["lik"], res["lik"][:ns], rtol=1e-9, atol=0)
+                and np.allclose(th_g, th_o, rtol=1e-6, atol=1e-12))
 
 
 def run_oracle(sample, args, threads):
@@ -140,6 +158,123 @@ def run_oracle(sample, args, threads):
     return time.perf_counter() - t0, r
 
 
+def oracle_check(w, res, args, seconds):
+    """Oracle (CPU port of src/EM.cpp) on the first groups of `w` against the GPU results `res` of the
+    whole job: returns (cpu record, match flag)."""
+    cores = host_cores()
+    g = cpu_sample_groups(w, seconds, cores)
+    sample = W.subset(w, g)
+    dt, ro = run_oracle(sample, args, cores)
+    ns = int(sample["fit_group"].size)
+    return {"value": ns / dt, "unit": "fits/s", "cores": cores, "kind": "port",
+            "sample": "first %d of %d groups (%d fits), %.1f s" % (g, len(w["group_series"]), ns, dt)}, \
+        matches_oracle(ro, res, ns, g)
+
+
+def device_steps(plan, args, steps, warmup, torch, flush, stream):
+    """`warmup` untimed + `steps` timed passes of plan.em on the current stream: CUDA-event ms per step."""
+    for _ in range(warmup):
+        plan.em(args.niter, args.tol, chunk_iters=args.chunk, stream=stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stats = []
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        stats.append(plan.em(args.niter, args.tol, chunk_iters=args.chunk, stream=stream))
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev], stats
+
+
+def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak):
+    """BASELINE config 3 (48 stations x 100 folds x 100 restarts = 480 000 fits, T=400, p=q=10) as ONE job
+    shared by the ranks: groups dealt by ldsr_shard_groups (the partition ldsr_em_batch itself uses), no
+    data-path collective; the step time is the slowest rank's.  Rank 0 then runs the same job through the
+    one-process host-buffer call ldsr_em_batch(n_devices=world) (what an R session calls)."""
+    from ldsr_b200 import _lib
+    w3 = build_workload(args.strong_workload, 0)  # the same job on every rank
+    ng, nf = len(w3["group_series"]), int(w3["fit_group"].size)
+    shard = _lib.shard_groups(w3["series"], w3["group_series"], w3["held"], w3["fit_group"], w3["theta0"], world)
+    mine = W.take_groups(w3, np.nonzero(shard == rank)[0])
+    plan = _lib.Plan(mine["series"], mine["group_series"], mine["held"], mine["fit_group"], mine["theta0"], device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        dist.barrier()
+    step_ms, stats = device_steps(plan, args, args.strong_steps, 1, torch, flush, stream)
+    res = plan.fetch(want_traj=False)
+    my = torch.tensor([sum(step_ms) / len(step_ms), float(res["iters"].sum()), total_flops(mine, res["iters"]),
+                       float(np.mean([st["em_kernel_ns"] for st in stats])) * 1e-6], dtype=torch.float64, device=dev)
+    allv = [torch.zeros_like(my) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allv, my)
+    else:
+        allv = [my]
+    allv = np.array([a.cpu().numpy() for a in allv])
+    plan.close()
+    del plan
+    per_rank_ms = allv[:, 0]
+    step = float(per_rank_ms.max())
+    if world > 1:
+        dist.barrier()
+    out = None
+    if rank == 0:
+        flops = float(allv[:, 2].sum())
+        out = {"workload": w3["name"], "scaling": "strong", "n_fits": nf, "n_groups": ng, "n_gpus": world,
+               "steps": args.strong_steps, "value": nf / (step * 1e-3), "unit": "fits/s", "ms_per_step": step,
+               "per_rank_ms": [round(float(x), 3) for x in per_rank_ms],
+               "per_rank_em_kernel_ms": [round(float(x), 3) for x in allv[:, 3]],
+               "imbalance": float(per_rank_ms.max() / per_rank_ms.mean() - 1.0),
+               "mean_iters": float(allv[:, 1].sum() / nf),
+               "roofline": {"bound": "fp64", "achieved": flops / (step * 1e-3) / 1e12, "peak": fp64_peak * world,
+                            "unit": "TFLOP/s", "frac": flops / (step * 1e-3) / 1e12 / (fp64_peak * world),
+                            "note": "algorithmic flops of all ranks / slowest rank's step time / (N x DFMA peak)"},
+               "partition": "ldsr_shard_groups (whole groups, greedy LPT), no collective on the data path"}
+        # ---- the one-process path: host buffers in and out, one worker thread + stream per device
+        ndev = min(world, _lib.device_count())
+        ctx = _lib.Ctx(devices=list(range(ndev)))
+        call = lambda: _lib.em_batch(w3["series"], w3["group_series"], w3["held"], w3["fit_group"], w3["theta0"],
+                                     args.niter, args.tol, chunk_iters=args.chunk, ctx=ctx, n_devices=ndev)
+        r = call()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            r = call()
+        dt = (time.perf_counter() - t0) / 2
+        out["e2e_sharded"] = {"value": nf / dt, "unit": "fits/s", "ms_per_call": dt * 1e3, "n_devices": ndev,
+                              "timing": "wall clock around one-process ldsr_em_batch(n_devices=%d), host buffers" % ndev}
+        if not args.no_cpu:
+            cpu, same = oracle_check(w3, r, args, args.strong_cpu_seconds)
+            out["cpu_baseline"] = dict(cpu, gpu_matches_oracle_on_sample=same,
+                                       checked="ldsr_em_batch(n_devices=%d) results vs the oracle" % ndev)
+        ctx.close()
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def config1_block(args, local, torch, flush):
+    """BASELINE config 1: LDS_reconstruction(NPannual, NPpc, NPpc, start.year=1600, num.restarts=100) -- 100
+    restarts of one series (1 group), and a single LDS_EM fit.  Device time per call."""
+    from ldsr_b200 import _lib
+    stream = torch.cuda.current_stream().cuda_stream
+    w = build_workload("np_restarts", 0)
+    out = {}
+    for name, n in (("restarts_100", 100), ("single_fit", 1)):
+        sub = dict(w, fit_group=w["fit_group"][:n], theta0=w["theta0"][:n])
+        plan = _lib.Plan(sub["series"], sub["group_series"], sub["held"], sub["fit_group"], sub["theta0"], device=local)
+        ms, stats = device_steps(plan, args, 5, 2, torch, flush, stream)
+        res = plan.fetch(want_traj=False)
+        rec = {"n_fits": n, "ms": float(np.median(ms)), "value": n / (float(np.median(ms)) * 1e-3), "unit": "fits/s",
+               "mean_iters": float(res["iters"].mean()), "kernel": stats[0]["kernel"]}
+        if not args.no_cpu:
+            _, ro = run_oracle(sub, args, host_cores())
+            rec["gpu_matches_oracle"] = matches_oracle(ro, res, n, 1)
+        out[name] = rec
+        plan.close()
+    out["workload"] = w["name"]
+    return out
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU algorithm (oracle/ldsr_oracle.c, restating src/EM.cpp) on all host threads.
     The real Rcpp/Armadillo build cannot run here (no R): see DESIGN.md."""
@@ -148,7 +283,7 @@ def reference_arm(args, rank, world):
     cores = host_cores()
     w = build_workload(args.workload, 0)
     K, Wm = args.steps, args.warmup
-    g = cpu_sample_groups(w, min(args.cpu_seconds, 150.0 / max(1, K + Wm)), cores)
+    g = cpu_sample_groups(w, cpu_sample_seconds(args), cores)
     sample = W.subset(w, g)
     nf = int(sample["fit_group"].size)
     for _ in range(Wm):
@@ -185,6 +320,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="oracle work per cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong-workload", default="synthetic", help="job shared by the ranks in the `strong` block")
+    ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--strong-cpu-seconds", type=float, default=3.0)
+    ap.add_argument("--no-strong", action="store_true", help="skip the `strong` block (config 3)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (configs 1, 4, 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -270,6 +410,12 @@ def main():
     d2h = sum(r_e2e[k].nbytes for k in ("theta", "lik", "iters", "status", "best", "X", "Y", "V", "J"))
     assert np.array_equal(r_e2e["iters"], res["iters"]) and np.array_equal(r_e2e["best"], res["best"])
 
+    # ---------------- BASELINE config 3 shared by the ranks (strong scaling) ----------------
+    del plan
+    ctx.close()
+    strong = None
+    if not args.no_strong and args.workload == "np_cv":
+        strong = strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,16 +426,20 @@ def main():
     em_ns = float(np.mean([s["em_kernel_ns"] for s in stats]))
     chunks = float(np.mean([s["chunks"] for s in stats]))
     achieved = flops / (em_ns * 1e-9) / 1e12
-    traffic = None  # DRAM bytes per launch of the EM kernel, from the committed ncu --set full capture
+    # DRAM bytes per launch and FP64-pipe activity of the EM kernel: counters of the committed
+    # `ncu --set full` capture of this command (a profiler run is never timed; profiles/README.md)
+    traffic, pipe_pct, ncu_src = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "em_split_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("kernel") == stats[0].get("kernel") and args.workload == "np_cv":
             traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+            pipe_pct, ncu_src = tj.get("sm__pipe_fp64_cycles_active_pct"), tj.get("source")
     except Exception:
         traffic = None
     roofline = {"bound": "fp64", "kernel": stats[0].get("kernel", "em_chunk_kernel"), "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak, "traffic": traffic,
+                "ncu": {"sm__pipe_fp64_cycles_active_pct": pipe_pct, "source": ncu_src},
                 "peak_source": "DFMA microbenchmark in this run (ldsr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flops_per_launch": flops / chunks, "launch_ms": em_ns * 1e-6 / chunks, "launches_per_step": chunks,
                 "kernel_share_of_step": em_ns * 1e-6 / (tot_ms / K)}
@@ -309,23 +459,26 @@ def main():
     # ---------------- CPU baseline (oracle port of src/EM.cpp), bounded sample ----------------
     cpu = None
     if not args.no_cpu and world == 1:
-        cores = host_cores()
-        g = cpu_sample_groups(w, args.cpu_seconds, cores)
-        sample = W.subset(w, g)
-        dt, ro = run_oracle(sample, args, cores)
-        ns = int(sample["fit_group"].size)
-        same = bool(np.array_equal(ro["iters"], res["iters"][:ns]) and np.array_equal(ro["best"], res["best"][:g])
-                    and np.allclose(ro["lik"], res["lik"][:ns], rtol=1e-9, atol=0))
-        cpu = {"value": ns / dt, "unit": "fits/s", "cores": cores, "kind": "port",
-               "sample": "first %d of %d groups (%d fits), %.1f s" % (g, len(w["group_series"]), ns, dt),
-               "gpu_matches_oracle_on_sample": same}
+        cpu, same = oracle_check(w, res, args, cpu_sample_seconds(args))
+        cpu["gpu_matches_oracle_on_sample"] = same
+        cpu["checked"] = "iters and best identical, lik rel 1e-9, theta rel 1e-6"
+
+    configs = None
+    if not args.no_configs and args.workload == "np_cv" and world == 1:
+        configs = {"config1": config1_block(args, local, torch, flush)}
+        if strong is not None:
+            configs["config3"] = {k: strong[k] for k in ("workload", "value", "unit", "ms_per_step", "mean_iters")}
+            configs["config3"]["frac"] = strong["roofline"]["frac"]
+            configs["config3"]["gpu_matches_oracle_on_sample"] = (strong.get("cpu_baseline") or {}).get(
+                "gpu_matches_oracle_on_sample")
 
     out = {
         "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "bundled NP series (tests/golden/np.json) + synthetic initial values/folds (seeded)",
-        "config": dict(workload_config(w, args), l2="flushed (256 MiB write) between timed steps",
-                       mean_iters=float(iters.mean()), parallelism="groups sharded over %d GPU(s), no collective" % world),
+        "config": workload_config(w, args),
+        "run": {"l2": "flushed (256 MiB write) between timed steps", "mean_iters": float(iters.mean()),
+                "parallelism": "one batch per rank (weak), %d GPU(s), no collective; the shared job is in `strong`" % world},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "timing": "wall clock around ldsr_em_batch (host packing + pageable H2D + EM + D2H)"},
@@ -333,6 +486,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu,
         "iter_steps_per_s": world * float(iters.sum()) * w["series"][0]["y"].size / (tot_ms / K * 1e-3),
         "step_ms": [round(x, 3) for x in step_ms],
+        "strong": strong, "configs": configs,
     }
     print(json.dumps(out))
     if world > 1:

@@ -237,7 +237,9 @@ int ldsr_objective_batch(ldsr_ctx *ctx, const ldsr_batch *batch, int kind, doubl
  *   X, V, Y [n][T]: smoothed state, its variance, smoothed output of every member (fit$X, fit$V, fit$Y)
  *   C, R [n]: each member's theta$C and theta$R;  mu: mean of the transformed observations
  *   transform 0 = none, 1 = log, 2 = boxcox with `lambda`
- *   out [n][6][T]: X, Xl, Xu, Q, Ql, Qu (the columns of `rec`);  mean [2][T] (may be NULL): mean X, mean Q */
+ *   out [n][6][T]: X, Xl, Xu, Q, Ql, Qu (the columns of `rec`);  mean [2][T] (may be NULL): mean X, mean Q
+ * Deviation: boxcox with lambda == 0 uses exp_ci(Y + mu, sdY) like the log branch; the reference passes the
+ * centred observations `y` there (R/LDS_reconstruction.R:205), which is not what its own log branch does. */
 int ldsr_construct_rec_batch(int device, int n, int T, const double *X, const double *V, const double *Y,
                              const double *C, const double *R, double mu, int transform, double lambda, double *out,
                              double *mean, char *errbuf, int errlen);

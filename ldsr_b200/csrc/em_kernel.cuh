@@ -13,8 +13,8 @@
 //           segment bodies are straight-line code: no votes, no bounds checks);
 //   M-step  closed form from the sums (lds_math.cuh).
 // No O(T) trajectory ever goes to memory: per fit and iteration the kernel touches 2 doubles per
-// SEG steps of checkpoint.  Steps no lane of the warp observes (warp vote on the mask bits) take a
-// short path without the measurement update.
+// SEG steps of checkpoint.  Segments in which the series has no observation at all take a short path
+// without the measurement update.
 // A launch runs at most `chunk` iterations; live fits are re-compacted between launches
 // (compact_kernel) so finished fits do not hold lanes.
 #pragma once
@@ -309,15 +309,22 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     if (STAGED) mbar_wait(&bar, phase);
     const bool warp_has_fits = warp * 32 < task.z; // else the whole warp idles through this task
 
-    // Which segments hold an observed step for some lane of this warp: fixed for the whole launch,
-    // so the vote is taken once here (bitmap in two registers covers 128 segments = T <= 128*SEG;
-    // longer series fall back to a vote per segment).
+    // Which segments hold an observed step: taken from the SERIES (is y finite?), not from a vote over
+    // the hold-out masks of the 32 fits that happen to share the warp -- the code path a fit takes must
+    // not depend on its neighbours, or its last bits (and, near the tolerance, its iteration count)
+    // would change with the order of the batch and with the compaction between launches.  Fixed for the
+    // whole launch, so it is computed once here (bitmap in two registers covers 128 segments =
+    // T <= 128*SEG; longer series test the segment's y values each time).
+    auto seg_has_obs = [&](int sg) -> bool {
+        bool m = false;
+        for (int t = sg * SEG; t < T && t < (sg + 1) * SEG; ++t) m = m || (ys[t] == ys[t]);
+        return m;
+    };
     unsigned long long mix0 = 0ull, mix1 = 0ull;
     const bool have_map = nseg <= 128;
     if (have_map)
         for (int sg = 0; sg < nseg; ++sg) {
-            const bool m = __any_sync(FULL, seg_bits(mw, sg * SEG, SEG) != 0u);
-            if (m) {
+            if (seg_has_obs(sg)) {
                 if (sg < 64)
                     mix0 |= 1ull << sg;
                 else
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
         }
     auto seg_is_mixed = [&](int sg) -> bool {
         if (have_map) return ((sg < 64 ? mix0 >> sg : mix1 >> (sg - 64)) & 1ull) != 0ull;
-        return __any_sync(FULL, seg_bits(mw, sg * SEG, SEG) != 0u);
+        return seg_has_obs(sg);
     };
 
     for (int it = 0; warp_has_fits && it < P.chunk; ++it) {

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -219,6 +220,7 @@ struct ldsr_plan {
     std::vector<SeriesDev> h_series;
     std::vector<int> g_user, f_user, h_g_series, h_g_fit_ptr, h_f_group;
     std::vector<int> s_p, s_q, s_T;
+    std::vector<int> user_fit_series; // per USER fit: its series (filled only when the rows differ in width)
     std::vector<long long> h_traj_ptr_user; // per USER group: offset of its trajectory row
     long long traj_total = 0;
     std::vector<void *> allocs;
@@ -264,6 +266,16 @@ struct ldsr_plan {
         allocs.push_back(p);
         *out = static_cast<T *>(p);
         return Err();
+    }
+    // grow a block: the old one goes back to the pool at once (a plan re-used with a larger niter or
+    // with trace_liks must not accumulate dead blocks until it is destroyed)
+    template <class T> Err drealloc(T **ptr, size_t n) {
+        if (*ptr) {
+            allocs.erase(std::remove(allocs.begin(), allocs.end(), static_cast<void *>(*ptr)), allocs.end());
+            pool->release(*ptr);
+            *ptr = nullptr;
+        }
+        return dalloc(ptr, n);
     }
     template <class T> Err upload(T **out, const std::vector<T> &h) {
         Err e = dalloc(out, h.size());
@@ -517,6 +529,10 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->upload(&P->d_f_user, P->f_user)).ok()) return e;
     if (!(e = P->upload(&P->d_g_user, P->g_user)).ok()) return e;
     for (int s = 0; s < ns; s++) P->same_width = P->same_width && b->p[s] + b->q[s] + 6 == b->theta_stride;
+    if (!P->same_width) {
+        P->user_fit_series.resize(nf);
+        for (int f = 0; f < nf; f++) P->user_fit_series[f] = b->group_series[b->fit_group[f]];
+    }
     P->res_head = (size_t)nf * b->theta_stride + nf + ((size_t)2 * nf + ng + 1) / 2;
     P->res_total = P->res_head + 4 * (size_t)P->traj_total; // allocated by the first ldsr_plan_em
     if (!(e = P->upload(&P->d_theta0, th0)).ok()) return e;
@@ -600,7 +616,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     if (want_liks) {
         const size_t need = (size_t)nf * niter;
         if (P->liks_cap < need) {
-            Err e = P->dalloc(&P->d_liks, need);
+            P->liks_cap = 0;
+            Err e = P->drealloc(&P->d_liks, need);
             if (!e.ok()) return e;
             P->liks_cap = need;
         }
@@ -680,12 +697,15 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // callback the host synchronises after every chunk, as the reference polls for interrupts
     // every 100 iterations (EM.cpp:261).
     const int max_chunks = (niter + chunk - 1) / chunk;
-    const bool sync_each = (opt && opt->poll) || false;
+    // abort_flag != NULL: this is a per-device worker of a sharded call whose CALLER polls.  The worker
+    // never runs the callback itself (it belongs to the calling thread: an R shim runs
+    // R_CheckUserInterrupt there); it only looks at the flag the calling thread raises.
+    const bool sync_each = (opt && opt->poll) || abort_flag != nullptr;
     int grid0 = 0; // task count of the first chunk: every fit is live
     for (int s = 0; s < ns; s++)
         grid0 += (P->h_series[s].fit_end - P->h_series[s].fit_begin + fits_per_cta - 1) / fits_per_cta;
     if ((int)P->counts_cap < 2 * max_chunks) {
-        Err e = P->dalloc(&P->d_counts, (size_t)2 * max_chunks);
+        Err e = P->drealloc(&P->d_counts, (size_t)2 * max_chunks);
         if (!e.ok()) return e;
         P->counts_cap = 2 * max_chunks;
         if (P->h_counts) P->pool->release_pinned(P->h_counts);
@@ -696,7 +716,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     }
     const size_t ck_need = (mode == 2 || use_split) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
     if (P->ckpt_cap < ck_need) {
-        Err e = P->dalloc(&P->d_ckpt, ck_need);
+        P->ckpt_cap = 0;
+        Err e = P->drealloc(&P->d_ckpt, ck_need);
         if (!e.ok()) return e;
         P->ckpt_cap = ck_need;
     }
@@ -719,13 +740,20 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         // ahead of live ones would push three live CTAs onto some SMs while others hold one
         // (measured: 2.48 ms instead of 1.83 ms per chunk on the 10 000-fit job).
         int grid = (c == 0 || grid0 > 3 * P->n_sm) ? grid0 : std::min(grid0, 2 * P->n_sm);
+        // development: LDSR_MAX_GRID caps the grid so that a small batch exercises the task loop of the
+        // kernels (tools/sanitize.py runs it under compute-sanitizer)
+        static const int grid_cap = std::getenv("LDSR_MAX_GRID") ? std::atoi(std::getenv("LDSR_MAX_GRID")) : 0;
+        if (grid_cap > 0) grid = std::min(grid, grid_cap);
         if (sync_each) {
             CU(cudaMemcpyAsync(P->h_counts + 2 * c, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             grid = std::max(1, P->h_counts[2 * c]);
             if (P->h_counts[2 * c + 1] == 0) break;
-            if (abort_flag && abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
-            if (opt->poll(opt->poll_arg)) return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
+            if (abort_flag) {
+                if (abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
+            } else if (opt->poll(opt->poll_arg)) {
+                return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
+            }
         }
         ep.n_tasks = cnt;
         if (stats) {
@@ -882,7 +910,16 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     return Err();
 }
 
-static Err plan_fetch(ldsr_plan *P, ldsr_em_result *out) {
+// Where the rows of a sub-batch (one device's share of a sharded call) go in the caller's arrays: local
+// fit i is the caller's fit fits[i], local group gl the caller's group groups[gl], whose trajectory
+// row starts at traj_ptr[groups[gl]].  Workers of different devices write disjoint rows.
+struct FetchMap {
+    const int *fits, *groups;
+    const long long *traj_ptr; // caller-wide, [n_groups + 1]
+    int niter;
+};
+
+static Err plan_fetch(ldsr_plan *P, ldsr_em_result *out, const FetchMap *map = nullptr) {
     if (!P->em_done) return fail(LDSR_ERR_ARG, "ldsr_plan_fetch before a successful ldsr_plan_em");
     if (!out) return fail(LDSR_ERR_ARG, "result struct is NULL");
     CU(cudaSetDevice(P->device));
@@ -922,14 +959,53 @@ static Err plan_fetch(ldsr_plan *P, ldsr_em_result *out) {
     const bool traj = out->X || out->Y || out->V || out->J;
     CU(cudaMemcpyAsync(P->h_res, P->d_res, (traj ? P->res_total : P->res_head) * sizeof(double),
                        cudaMemcpyDeviceToHost, st));
+    std::vector<double> liks_tmp; // sharded call: the trace rows are scattered on the host
     if (out->liks) {
         if (!P->d_liks) return fail(LDSR_ERR_ARG, "liks requested at fetch but not at ldsr_plan_em time");
-        CU(cudaMemcpyAsync(out->liks, P->d_liks, (size_t)nf * P->last_niter * sizeof(double), cudaMemcpyDeviceToHost,
-                           st));
+        double *dst = out->liks;
+        if (map) {
+            liks_tmp.resize((size_t)nf * P->last_niter);
+            dst = liks_tmp.data();
+        }
+        CU(cudaMemcpyAsync(dst, P->d_liks, (size_t)nf * P->last_niter * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
     const double *h_theta = P->h_res, *h_lik = h_theta + (size_t)nf * stride;
     const int *h_int = reinterpret_cast<const int *>(h_lik + nf);
+    if (map) {
+        // straight from the pinned block into the caller's rows (no per-shard staging vectors)
+        const int *h_it = h_int, *h_st = h_int + nf, *h_best = h_int + 2 * (size_t)nf;
+        for (int i = 0; i < nf; i++) {
+            const int f = map->fits[i];
+            if (out->theta) { // the tail of a caller row beyond its series' p + q + 6 is left as the caller set it
+                int w = stride;
+                if (!P->same_width) {
+                    const int s = P->user_fit_series[i];
+                    w = P->s_p[s] + P->s_q[s] + 6;
+                }
+                std::memcpy(out->theta + (size_t)f * stride, h_theta + (size_t)i * stride, sizeof(double) * w);
+            }
+            if (out->lik) out->lik[f] = h_lik[i];
+            if (out->iters) out->iters[f] = h_it[i];
+            if (out->status) out->status[f] = h_st[i];
+            if (out->liks)
+                std::memcpy(out->liks + (size_t)f * map->niter, &liks_tmp[(size_t)i * P->last_niter],
+                            sizeof(double) * P->last_niter);
+        }
+        const size_t tt = (size_t)P->traj_total;
+        const double *h_traj = P->h_res + P->res_head;
+        for (int gl = 0; gl < ng; gl++) {
+            const int g = map->groups[gl];
+            if (out->best) out->best[g] = h_best[gl] < 0 ? -1 : map->fits[h_best[gl]];
+            const size_t n = (size_t)(P->h_traj_ptr_user[gl + 1] - P->h_traj_ptr_user[gl]) * sizeof(double);
+            const size_t src = (size_t)P->h_traj_ptr_user[gl], dst = (size_t)map->traj_ptr[g];
+            if (out->X) std::memcpy(out->X + dst, h_traj + src, n);
+            if (out->Y) std::memcpy(out->Y + dst, h_traj + tt + src, n);
+            if (out->V) std::memcpy(out->V + dst, h_traj + 2 * tt + src, n);
+            if (out->J) std::memcpy(out->J + dst, h_traj + 3 * tt + src, n);
+        }
+        return Err();
+    }
     if (out->theta) {
         if (P->same_width)
             std::memcpy(out->theta, h_theta, sizeof(double) * (size_t)nf * stride);
@@ -1069,95 +1145,103 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
         if (fit_lo[g] < 0) fit_lo[g] = f;
         fit_hi[g] = f + 1;
     }
+    {   // a group without fits costs nothing: never more shards than groups that have work, so that no
+        // device is handed an empty sub-batch
+        int nonempty = 0;
+        for (int g = 0; g < ng; g++) nonempty += fit_lo[g] >= 0 ? 1 : 0;
+        nd = std::max(1, std::min(nd, nonempty));
+    }
     std::vector<int> shard(ng);
     shard_groups(b, nd, shard.data());
     std::vector<std::vector<int>> dev_groups(nd);
     for (int g = 0; g < ng; g++) dev_groups[shard[g]].push_back(g);
+    std::vector<long long> traj_ptr(ng + 1, 0);
+    for (int g = 0; g < ng; g++) traj_ptr[g + 1] = traj_ptr[g] + b->T[b->group_series[g]];
 
+    // Workers never run the caller's poll callback (it belongs to the calling thread: the R shim's
+    // callback enters the R API).  When the caller polls, the workers synchronise after every chunk
+    // and look at abort_flag, which the calling thread raises; otherwise they enqueue the whole run.
+    ldsr_options wopt;
+    std::memset(&wopt, 0, sizeof wopt);
+    if (opt) wopt = *opt;
+    wopt.poll = nullptr;
+    wopt.poll_arg = nullptr;
+    const bool caller_polls = opt && opt->poll;
     std::vector<SubBatch> subs(nd);
     std::vector<Err> errs(nd);
-    std::atomic<int> abort_flag(0), running(nd);
-    struct Res {
-        std::vector<double> theta, lik, liks, X, Y, V, J;
-        std::vector<int> iters, status, best;
-    };
-    std::vector<Res> res(nd);
+    std::atomic<int> abort_flag(0);
+    std::mutex mu;
+    std::condition_variable cv;
+    int running = nd;
+    static const bool timing = std::getenv("LDSR_TIMING") != nullptr;
+    std::vector<double> dev_ms(nd, 0.0);
     std::vector<std::thread> workers;
     for (int d = 0; d < nd; d++) {
-        make_sub(b, dev_groups[d], fit_lo, fit_hi, subs[d]);
         workers.emplace_back([&, d]() {
+            const auto t0 = std::chrono::steady_clock::now();
             SubBatch &sb = subs[d];
-            Res &r = res[d];
-            ldsr_plan *P = nullptr;
-            Err er = plan_build(&sb.b, ctx->devices[d], ctx->pools[d].get(), &P);
-            if (er.ok()) {
-                std::unique_ptr<ldsr_plan> guard(P);
-                er = plan_em(P, niter, tol, opt, nullptr, want_liks, &abort_flag, nullptr);
+            make_sub(b, dev_groups[d], fit_lo, fit_hi, sb); // each worker packs its own share
+            Err er;
+            if (sb.fits.empty()) { // only groups without fits: nothing to run
+                const double nan = std::nan("");
+                for (int g : sb.groups) {
+                    if (out->best) out->best[g] = -1;
+                    for (double *rowp : {out->X, out->Y, out->V, out->J})
+                        if (rowp) std::fill(rowp + traj_ptr[g], rowp + traj_ptr[g + 1], nan);
+                }
+            } else {
+                ldsr_plan *P = nullptr;
+                er = plan_build(&sb.b, ctx->devices[d], ctx->pools[d].get(), &P);
                 if (er.ok()) {
-                    const size_t nfl = sb.fits.size(), ngl = sb.groups.size();
-                    ldsr_em_result o;
-                    std::memset(&o, 0, sizeof o);
-                    if (out->theta) { r.theta.resize(nfl * b->theta_stride); o.theta = r.theta.data(); }
-                    if (out->lik) { r.lik.resize(nfl); o.lik = r.lik.data(); }
-                    if (out->iters) { r.iters.resize(nfl); o.iters = r.iters.data(); }
-                    if (out->status) { r.status.resize(nfl); o.status = r.status.data(); }
-                    if (out->liks) { r.liks.resize(nfl * (size_t)niter); o.liks = r.liks.data(); }
-                    if (out->best) { r.best.resize(ngl); o.best = r.best.data(); }
-                    const size_t tt = (size_t)sb.traj_ptr.back();
-                    if (out->X) { r.X.resize(tt); o.X = r.X.data(); }
-                    if (out->Y) { r.Y.resize(tt); o.Y = r.Y.data(); }
-                    if (out->V) { r.V.resize(tt); o.V = r.V.data(); }
-                    if (out->J) { r.J.resize(tt); o.J = r.J.data(); }
-                    er = plan_fetch(P, &o);
+                    std::unique_ptr<ldsr_plan> guard(P);
+                    er = plan_em(P, niter, tol, &wopt, nullptr, want_liks, caller_polls ? &abort_flag : nullptr, nullptr);
+                    if (er.ok()) {
+                        FetchMap map{sb.fits.data(), sb.groups.data(), traj_ptr.data(), niter};
+                        er = plan_fetch(P, out, &map);
+                    }
                 }
             }
             if (!er.ok()) abort_flag.store(1);
             errs[d] = er;
-            running.fetch_sub(1);
+            dev_ms[d] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                running--;
+            }
+            cv.notify_all();
         });
     }
-    // the poll callback runs HERE, on the calling thread
+    // the poll callback runs HERE, on the calling thread; completion is signalled, not polled for
     bool interrupted = false;
-    while (running.load() > 0) {
-        std::this_thread::sleep_for(std::chrono::milliseconds(opt && opt->poll ? 20 : 2));
-        if (opt && opt->poll && !interrupted && opt->poll(opt->poll_arg)) {
-            interrupted = true;
-            abort_flag.store(1);
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        while (running > 0) {
+            if (!caller_polls) {
+                cv.wait(lk);
+                continue;
+            }
+            cv.wait_for(lk, std::chrono::milliseconds(20));
+            if (running > 0 && !interrupted) {
+                lk.unlock();
+                const bool stop = opt->poll(opt->poll_arg) != 0;
+                lk.lock();
+                if (stop) {
+                    interrupted = true;
+                    abort_flag.store(1);
+                }
+            }
         }
     }
     for (auto &w : workers) w.join();
+    if (timing)
+        for (int d = 0; d < nd; d++)
+            std::fprintf(stderr, "ldsr_em_batch: device %d: %zu groups, %zu fits, %.3f ms\n", ctx->devices[d],
+                         subs[d].groups.size(), subs[d].fits.size(), dev_ms[d]);
     if (interrupted) return fail(LDSR_ERR_INTERRUPTED, "interrupted by the poll callback");
     for (int d = 0; d < nd; d++)
         if (!errs[d].ok() && errs[d].code != LDSR_ERR_INTERRUPTED) return errs[d];
     for (int d = 0; d < nd; d++)
         if (!errs[d].ok()) return errs[d];
-
-    // ---- gather (host concatenation; no collective)
-    std::vector<long long> traj_ptr(ng + 1, 0);
-    for (int g = 0; g < ng; g++) traj_ptr[g + 1] = traj_ptr[g] + b->T[b->group_series[g]];
-    for (int d = 0; d < nd; d++) {
-        const SubBatch &sb = subs[d];
-        const Res &r = res[d];
-        for (size_t i = 0; i < sb.fits.size(); i++) {
-            const int f = sb.fits[i];
-            if (out->theta)
-                std::memcpy(out->theta + (size_t)f * b->theta_stride, &r.theta[i * b->theta_stride],
-                            sizeof(double) * b->theta_stride);
-            if (out->lik) out->lik[f] = r.lik[i];
-            if (out->iters) out->iters[f] = r.iters[i];
-            if (out->status) out->status[f] = r.status[i];
-            if (out->liks) std::memcpy(out->liks + (size_t)f * niter, &r.liks[i * (size_t)niter], sizeof(double) * niter);
-        }
-        for (size_t gl = 0; gl < sb.groups.size(); gl++) {
-            const int g = sb.groups[gl];
-            if (out->best) out->best[g] = r.best[gl] < 0 ? -1 : sb.fits[r.best[gl]];
-            const size_t n = (size_t)(traj_ptr[g + 1] - traj_ptr[g]);
-            if (out->X) std::memcpy(out->X + traj_ptr[g], &r.X[sb.traj_ptr[gl]], n * sizeof(double));
-            if (out->Y) std::memcpy(out->Y + traj_ptr[g], &r.Y[sb.traj_ptr[gl]], n * sizeof(double));
-            if (out->V) std::memcpy(out->V + traj_ptr[g], &r.V[sb.traj_ptr[gl]], n * sizeof(double));
-            if (out->J) std::memcpy(out->J + traj_ptr[g], &r.J[sb.traj_ptr[gl]], n * sizeof(double));
-        }
-    }
     return Err();
 }
 

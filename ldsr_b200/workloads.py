@@ -20,14 +20,17 @@ def _np_data():
 
 
 def make_init_array(rng, p, q, n):
-    """n flat thetas [A, B(p), C, D(q), Q=1, R=1, mu1=0, V1=1] in make_init's draw order."""
+    """n flat thetas [A, B(p), C, D(q), Q=1, R=1, mu1=0, V1=1] in make_init's draw order (per restart:
+    runif A, runif(p,-1,1) B, runif C, runif(q,-1,1) D).  One vectorised draw: numpy's Generator takes
+    one 64-bit word per double whether asked for scalars or an array, and uniform(a, b) is
+    a + (b - a) * random(), so this is bit-identical to drawing restart by restart."""
+    r = rng.random((n, p + q + 2))
     out = np.empty((n, p + q + 6))
-    for i in range(n):
-        out[i, 0] = rng.uniform()
-        out[i, 1:1 + p] = rng.uniform(-1, 1, p)
-        out[i, 1 + p] = rng.uniform()
-        out[i, 2 + p:2 + p + q] = rng.uniform(-1, 1, q)
-        out[i, 2 + p + q:] = (1.0, 1.0, 0.0, 1.0)
+    out[:, 0] = r[:, 0]
+    out[:, 1:1 + p] = -1.0 + 2.0 * r[:, 1:1 + p]
+    out[:, 1 + p] = r[:, 1 + p]
+    out[:, 2 + p:2 + p + q] = -1.0 + 2.0 * r[:, 2 + p:2 + p + q]
+    out[:, 2 + p + q:] = (1.0, 1.0, 0.0, 1.0)
     return out
 
 
@@ -112,6 +115,18 @@ def subset(w, n_groups):
     out = dict(w)
     out.update(group_series=w["group_series"][:n_groups], held=w["held"][:n_groups],
                fit_group=w["fit_group"][keep], theta0=w["theta0"][keep])
+    return out
+
+
+def take_groups(w, groups):
+    """The workload restricted to `groups` (sorted group ids): one rank's shard of a job.  Fits keep
+    their order; `fits` in the result are their indices in the full job."""
+    groups = np.asarray(groups, dtype=np.int64)
+    keep = np.nonzero(np.isin(w["fit_group"], groups))[0]
+    out = dict(w)
+    out.update(group_series=w["group_series"][groups], held=[w["held"][g] for g in groups],
+               fit_group=np.searchsorted(groups, w["fit_group"][keep]).astype(np.int32),
+               theta0=w["theta0"][keep], fits=keep, groups=groups)
     return out
 
 

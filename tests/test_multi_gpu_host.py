@@ -105,3 +105,20 @@ def test_tbrm_and_stored_cv_aggregate():
     assert abs(api.tbrm(x) - 3.0) < 1e-12
     assert abs(api.tbrm(np.append(x, 1e6)) - api.tbrm(np.append(x, 3.5))) < 0.5
     assert np.isnan(api.tbrm([np.nan]))
+
+
+def test_take_groups_partitions_a_job_by_shard():
+    """bench.py's `strong` block: every rank takes the groups ldsr_shard_groups gives it; together the
+    shards hold every fit exactly once, in order, with local group ids."""
+    w = W.synthetic_stations(n_stations=3, T=120, p=2, n_folds=5, n_restarts=4)
+    n = 4
+    sh = _lib.shard_groups(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], n)
+    seen = []
+    for r in range(n):
+        sub = W.take_groups(w, np.nonzero(sh == r)[0])
+        assert np.all(np.diff(sub["fit_group"]) >= 0) and sub["fit_group"].max() == len(sub["group_series"]) - 1
+        assert np.array_equal(sub["theta0"], w["theta0"][sub["fits"]])
+        assert np.array_equal(sub["groups"][sub["fit_group"]], w["fit_group"][sub["fits"]])
+        assert all(np.array_equal(a, w["held"][g]) for a, g in zip(sub["held"], sub["groups"]))
+        seen.append(sub["fits"])
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(w["fit_group"].size))
