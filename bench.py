@@ -187,7 +187,7 @@ def device_steps(plan, args, steps, warmup, torch, flush, stream):
     return [a.elapsed_time(b) for a, b in ev], stats
 
 
-def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak):
+def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak, cpu_group):
     """BASELINE config 3 (48 stations x 100 folds x 100 restarts = 480 000 fits, T=400, p=q=10) as ONE job
     shared by the ranks: groups dealt by ldsr_shard_groups (the partition ldsr_em_batch itself uses), no
     data-path collective; the step time is the slowest rank's.  Rank 0 then runs the same job through the
@@ -217,6 +217,7 @@ def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak):
     step = float(per_rank_ms.max())
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
     out = None
     if rank == 0:
         flops = float(allv[:, 2].sum())
@@ -248,7 +249,10 @@ def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak):
                                        checked="ldsr_em_batch(n_devices=%d) results vs the oracle" % ndev)
         ctx.close()
     if world > 1:
-        dist.barrier()
+        # the other ranks wait on the HOST (gloo): a pending NCCL barrier is a kernel spinning on their
+        # GPU, and without MPS it would time-slice with rank 0's worker on that device (measured: the
+        # second device of ldsr_em_batch(n_devices=2) took 1455 ms instead of 697 ms)
+        dist.barrier(group=cpu_group)
     return out
 
 
@@ -342,8 +346,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not occupy a GPU
 
     w = build_workload(args.workload, rank)
     nf = int(w["fit_group"].size)
@@ -415,7 +421,7 @@ def main():
     ctx.close()
     strong = None
     if not args.no_strong and args.workload == "np_cv":
-        strong = strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak)
+        strong = strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak, cpu_group)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
