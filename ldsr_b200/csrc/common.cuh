@@ -1,7 +1,18 @@
 // common.cuh -- device-side tables, PTX helpers (mbarrier + TMA bulk copy) shared by the kernels.
 #pragma once
 #include <cstdint>
+#ifndef LDSR_HOST_SIM
 #include <cuda_runtime.h>
+// shared memory declarations inside a kernel (tests/host_simt/ re-defines them to run the kernel
+// source on the CPU; see LDSR_HOST_SIM below)
+#define LDSR_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define LDSR_STATIC_SMEM(type, name) __shared__ type name
+#else
+// TEST BUILD ONLY (tests/host_simt/host_simt.h): the kernels' source compiled by g++ and run by a
+// coroutine-per-thread emulator.  Never part of the product library.
+#define LDSR_DYN_SMEM(name) unsigned char *const name = ::hostsim::dyn_smem()
+#define LDSR_STATIC_SMEM(type, name) static type name
+#endif
 
 namespace ldsr {
 
@@ -29,6 +40,7 @@ struct SeriesDev {
 // observed steps): [ Syy, n_obs, Syv[PQ], wy[PQ] = SvvInv*Syv, SvvInv[PQ*PQ] ]
 __host__ __device__ inline int gconst_stride(int pq) { return 2 + 2 * pq + pq * pq; }
 
+#ifndef LDSR_HOST_SIM
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
     return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
@@ -61,6 +73,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     } while (!ok);
 }
 
+#else
+// emulation: *bar counts completed phases; a wait on parity p returns once phase p has completed
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned) { *bar = 0; }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *) {
+    std::memcpy(dst_smem, src_gmem, bytes);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    while (((*(volatile uint64_t *)bar) & 1u) == parity) ::hostsim::yield();
+}
+#endif
+
 // Stage `bytes` (multiple of 16) from global to shared with TMA bulk copies issued by one thread.
 // Pieces of <= 32 KB keep each transaction well inside the mbarrier tx-count range.
 __device__ __forceinline__ void stage_blob(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
@@ -70,6 +95,9 @@ __device__ __forceinline__ void stage_blob(void *dst_smem, const void *src_gmem,
         unsigned n = bytes - off < PIECE ? bytes - off : PIECE;
         bulk_g2s(static_cast<char *>(dst_smem) + off, static_cast<const char *>(src_gmem) + off, n, bar);
     }
+#ifdef LDSR_HOST_SIM
+    *bar += 1; // all bytes have landed: the phase completes
+#endif
 }
 
 } // namespace ldsr

@@ -250,8 +250,8 @@ __device__ __forceinline__ void smooth_segment(const Theta<PQ> &th, double A, do
 template <int PQ, int SEG, int W, int MODE>
 __global__ void __launch_bounds__(W * 32, 1) em_chunk_kernel(const EmParams P) {
     constexpr bool STAGED = MODE >= 1;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    LDSR_DYN_SMEM(smem_raw);
+    LDSR_STATIC_SMEM(__align__(8) uint64_t, bar);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (STAGED) {

@@ -784,8 +784,8 @@ template <int PQ, int NW, int MINB, int MSEG, int UW>
 __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitParams SP) {
     static_assert(MSEG == 4 || MSEG == 8, "M unit is 4 or 8 steps");
     const EmParams &P = SP.em;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    LDSR_DYN_SMEM(smem_raw);
+    LDSR_STATIC_SMEM(__align__(8) uint64_t, bar);
     constexpr int NST = split_nstat<PQ>();
     constexpr int NP = 2 * NW; // pieces
     constexpr bool PAIR = split_pairwise<PQ, NW>();

@@ -64,7 +64,11 @@ template <int PQ> __device__ __forceinline__ void store_theta(const Theta<PQ> &t
 // still has a finite likelihood.
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
+#ifndef LDSR_HOST_SIM
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+    r = (double)(1.0f / (float)x); // a seed of similar accuracy for the CPU emulation (tests/host_simt)
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);

@@ -1,0 +1,100 @@
+"""The EM kernels' SOURCE run on the CPU by a coroutine-per-thread emulator (tests/host_simt/): checks,
+without a GPU and without compute-sanitizer (closed on the GPU pool), that
+  * the kernels' control flow, shared-memory carve-up and cross-warp exchanges reproduce the oracle,
+  * results are BIT-IDENTICAL under different orders of resuming the CTA's threads between
+    synchronisation points -- a shared-memory race (two accesses to one word that no barrier orders)
+    shows up as a difference (the racecheck stand-in),
+  * no thread reads shared memory that was never written (it starts as NaN) or past its end (traps).
+The arithmetic differs from the GPU build only in the reciprocal seed (lds_math.cuh, fast_rcp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import data
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_simt")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(HERE, "libldsr_hostsim.so")
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+def _lib():
+    srcs = [os.path.join(HERE, f) for f in ("sim_em.cpp", "host_simt.h")]
+    csrc = os.path.join(ROOT, "ldsr_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        wide = ["-DLDSR_HAVE_WIDE"] if os.path.exists(os.path.join(csrc, "em_wide_kernel.cuh")) else []
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-DLDSR_HOST_SIM", "-Wno-unknown-pragmas", "-mfma",
+                        "-ffp-contract=off", "-shared", "-fPIC"] + wide +
+                       [os.path.join(HERE, "sim_em.cpp"), "-o", SO], check=True)
+    return C.CDLL(SO)
+
+
+def sim_em(kind, y, u, v, held, fit_group, theta0, niter, tol=1e-5, chunk=100, order=0, grid_cap=0):
+    L = _lib()
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    T = y.size
+    uf = None if u is None else np.ascontiguousarray(np.asarray(u, dtype=np.float64).T)
+    vf = None if v is None else np.ascontiguousarray(np.asarray(v, dtype=np.float64).T)
+    p = 1 if uf is None else uf.shape[1]
+    q = 1 if vf is None else vf.shape[1]
+    hp = np.zeros(len(held) + 1, dtype=np.int32)
+    hp[1:] = np.cumsum([len(h) for h in held])
+    hi = np.ascontiguousarray(np.concatenate([np.asarray(h, dtype=np.int32) for h in held] + [np.zeros(1, np.int32)]))
+    fg = np.ascontiguousarray(fit_group, dtype=np.int32)
+    th0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    nf = fg.size
+    th = np.full_like(th0, np.nan)
+    lik = np.empty(nf)
+    it = np.empty(nf, dtype=np.int32)
+    d = lambda a: None if a is None else a.ctypes.data_as(_dp)
+    i = lambda a: a.ctypes.data_as(_ip)
+    rc = L.hostsim_em(kind, T, p, q, d(y), d(uf), d(vf), len(held), i(hp), i(hi), nf, i(fg), d(th0), niter,
+                      C.c_double(tol), chunk, order, grid_cap, d(th), d(lik), i(it))
+    assert rc == 0, rc
+    return dict(theta=th, lik=lik, iters=it)
+
+
+def rand_theta0(rng, p, q, n):
+    return np.stack([np.concatenate([[rng.uniform()], rng.uniform(-1, 1, p), [rng.uniform()],
+                                     rng.uniform(-1, 1, q), [1, 1, 0, 1]]) for _ in range(n)])
+
+
+def _np_job(n_folds=3, n_rest=14, seed=5):
+    y, u, mu, inst = data.np_case(601, 1800)  # T = 213
+    rng = np.random.default_rng(seed)
+    held = [np.sort(rng.choice(inst, 11, replace=False)) for _ in range(n_folds)]
+    fg = np.repeat(np.arange(n_folds), n_rest)
+    return y, u, held, fg, rand_theta0(rng, 3, 3, n_folds * n_rest)
+
+
+def _check_vs_oracle(r, y, u, v, held, fg, th0, niter):
+    o = O.em_batch([dict(y=y, u=u, v=v)], np.zeros(len(held), dtype=int), held, fg, th0, niter, 1e-5)
+    assert np.array_equal(r["iters"], o["iters"])
+    assert np.allclose(r["lik"], o["lik"], rtol=1e-9, atol=0)
+    assert np.allclose(r["theta"], o["theta"], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", [3, 2])
+def test_emulated_kernel_matches_oracle_and_is_schedule_independent(kind):
+    y, u, held, fg, th0 = _np_job()
+    niter = 7
+    base = sim_em(kind, y, u, u, held, fg, th0, niter, chunk=4, order=0)
+    _check_vs_oracle(base, y, u, u, held, fg, th0, niter)
+    for order in (1, 2, 3):
+        r = sim_em(kind, y, u, u, held, fg, th0, niter, chunk=4, order=order)
+        for k in ("theta", "lik", "iters"):
+            assert np.array_equal(base[k], r[k]), (order, k)
+
+
+def test_emulated_task_loop_reuses_shared_memory_safely():
+    # one CTA takes both tasks in turn (grid_cap = 1): the arena is re-used across tasks
+    y, u, held, fg, th0 = _np_job(n_folds=3, n_rest=14)  # 42 fits = 2 tasks of the time-split kernel
+    a = sim_em(3, y, u, u, held, fg, th0, 5, chunk=5, order=2, grid_cap=1)
+    b = sim_em(3, y, u, u, held, fg, th0, 5, chunk=5, order=0, grid_cap=0)
+    for k in ("theta", "lik", "iters"):
+        assert np.array_equal(a[k], b[k]), k
