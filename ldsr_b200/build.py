@@ -15,7 +15,8 @@ OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libldsr_b200.so")
 PQ_LIST = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 32)  # keep in sync with LDSR_PQ_LIST in ldsr_abi.cu
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SPLIT_TU_FROM_PQ = 12  # widths from here on are compiled as 5 translation units each
+SPLIT_TU_FROM_PQ = 12  # widths from here on are compiled as 6 translation units each
+WIDE_FROM_PQ = 5       # keep in sync with WIDE_MIN_PQ (kernel_table.h): these widths have the wide-input kernel
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
 
@@ -60,8 +61,8 @@ def build(force=False, verbose=False, ptxas_info=False):
     # per-object dependencies, so that touching the ABI or the scan kernels does not recompile the
     # thirteen per-width EM translation units (minutes)
     c = lambda *names: [os.path.join(CSRC, n) for n in names]
-    em_deps = c("kernels_inst.cu", "kernel_table.h", "em_kernel.cuh", "em_split_kernel.cuh", "aux_kernels.cuh",
-                "lds_math.cuh", "common.cuh")
+    em_deps = c("kernels_inst.cu", "kernel_table.h", "em_kernel.cuh", "em_split_kernel.cuh", "em_wide_kernel.cuh",
+                "aux_kernels.cuh", "lds_math.cuh", "common.cuh")
     scan_deps = c("scan_inst.cu", "scan_kernels.cuh", "common.cuh")
     obj_deps = {}
     os.makedirs(OBJ, exist_ok=True)
@@ -73,10 +74,12 @@ def build(force=False, verbose=False, ptxas_info=False):
     # widest first (longest jobs first); a wide PQ is cut into 5 parts (see kernels_inst.cu) so that no
     # single nvcc process is the critical path of the build
     for pq in sorted(PQ_LIST, reverse=True):
-        parts = [None] if pq < SPLIT_TU_FROM_PQ else [1, 2, 3, 4, 0]
+        # None: everything in one unit; "main": everything but the wide-input kernel (its own unit, part 5)
+        parts = [None] if pq < WIDE_FROM_PQ else (["main", 5] if pq < SPLIT_TU_FROM_PQ else [1, 2, 3, 4, 5, 0])
         for part in parts:
-            o = os.path.join(OBJ, "kernels_pq%d%s.o" % (pq, "" if part is None else "_part%d" % part))
-            cmd = [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq] + ([] if part is None else ["-DLDSR_PART=%d" % part])
+            o = os.path.join(OBJ, "kernels_pq%d%s.o" % (pq, "" if part is None else "_part%s" % part))
+            sel = [] if part is None else (["-DLDSR_NO_PART=5"] if part == "main" else ["-DLDSR_PART=%d" % part])
+            cmd = [NVCC] + FLAGS + extra + ["-DLDSR_PQ=%d" % pq] + sel
             jobs.append((o, cmd + ["-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o]))
             obj_deps[o] = em_deps
     o_scan = os.path.join(OBJ, "scan_inst.o")

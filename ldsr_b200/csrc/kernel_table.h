@@ -5,6 +5,7 @@
 #include "aux_kernels.cuh"
 #include "em_kernel.cuh"
 #include "em_split_kernel.cuh"
+#include "em_wide_kernel.cuh"
 
 namespace ldsr {
 
@@ -35,6 +36,11 @@ constexpr int split_minb_for(int pq) {
 #endif
 }
 
+// wide-input kernel (em_wide_kernel.cuh): compiled for PQ >= WIDE_MIN_PQ, one CTA of WIDE_NW warps per SM
+constexpr int WIDE_MIN_PQ = 5;
+constexpr int WIDE_NW = 8;
+constexpr int WIDE_MSEG = 8;
+
 struct KernelTable {
     int pq;
     cudaError_t (*em_prepare)(size_t smem_bytes); // opt in to > 48 KB dynamic shared memory
@@ -46,6 +52,10 @@ struct KernelTable {
     // the same kernel compiled for 2 CTAs/SM (255 registers): 9 % faster per launch when the batch
     // needs no more than two CTAs per SM; the same function as em_split when split_minb == 2
     cudaError_t (*em_split_wide)(const SplitParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
+    // wide-input kernel: wide_nw == 0 when this width has none (PQ < WIDE_MIN_PQ)
+    int wide_nw, wide_mseg;
+    cudaError_t (*em_wide_prepare)(size_t smem_bytes);
+    cudaError_t (*em_wide)(const WideParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);
     cudaError_t (*mstep)(const MstepParams &, cudaStream_t);
     cudaError_t (*propagate)(const SmootherParams &, cudaStream_t);

@@ -1,8 +1,9 @@
 // kernels_inst.cu -- compiled once per supported padded width: nvcc -DLDSR_PQ=<n>.
 // A wide PQ takes minutes to compile (fully unrolled PQ x PQ bodies), so the build may cut the
 // translation unit into parts, one nvcc process each: -DLDSR_PART=0 (table + single-step kernels),
-// 1, 2, 3 (lane-per-fit EM kernel, MODE 0 / 1 / 2), 4 (time-split EM kernel).  Without LDSR_PART
-// everything is in one unit.
+// 1, 2, 3 (lane-per-fit EM kernel, MODE 0 / 1 / 2), 4 (time-split EM kernel), 5 (wide-input EM kernel,
+// PQ >= WIDE_MIN_PQ).  -DLDSR_NO_PART=k compiles everything but part k; without either macro everything
+// is in one unit.
 #include "kernel_table.h"
 
 #ifndef LDSR_PQ
@@ -10,6 +11,8 @@
 #endif
 #ifdef LDSR_PART
 #define LDSR_HAS_PART(k) (LDSR_PART == (k))
+#elif defined(LDSR_NO_PART)
+#define LDSR_HAS_PART(k) (LDSR_NO_PART != (k))
 #else
 #define LDSR_HAS_PART(k) 1
 #endif
@@ -77,6 +80,34 @@ template <> cudaError_t split_launch<PQ, 1>(const SplitParams &p, int n_tasks, s
 }
 #endif
 
+// wide-input kernel
+template <int PQV> cudaError_t wide_prepare(size_t smem_bytes);
+template <int PQV> cudaError_t wide_launch(const WideParams &, int, size_t, cudaStream_t);
+template <> cudaError_t wide_prepare<PQ>(size_t);
+template <> cudaError_t wide_launch<PQ>(const WideParams &, int, size_t, cudaStream_t);
+#if LDSR_HAS_PART(5)
+template <int PQV, bool HAVE> struct WideLaunch { // widths below WIDE_MIN_PQ have no wide-input kernel
+    static cudaError_t prepare(size_t) { return cudaErrorNotSupported; }
+    static cudaError_t launch(const WideParams &, int, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+};
+template <int PQV> struct WideLaunch<PQV, true> {
+    static cudaError_t prepare(size_t smem_bytes) {
+        return cudaFuncSetAttribute(em_wide_kernel<PQV, WIDE_NW, WIDE_MSEG, SPLIT_UW>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
+    static cudaError_t launch(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+        em_wide_kernel<PQV, WIDE_NW, WIDE_MSEG, SPLIT_UW><<<n_tasks, WIDE_NW * 32, smem_bytes, st>>>(p);
+        return cudaGetLastError();
+    }
+};
+template <> cudaError_t wide_prepare<PQ>(size_t smem_bytes) {
+    return WideLaunch<PQ, (PQ >= WIDE_MIN_PQ)>::prepare(smem_bytes);
+}
+template <> cudaError_t wide_launch<PQ>(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    return WideLaunch<PQ, (PQ >= WIDE_MIN_PQ)>::launch(p, n_tasks, smem_bytes, st);
+}
+#endif
+
 #if LDSR_HAS_PART(0)
 namespace {
 
@@ -99,6 +130,10 @@ cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaS
 cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     return split_launch<PQ, 1>(p, n_tasks, smem_bytes, st);
 }
+cudaError_t em_wide_prepare(size_t smem_bytes) { return wide_prepare<PQ>(smem_bytes); }
+cudaError_t em_wide(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    return wide_launch<PQ>(p, n_tasks, smem_bytes, st);
+}
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
     smoother_kernel<PQ><<<(p.n_jobs + 63) / 64, 64, 0, st>>>(p);
     return cudaGetLastError();
@@ -116,8 +151,24 @@ cudaError_t rep(const RepParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-const KernelTable table = {PQ,    em_prepare,       em_chunk, SPLIT_NW,      MINB,     SPLIT_MSEG, SPLIT_UW,
-                           em_split_prepare, em_split, em_split_wide, smoother, mstep,      propagate, rep};
+const KernelTable table = {PQ,
+                           em_prepare,
+                           em_chunk,
+                           SPLIT_NW,
+                           MINB,
+                           SPLIT_MSEG,
+                           SPLIT_UW,
+                           em_split_prepare,
+                           em_split,
+                           em_split_wide,
+                           PQ >= WIDE_MIN_PQ ? WIDE_NW : 0,
+                           WIDE_MSEG,
+                           em_wide_prepare,
+                           em_wide,
+                           smoother,
+                           mstep,
+                           propagate,
+                           rep};
 
 } // namespace
 

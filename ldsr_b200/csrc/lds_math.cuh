@@ -123,14 +123,13 @@ template <int PQ> struct Stats {
 //   Q = (Tx1x1 - A Tx1x - B.Tx1u)/(T-1)                                     (EM.cpp:210)
 // With TuuInv = 0 (no u) this reduces to A = Tx1x/Txx, B = 0 (EM.cpp:212-213); likewise C, D.
 // gc -> [Syy, n_obs, Syv[PQ], wy[PQ], SvvInv[PQ*PQ]] (per group), tuu_inv -> [PQ*PQ] (per series).
+// The observation block: C, D, R (EM.cpp:164-177).
 template <int PQ>
-__device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const double *__restrict__ gc,
-                                                 const double *__restrict__ tuu_inv, int T, Theta<PQ> &th) {
+__device__ __forceinline__ void mstep_obs_block(const Stats<PQ> &s, const double *__restrict__ gc, Theta<PQ> &th) {
     const double Syy = gc[0], n_obs = gc[1];
     const double *Syv = gc + 2, *wy = gc + 2 + PQ, *svv_inv = gc + 2 + 2 * PQ;
-    // ---- C, D, R
     double z[PQ];
-    const double Sxx = s.Sxx + s.Sxxv, Txx = s.Txx + s.Txxv, Tx1x = s.Tx1x + s.Tx1xv; // EM.cpp:152,180,181
+    const double Sxx = s.Sxx + s.Sxxv; // EM.cpp:152
     double num = s.Syx, den = Sxx;
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
@@ -154,10 +153,14 @@ __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const doubl
     }
     th.C = Cn;
     th.R = racc / n_obs;
-    // ---- A, B, Q
-    double w[PQ];
-    num = Tx1x;
-    den = Txx;
+}
+// The transition block: A, B, Q, mu1, V1 (EM.cpp:180-219).
+template <int PQ>
+__device__ __forceinline__ void mstep_trans_block(const Stats<PQ> &s, const double *__restrict__ tuu_inv, int T,
+                                                  Theta<PQ> &th) {
+    const double Txx = s.Txx + s.Txxv, Tx1x = s.Tx1x + s.Tx1xv; // EM.cpp:180,181
+    double z[PQ], w[PQ];
+    double num = Tx1x, den = Txx;
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
         double acc = 0.0, acw = 0.0;
@@ -189,6 +192,12 @@ __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const doubl
     th.Q = qacc / (double)(T - 1);
     th.mu1 = s.X0; // EM.cpp:218-219
     th.V1 = s.V0;
+}
+template <int PQ>
+__device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const double *__restrict__ gc,
+                                                 const double *__restrict__ tuu_inv, int T, Theta<PQ> &th) {
+    mstep_obs_block<PQ>(s, gc, th);
+    mstep_trans_block<PQ>(s, tuu_inv, T, th);
 }
 
 } // namespace ldsr

@@ -213,6 +213,7 @@ struct ldsr_plan {
     int n_series = 0, n_groups = 0, n_fits = 0, theta_stride = 0;
     int max_T = 0, max_seg = 0;
     int max_units = 0; // time-split kernel: upper bound on units per series (em_split_kernel.cuh)
+    int wide_units = 0, wide_msteps = 0; // wide-input kernel: units / steps of observed units (em_wide_kernel.cuh)
     size_t max_blob_bytes = 0;
     bool blob_in_smem = true;
     int last_niter = 0;
@@ -463,6 +464,12 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
         }
         P->max_T = std::max(P->max_T, T);
         P->max_units = std::max(P->max_units, split_units_upper_bound(b->y[s], T, P->kt->split_mseg, P->kt->split_uw));
+        if (P->kt->wide_nw > 0) {
+            int nu = 0, nm = 0;
+            wide_count_units(b->y[s], T, P->kt->wide_mseg, P->kt->split_uw, &nu, &nm);
+            P->wide_units = std::max(P->wide_units, nu);
+            P->wide_msteps = std::max(P->wide_msteps, nm);
+        }
         { // window Gram blocks of u for the time-split kernel's unobserved units (theta-independent)
             const int UWn = P->kt->split_uw, nwin = (T + UWn - 1) / UWn;
             S.uwin_off = (int)uwin.size();
@@ -644,22 +651,35 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             smem = blob_sm + ck_sm;
         }
     }
-    // time-split kernel (em_split_kernel.cuh): 32 fits per CTA, the warps of the CTA share the time
-    // axis.  Default whenever blob + checkpoints + exchange buffers fit in shared memory.
-    // variant: 0 auto, 1 lane kernel with global checkpoints, 2 lane kernel, 3 time-split kernel
+    // time-split kernels: 32 fits per CTA, the warps of the CTA share the time axis.
+    //   em_split_kernel (em_split_kernel.cuh): everything in registers -- the kernel of narrow inputs;
+    //   em_wide_kernel  (em_wide_kernel.cuh): the input-row work in separate phases through shared memory --
+    //   the kernel of wide inputs (PQ >= 5) whenever its shared-memory plan fits.
+    // variant: 0 auto, 1 lane kernel with global checkpoints, 2 lane kernel, 3 time-split kernel,
+    //          4 wide-input time-split kernel
     const int variant = opt ? opt->variant : 0;
     const int max_uunits = (P->max_T + P->kt->split_uw - 1) / P->kt->split_uw;
     const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units, max_uunits);
-    bool use_split = P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
+    const size_t wide_sm = P->kt->wide_nw > 0
+                               ? blob_sm + wide_smem_bytes(P->PQ, P->kt->wide_nw, P->max_T, P->wide_units, P->wide_msteps)
+                               : ~size_t(0);
+    const bool use_wide = P->kt->wide_nw > 0 && P->blob_in_smem && wide_sm <= 227 * 1024 && (variant == 0 || variant == 4);
+    if (variant == 4 && !use_wide)
+        return fail(LDSR_ERR_UNSUPPORTED, "variant 4 (wide-input kernel) needs width >= 5 and %zu bytes of shared memory",
+                    wide_sm);
+    bool use_split = !use_wide && P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
     if (variant == 3 && !use_split)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 3 (time-split kernel) needs %zu bytes of shared memory", split_sm);
-    if (use_split) {
+    if (use_wide) {
+        smem = wide_sm;
+        CU(P->kt->em_wide_prepare(smem));
+    } else if (use_split) {
         smem = split_sm;
         CU(P->kt->em_split_prepare(smem));
     } else {
         CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
     }
-    const int fits_per_cta = use_split ? 32 : 32 * EM_WARPS;
+    const int fits_per_cta = (use_split || use_wide) ? 32 : 32 * EM_WARPS;
 
     EmParams ep;
     ep.series = P->d_series;
@@ -714,7 +734,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         CU(P->pool->alloc_pinned((size_t)2 * max_chunks * sizeof(int), &hp));
         P->h_counts = static_cast<int *>(hp);
     }
-    const size_t ck_need = (mode == 2 || use_split) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
+    const size_t ck_need = (mode == 2 || use_split || use_wide) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
     if (P->ckpt_cap < ck_need) {
         P->ckpt_cap = 0;
         Err e = P->drealloc(&P->d_ckpt, ck_need);
@@ -740,6 +760,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         // ahead of live ones would push three live CTAs onto some SMs while others hold one
         // (measured: 2.48 ms instead of 1.83 ms per chunk on the 10 000-fit job).
         int grid = (c == 0 || grid0 > 3 * P->n_sm) ? grid0 : std::min(grid0, 2 * P->n_sm);
+        // the wide-input kernel holds one CTA per SM: one CTA per task, dealt to the SMs by the hardware as
+        // they finish (tasks differ in length: fits stop at different iterations)
+        if (use_wide) grid = grid0;
         // development: LDSR_MAX_GRID caps the grid so that a small batch exercises the task loop of the
         // kernels (tools/sanitize.py runs it under compute-sanitizer)
         static const int grid_cap = std::getenv("LDSR_MAX_GRID") ? std::atoi(std::getenv("LDSR_MAX_GRID")) : 0;
@@ -764,7 +787,19 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             evs.push_back(b);
             CU(cudaEventRecord(a, st));
         }
-        if (use_split) {
+        if (use_wide) {
+            WideParams wp;
+            wp.em = ep;
+            wp.max_units = P->wide_units;
+            wp.max_msteps = P->wide_msteps;
+            wp.max_T = P->max_T;
+            wp.blob_smem = (int)blob_sm;
+            // relative cost of an unobserved word and of an observed unit in P2 + P4 (scalar work only:
+            // about 8.5 instructions per unobserved step, 90 per step of an observed unit)
+            wp.cost_u = P->kt->split_uw * 17 / 2;
+            wp.cost_m = P->kt->wide_mseg * 90;
+            CU(P->kt->em_wide(wp, grid, smem, st));
+        } else if (use_split) {
             SplitParams sp;
             sp.em = ep;
             sp.max_units = P->max_units;
@@ -904,7 +939,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         stats[1] = chunks;
         stats[2] = (long long)total;
         stats[3] = (long long)(em_ms * 1e6);
-        stats[4] = use_split ? 1 : 0; // which EM kernel ran
+        stats[4] = use_wide ? 2 : (use_split ? 1 : 0); // which EM kernel ran
         stats[5] = stats[6] = stats[7] = 0;
     }
     return Err();

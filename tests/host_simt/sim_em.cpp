@@ -79,6 +79,26 @@ struct Job {
     int *iters_out;
 };
 
+#ifdef LDSR_HAVE_WIDE
+template <int PQ> int launch_wide_hostsim(const EmParams &ep, const SeriesDev &S, const double *y, size_t blob_sm,
+                                          int grid, int order) {
+    constexpr int NW = 8, MSEG = 8, UW = 32;
+    int nu = 0, nm = 0;
+    wide_count_units(y, S.T, MSEG, UW, &nu, &nm);
+    WideParams wp;
+    wp.em = ep;
+    wp.max_units = nu;
+    wp.max_msteps = nm;
+    wp.max_T = S.T;
+    wp.blob_smem = (int)blob_sm;
+    wp.cost_u = UW * 17 / 2;
+    wp.cost_m = MSEG * 90;
+    const size_t smem = blob_sm + wide_smem_bytes(PQ, NW, S.T, nu, nm);
+    hostsim::launch(grid, NW * 32, smem, order, [&] { em_wide_kernel<PQ, NW, MSEG, UW>(wp); });
+    return 0;
+}
+#endif
+
 template <int PQ> int run(const Job &J) {
     constexpr int NW = 4, MSEG = 4, UW = 32;
     const int T = J.T, p = J.p, q = J.q, ng = J.n_groups, nf = J.n_fits;

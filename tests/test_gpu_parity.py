@@ -360,10 +360,20 @@ def test_em_batch_across_two_devices_matches_single_device():
         assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
-@pytest.mark.parametrize("variant", VARIANTS)
-@pytest.mark.parametrize("p,q", [(10, 10), (18, 20), (32, 29)])
+def _run_variant(fn, variant):
+    """variant 4 (wide-input kernel) exists for widths >= 5 and only when its shared-memory plan fits."""
+    try:
+        return fn()
+    except _lib.LdsrError as e:
+        if variant == 4 and e.code == _lib.ERR_UNSUPPORTED:
+            pytest.skip("the wide-input kernel's shared-memory plan does not fit this case")
+        raise
+
+
+@pytest.mark.parametrize("variant", VARIANTS + [4, 0])
+@pytest.mark.parametrize("p,q", [(5, 5), (7, 6), (10, 10), (12, 11), (16, 16), (18, 20), (32, 29)])
 def test_wide_inputs(variant, p, q):
-    # the padded widths 10 / 24 / 32 (the last two are built as several translation units)
+    # the padded widths 5 .. 32 (24 and 32 are built as several translation units)
     rng = np.random.default_rng(p * 100 + q)
     T = 150
     u = rng.standard_normal((p, T))
@@ -377,7 +387,46 @@ def test_wide_inputs(variant, p, q):
     th0[:, 1:1 + p] *= 0.1
     th0[:, 2 + p:2 + p + q] *= 0.1
     held = [np.array([], dtype=int), np.arange(70, 90)]
-    check_batch([dict(y=y, u=u, v=v)], [0, 0], held, np.repeat([0, 1], 3), th0, 25, 1e-6, variant=variant)
+    _run_variant(lambda: check_batch([dict(y=y, u=u, v=v)], [0, 0], held, np.repeat([0, 1], 3), th0, 25, 1e-6,
+                                     variant=variant), variant)
+
+
+@pytest.mark.parametrize("T", [2, 3, 9, 31, 32, 33, 40, 64, 65, 97, 150])
+def test_wide_kernel_ragged_lengths(T):
+    """em_wide_kernel on series shorter than a unit, exactly one word, a word + a ragged tail ...: the
+    slices of phases A / C, the piece bounds and the partial-sum slots that alias the trajectory must
+    hold for every length (fully observed and with an unobserved prefix)."""
+    rng = np.random.default_rng(T)
+    p = 6
+    u = rng.standard_normal((p, T))
+    for lead in (0, T // 2):
+        y = 0.3 * rng.standard_normal(T)
+        y[:lead] = np.nan
+        if T > 8:
+            y[lead + 2] = np.nan
+        th0 = rand_theta0(rng, p, p, 37)
+        th0[:, 1:1 + p] *= 0.2
+        th0[:, 2 + p:2 + 2 * p] *= 0.2
+        held = [np.array([], dtype=int), np.array([T - 1]) if T > 14 else np.array([], dtype=int)]
+        check_batch([dict(y=y, u=u, v=u)], [0, 0], held, np.sort(rng.integers(0, 2, 37)), th0, 12, 1e-7, variant=4)
+
+
+def test_wide_kernel_full_length_convergence_matches_oracle():
+    """One station of BASELINE config 3 (T = 400, p = q = 10) x 2 folds x 50 restarts run to niter = 1000:
+    the stop rule (EM.cpp:272) must fire at the SAME iteration as in the oracle after hundreds of
+    iterations of the phase-split arithmetic; lik 1e-9, theta 1e-6, same selected restarts."""
+    from ldsr_b200 import workloads as W
+    w = W.synthetic_stations(n_stations=1, n_folds=2, n_restarts=50)
+    g = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 1000, 1e-5, variant=4)
+    o = O.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 1000, 1e-5)
+    assert np.array_equal(g["iters"], o["iters"]), np.nonzero(g["iters"] != o["iters"])
+    assert g["iters"].max() > 300
+    assert np.allclose(g["lik"], o["lik"], rtol=LIK_RTOL, atol=0)
+    assert_theta_close(g["theta"], o["theta"])
+    assert np.array_equal(g["best"], o["best"])
+    # and the time-split kernel of narrow inputs on the same job (the fallback when the plan does not fit)
+    s = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 1000, 1e-5, variant=3)
+    assert np.array_equal(s["iters"], o["iters"]) and np.array_equal(s["best"], o["best"])
 
 
 def test_full_size_cvlds_job_properties():

@@ -98,3 +98,46 @@ def test_emulated_task_loop_reuses_shared_memory_safely():
     b = sim_em(3, y, u, u, held, fg, th0, 5, chunk=5, order=0, grid_cap=0)
     for k in ("theta", "lik", "iters"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def _wide_job(p=10, T=150, n_fits=40, seed=3, first_obs=60):
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((p, T)) * np.sqrt(4.0 / np.arange(1, p + 1))[:, None]
+    x = np.zeros(T)
+    for t in range(1, T):
+        x[t] = 0.6 * x[t - 1] + 0.1 * u[0, t - 1] + 0.5 * rng.standard_normal()
+    y = 0.8 * x + 0.05 * u[0] + 0.3 * rng.standard_normal(T)
+    y[:first_obs] = np.nan
+    y[first_obs + 9] = np.nan  # a gap inside the instrumental period
+    held = [np.array([first_obs + 3, first_obs + 4, T - 1]), np.array([], dtype=int), np.array([T - 2])]
+    fg = np.sort(rng.integers(0, 3, n_fits))
+    return y, u, held, fg, rand_theta0(rng, p, p, n_fits)
+
+
+@pytest.mark.parametrize("p,T,first_obs", [(10, 150, 60), (10, 77, 5), (3, 213, None), (6, 130, 70)])
+def test_emulated_wide_kernel(p, T, first_obs):
+    """em_wide_kernel (phase A / scalar recursions / phase C): oracle parity and schedule independence,
+    incl. a series observed almost everywhere (no unobserved word), a ragged tail and a narrow width."""
+    if first_obs is None:
+        y, u, held, fg, th0 = _np_job()
+    else:
+        y, u, held, fg, th0 = _wide_job(p, T, 40, seed=p * T, first_obs=first_obs)
+    niter = 6
+    base = sim_em(4, y, u, u, held, fg, th0, niter, chunk=4, order=0)
+    _check_vs_oracle(base, y, u, u, held, fg, th0, niter)
+    for order in (1, 5):
+        r = sim_em(4, y, u, u, held, fg, th0, niter, chunk=4, order=order)
+        for k in ("theta", "lik", "iters"):
+            assert np.array_equal(base[k], r[k]), (order, k)
+
+
+def test_emulated_wide_kernel_separate_v_and_task_loop():
+    y, u, held, fg, th0 = _wide_job(10, 120, 70, seed=9, first_obs=40)
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((7, 120))
+    th0 = rand_theta0(rng, 10, 7, 70)
+    a = sim_em(4, y, u, v, held, fg, th0, 5, chunk=5, order=0)
+    _check_vs_oracle(a, y, u, v, held, fg, th0, 5)
+    b = sim_em(4, y, u, v, held, fg, th0, 5, chunk=2, order=3, grid_cap=1)  # 3 tasks on one CTA, 3 launches
+    for k in ("theta", "lik", "iters"):
+        assert np.array_equal(a[k], b[k]), k
