@@ -117,7 +117,8 @@ typedef struct {
                             fits -- the wide-input one for input widths >= 5 -- else the
                             lane-per-fit kernel); 1 = lane-per-fit kernel with checkpoints in global
                             memory; 2 = lane-per-fit kernel; 3 = time-split kernel, 4 = wide-input
-                            time-split kernel, or LDSR_ERR_UNSUPPORTED.  See DESIGN.md section 4. */
+                            time-split kernel, 5 = small-batch scan kernel (one CTA per fit; auto for
+                            up to 600 fits of width <= 4), or LDSR_ERR_UNSUPPORTED.  DESIGN.md section 4. */
     int trace_liks;      /* ldsr_plan_em only: record the likelihood trace so that
                             ldsr_plan_fetch can return liks (ldsr_em_batch infers it from
                             out->liks)                                                       */
@@ -148,7 +149,7 @@ int ldsr_plan_create(const ldsr_batch *batch, int device, ldsr_plan **out, char 
  * are returned through the optional long long[8] `stats`:
  * {kernel launches issued, EM chunks (= em_chunk_kernel launches), total E-steps executed (all
  *  fits), summed device time of the EM kernel launches in ns (CUDA events on `stream`),
- *  which EM kernel ran: 0 lane-per-fit, 1 time-split, 2 wide-input time-split; 0, 0, 0}. */
+ *  which EM kernel ran: 0 lane-per-fit, 1 time-split, 2 wide-input time-split, 3 small-batch scan; 0, 0, 0}. */
 int ldsr_plan_em(ldsr_plan *plan, int niter, double tol, const ldsr_options *opt, void *stream,
                  long long *stats, char *errbuf, int errlen);
 int ldsr_plan_set_theta0(ldsr_plan *plan, const double *theta0_host, char *errbuf, int errlen);

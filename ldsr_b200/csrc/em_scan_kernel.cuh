@@ -1,0 +1,502 @@
+// em_scan_kernel.cuh -- the LDS_EM loop (src/EM.cpp:245-280) for SMALL batches: ONE CTA = ONE FIT,
+// one thread = L consecutive time steps, the recursions over time done as parallel scans.
+//
+// Why: the batched kernels put a fit on a lane, so a call with few fits -- LDS_EM (1 fit),
+// LDS_EM_restart / LDS_reconstruction with 20..100 restarts (R/LDS_reconstruction.R:42-62, the call
+// every user makes) -- fills a handful of CTAs and pays the full serial latency of an iteration
+// (10 us at T = 413: 10 ms for 1000 iterations whether 1 or 4000 fits run).  Here the time axis of ONE
+// fit is spread over the threads of a CTA and every dependency along t becomes a scan of depth
+// log2(threads) (hard parts (ii); Appendix D.4):
+//
+//   P1  each thread composes the VARIANCE map of its L steps -- in 1-D the Riccati step is a Moebius map
+//       of Vp, a 2x2 matrix on homogeneous coordinates (em_split_kernel.cuh) -- exclusive scan of 2x2
+//       matrices (warp shuffles, then the warp totals through shared memory)  -> Vp entering every thread
+//   P2  forward over the L steps with the true variances; the mean in the (P, q) basis of its unknown
+//       incoming value; scan of the affine maps -> incoming mean of every thread, the likelihood terms
+//       (a quadratic in the incoming mean) summed over the CTA -> stop rule (EM.cpp:272)
+//   P3  suffix scan of the threads' affine BACKWARD maps (Xs_first = PJ Xs_in + g, Vs_first = PJ^2 Vs_in
+//       + L), started from the prior of the virtual step T (which makes Xs_{T-1} = Xu_{T-1}, EM.cpp:94-95)
+//   P4  backward over the L steps (gains kept in registers from P2), M-step sums; a transposing
+//       shuffle reduction brings the 7 + 3 PQ sums of the CTA together; M-step by two threads
+//       (observation block / transition block); theta back to every thread through shared memory.
+//
+// The thread's rows of y, u, v stay in REGISTERS for the whole launch (they never change); steps at or
+// beyond T (the last thread's ragged end, idle threads) are exact identities of every map.
+// Five barriers per iteration; nothing per step goes to shared or global memory.
+#pragma once
+#include "em_split_kernel.cuh"
+
+namespace ldsr {
+
+constexpr int SCAN_MAX_WARPS = 8;
+
+template <int PQ> __host__ __device__ constexpr int scan_nsum() { return 7 + 3 * PQ; }
+template <int PQ> __host__ __device__ constexpr int scan_nsum_pad() { return scan_nsum<PQ>() <= 16 ? 16 : 32; }
+
+// ---- warp scans (Hillis-Steele over the 32 lanes) -------------------------------------------------
+// inclusive prefix product of 2x2 matrices: lane l ends with M_l M_{l-1} ... M_0
+__device__ __forceinline__ void scan_mobius_incl(double &m11, double &m12, double &m21, double &m22, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double p11 = __shfl_up_sync(FULL, m11, o), p12 = __shfl_up_sync(FULL, m12, o);
+        const double p21 = __shfl_up_sync(FULL, m21, o), p22 = __shfl_up_sync(FULL, m22, o);
+        if (lane >= o) {
+            const double n11 = fma(m11, p11, m12 * p21), n12 = fma(m11, p12, m12 * p22);
+            const double n21 = fma(m21, p11, m22 * p21), n22 = fma(m21, p12, m22 * p22);
+            m11 = n11;
+            m12 = n12;
+            m21 = n21;
+            m22 = n22;
+        }
+    }
+}
+// inclusive prefix composition of affine maps x -> P x + q (lane l: maps of lanes 0..l applied in order)
+__device__ __forceinline__ void scan_affine_incl(double &P, double &q, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Pp = __shfl_up_sync(FULL, P, o), qp = __shfl_up_sync(FULL, q, o);
+        if (lane >= o) {
+            q = fma(P, qp, q);
+            P *= Pp;
+        }
+    }
+}
+// inclusive SUFFIX composition of backward maps (x, v) -> (PJ x + g, PJ^2 v + Lc): lane l ends with its own
+// map applied after those of lanes l+1 .. 31
+__device__ __forceinline__ void scan_backward_incl(double &PJ, double &g, double &Lc, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double PJr = __shfl_down_sync(FULL, PJ, o), gr = __shfl_down_sync(FULL, g, o);
+        const double Lr = __shfl_down_sync(FULL, Lc, o);
+        if (lane + o < 32) {
+            g = fma(PJ, gr, g);
+            Lc = fma(PJ * PJ, Lr, Lc);
+            PJ *= PJr;
+        }
+    }
+}
+__device__ __forceinline__ double scan_warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+// Transposing reduction of N (16 or 32) values per lane over the warp: halving exchanges, so that after
+// log2(N) rounds every lane holds ONE value summed over a group of lanes, then the remaining rounds
+// finish it.  Returns the warp total of value index (lane * N) / 32  (N = 16: lane >> 1; N = 32: lane).
+// 2 N - 2 (+ 32/N - 1) value exchanges instead of 5 N.
+template <int N> __device__ __forceinline__ double scan_reduce_many(double (&v)[N], int lane) {
+    static_assert(N == 16 || N == 32, "N is 16 or 32");
+    int off = 16;
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            const double send = upper ? v[i] : v[i + h];
+            const double keep = upper ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, off);
+        }
+    }
+    double r = v[0];
+    if (N == 16) r += __shfl_xor_sync(FULL, r, 1);
+    return r;
+}
+
+template <int PQ, int L>
+__global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
+    static_assert(L == 2 || L == 4 || L == 8, "steps per thread");
+    constexpr int NS = scan_nsum<PQ>(), NSP = scan_nsum_pad<PQ>();
+    constexpr int TL = theta_pad_len<PQ>();
+    LDSR_STATIC_SMEM(double, S1[SCAN_MAX_WARPS * 4]);  // variance-map totals of the warps
+    LDSR_STATIC_SMEM(double, S2[SCAN_MAX_WARPS * 2]);  // mean-map totals
+    LDSR_STATIC_SMEM(double, S3[SCAN_MAX_WARPS]);      // likelihood partial sums
+    LDSR_STATIC_SMEM(double, S4[SCAN_MAX_WARPS * 3]);  // backward-map totals
+    LDSR_STATIC_SMEM(double, S5[SCAN_MAX_WARPS * 32]); // M-step partial sums [warp][NSP]
+    LDSR_STATIC_SMEM(double, TOTS[2 * 32]);            // their totals, one copy per M-step warp
+    LDSR_STATIC_SMEM(double, ENDS[4]);                 // X0, V0, XT, VT
+    LDSR_STATIC_SMEM(double, THS[TL]);                 // theta after the M-step
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_tasks = *P.n_tasks;
+    for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x) {
+    if (ti != (int)blockIdx.x) __syncthreads();
+    const int4 task = P.tasks[ti];
+    const SeriesDev S = P.series[task.x];
+    const int T = S.T;
+    const int fit = P.active[task.y];
+    const int grp = P.f_group[fit];
+    const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);
+    const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
+    const double n_obs = gc[1];
+
+    // ---- this thread's steps: rows and mask bits, in registers for the whole launch
+    const int t0 = (int)threadIdx.x * L;
+    double yr[L], ur[L * PQ], vr[L * PQ];
+    unsigned bits = 0u; // observed steps (the group's mask: finite(y) minus the hold-outs)
+    {
+        const double *__restrict__ blob = P.blobs + S.blob_off;
+        const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int t = t0 + j;
+            const bool real = t < T;
+            yr[j] = real ? blob[S.y_off + t] : 0.0;
+#pragma unroll
+            for (int i = 0; i < PQ; i++) {
+                ur[j * PQ + i] = real ? blob[S.u_off + (size_t)t * PQ + i] : 0.0;
+                vr[j * PQ + i] = real ? blob[S.v_off + (size_t)t * PQ + i] : 0.0;
+            }
+            if (real && ((mw[t >> 5] >> (t & 31)) & 1u)) bits |= 1u << j;
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++)
+            if (!((bits >> j) & 1u)) yr[j] = 0.0; // y is NaN where missing: never let it into the arithmetic
+    }
+    Theta<PQ> th;
+    load_theta<PQ>(th, P.theta + (size_t)fit * TL);
+    double l1 = P.l1[fit], l2 = P.l2[fit], lik = P.lik[fit];
+    int ne = P.ne[fit];
+    bool live = P.done[fit] == 0;
+    if (live && P.g_status[grp] != 0) { // Gram block not invertible: the reference would throw
+        live = false;
+        lik = __longlong_as_double(0x7ff8000000000000ULL);
+    }
+
+    for (int it = 0; live && it < P.chunk; ++it) {
+        const double A = th.A, A2 = th.A * th.A, Q = th.Q, Cc = th.C, R = th.R;
+        MixedConst<PQ> mc;
+        mc.set(th, A2);
+
+        // ================= P1: variance map of my steps, scan =================
+        double e11, e12, e21, e22; // exclusive prefix inside the warp
+        {
+            double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const bool real = t0 + j < T, obs = (bits >> j) & 1u;
+                const double s11 = obs ? mc.a11 : (real ? A2 : 1.0), s12 = obs ? mc.a12 : (real ? Q : 0.0);
+                const double s21 = obs ? mc.C2 : 0.0, s22 = obs ? R : 1.0;
+                const double n11 = fma(s11, m11, s12 * m21), n12 = fma(s11, m12, s12 * m22);
+                const double n21 = fma(s21, m11, s22 * m21), n22 = fma(s21, m12, s22 * m22);
+                m11 = n11;
+                m12 = n12;
+                m21 = n21;
+                m22 = n22;
+            }
+            rescale4(m11, m12, m21, m22);
+            scan_mobius_incl(m11, m12, m21, m22, lane);
+            if (lane == 31) {
+                S1[warp * 4 + 0] = m11;
+                S1[warp * 4 + 1] = m12;
+                S1[warp * 4 + 2] = m21;
+                S1[warp * 4 + 3] = m22;
+            }
+            e11 = __shfl_up_sync(FULL, m11, 1);
+            e12 = __shfl_up_sync(FULL, m12, 1);
+            e21 = __shfl_up_sync(FULL, m21, 1);
+            e22 = __shfl_up_sync(FULL, m22, 1);
+            if (lane == 0) {
+                e11 = e22 = 1.0;
+                e12 = e21 = 0.0;
+            }
+        }
+        __syncthreads(); // B1
+        double Vin, vend; // prior variance entering my steps; prior variance of the virtual step after the last
+        {
+            double n = th.V1, d = 1.0, nwp = th.V1, dwp = 1.0;
+            for (int w = 0; w < nw; ++w) {
+                if (w == warp) {
+                    nwp = n;
+                    dwp = d;
+                }
+                const double nn = fma(S1[w * 4 + 0], n, S1[w * 4 + 1] * d), dd = fma(S1[w * 4 + 2], n, S1[w * 4 + 3] * d);
+                n = nn;
+                d = dd;
+                if ((w & 1) == 1) { // keep the pair in range (ratios only matter)
+                    const int e = ((__double2hiint(n + d) >> 20) & 0x7ff) - 1023;
+                    const double sc = __hiloint2double((1023 - e) << 20, 0);
+                    n *= sc;
+                    d *= sc;
+                }
+            }
+            vend = n * fast_rcp(d);
+            const double ni = fma(e11, nwp, e12 * dwp), di = fma(e21, nwp, e22 * dwp);
+            Vin = ni * fast_rcp(di);
+        }
+
+        // ================= P2: forward over my steps (EM.cpp:70-90), mean in the (P, q) basis =================
+        double Kg[L], Jg[L], Lg[L], g0[L], gP[L]; // kept for P4
+        double Pth, qth;                           // my affine map of the mean
+        double acc_l0, acc_l1, acc_l2;             // sum_obs delta^2/Sigma = l0 - 2 C x l1 + C^2 x^2 l2
+        double PJ, G0, GG, Lc;                     // my backward map
+        {
+            double Bu[L], ymd[L];
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                double b = 0.0, dv = 0.0;
+#pragma unroll
+                for (int i = 0; i < PQ; i++) {
+                    b = fma(th.B[i], ur[j * PQ + i], b);
+                    dv = fma(th.D[i], vr[j * PQ + i], dv);
+                }
+                Bu[j] = b;
+                ymd[j] = yr[j] - dv;
+            }
+            // gains: the variance in homogeneous coordinates (n, d), all reciprocals after the chain
+            double nj[L], dj[L], nn[L], dd[L];
+            {
+                double n = Vin, d = 1.0;
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    const bool real = t0 + j < T, obs = (bits >> j) & 1u;
+                    const double s11 = obs ? mc.a11 : (real ? A2 : 1.0), s12 = obs ? mc.a12 : (real ? Q : 0.0);
+                    const double s21 = obs ? mc.C2 : 0.0, s22 = obs ? R : 1.0;
+                    nj[j] = n;
+                    dj[j] = d;
+                    nn[j] = fma(s11, n, s12 * d);
+                    dd[j] = fma(s21, n, s22 * d);
+                    n = nn[j];
+                    d = dd[j];
+                }
+            }
+            double rS[L], alpha[L];
+            double dend = dd[L - 1];
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const bool real = t0 + j < T, obs = (bits >> j) & 1u;
+                const double rho = fast_rcp(dd[j]), rn = fast_rcp(nn[j]);
+                const double K = obs ? Cc * nj[j] * rho : 0.0;
+                const double nu = obs ? R * nj[j] : nj[j];
+                const double vu = nu * rho;
+                const double J = real ? A * nu * rn : 1.0;
+                Kg[j] = K;
+                rS[j] = obs ? dj[j] * rho : 0.0; // 1/Sigma
+                alpha[j] = real ? fma(-mc.AC, K, A) : 1.0;
+                Jg[j] = J;
+                Lg[j] = real ? vu * fma(-A, J, 1.0) : 0.0; // Vu - J^2 Vp' with J Vp' = A Vu
+            }
+            double q[L + 1], Pc[L + 1];
+            q[0] = 0.0;
+            Pc[0] = 1.0;
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const bool real = t0 + j < T;
+                const double beta = real ? fma(A * Kg[j], ymd[j], Bu[j]) : 0.0;
+                q[j + 1] = fma(alpha[j], q[j], beta);
+                Pc[j + 1] = alpha[j] * Pc[j];
+            }
+            acc_l0 = acc_l1 = acc_l2 = 0.0;
+            PJ = 1.0;
+            G0 = GG = Lc = 0.0;
+            double pj2 = 1.0;
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const double d0 = fma(-Cc, q[j], ymd[j]); // innovation for x_in = 0
+                const double w0 = rS[j] * d0;
+                acc_l0 = fma(w0, d0, acc_l0);
+                acc_l1 = fma(w0, Pc[j], acc_l1);
+                acc_l2 = fma(rS[j] * Pc[j], Pc[j], acc_l2);
+                const double xu0 = fma(Kg[j], d0, q[j]);
+                const double xuP = Pc[j] * fma(-Kg[j], Cc, 1.0);
+                g0[j] = fma(-Jg[j], q[j + 1], xu0);
+                gP[j] = fma(-Jg[j], Pc[j + 1], xuP);
+                G0 = fma(PJ, g0[j], G0);
+                GG = fma(PJ, gP[j], GG);
+                Lc = fma(pj2, Lg[j], Lc);
+                PJ *= Jg[j];
+                pj2 *= Jg[j] * Jg[j];
+            }
+            Pth = Pc[L];
+            qth = q[L];
+            if (bits) acc_l0 += log(dend); // sum_obs log Sigma = log prod Sigma (d started at 1)
+        }
+        double xin, xend; // prior mean entering my steps; prior mean of the virtual step after the last
+        {
+            double Pi = Pth, qi = qth;
+            scan_affine_incl(Pi, qi, lane);
+            if (lane == 31) {
+                S2[warp * 2 + 0] = Pi;
+                S2[warp * 2 + 1] = qi;
+            }
+            double Pe = __shfl_up_sync(FULL, Pi, 1), qe = __shfl_up_sync(FULL, qi, 1);
+            if (lane == 0) {
+                Pe = 1.0;
+                qe = 0.0;
+            }
+            __syncthreads(); // B2
+            double x = th.mu1, xw = th.mu1; // prior of step 0 (EM.cpp:48)
+            for (int w = 0; w < nw; ++w) {
+                if (w == warp) xw = x;
+                x = fma(S2[w * 2 + 0], x, S2[w * 2 + 1]);
+            }
+            xend = x;
+            xin = fma(Pe, xw, qe);
+        }
+        // ---- likelihood partial sums and the backward maps, one barrier for both
+        const double gk = fma(GG, xin, G0);
+        double PJs = PJ, gs = gk, Ls = Lc;
+        {
+            const double tC = Cc * xin;
+            const double accw = scan_warp_sum(fma(tC, fma(tC, acc_l2, -2.0 * acc_l1), acc_l0));
+            scan_backward_incl(PJs, gs, Ls, lane);
+            if (lane == 0) {
+                S3[warp] = accw;
+                S4[warp * 3 + 0] = PJs;
+                S4[warp * 3 + 1] = gs;
+                S4[warp * 3 + 2] = Ls;
+            }
+        }
+        double PJe = __shfl_down_sync(FULL, PJs, 1), ge = __shfl_down_sync(FULL, gs, 1);
+        double Le = __shfl_down_sync(FULL, Ls, 1);
+        if (lane == 31) {
+            PJe = 1.0;
+            ge = 0.0;
+            Le = 0.0;
+        }
+        __syncthreads(); // B3
+        double acc = 0.0;
+        for (int w = 0; w < nw; ++w) acc += S3[w];
+        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs; // EM.cpp:122-124
+
+        // ================= stop rule (EM.cpp:259-275): the same in every thread =================
+        lik = lik_new;
+        ne += 1;
+        if (threadIdx.x == 0 && P.liks) P.liks[(size_t)P.f_user[fit] * P.niter + (ne - 1)] = lik_new;
+        {
+            const bool conv = (ne >= 3) && (fabs(lik_new - l1) < P.tol) && (fabs(l1 - l2) < P.tol);
+            if (conv || ne >= P.niter) live = false;
+        }
+        if (!live) break;
+
+        // ---- smoothed state entering my steps from the right: the chain starts from the prior of the
+        //      virtual step after the last one, Xs_{T-1} = Xu_{T-1} (EM.cpp:94-95)
+        double Xs1, Vs1;
+        {
+            double X = xend, V = vend;
+            for (int w = nw - 1; w > warp; --w) {
+                const double pj = S4[w * 3 + 0];
+                X = fma(pj, X, S4[w * 3 + 1]);
+                V = fma(pj * pj, V, S4[w * 3 + 2]);
+            }
+            Xs1 = fma(PJe, X, ge);
+            Vs1 = fma(PJe * PJe, V, Le);
+        }
+
+        // ================= P4: backward over my steps (EM.cpp:99-104), M-step sums =================
+        double sums[NSP];
+#pragma unroll
+        for (int i = 0; i < NSP; i++) sums[i] = 0.0;
+        // layout: 0 Syx, 1 Sxx, 2 Sxxv, 3 Tx1x, 4 Tx1xv, 5 Txx, 6 Txxv, 7.. Sxv, 7+PQ.. Tx1u, 7+2PQ.. Tux
+        {
+            double Xs[L + 1], Vs[L + 1];
+            Xs[L] = Xs1;
+            Vs[L] = Vs1;
+#pragma unroll
+            for (int j = L - 1; j >= 0; j--) {
+                Xs[j] = fma(Jg[j], Xs[j + 1], fma(gP[j], xin, g0[j]));
+                Vs[j] = fma(Jg[j] * Jg[j], Vs[j + 1], Lg[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const int t = t0 + j;
+                const bool trans = t < T - 1, obs = (bits >> j) & 1u;
+                const double xa = trans ? Xs[j] : 0.0, xb = trans ? Xs[j + 1] : 0.0;
+                sums[3] = fma(xb, xa, sums[3]);
+                sums[4] = fma(trans ? Vs[j + 1] : 0.0, Jg[j], sums[4]);
+                sums[5] = fma(xa, xa, sums[5]);
+                sums[6] += trans ? Vs[j] : 0.0;
+                const double xo = obs ? Xs[j] : 0.0;
+                sums[0] = fma(yr[j], xo, sums[0]);
+                sums[1] = fma(xo, xo, sums[1]);
+                sums[2] += obs ? Vs[j] : 0.0;
+#pragma unroll
+                for (int i = 0; i < PQ; i++) {
+                    sums[7 + i] = fma(xo, vr[j * PQ + i], sums[7 + i]);
+                    sums[7 + PQ + i] = fma(xb, ur[j * PQ + i], sums[7 + PQ + i]);
+                    sums[7 + 2 * PQ + i] = fma(ur[j * PQ + i], xa, sums[7 + 2 * PQ + i]);
+                }
+                if (t == T - 1) {
+                    ENDS[2] = Xs[j];
+                    ENDS[3] = Vs[j];
+                }
+            }
+            if (threadIdx.x == 0) {
+                ENDS[0] = Xs[0];
+                ENDS[1] = Vs[0];
+            }
+        }
+        {
+            const double r = scan_reduce_many<NSP>(sums, lane);
+            if (NSP == 32)
+                S5[warp * 32 + lane] = r;
+            else if ((lane & 1) == 0)
+                S5[warp * 32 + (lane >> 1)] = r;
+        }
+        __syncthreads(); // B4
+
+        // ================= M-step (EM.cpp:139-229): thread 0 the observation block, thread 32 the transition block ====
+        const bool do_obs = warp == 0, do_trans = nw > 1 ? warp == 1 : warp == 0; // one warp: warp 0 does both
+        if (do_obs || do_trans) {
+            if (lane < NS) {
+                double a = 0.0;
+                for (int w = 0; w < nw; ++w) a += S5[w * 32 + lane];
+                TOTS[warp * 32 + lane] = a;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                Stats<PQ> st;
+                const double *o = TOTS + warp * 32;
+                st.Syx = o[0];
+                st.Sxx = o[1];
+                st.Sxxv = o[2];
+                st.Tx1x = o[3];
+                st.Tx1xv = o[4];
+                st.Txx = o[5];
+                st.Txxv = o[6];
+#pragma unroll
+                for (int i = 0; i < PQ; i++) {
+                    st.Sxv[i] = o[7 + i];
+                    st.Tx1u[i] = o[7 + PQ + i];
+                    st.Tux[i] = o[7 + 2 * PQ + i];
+                }
+                st.X0 = ENDS[0];
+                st.V0 = ENDS[1];
+                st.XT = ENDS[2];
+                st.VT = ENDS[3];
+                Theta<PQ> tn = th;
+                if (do_obs) {
+                    mstep_obs_block<PQ>(st, gc, tn);
+                    THS[1 + PQ] = tn.C;
+#pragma unroll
+                    for (int i = 0; i < PQ; i++) THS[2 + PQ + i] = tn.D[i];
+                    THS[3 + 2 * PQ] = tn.R;
+                }
+                if (do_trans) {
+                    mstep_trans_block<PQ>(st, tuu_inv, T, tn);
+                    THS[0] = tn.A;
+#pragma unroll
+                    for (int i = 0; i < PQ; i++) THS[1 + i] = tn.B[i];
+                    THS[2 + 2 * PQ] = tn.Q;
+                    THS[4 + 2 * PQ] = tn.mu1;
+                    THS[5 + 2 * PQ] = tn.V1;
+                }
+            }
+        }
+        __syncthreads(); // B5: the new theta is published
+        load_theta<PQ>(th, THS);
+        l2 = l1;
+        l1 = lik;
+    }
+
+    if (threadIdx.x == 0) {
+        store_theta<PQ>(th, P.theta + (size_t)fit * TL);
+        P.l1[fit] = l1;
+        P.l2[fit] = l2;
+        P.lik[fit] = lik;
+        P.ne[fit] = ne;
+        P.done[fit] = live ? 0 : 1;
+    }
+    } // task loop
+}
+
+} // namespace ldsr

@@ -42,10 +42,10 @@ struct WideParams {
     int cost_u, cost_m;
 };
 
-// rows of the trajectory area: one per step, and room for the NW slots of partial sums that later
-// alias it
+// rows of the trajectory area: one per step, and room for what aliases it after phase C (the NW slots
+// of partial sums, their totals, the matrix-vector rows of the M-step)
 __host__ __device__ inline size_t wide_traj_rows(int pq, int nw, int max_T) {
-    const size_t st = (size_t)nw * (11 + 3 * pq);
+    const size_t st = (size_t)(nw + 1) * (11 + 3 * pq) + 3 * pq; // NW slots, the totals, the 3 PQ rows of the M-step
     return (size_t)max_T > st ? (size_t)max_T : st;
 }
 // dynamic shared memory after the series blob, in bytes
@@ -350,6 +350,7 @@ template <int PQ, int NW, int MSEG, int UW>
 __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP) {
     static_assert(MSEG == 4 || MSEG == 8, "observed unit is 4 or 8 steps");
     static_assert(NW <= 16, "piece and slice bounds share one 256-byte block");
+    static_assert(PQ >= 2, "the row products are split into two partial sums");
     const EmParams &P = WP.em;
     LDSR_DYN_SMEM(smem_raw);
     LDSR_STATIC_SMEM(__align__(8) uint64_t, bar);
@@ -503,28 +504,39 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             double Bv[PQ];
 #pragma unroll
             for (int i = 0; i < PQ; i++) Bv[i] = TB[i * 32];
-            int t = sa;
+            const double *__restrict__ row = us + sa * PQ;
+            double *__restrict__ o = TR + sa * 32;
+            int n = sb - sa;
 #pragma unroll 1
-            for (; t + 4 <= sb; t += 4) {
+            for (; n >= 4; n -= 4, row += 4 * PQ, o += 4 * 32) {
                 double r[4 * PQ];
-                load_vec<4 * PQ>(us + t * PQ, r);
-                double acc[4];
+                load_vec<4 * PQ>(row, r);
+                // two partial sums per row: eight independent chains of PQ/2 multiply-adds
+                double lo[4], hi[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    double a = 0.0;
-#pragma unroll
-                    for (int i = 0; i < PQ; i++) a = fma(Bv[i], r[j * PQ + i], a);
-                    acc[j] = a;
+                    lo[j] = Bv[0] * r[j * PQ];
+                    hi[j] = Bv[1] * r[j * PQ + 1];
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) TR[(t + j) * 32] = acc[j];
+                for (int i = 2; i < PQ; i++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (i & 1)
+                            hi[j] = fma(Bv[i], r[j * PQ + i], hi[j]);
+                        else
+                            lo[j] = fma(Bv[i], r[j * PQ + i], lo[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[j * 32] = lo[j] + hi[j];
             }
 #pragma unroll 1
-            for (; t < sb; ++t) {
+            for (; n > 0; --n, row += PQ, o += 32) {
                 double a = 0.0;
 #pragma unroll
-                for (int i = 0; i < PQ; i++) a = fma(Bv[i], us[t * PQ + i], a);
-                TR[t * 32] = a;
+                for (int i = 0; i < PQ; i++) a = fma(Bv[i], row[i], a);
+                o[0] = a;
             }
         }
         {
@@ -537,12 +549,18 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 if (!(u0 & (UNIT_M | UNIT_M1))) continue;
                 const int t0 = u0 & UNIT_T0, n = (u0 & UNIT_M) ? MSEG : 1;
                 double *__restrict__ o = YM + (size_t)ubase[un] * 32;
+                const double *__restrict__ row = vs + t0 * PQ;
 #pragma unroll 1
-                for (int j = 0; j < n; ++j) {
-                    double a = 0.0;
+                for (int j = 0; j < n; ++j, row += PQ) {
+                    double a0 = Dq[0] * row[0], a1 = Dq[1] * row[1];
 #pragma unroll
-                    for (int i = 0; i < PQ; i++) a = fma(Dq[i], vs[(t0 + j) * PQ + i], a);
-                    o[j * 32] = a;
+                    for (int i = 2; i < PQ; i++) {
+                        if (i & 1)
+                            a1 = fma(Dq[i], row[i], a1);
+                        else
+                            a0 = fma(Dq[i], row[i], a0);
+                    }
+                    o[j * 32] = a0 + a1;
                 }
             }
         }
@@ -728,31 +746,56 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         }
         __syncthreads(); // B3: every Xs_t is in place
 
-        // ================= phase C: the row sums of EM.cpp:153-161, 184-193 over my slice =================
+        // ================= phase C: the row sums of EM.cpp:153-161, 184-193 =================
         Stats<PQ> st;
         st.zero();
-        {
-            const bool same_uv = S.same_uv != 0;
-            double z = sa < sb ? TR[sa * 32] : 0.0;
+        { // transitions t = 0 .. T-2 of my slice: Tux += u_t Xs_t, Tx1u += u_t Xs_{t+1}
+            const int te = sb < T - 1 ? sb : T - 1;
+            const double *__restrict__ row = us + sa * PQ;
+            const double *__restrict__ zp = TR + sa * 32;
+            int n = te - sa;
+            double z0 = n > 0 ? zp[0] : 0.0;
 #pragma unroll 1
-            for (int t = sa; t < sb; ++t) {
-                const double z1 = t + 1 < T ? TR[(t + 1) * 32] : 0.0;
-                double r[PQ];
-                load_vec<PQ>(us + t * PQ, r);
-                if (t < T - 1) {
+            for (; n >= 4; n -= 4, row += 4 * PQ, zp += 4 * 32) {
+                double r[4 * PQ], z[5];
+                load_vec<4 * PQ>(row, r);
+                z[0] = z0;
+#pragma unroll
+                for (int j = 1; j <= 4; j++) z[j] = zp[j * 32];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
 #pragma unroll
                     for (int i = 0; i < PQ; i++) {
-                        st.Tux[i] = fma(r[i], z, st.Tux[i]);
-                        st.Tx1u[i] = fma(r[i], z1, st.Tx1u[i]);
+                        st.Tux[i] = fma(r[j * PQ + i], z[j], st.Tux[i]);
+                        st.Tx1u[i] = fma(r[j * PQ + i], z[j + 1], st.Tx1u[i]);
                     }
                 }
-                if (ys[t] == ys[t]) { // the series has an observation here: some fits of the CTA use it
-                    const double xo = ((MW[(t >> 5) * 32] >> (t & 31)) & 1u) ? z : 0.0;
-                    if (!same_uv) load_vec<PQ>(vs + t * PQ, r);
+                z0 = z[4];
+            }
+#pragma unroll 1
+            for (; n > 0; --n, row += PQ, zp += 32) {
+                const double z1 = zp[32];
 #pragma unroll
-                    for (int i = 0; i < PQ; i++) st.Sxv[i] = fma(xo, r[i], st.Sxv[i]);
+                for (int i = 0; i < PQ; i++) {
+                    st.Tux[i] = fma(row[i], z0, st.Tux[i]);
+                    st.Tx1u[i] = fma(row[i], z1, st.Tx1u[i]);
                 }
-                z = z1;
+                z0 = z1;
+            }
+        }
+#pragma unroll 1
+        for (int un = warp; un < n_units; un += NW) { // observed units, dealt round-robin: Sxv += v_t Xs_t where observed
+            const int u0 = units[un];
+            if (!(u0 & (UNIT_M | UNIT_M1))) continue;
+            const int t0 = u0 & UNIT_T0, n = (u0 & UNIT_M) ? MSEG : 1;
+            const unsigned bits = mask_bits(t0, n);
+            const double *__restrict__ row = vs + t0 * PQ;
+            const double *__restrict__ zp = TR + t0 * 32;
+#pragma unroll 1
+            for (int j = 0; j < n; ++j, row += PQ) {
+                const double xo = ((bits >> j) & 1u) ? zp[j * 32] : 0.0;
+#pragma unroll
+                for (int i = 0; i < PQ; i++) st.Sxv[i] = fma(xo, row[i], st.Sxv[i]);
             }
         }
         __syncthreads(); // B4: nobody reads the trajectory any more: it becomes the partial sums
@@ -770,30 +813,90 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
         __syncthreads(); // B5
 
-        // ================= M-step (EM.cpp:139-229): warp 0 the observation block, warp 1 the transition block ======
-        if (warp < 2) {
-            st.zero();
+        // ================= M-step (EM.cpp:139-229), spread over the warps =================
+        // (1) totals: warp w adds the NW partial sums of the entries w, w + NW, ...
+        double *const TOT = ST + (size_t)NW * NST * 32; // [NST]
+        double *const ZW = TOT + (size_t)NST * 32;      // [3 PQ]: SvvInv Sxv | TuuInv Tux | TuuInv Tx1u
 #pragma unroll 1
-            for (int w = 0; w < NW; ++w) stats_add<PQ>(st, ST + (size_t)w * NST * 32);
-            if (warp == 0) {
-                if (live) {
-                    mstep_obs_block<PQ>(st, gc, th);
+        for (int j = warp; j < NST; j += NW) {
+            double a = ST[j * 32];
 #pragma unroll
-                    for (int i = 0; i < PQ; i++) TD[i * 32] = th.D[i];
-                }
-                TH[1 * 32] = th.C;
-                TH[3 * 32] = th.R;
-            } else {
-                if (live) {
-                    mstep_trans_block<PQ>(st, tuu_inv, T, th);
+            for (int w = 1; w < NW; ++w) a += ST[((size_t)w * NST + j) * 32];
+            TOT[j * 32] = a;
+        }
+        __syncthreads(); // B5b
+        // (2) the three matrix-vector products of the block elimination (lds_math.cuh), one row per warp at a time
+        {
+            const double *__restrict__ svv_inv = gc + 2 + 2 * PQ;
+#pragma unroll 1
+            for (int rr = warp; rr < 3 * PQ; rr += NW) {
+                const int which = rr / PQ, a = rr - which * PQ;
+                const double *__restrict__ m = (which == 0 ? svv_inv : tuu_inv) + a * PQ;
+                // the vector, in stats_store order: Sxv at 11, Tx1u at 11 + PQ, Tux at 11 + 2 PQ
+                const double *__restrict__ xv = TOT + (size_t)(which == 0 ? 11 : (which == 1 ? 11 + 2 * PQ : 11 + PQ)) * 32;
+                double acc = 0.0;
 #pragma unroll
-                    for (int i = 0; i < PQ; i++) TB[i * 32] = th.B[i];
-                }
-                TH[0 * 32] = th.A;
-                TH[2 * 32] = th.Q;
-                TH[4 * 32] = th.mu1;
-                TH[5 * 32] = th.V1;
+                for (int b2 = 0; b2 < PQ; b2++) acc = fma(m[b2], xv[b2 * 32], acc);
+                ZW[rr * 32] = acc;
             }
+        }
+        __syncthreads(); // B5c
+        // (3) the scalars: warp 0 the observation block (C, D, R), warp 1 the transition block (A, B, Q, mu1, V1)
+        if (warp == 0) {
+            if (live) {
+                const double Syy = gc[0];
+                const double *Syv = gc + 2, *wy = gc + 2 + PQ;
+                const double Syx = TOT[0 * 32], Sxx = TOT[1 * 32] + TOT[2 * 32]; // EM.cpp:152
+                double num = Syx, den = Sxx;
+#pragma unroll
+                for (int a = 0; a < PQ; a++) {
+                    const double sxv = TOT[(11 + a) * 32];
+                    num = fma(-wy[a], sxv, num);
+                    den = fma(-sxv, ZW[a * 32], den);
+                }
+                const double Cn = num / den;
+                double racc = fma(-Cn, Syx, Syy);
+#pragma unroll
+                for (int a = 0; a < PQ; a++) {
+                    const double d = fma(-Cn, ZW[a * 32], wy[a]);
+                    TD[a * 32] = d;
+                    racc = fma(-d, Syv[a], racc);
+                }
+                th.C = Cn;
+                th.R = racc / n_obs;
+            }
+            TH[1 * 32] = th.C;
+            TH[3 * 32] = th.R;
+        } else if (warp == 1) {
+            if (live) {
+                const double Txx = TOT[5 * 32] + TOT[6 * 32], Tx1x = TOT[3 * 32] + TOT[4 * 32]; // EM.cpp:180,181
+                const double X0 = TOT[7 * 32], V0 = TOT[8 * 32], XT = TOT[9 * 32], VT = TOT[10 * 32];
+                double num = Tx1x, den = Txx;
+#pragma unroll
+                for (int a = 0; a < PQ; a++) {
+                    const double z = ZW[(PQ + a) * 32];
+                    num = fma(-TOT[(11 + PQ + a) * 32], z, num);     // Tx1u . z
+                    den = fma(-TOT[(11 + 2 * PQ + a) * 32], z, den); // Tux . z
+                }
+                const double An = num / den;
+                // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
+                const double Tx1x1 = Txx - fma(X0, X0, V0) + fma(XT, XT, VT);
+                double qacc = fma(-An, Tx1x, Tx1x1);
+#pragma unroll
+                for (int a = 0; a < PQ; a++) {
+                    const double bb = fma(-An, ZW[(PQ + a) * 32], ZW[(2 * PQ + a) * 32]);
+                    TB[a * 32] = bb;
+                    qacc = fma(-bb, TOT[(11 + PQ + a) * 32], qacc);
+                }
+                th.A = An;
+                th.Q = qacc / (double)(T - 1);
+                th.mu1 = X0; // EM.cpp:218-219
+                th.V1 = V0;
+            }
+            TH[0 * 32] = th.A;
+            TH[2 * 32] = th.Q;
+            TH[4 * 32] = th.mu1;
+            TH[5 * 32] = th.V1;
         }
         __syncthreads(); // B6: the new theta is published
         th.A = TH[0 * 32];

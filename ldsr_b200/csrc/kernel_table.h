@@ -6,6 +6,7 @@
 #include "em_kernel.cuh"
 #include "em_split_kernel.cuh"
 #include "em_wide_kernel.cuh"
+#include "em_scan_kernel.cuh"
 
 namespace ldsr {
 
@@ -41,6 +42,10 @@ constexpr int WIDE_MIN_PQ = 5;
 constexpr int WIDE_NW = 8;
 constexpr int WIDE_MSEG = 8;
 
+// small-batch scan kernel (em_scan_kernel.cuh): one CTA per fit, SCAN_L steps per thread; compiled for PQ <= SCAN_MAX_PQ
+constexpr int SCAN_MAX_PQ = 4;
+constexpr int SCAN_L = 4;
+
 struct KernelTable {
     int pq;
     cudaError_t (*em_prepare)(size_t smem_bytes); // opt in to > 48 KB dynamic shared memory
@@ -56,6 +61,10 @@ struct KernelTable {
     int wide_nw, wide_mseg;
     cudaError_t (*em_wide_prepare)(size_t smem_bytes);
     cudaError_t (*em_wide)(const WideParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
+    // small-batch scan kernel: scan_l == 0 when this width has none (PQ > SCAN_MAX_PQ); series up to
+    // scan_l * 32 * SCAN_MAX_WARPS steps; `warps` = ceil(T_max / (32 scan_l))
+    int scan_l;
+    cudaError_t (*em_scan)(const EmParams &, int n_tasks, int warps, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);
     cudaError_t (*mstep)(const MstepParams &, cudaStream_t);
     cudaError_t (*propagate)(const SmootherParams &, cudaStream_t);

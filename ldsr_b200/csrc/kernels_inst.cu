@@ -2,7 +2,7 @@
 // A wide PQ takes minutes to compile (fully unrolled PQ x PQ bodies), so the build may cut the
 // translation unit into parts, one nvcc process each: -DLDSR_PART=0 (table + single-step kernels),
 // 1, 2, 3 (lane-per-fit EM kernel, MODE 0 / 1 / 2), 4 (time-split EM kernel), 5 (wide-input EM kernel,
-// PQ >= WIDE_MIN_PQ).  -DLDSR_NO_PART=k compiles everything but part k; without either macro everything
+// PQ >= WIDE_MIN_PQ; also the small-batch scan kernel, PQ <= SCAN_MAX_PQ).  -DLDSR_NO_PART=k compiles everything but part k; without either macro everything
 // is in one unit.
 #include "kernel_table.h"
 
@@ -108,6 +108,24 @@ template <> cudaError_t wide_launch<PQ>(const WideParams &p, int n_tasks, size_t
 }
 #endif
 
+// small-batch scan kernel
+template <int PQV> cudaError_t scan_launch(const EmParams &, int, int, cudaStream_t);
+template <> cudaError_t scan_launch<PQ>(const EmParams &, int, int, cudaStream_t);
+#if LDSR_HAS_PART(5)
+template <int PQV, bool HAVE> struct ScanLaunch { // widths above SCAN_MAX_PQ have no scan kernel
+    static cudaError_t launch(const EmParams &, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+};
+template <int PQV> struct ScanLaunch<PQV, true> {
+    static cudaError_t launch(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
+        em_scan_kernel<PQV, SCAN_L><<<n_tasks, warps * 32, 0, st>>>(p);
+        return cudaGetLastError();
+    }
+};
+template <> cudaError_t scan_launch<PQ>(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
+    return ScanLaunch<PQ, (PQ <= SCAN_MAX_PQ)>::launch(p, n_tasks, warps, st);
+}
+#endif
+
 #if LDSR_HAS_PART(0)
 namespace {
 
@@ -133,6 +151,9 @@ cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, 
 cudaError_t em_wide_prepare(size_t smem_bytes) { return wide_prepare<PQ>(smem_bytes); }
 cudaError_t em_wide(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     return wide_launch<PQ>(p, n_tasks, smem_bytes, st);
+}
+cudaError_t em_scan(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
+    return scan_launch<PQ>(p, n_tasks, warps, st);
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
     smoother_kernel<PQ><<<(p.n_jobs + 63) / 64, 64, 0, st>>>(p);
@@ -165,6 +186,8 @@ const KernelTable table = {PQ,
                            WIDE_MSEG,
                            em_wide_prepare,
                            em_wide,
+                           PQ <= SCAN_MAX_PQ ? SCAN_L : 0,
+                           em_scan,
                            smoother,
                            mstep,
                            propagate,

@@ -201,6 +201,7 @@ struct ldsr_ctx {
 };
 
 // ---- plan -----------------------------------------------------------------------------------
+constexpr int SCAN_MAX_FITS = 600; // batches up to this size run the scan kernel (one CTA per fit) when it exists
 constexpr size_t COUNTS_CAP = 256; // (tasks, live fits) per chunk: room for 128 chunks without regrowing
 struct ldsr_plan {
     int device = 0;
@@ -562,7 +563,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->dalloc(&P->d_sum, 1)).ok()) return e;
     if (!(e = P->dalloc(&P->d_ticket, 1)).ok()) return e;
     CU(cudaMemsetAsync(P->d_ticket, 0, sizeof(unsigned), P->stream));
-    P->max_tasks = nf / 32 + ns + 1; // the time-split kernel takes 32 fits per CTA
+    // the time-split kernels take 32 fits per CTA; the small-batch scan kernel one fit per CTA
+    P->max_tasks = std::max(nf / 32, std::min(nf, SCAN_MAX_FITS)) + ns + 1;
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
 
@@ -667,10 +669,21 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     if (variant == 4 && !use_wide)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 4 (wide-input kernel) needs width >= 5 and %zu bytes of shared memory",
                     wide_sm);
-    bool use_split = !use_wide && P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
+    // small batches of narrow inputs: one CTA per fit, the time axis spread over its threads (em_scan_kernel.cuh).
+    // A batched kernel needs 10 us per iteration however few fits it holds; the scan kernel 2-3 us for up
+    // to one fit per SM and about n/148 times that beyond, so it wins below a few hundred fits.
+    const int scan_warps = P->kt->scan_l > 0 ? (P->max_T + 32 * P->kt->scan_l - 1) / (32 * P->kt->scan_l) : 0;
+    const bool scan_ok = P->kt->scan_l > 0 && scan_warps <= SCAN_MAX_WARPS;
+    const bool use_scan = scan_ok && nf <= SCAN_MAX_FITS && (variant == 0 || variant == 5);
+    if (variant == 5 && !use_scan)
+        return fail(LDSR_ERR_UNSUPPORTED, "variant 5 (scan kernel) needs input width <= %d, T <= %d and at most %d fits",
+                    SCAN_MAX_PQ, 32 * SCAN_L * SCAN_MAX_WARPS, SCAN_MAX_FITS);
+    bool use_split = !use_scan && !use_wide && P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
     if (variant == 3 && !use_split)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 3 (time-split kernel) needs %zu bytes of shared memory", split_sm);
-    if (use_wide) {
+    if (use_scan) {
+        smem = 0;
+    } else if (use_wide) {
         smem = wide_sm;
         CU(P->kt->em_wide_prepare(smem));
     } else if (use_split) {
@@ -679,7 +692,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     } else {
         CU(P->kt->em_prepare(std::max<size_t>(smem, 1024)));
     }
-    const int fits_per_cta = (use_split || use_wide) ? 32 : 32 * EM_WARPS;
+    const int fits_per_cta = use_scan ? 1 : ((use_split || use_wide) ? 32 : 32 * EM_WARPS);
 
     EmParams ep;
     ep.series = P->d_series;
@@ -734,7 +747,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         CU(P->pool->alloc_pinned((size_t)2 * max_chunks * sizeof(int), &hp));
         P->h_counts = static_cast<int *>(hp);
     }
-    const size_t ck_need = (mode == 2 || use_split || use_wide) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
+    const size_t ck_need = (mode == 2 || use_split || use_wide || use_scan) ? 0 : (size_t)grid0 * EM_WARPS * P->max_seg * 64;
     if (P->ckpt_cap < ck_need) {
         P->ckpt_cap = 0;
         Err e = P->drealloc(&P->d_ckpt, ck_need);
@@ -762,7 +775,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         int grid = (c == 0 || grid0 > 3 * P->n_sm) ? grid0 : std::min(grid0, 2 * P->n_sm);
         // the wide-input kernel holds one CTA per SM: one CTA per task, dealt to the SMs by the hardware as
         // they finish (tasks differ in length: fits stop at different iterations)
-        if (use_wide) grid = grid0;
+        if (use_wide || use_scan) grid = grid0;
         // development: LDSR_MAX_GRID caps the grid so that a small batch exercises the task loop of the
         // kernels (tools/sanitize.py runs it under compute-sanitizer)
         static const int grid_cap = std::getenv("LDSR_MAX_GRID") ? std::atoi(std::getenv("LDSR_MAX_GRID")) : 0;
@@ -787,7 +800,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             evs.push_back(b);
             CU(cudaEventRecord(a, st));
         }
-        if (use_wide) {
+        if (use_scan) {
+            CU(P->kt->em_scan(ep, grid, scan_warps, st));
+        } else if (use_wide) {
             WideParams wp;
             wp.em = ep;
             wp.max_units = P->wide_units;
@@ -939,7 +954,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         stats[1] = chunks;
         stats[2] = (long long)total;
         stats[3] = (long long)(em_ms * 1e6);
-        stats[4] = use_wide ? 2 : (use_split ? 1 : 0); // which EM kernel ran
+        stats[4] = use_scan ? 3 : (use_wide ? 2 : (use_split ? 1 : 0)); // which EM kernel ran
         stats[5] = stats[6] = stats[7] = 0;
     }
     return Err();

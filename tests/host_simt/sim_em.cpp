@@ -12,6 +12,9 @@
 #ifdef LDSR_HAVE_WIDE
 #include "../../ldsr_b200/csrc/em_wide_kernel.cuh"
 #endif
+#ifdef LDSR_HAVE_SCAN
+#include "../../ldsr_b200/csrc/em_scan_kernel.cuh"
+#endif
 
 #include <vector>
 
@@ -197,7 +200,7 @@ template <int PQ> int run(const Job &J) {
         for (int k = 0; k < 4; k++) dst[2 + 2 * PQ + k] = src[2 + p + q + k];
     }
     std::vector<int> active(nf, 0);
-    std::vector<int4> tasks(nf / 32 + 2);
+    std::vector<int4> tasks(nf + 2);
     int n_tasks = 0;
 
     EmParams ep;
@@ -233,7 +236,7 @@ template <int PQ> int run(const Job &J) {
     const int max_chunks = (J.niter + J.chunk - 1) / J.chunk;
     for (int c = 0; c < max_chunks; c++) {
         // compact_kernel: live fits in order, 32 (or 128) per CTA
-        const int per = J.kind == 2 ? 32 * 4 : 32;
+        const int per = J.kind == 2 ? 32 * 4 : (J.kind == 5 ? 1 : 32);
         int nl = 0;
         for (int f = 0; f < nf; f++)
             if (!done[f]) active[nl++] = f;
@@ -267,6 +270,17 @@ template <int PQ> int run(const Job &J) {
             if (rc) return rc;
         }
 #endif
+#ifdef LDSR_HAVE_SCAN
+        else if (J.kind == 5) {
+            constexpr int L = 4;
+            const int nwarps = (T + 32 * L - 1) / (32 * L);
+            if (nwarps > SCAN_MAX_WARPS) return 14;
+            if constexpr (PQ <= 4)
+                hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, L>(ep); });
+            else
+                return 15;
+        }
+#endif
         else
             return 12;
     }
@@ -286,7 +300,8 @@ template <int PQ> int run(const Job &J) {
 
 } // namespace
 
-// kind: 2 = lane-per-fit kernel (MODE 2), 3 = time-split kernel, 4 = wide time-split kernel.
+// kind: 2 = lane-per-fit kernel (MODE 2), 3 = time-split kernel, 4 = wide time-split kernel, 5 = scan kernel
+// (one CTA per fit).
 // One series; u, v are [T][p] / [T][q] (an R p x T matrix, column-major).  order: thread schedule of the
 // emulator (0 forward, 1 reverse, >= 2 seeded shuffle).  grid_cap > 0 makes CTAs loop over tasks.
 extern "C" int hostsim_em(int kind, int T, int p, int q, const double *y, const double *u, const double *v, int n_groups,

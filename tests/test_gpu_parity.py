@@ -87,7 +87,7 @@ def _np213():
 
 
 def check_batch(series, group_series, held, fit_group, th0, niter, tol, **kw):
-    g = _lib.em_batch(series, group_series, held, fit_group, th0, niter, tol, want_liks=True, **kw)
+    g = em_variant(series, group_series, held, fit_group, th0, niter, tol, want_liks=True, **kw)
     o = O.em_batch(series, group_series, held, fit_group, th0, niter, tol)
     assert np.array_equal(g["status"], o["status"])
     assert np.array_equal(g["iters"], o["iters"]), np.nonzero(g["iters"] != o["iters"])
@@ -104,7 +104,17 @@ def check_batch(series, group_series, held, fit_group, th0, niter, tol, **kw):
 
 # both EM kernels must agree with the oracle: 2 = lane-per-fit (em_kernel.cuh), 3 = time-split
 # (em_split_kernel.cuh); 0 = whatever the plan picks
-VARIANTS = [2, 3]
+VARIANTS = [2, 3, 5]  # lane-per-fit, time-split, small-batch scan kernel (4 = wide-input kernel: wide tests)
+
+
+def em_variant(*a, **kw):
+    """_lib.em_batch; variants 4 / 5 exist for some widths, lengths and batch sizes only: skip where they do not."""
+    try:
+        return _lib.em_batch(*a, **kw)
+    except _lib.LdsrError as e:
+        if kw.get("variant") in (4, 5) and e.code == _lib.ERR_UNSUPPORTED:
+            pytest.skip("kernel variant %d does not cover this case" % kw["variant"])
+        raise
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -135,8 +145,8 @@ def test_chunking_does_not_change_results(variant):
     rng = np.random.default_rng(5)
     th0 = rand_theta0(rng, 3, 3, 40)
     ser = [dict(y=y, u=u, v=u)]
-    a = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=100, variant=variant)
-    b = _lib.em_batch(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=7, variant=variant)
+    a = em_variant(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=100, variant=variant)
+    b = em_variant(ser, [0], None, np.zeros(40, dtype=int), th0, 150, 1e-5, chunk_iters=7, variant=variant)
     for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):
         assert np.array_equal(a[k], b[k]), k
 
@@ -370,7 +380,7 @@ def _run_variant(fn, variant):
         raise
 
 
-@pytest.mark.parametrize("variant", VARIANTS + [4, 0])
+@pytest.mark.parametrize("variant", [2, 3, 4, 0])
 @pytest.mark.parametrize("p,q", [(5, 5), (7, 6), (10, 10), (12, 11), (16, 16), (18, 20), (32, 29)])
 def test_wide_inputs(variant, p, q):
     # the padded widths 5 .. 32 (24 and 32 are built as several translation units)
@@ -391,23 +401,24 @@ def test_wide_inputs(variant, p, q):
                                      variant=variant), variant)
 
 
-@pytest.mark.parametrize("T", [2, 3, 9, 31, 32, 33, 40, 64, 65, 97, 150])
+@pytest.mark.parametrize("T", [8, 12, 16, 31, 32, 33, 40, 64, 65, 97, 150])
 def test_wide_kernel_ragged_lengths(T):
-    """em_wide_kernel on series shorter than a unit, exactly one word, a word + a ragged tail ...: the
-    slices of phases A / C, the piece bounds and the partial-sum slots that alias the trajectory must
-    hold for every length (fully observed and with an unobserved prefix)."""
+    """em_wide_kernel on series shorter than a word, exactly one word, a word + a ragged tail ...: the
+    slices of phases A / C, the piece bounds and what aliases the trajectory after phase C must hold for
+    every length (fully observed and with an unobserved prefix; always enough steps for the Gram blocks
+    of the p = 5 inputs to be invertible)."""
     rng = np.random.default_rng(T)
-    p = 6
+    p = 5
     u = rng.standard_normal((p, T))
-    for lead in (0, T // 2):
+    for lead in ((0,) if T < 16 else (0, T // 4)):
         y = 0.3 * rng.standard_normal(T)
         y[:lead] = np.nan
-        if T > 8:
+        if T >= 16:
             y[lead + 2] = np.nan
         th0 = rand_theta0(rng, p, p, 37)
         th0[:, 1:1 + p] *= 0.2
         th0[:, 2 + p:2 + 2 * p] *= 0.2
-        held = [np.array([], dtype=int), np.array([T - 1]) if T > 14 else np.array([], dtype=int)]
+        held = [np.array([], dtype=int), np.array([T - 1]) if T >= 16 else np.array([], dtype=int)]
         check_batch([dict(y=y, u=u, v=u)], [0, 0], held, np.sort(rng.integers(0, 2, 37)), th0, 12, 1e-7, variant=4)
 
 
@@ -479,7 +490,7 @@ def test_task_loop_when_later_chunks_have_more_tasks_than_ctas():
     results must equal the single-launch run bit for bit."""
     from ldsr_b200 import workloads as W
     w = W.np_cv(120, 100)  # 12 000 fits = 375 tasks of 32
-    for variant in VARIANTS:
+    for variant in (2, 3):
         a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 60, 1e-5,
                           chunk_iters=60, want_traj=False, variant=variant)
         b = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 60, 1e-5,
@@ -543,7 +554,7 @@ def test_unusual_initial_values(variant):
     th = np.stack(th)
     fg = np.zeros(len(th), dtype=int)
     none = [np.array([], dtype=int)]
-    g = _lib.em_batch([dict(y=y, u=u, v=u)], [0], none, fg, th, 4, 0.0, want_liks=True, variant=variant)
+    g = em_variant([dict(y=y, u=u, v=u)], [0], none, fg, th, 4, 0.0, want_liks=True, variant=variant)
     o = O.em_batch([dict(y=y, u=u, v=u)], [0], none, fg, th, 4, 0.0)
     assert np.array_equal(g["iters"], o["iters"])
     # a stable start is held to the usual bars; an explosive one (A = 1.02: the predicted variance reaches

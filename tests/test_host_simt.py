@@ -28,6 +28,7 @@ def _lib():
     srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         wide = ["-DLDSR_HAVE_WIDE"] if os.path.exists(os.path.join(csrc, "em_wide_kernel.cuh")) else []
+        wide += ["-DLDSR_HAVE_SCAN"] if os.path.exists(os.path.join(csrc, "em_scan_kernel.cuh")) else []
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-DLDSR_HOST_SIM", "-Wno-unknown-pragmas", "-mfma",
                         "-ffp-contract=off", "-shared", "-fPIC"] + wide +
                        [os.path.join(HERE, "sim_em.cpp"), "-o", SO], check=True)
@@ -141,3 +142,22 @@ def test_emulated_wide_kernel_separate_v_and_task_loop():
     b = sim_em(4, y, u, v, held, fg, th0, 5, chunk=2, order=3, grid_cap=1)  # 3 tasks on one CTA, 3 launches
     for k in ("theta", "lik", "iters"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("T", [213, 40, 129, 14])
+def test_emulated_scan_kernel(T):
+    """em_scan_kernel (one CTA per fit, one thread per 4 steps, the recursions as scans): oracle parity and
+    schedule independence; lengths that leave the last warp ragged, fill one warp exactly or not at all."""
+    y, u, held, fg, th0 = _np_job(n_folds=2, n_rest=3)
+    if T != 213:
+        y, u = y[213 - T:], u[:, 213 - T:]
+        if T == 14:
+            y = np.array([0.1, -0.2, np.nan, 0.3, 0.05, 0.2, -0.1, 0.15, np.nan, -0.3, 0.25, 0.1, -0.05, 0.12])
+        held = [np.array([T - 1]), np.array([], dtype=int)]
+    niter = 9
+    base = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=0)
+    _check_vs_oracle(base, y, u, u, held, fg, th0, niter)
+    for order in (1, 4):
+        r = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=order, grid_cap=2 if order == 4 else 0)
+        for k in ("theta", "lik", "iters"):
+            assert np.array_equal(base[k], r[k]), (order, k)
