@@ -279,6 +279,67 @@ def config1_block(args, local, torch, flush):
     return out
 
 
+def config4_block(args, hbm_peak):
+    """BASELINE config 4: LDS_rep, 100 000 stochastic replicates of the fitted NP model (theta = data/theta.rda,
+    u = v = t(NPpc), T = 813): 81.3 M (x, y, Q) triples.  Device time of the replicate kernels (CUDA events,
+    ldsr_last_device_ms) against the HBM roofline -- 24 B written per (replicate, step) -- and the wall clock
+    of the host-buffer call (kernels + PCIe + the copy into the caller's arrays, pipelined)."""
+    from ldsr_b200 import _lib
+    from tests import data
+    d = data.load("np.json")
+    th = data.theta_of(d["theta"])
+    y, u, mu, inst = data.np_case(1, 1200)
+    T, n_reps = y.size, args.rep_replicates
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = _lib.rep_batch(th, u, u, T, n_reps, seed=W.SEED, mu=mu)
+        wall = time.perf_counter() - t0
+        if best is None or r["device_ms"] < best[0]:
+            best = (r["device_ms"], wall)
+    nbytes = 24.0 * n_reps * T
+    gbs = nbytes / (best[0] * 1e-3) / 1e9
+    simq = np.asarray(r["simQ"])
+    return {"workload": "LDS_rep %d replicates x T=%d (NP model), simX+simY+simQ" % (n_reps, T),
+            "value": n_reps * T / (best[0] * 1e-3), "unit": "(replicate,step)/s", "device_ms": best[0],
+            "wall_ms": best[1] * 1e3, "bytes_out": nbytes,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "note": "algorithmic bytes (24 B per replicate and step) / device time of the replicate "
+                                 "kernels; the noise is generated in the kernel (two FP64 normals per step), "
+                                 "which is what bounds it"},
+            "finite": bool(np.isfinite(simq).all()), "median_simQ": float(np.median(simq))}
+
+
+def config5_block(args):
+    """BASELINE config 5: state dimension 4, 20 proxies, T = 100 000, 10 % missing: associative-scan smoother
+    against the sequential recursion on the device (beyond the reference, which is scalar-state only)."""
+    from ldsr_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    rng = np.random.default_rng(W.SEED)
+    d, p, q, T = 4, 20, 20, args.scan_T
+    M = rng.standard_normal((d, d))
+    A = 0.9 * M / np.max(np.abs(np.linalg.eigvals(M)))
+    L = 0.4 * rng.standard_normal((d, d))
+    th = np.concatenate([A.ravel(), (0.3 * rng.standard_normal((d, p)) / np.sqrt(p)).ravel(), rng.standard_normal(d),
+                         0.3 * rng.standard_normal(q) / np.sqrt(q), (L @ L.T + 0.1 * np.eye(d)).ravel(), [0.3],
+                         np.zeros(d), np.eye(d).ravel()])
+    u, v = rng.standard_normal((p, T)), rng.standard_normal((q, T))
+    y = rng.standard_normal(T)
+    y[rng.uniform(size=T) < 0.1] = np.nan
+    _lib.smoother_d(d, y, u, v, th, method=1, want=())  # warm-up
+    seq = _lib.smoother_d(d, y, u, v, th, method=0, want=("X", "V"))
+    best = None
+    for _ in range(3):
+        sc = _lib.smoother_d(d, y, u, v, th, method=1, want=("X", "V"))
+        best = sc["kernel_ms"] if best is None else min(best, sc["kernel_ms"])
+    return {"workload": "d=%d state, %d proxies, T=%d, 10%% missing, 1 parameter set" % (d, p, T),
+            "scan_ms": best, "sequential_ms": seq["kernel_ms"], "speedup": seq["kernel_ms"] / best,
+            "value": T / (best * 1e-3), "unit": "steps/s",
+            "max_abs_dX": float(np.max(np.abs(sc["X"] - seq["X"]))), "max_abs_dV": float(np.max(np.abs(sc["V"] - seq["V"]))),
+            "rel_dlik": float(np.max(np.abs(sc["lik"] - seq["lik"]) / np.abs(seq["lik"]))),
+            "parity": "scan vs sequential recursion on the device; both vs the general-d oracle in tests/test_gpu_scan.py"}
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU algorithm (oracle/ldsr_oracle.c, restating src/EM.cpp) on all host threads.
     The real Rcpp/Armadillo build cannot run here (no R): see DESIGN.md."""
@@ -329,6 +390,8 @@ def main():
     ap.add_argument("--strong-cpu-seconds", type=float, default=3.0)
     ap.add_argument("--no-strong", action="store_true", help="skip the `strong` block (config 3)")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (configs 1, 4, 5)")
+    ap.add_argument("--rep-replicates", type=int, default=100000, help="config 4: LDS_rep replicates")
+    ap.add_argument("--scan-T", type=int, default=100000, help="config 5: series length")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -471,7 +534,14 @@ def main():
 
     configs = None
     if not args.no_configs and args.workload == "np_cv" and world == 1:
-        configs = {"config1": config1_block(args, local, torch, flush)}
+        hbm_peak = 6650.0  # fallback of B200_PROFILING.md
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = float(json.load(f)["hbm_gbs"])
+        except Exception:
+            pass
+        configs = {"config1": config1_block(args, local, torch, flush), "config4": config4_block(args, hbm_peak),
+                   "config5": config5_block(args)}
         if strong is not None:
             configs["config3"] = {k: strong[k] for k in ("workload", "value", "unit", "ms_per_step", "mean_iters")}
             configs["config3"]["frac"] = strong["roofline"]["frac"]

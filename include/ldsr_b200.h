@@ -187,6 +187,10 @@ int ldsr_rep_batch_r(ldsr_ctx *ctx, const double *theta, const double *u, const 
                      int p, int q, int n_reps, unsigned int r_seed, double mu, int exp_trans,
                      double *simX, double *simY, double *simQ, char *errbuf, int errlen);
 
+/* Device time in ms (CUDA events around the kernels, summed) of the last ldsr_rep_batch / ldsr_rep_batch_r call
+ * made by the calling thread: the measurement hook of bench.py's config-4 record. */
+double ldsr_last_device_ms(void);
+
 /* ---- the reference's random numbers (R's default generators after set.seed) ---------------
  * The reference draws its restarts' initial values with runif (make_init, R/LDS_reconstruction.R:
  * 14-30) and its replicates with rnorm; a caller outside R reproduces a seeded reference run by

@@ -21,7 +21,7 @@ EXPORTS = ("ldsr_abi_version", "ldsr_device_count", "ldsr_ctx_create", "ldsr_ctx
            "ldsr_propagate_batch", "ldsr_rep_batch", "ldsr_shard_groups", "ldsr_measure_fp64_peak",
            "ldsr_smoother_d_batch", "ldsr_cv_metrics_batch", "ldsr_construct_rec_batch",
            "ldsr_objective_batch", "ldsr_rep_batch_r", "ldsr_r_rng_create", "ldsr_r_rng_unif", "ldsr_r_rng_norm",
-           "ldsr_r_rng_sample", "ldsr_r_rng_destroy", "ldsr_r_rnorm_device")
+           "ldsr_r_rng_sample", "ldsr_r_rng_destroy", "ldsr_r_rnorm_device", "ldsr_last_device_ms")
 
 
 class LdsrError(RuntimeError):
@@ -68,6 +68,7 @@ def lib():
         L.ldsr_ctx_trim.restype = C.c_longlong
         L.ldsr_r_rng_destroy.restype = None
         L.ldsr_plan_destroy.restype = None
+        L.ldsr_last_device_ms.restype = C.c_double
         _lib = L
     return _lib
 
@@ -355,7 +356,9 @@ def rep_batch(theta, u, v, n, n_reps, z=None, seed=0, mu=0.0, exp_trans=True, p=
                                   C.c_ulonglong(seed), C.c_double(mu), int(exp_trans), _d(outs["simX"]),
                                   _d(outs["simY"]), _d(outs["simQ"]), err, 512)
     _check(rc, err)
-    return {k: v for k, v in outs.items() if v is not None}
+    res = {k: v for k, v in outs.items() if v is not None}
+    res["device_ms"] = float(lib().ldsr_last_device_ms())  # CUDA-event time of the replicate kernels
+    return res
 
 
 class RRandom:

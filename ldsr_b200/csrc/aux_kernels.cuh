@@ -277,11 +277,15 @@ template <int PQ> __global__ void propagate_kernel(const SmootherParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// LDS_rep (R/stochastics.R:18-63): one lane per replicate.  The noise is either read from z
-// (n_reps x (1+2n), reference draw order) or generated from a counter-based generator
-// (splitmix64 -> Box-Muller) keyed by (seed, replicate, index).  Outputs are written
-// TIME-MAJOR into a [n][n_reps] staging layout so that warps store coalesced; the host-facing
-// layout (replicate-major) is produced by transpose_kernel.
+// LDS_rep (R/stochastics.R:18-63): one lane per replicate, one warp per 32 replicates, ONE pass for all
+// requested outputs.  The noise is either read from z (n_reps x (1+2n), the reference's draw order) or
+// generated from a counter-based generator (splitmix64 -> Box-Muller, both outputs of a pair used: the state
+// and the observation draw of a step) keyed by (seed, replicate, step).
+// Outputs are REPLICATE-MAJOR (the reference's rbindlist order) and every byte is written once: the warp
+// simulates REP_TT steps into a [step][replicate] tile in shared memory (row stride 33: conflict-free both
+// ways) and writes it out replicate by replicate, 128 contiguous bytes per half-warp; caller noise is read
+// the same way (one instruction fetches the state draws and the observation draws of a replicate's tile).
+// HBM traffic: 8 B per requested output and (replicate, step) + 16 B of noise when z is given.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -289,46 +293,105 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
-__device__ __forceinline__ double counter_normal(unsigned long long seed, unsigned long long rep,
-                                                 unsigned long long idx) {
-    const unsigned long long k = splitmix64(seed ^ splitmix64(rep * 0xD1342543DE82EF95ULL + 1));
-    const unsigned long long a = splitmix64(k + 2 * idx), b = splitmix64(k + 2 * idx + 1);
+// two independent standard normals from counter (key, idx)
+__device__ __forceinline__ void counter_normal_pair(unsigned long long key, unsigned long long idx, double &z0,
+                                                    double &z1) {
+    const unsigned long long a = splitmix64(key + 2 * idx), b = splitmix64(key + 2 * idx + 1);
     const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    return sqrt(-2.0 * log(u1)) * c;
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    const double r = sqrt(-2.0 * log(u1));
+    z0 = r * cs;
+    z1 = r * sn;
 }
+__device__ __forceinline__ unsigned long long counter_key(unsigned long long seed, unsigned long long rep) {
+    return splitmix64(seed ^ splitmix64(rep * 0xD1342543DE82EF95ULL + 1));
+}
+
+constexpr int REP_TT = 16;     // steps per tile
+constexpr int REP_WARPS = 4;   // warps per CTA
+constexpr int REP_TILE = REP_TT * 33; // doubles per tile
 
 struct RepParams {
     const double *theta; // padded, one model
     const double *u, *v; // [n][PQ] padded, time-major (zeros when absent)
-    const double *z;     // optional caller noise [n_reps][1+2n]
+    const double *z;     // optional noise [n_reps][1+2n], row 0 = replicate rep0
     unsigned long long seed;
-    int n, n_reps;
+    int n, n_reps;       // steps; replicates of THIS launch
+    long long rep0;      // global index of the launch's first replicate (keys the generator)
     double mu;
     int exp_trans;
-    double *simX, *simY, *simQ; // [n][n_reps] (time-major staging), any may be null
+    double *simX, *simY, *simQ; // [n_reps][n] replicate-major, any may be null
 };
+__host__ __device__ inline size_t rep_smem_bytes(bool with_z) {
+    return (size_t)REP_WARPS * (3 + (with_z ? 2 : 0)) * REP_TILE * sizeof(double);
+}
 
-template <int PQ> __global__ void rep_kernel(const RepParams P) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P.n_reps) return;
+template <int PQ> __global__ void __launch_bounds__(REP_WARPS * 32) rep_kernel(const RepParams P) {
+    LDSR_DYN_SMEM(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = P.n;
+    const long long r0 = ((long long)blockIdx.x * REP_WARPS + warp) * 32; // first replicate of the warp
+    if (r0 >= P.n_reps) return;
+    const int n_rows = (int)(P.n_reps - r0 < 32 ? P.n_reps - r0 : 32);
+    const bool have_z = P.z != nullptr;
+    double *const tiles = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (3 + (have_z ? 2 : 0)) * REP_TILE;
+    double *const tX = tiles, *const tY = tiles + REP_TILE, *const tQ = tiles + 2 * REP_TILE;
+    double *const tZq = tiles + 3 * REP_TILE, *const tZe = tiles + 4 * REP_TILE;
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta);
     const double sQ = sqrt(th.Q), sR = sqrt(th.R), sV = sqrt(th.V1);
-    const int n = P.n;
-    const double *zr = P.z ? P.z + (size_t)r * (1 + 2 * n) : nullptr;
-    double x = (zr ? zr[0] : counter_normal(P.seed, r, 0)) * sV; // mean 0, not mu1 (stochastics.R:23)
-    for (int t = 0; t < n; t++) {
-        const double zq = zr ? zr[1 + t] : counter_normal(P.seed, r, 1 + t);
-        const double ze = zr ? zr[1 + n + t] : counter_normal(P.seed, r, 1 + n + t);
-        const double y = fma(th.C, x, dot_row<PQ>(th.D, P.v + (size_t)t * PQ)) + ze * sR;
-        const size_t o = (size_t)t * P.n_reps + r;
-        if (P.simX) P.simX[o] = x;
-        if (P.simY) P.simY[o] = y;
-        if (P.simQ) P.simQ[o] = P.exp_trans ? exp(y + P.mu) : y + P.mu;
-        x = fma(th.A, x, dot_row<PQ>(th.B, P.u + (size_t)t * PQ)) + zq * sQ;
+    const long long rep = r0 + lane; // my replicate (rows beyond n_rows compute garbage that is never stored)
+    const size_t zstride = 1 + 2 * (size_t)n;
+    const unsigned long long key = counter_key(P.seed, (unsigned long long)(P.rep0 + rep));
+    double x;
+    if (have_z) {
+        x = (lane < n_rows ? P.z[(size_t)rep * zstride] : 0.0) * sV; // mean 0, not mu1 (stochastics.R:23)
+    } else {
+        double a, b;
+        counter_normal_pair(key, 0, a, b);
+        x = a * sV;
+    }
+    const int half = lane >> 4, hl = lane & 15; // half-warp and lane inside it
+    for (int t0 = 0; t0 < n; t0 += REP_TT) {
+        const int cnt = n - t0 < REP_TT ? n - t0 : REP_TT;
+        if (have_z) { // state draws z[1 + t], observation draws z[1 + n + t]: lanes 0-15 / 16-31 of one instruction
+            __syncwarp();
+            for (int rr = 0; rr < n_rows; ++rr) {
+                if (hl < cnt) {
+                    const double val = P.z[(size_t)(r0 + rr) * zstride + 1 + (half ? n : 0) + t0 + hl];
+                    (half ? tZe : tZq)[hl * 33 + rr] = val;
+                }
+            }
+            __syncwarp();
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const int t = t0 + j;
+            double zq, ze;
+            if (have_z) {
+                zq = tZq[j * 33 + lane];
+                ze = tZe[j * 33 + lane];
+            } else {
+                counter_normal_pair(key, 1 + (unsigned long long)t, zq, ze);
+            }
+            const double y = fma(th.C, x, dot_row<PQ>(th.D, P.v + (size_t)t * PQ)) + ze * sR;
+            tX[j * 33 + lane] = x;
+            tY[j * 33 + lane] = y;
+            tQ[j * 33 + lane] = P.exp_trans ? exp(y + P.mu) : y + P.mu;
+            x = fma(th.A, x, dot_row<PQ>(th.B, P.u + (size_t)t * PQ)) + zq * sQ;
+        }
+        __syncwarp();
+        // write the tile out: each half-warp one replicate row (up to 128 contiguous bytes) per instruction
+        for (int rr = half; rr < n_rows; rr += 2) {
+            if (hl < cnt) {
+                const size_t o = (size_t)(r0 + rr) * n + t0 + hl;
+                if (P.simX) P.simX[o] = tX[hl * 33 + rr];
+                if (P.simY) P.simY[o] = tY[hl * 33 + rr];
+                if (P.simQ) P.simQ[o] = tQ[hl * 33 + rr];
+            }
+        }
+        __syncwarp();
     }
 }
 

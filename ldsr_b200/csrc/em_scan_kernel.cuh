@@ -48,7 +48,11 @@ __device__ __forceinline__ void scan_mobius_incl(double &m11, double &m12, doubl
             m21 = n21;
             m22 = n22;
         }
+        // only ratios matter: keep the common scale near 1 (the normalisation factors of 32 maps would
+        // otherwise multiply up to 2^-32 per map and leave the double range on extreme Q / R)
+        if (o == 2 || o == 8) rescale4(m11, m12, m21, m22);
     }
+    rescale4(m11, m12, m21, m22);
 }
 // inclusive prefix composition of affine maps x -> P x + q (lane l: maps of lanes 0..l applied in order)
 __device__ __forceinline__ void scan_affine_incl(double &P, double &q, int lane) {
@@ -104,7 +108,7 @@ template <int N> __device__ __forceinline__ double scan_reduce_many(double (&v)[
 
 template <int PQ, int L>
 __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
-    static_assert(L == 2 || L == 4 || L == 8, "steps per thread");
+    static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
     constexpr int NS = scan_nsum<PQ>(), NSP = scan_nsum_pad<PQ>();
     constexpr int TL = theta_pad_len<PQ>();
     LDSR_STATIC_SMEM(double, S1[SCAN_MAX_WARPS * 4]);  // variance-map totals of the warps
@@ -163,21 +167,28 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     }
 
     for (int it = 0; live && it < P.chunk; ++it) {
-        const double A = th.A, A2 = th.A * th.A, Q = th.Q, Cc = th.C, R = th.R;
-        MixedConst<PQ> mc;
-        mc.set(th, A2);
+        const double A = th.A, Q = th.Q, Cc = th.C, R = th.R;
 
         // ================= P1: variance map of my steps, scan =================
         double e11, e12, e21, e22; // exclusive prefix inside the warp
+        // Per-step coefficients of this iteration.  An unobserved step is the observed one with C = 0, R = 1
+        // ([[A^2 R + Q C^2, Q R],[C^2, R]] becomes [[A^2, Q],[0, 1]], K = 0, Vu = Vp), and a step at or beyond T
+        // is the unobserved one with A = 1, Q = 0 (the identity): two selects each instead of one per formula.
+        double Aj[L], Cj[L], Rj[L], s11[L], s12[L], s21[L];
         {
             double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;
 #pragma unroll
             for (int j = 0; j < L; j++) {
                 const bool real = t0 + j < T, obs = (bits >> j) & 1u;
-                const double s11 = obs ? mc.a11 : (real ? A2 : 1.0), s12 = obs ? mc.a12 : (real ? Q : 0.0);
-                const double s21 = obs ? mc.C2 : 0.0, s22 = obs ? R : 1.0;
-                const double n11 = fma(s11, m11, s12 * m21), n12 = fma(s11, m12, s12 * m22);
-                const double n21 = fma(s21, m11, s22 * m21), n22 = fma(s21, m12, s22 * m22);
+                Aj[j] = real ? A : 1.0;
+                const double Qj = real ? Q : 0.0;
+                Cj[j] = obs ? Cc : 0.0;
+                Rj[j] = obs ? R : 1.0;
+                s21[j] = Cj[j] * Cj[j];
+                s11[j] = fma(Aj[j] * Aj[j], Rj[j], Qj * s21[j]);
+                s12[j] = Qj * Rj[j];
+                const double n11 = fma(s11[j], m11, s12[j] * m21), n12 = fma(s11[j], m12, s12[j] * m22);
+                const double n21 = fma(s21[j], m11, Rj[j] * m21), n22 = fma(s21[j], m12, Rj[j] * m22);
                 m11 = n11;
                 m12 = n12;
                 m21 = n21;
@@ -248,13 +259,10 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 double n = Vin, d = 1.0;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const bool real = t0 + j < T, obs = (bits >> j) & 1u;
-                    const double s11 = obs ? mc.a11 : (real ? A2 : 1.0), s12 = obs ? mc.a12 : (real ? Q : 0.0);
-                    const double s21 = obs ? mc.C2 : 0.0, s22 = obs ? R : 1.0;
                     nj[j] = n;
                     dj[j] = d;
-                    nn[j] = fma(s11, n, s12 * d);
-                    dd[j] = fma(s21, n, s22 * d);
+                    nn[j] = fma(s11[j], n, s12[j] * d);
+                    dd[j] = fma(s21[j], n, Rj[j] * d);
                     n = nn[j];
                     d = dd[j];
                 }
@@ -265,23 +273,22 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             for (int j = 0; j < L; j++) {
                 const bool real = t0 + j < T, obs = (bits >> j) & 1u;
                 const double rho = fast_rcp(dd[j]), rn = fast_rcp(nn[j]);
-                const double K = obs ? Cc * nj[j] * rho : 0.0;
-                const double nu = obs ? R * nj[j] : nj[j];
+                const double K = Cj[j] * nj[j] * rho;
+                const double nu = Rj[j] * nj[j];
                 const double vu = nu * rho;
-                const double J = real ? A * nu * rn : 1.0;
+                const double J = real ? Aj[j] * nu * rn : 1.0;
                 Kg[j] = K;
                 rS[j] = obs ? dj[j] * rho : 0.0; // 1/Sigma
-                alpha[j] = real ? fma(-mc.AC, K, A) : 1.0;
+                alpha[j] = fma(-Aj[j] * Cj[j], K, Aj[j]);
                 Jg[j] = J;
-                Lg[j] = real ? vu * fma(-A, J, 1.0) : 0.0; // Vu - J^2 Vp' with J Vp' = A Vu
+                Lg[j] = real ? vu * fma(-Aj[j], J, 1.0) : 0.0; // Vu - J^2 Vp' with J Vp' = A Vu
             }
             double q[L + 1], Pc[L + 1];
             q[0] = 0.0;
             Pc[0] = 1.0;
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                const bool real = t0 + j < T;
-                const double beta = real ? fma(A * Kg[j], ymd[j], Bu[j]) : 0.0;
+                const double beta = fma(Aj[j] * Kg[j], ymd[j], Bu[j]); // rows at or beyond T are zero
                 q[j + 1] = fma(alpha[j], q[j], beta);
                 Pc[j + 1] = alpha[j] * Pc[j];
             }

@@ -40,6 +40,9 @@ struct WideParams {
     int max_T;      // longest series of the plan
     int blob_smem;  // bytes reserved for the series blob at the start of dynamic shared memory
     int cost_u, cost_m;
+#ifdef LDSR_PHASE_CLOCKS
+    long long *clk; // development build: [CTA][NW][21] cycles per phase of the iteration loop
+#endif
 };
 
 // rows of the trajectory area: one per step, and room for what aliases it after phase C (the NW slots
@@ -494,6 +497,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
     const int sa = sbound[warp], sb = sbound[warp + 1];
     const int ua = pbound[warp], ue = pbound[warp + 1];
 
+#ifdef LDSR_PHASE_CLOCKS
+    long long pc[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
     for (int it = 0; it < P.chunk; ++it) {
         if (!__any_sync(FULL, live)) break;
         SplitConst<PQ, UW> k;
@@ -565,6 +571,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             }
         }
 
+        LDSR_PHASE_MARK(16);
         // ================= P1: variance map of my piece =================
         if (warp == NW - 1) {
             uvar_constants<UW>(k.A2, k.Q, k.aVW, UV); // nothing is to the right of the last piece
@@ -591,7 +598,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             MC[(warp * 4 + 2) * 32] = m21;
             MC[(warp * 4 + 3) * 32] = m22;
         }
+        LDSR_PHASE_MARK(0);
         __syncthreads(); // B1: Bu, Dv, the maps and the variance-sum constants are in place
+        LDSR_PHASE_MARK(1);
         double Vin = th.V1; // prior variance entering my piece
         {
             double n = th.V1, d = 1.0;
@@ -653,7 +662,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             o[8 * 32] = c.Lc;
             o[9 * 32] = c.Vq;
         }
+        LDSR_PHASE_MARK(2);
         __syncthreads(); // B2
+        LDSR_PHASE_MARK(3);
 
         // ---- chain the pieces: x_in of every piece, likelihood (identical in every warp)
         double gk[NP];
@@ -705,6 +716,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             }
         }
 
+        LDSR_PHASE_MARK(17);
         // ================= P4: backward over my piece: scalar sums, Xs_t -> shared memory =================
         WideSums ws;
         ws.zero();
@@ -744,7 +756,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 ws.V0 = Vs1;
             }
         }
+        LDSR_PHASE_MARK(4);
         __syncthreads(); // B3: every Xs_t is in place
+        LDSR_PHASE_MARK(5);
 
         // ================= phase C: the row sums of EM.cpp:153-161, 184-193 =================
         Stats<PQ> st;
@@ -798,7 +812,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 for (int i = 0; i < PQ; i++) st.Sxv[i] = fma(xo, row[i], st.Sxv[i]);
             }
         }
+        LDSR_PHASE_MARK(6);
         __syncthreads(); // B4: nobody reads the trajectory any more: it becomes the partial sums
+        LDSR_PHASE_MARK(7);
         st.Syx = ws.Syx;
         st.Sxx = ws.Sxx;
         st.Sxxv = ws.Sxxv;
@@ -811,7 +827,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         st.XT = ws.XT;
         st.VT = ws.VT;
         stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
+        LDSR_PHASE_MARK(8);
         __syncthreads(); // B5
+        LDSR_PHASE_MARK(9);
 
         // ================= M-step (EM.cpp:139-229), spread over the warps =================
         // (1) totals: warp w adds the NW partial sums of the entries w, w + NW, ...
@@ -824,7 +842,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             for (int w = 1; w < NW; ++w) a += ST[((size_t)w * NST + j) * 32];
             TOT[j * 32] = a;
         }
+        LDSR_PHASE_MARK(10);
         __syncthreads(); // B5b
+        LDSR_PHASE_MARK(11);
         // (2) the three matrix-vector products of the block elimination (lds_math.cuh), one row per warp at a time
         {
             const double *__restrict__ svv_inv = gc + 2 + 2 * PQ;
@@ -840,7 +860,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 ZW[rr * 32] = acc;
             }
         }
+        LDSR_PHASE_MARK(12);
         __syncthreads(); // B5c
+        LDSR_PHASE_MARK(13);
         // (3) the scalars: warp 0 the observation block (C, D, R), warp 1 the transition block (A, B, Q, mu1, V1)
         if (warp == 0) {
             if (live) {
@@ -898,7 +920,9 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             TH[4 * 32] = th.mu1;
             TH[5 * 32] = th.V1;
         }
+        LDSR_PHASE_MARK(14);
         __syncthreads(); // B6: the new theta is published
+        LDSR_PHASE_MARK(15);
         th.A = TH[0 * 32];
         th.C = TH[1 * 32];
         th.Q = TH[2 * 32];
@@ -911,6 +935,10 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         }
     }
 
+#ifdef LDSR_PHASE_CLOCKS
+    if (lane == 0 && WP.clk)
+        for (int i = 0; i < 21; i++) WP.clk[((size_t)blockIdx.x * NW + warp) * 21 + i] = pc[i];
+#endif
     if (warp == 0 && valid) {
         double *g = P.theta + (size_t)fit * TL;
         g[0] = th.A;

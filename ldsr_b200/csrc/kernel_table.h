@@ -62,9 +62,10 @@ struct KernelTable {
     cudaError_t (*em_wide_prepare)(size_t smem_bytes);
     cudaError_t (*em_wide)(const WideParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     // small-batch scan kernel: scan_l == 0 when this width has none (PQ > SCAN_MAX_PQ); series up to
-    // scan_l * 32 * SCAN_MAX_WARPS steps; `warps` = ceil(T_max / (32 scan_l))
+    // scan_l * 32 * SCAN_MAX_WARPS steps.  Launched with 2 or 4 steps per thread; EmParams.max_seg carries
+    // the longest series of the plan (the block is sized from it).
     int scan_l;
-    cudaError_t (*em_scan)(const EmParams &, int n_tasks, int warps, cudaStream_t);
+    cudaError_t (*em_scan)(const EmParams &, int n_tasks, int steps_per_thread, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);
     cudaError_t (*mstep)(const MstepParams &, cudaStream_t);
     cudaError_t (*propagate)(const SmootherParams &, cudaStream_t);

@@ -116,8 +116,15 @@ template <int PQV, bool HAVE> struct ScanLaunch { // widths above SCAN_MAX_PQ ha
     static cudaError_t launch(const EmParams &, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 };
 template <int PQV> struct ScanLaunch<PQV, true> {
-    static cudaError_t launch(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
-        em_scan_kernel<PQV, SCAN_L><<<n_tasks, warps * 32, 0, st>>>(p);
+    static cudaError_t launch(const EmParams &p, int n_tasks, int steps_per_thread, cudaStream_t st) {
+        // one thread per `steps_per_thread` steps, whole warps
+        const int threads = (((p.max_seg + steps_per_thread - 1) / steps_per_thread + 31) / 32) * 32;
+        if (steps_per_thread == 2)
+            em_scan_kernel<PQV, 2><<<n_tasks, threads, 0, st>>>(p);
+        else if (steps_per_thread == 4)
+            em_scan_kernel<PQV, 4><<<n_tasks, threads, 0, st>>>(p);
+        else
+            return cudaErrorNotSupported;
         return cudaGetLastError();
     }
 };
@@ -168,7 +175,13 @@ cudaError_t propagate(const SmootherParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t rep(const RepParams &p, cudaStream_t st) {
-    rep_kernel<PQ><<<(p.n_reps + 127) / 128, 128, 0, st>>>(p);
+    const size_t smem = rep_smem_bytes(p.z != nullptr);
+    // above the 48 KB default: opt in (per device; a cheap call, repeated rather than cached per device)
+    cudaError_t e = cudaFuncSetAttribute(rep_kernel<PQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)rep_smem_bytes(true));
+    if (e != cudaSuccess) return e;
+    const int per_cta = REP_WARPS * 32;
+    rep_kernel<PQ><<<(p.n_reps + per_cta - 1) / per_cta, per_cta, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 #ifndef LDSR_HOST_SIM
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #else
-    r = (double)(1.0f / (float)x); // a seed of similar accuracy for the CPU emulation (tests/host_simt)
+    r = 1.0 / x; // CPU emulation (tests/host_simt): the Newton steps below leave it unchanged
 #endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);

@@ -672,8 +672,10 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // small batches of narrow inputs: one CTA per fit, the time axis spread over its threads (em_scan_kernel.cuh).
     // A batched kernel needs 10 us per iteration however few fits it holds; the scan kernel 2-3 us for up
     // to one fit per SM and about n/148 times that beyond, so it wins below a few hundred fits.
-    const int scan_warps = P->kt->scan_l > 0 ? (P->max_T + 32 * P->kt->scan_l - 1) / (32 * P->kt->scan_l) : 0;
-    const bool scan_ok = P->kt->scan_l > 0 && scan_warps <= SCAN_MAX_WARPS;
+    // steps per thread: 2 while the series fits 8 warps that way (T <= 512), else 4 (T <= 1024)
+    int scan_steps = P->max_T <= 2 * 32 * SCAN_MAX_WARPS ? 2 : 4;
+    if (const char *ev = std::getenv("LDSR_SCAN_L")) scan_steps = std::atoi(ev) == 4 ? 4 : scan_steps; // development
+    const bool scan_ok = P->kt->scan_l > 0 && P->max_T <= scan_steps * 32 * SCAN_MAX_WARPS;
     const bool use_scan = scan_ok && nf <= SCAN_MAX_FITS && (variant == 0 || variant == 5);
     if (variant == 5 && !use_scan)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 5 (scan kernel) needs input width <= %d, T <= %d and at most %d fits",
@@ -801,7 +803,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             CU(cudaEventRecord(a, st));
         }
         if (use_scan) {
-            CU(P->kt->em_scan(ep, grid, scan_warps, st));
+            ep.max_seg = P->max_T; // the scan kernel sizes its block from the longest series
+            CU(P->kt->em_scan(ep, grid, scan_steps, st));
         } else if (use_wide) {
             WideParams wp;
             wp.em = ep;
@@ -813,7 +816,32 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             // about 8.5 instructions per unobserved step, 90 per step of an observed unit)
             wp.cost_u = P->kt->split_uw * 17 / 2;
             wp.cost_m = P->kt->wide_mseg * 90;
+#ifdef LDSR_PHASE_CLOCKS
+            if (!sp_clk_last) cudaMalloc(&sp_clk_last, sizeof(long long) * 4096 * 21 * 8);
+            wp.clk = (c == 1 && grid <= 2048) ? sp_clk_last : nullptr;
+#endif
             CU(P->kt->em_wide(wp, grid, smem, st));
+#ifdef LDSR_PHASE_CLOCKS
+            if (c == 1 && grid <= 2048) {
+                const int nw = P->kt->wide_nw;
+                std::vector<long long> h((size_t)grid * nw * 21);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h.data(), sp_clk_last, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                static const char *names[21] = {"P1", "B1 wait", "prefix+P2", "B2 wait", "P4", "B3 wait", "phase C",
+                                                "B4 wait", "store sums", "B5 wait", "totals", "B5b wait", "matvec rows",
+                                                "B5c wait", "M-step scalars", "B6 wait", "phase A", "chain+stop", "-", "-", "-"};
+                std::fprintf(stderr, "[ldsr] wide kernel, phase clocks of launch 1 (cycles per iteration, mean over %d CTAs), per warp:\n", grid);
+                for (int i = 0; i < 18; i++) {
+                    std::fprintf(stderr, "[ldsr]   %-14s", names[i]);
+                    for (int w = 0; w < nw; w++) {
+                        double sum = 0;
+                        for (int b = 0; b < grid; b++) sum += (double)h[((size_t)b * nw + w) * 21 + i];
+                        std::fprintf(stderr, " %8.0f", sum / grid / chunk);
+                    }
+                    std::fprintf(stderr, "\n");
+                }
+            }
+#endif
         } else if (use_split) {
             SplitParams sp;
             sp.em = ep;
@@ -1295,6 +1323,9 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
     return Err();
 }
 
+// device time (CUDA events) of the kernels of the last ldsr_rep_batch* call of this thread (ldsr_last_device_ms)
+static thread_local double g_last_device_ms = 0.0;
+
 // ---- single-step batched entry points (one device: ctx device 0) ----------------------------
 enum class StepKind { Smoother, Propagate };
 
@@ -1483,46 +1514,137 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
             for (void *p : *h) pool->release(p);
         }
     } rel{pool, &held};
-    const size_t tot = (size_t)n * n_reps;
-    double *dth, *du, *dv, *dz = nullptr, *dstage, *dout;
+    double *dth, *du, *dv, *dz_all = nullptr;
     CU(dal(th.size() * 8, (void **)&dth));
     CU(dal(up.size() * 8, (void **)&du));
     CU(dal(vp.size() * 8, (void **)&dv));
-    CU(dal(tot * 8, (void **)&dstage));
-    CU(dal(tot * 8, (void **)&dout));
     CU(cudaMemcpy(dth, th.data(), th.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(du, up.data(), up.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dv, vp.data(), vp.size() * 8, cudaMemcpyHostToDevice));
-    if (z) {
-        CU(dal((size_t)n_reps * (1 + 2 * (size_t)n) * 8, (void **)&dz));
-        CU(cudaMemcpy(dz, z, (size_t)n_reps * (1 + 2 * (size_t)n) * 8, cudaMemcpyHostToDevice));
-    } else if (r_seed) { // the reference's own stream: set.seed(*r_seed); rnorm(...) in replicate order
-        const long long nz = (long long)n_reps * (1 + 2 * (long long)n);
-        CU(dal((size_t)nz * 8, (void **)&dz));
-        CU(r_rnorm_device(*r_seed, nz, dz, 0));
+    const size_t zrow = 1 + 2 * (size_t)n;
+    if (r_seed) { // the reference's own stream: set.seed(*r_seed); rnorm(...) in replicate order, made on the device
+        const long long nz = (long long)n_reps * (long long)zrow;
+        CU(dal((size_t)nz * 8, (void **)&dz_all));
+        CU(r_rnorm_device(*r_seed, nz, dz_all, 0));
     }
-    // one pass per requested output keeps the staging footprint at 2 arrays
+    // One pass over the replicates in chunks: the kernel of chunk c+1 runs while chunk c crosses PCIe into a
+    // pinned slot and chunk c-1 is copied from its slot into the caller's (pageable) arrays by host threads.
     double *outs[3] = {simX, simY, simQ};
-    for (int k = 0; k < 3; k++) {
-        if (!outs[k]) continue;
+    int n_out = 0;
+    for (double *o : outs) n_out += o ? 1 : 0;
+    g_last_device_ms = 0.0;
+    if (n_out == 0) return Err();
+    int chunk = (int)std::max<size_t>(128, ((size_t)24 << 20) / ((size_t)n * 8)); // ~24 MB per output and chunk
+    chunk = std::min(n_reps, (chunk + 127) / 128 * 128);
+    const int n_chunks = (n_reps + chunk - 1) / chunk;
+    const size_t slot_doubles = (size_t)n_out * chunk * n;
+    constexpr int SLOTS = 2;
+    double *d_out[SLOTS] = {nullptr, nullptr}, *h_out[SLOTS] = {nullptr, nullptr}, *d_z[SLOTS] = {nullptr, nullptr};
+    cudaEvent_t ev_k[SLOTS] = {nullptr, nullptr}, ev_c[SLOTS] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_t;
+    cudaStream_t sk = nullptr, sc = nullptr;
+    struct Cleanup {
+        DevicePool *pool;
+        double **h;
+        cudaEvent_t *a, *b;
+        std::vector<cudaEvent_t> *t;
+        cudaStream_t *sk, *sc;
+        ~Cleanup() {
+            if (*sk) cudaStreamSynchronize(*sk);
+            if (*sc) cudaStreamSynchronize(*sc);
+            for (int i = 0; i < SLOTS; i++) {
+                if (h[i]) pool->release_pinned(h[i]);
+                if (a[i]) cudaEventDestroy(a[i]);
+                if (b[i]) cudaEventDestroy(b[i]);
+            }
+            for (cudaEvent_t e : *t) cudaEventDestroy(e);
+            if (*sk) pool->put_stream(*sk);
+            if (*sc) pool->put_stream(*sc);
+        }
+    } cleanup{pool, h_out, ev_k, ev_c, &ev_t, &sk, &sc};
+    CU(pool->get_stream(&sk));
+    CU(pool->get_stream(&sc));
+    for (int i = 0; i < SLOTS && i < n_chunks; i++) {
+        CU(dal(slot_doubles * 8, (void **)&d_out[i]));
+        void *hp = nullptr;
+        CU(pool->alloc_pinned(slot_doubles * 8, &hp));
+        h_out[i] = static_cast<double *>(hp);
+        if (z) CU(dal((size_t)chunk * zrow * 8, (void **)&d_z[i]));
+        CU(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
+    }
+    auto copy_out = [&](int c) { // pinned slot -> the caller's arrays, a few host threads
+        const int slot = c % SLOTS, r0 = c * chunk, nr = std::min(chunk, n_reps - r0);
+        const size_t bytes = (size_t)nr * n * 8;
+        std::vector<std::thread> th;
+        int k = 0;
+        for (int o = 0; o < 3; o++) {
+            if (!outs[o]) continue;
+            const char *src = reinterpret_cast<const char *>(h_out[slot] + (size_t)k * chunk * n);
+            char *dst = reinterpret_cast<char *>(outs[o] + (size_t)r0 * n);
+            const int parts = bytes > ((size_t)4 << 20) ? 2 : 1;
+            for (int pi = 0; pi < parts; pi++) {
+                const size_t lo = bytes * pi / parts, hi = bytes * (pi + 1) / parts;
+                th.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
+            }
+            k++;
+        }
+        for (auto &t : th) t.join();
+    };
+    for (int c = 0; c < n_chunks; c++) {
+        const int slot = c % SLOTS, r0 = c * chunk, nr = std::min(chunk, n_reps - r0);
+        if (c >= SLOTS) { // the slot's previous chunk must have left the device, then leave the pinned block
+            CU(cudaEventSynchronize(ev_c[slot]));
+            copy_out(c - SLOTS);
+        }
         RepParams rp;
         rp.theta = dth;
         rp.u = du;
         rp.v = dv;
-        rp.z = dz;
+        rp.z = nullptr;
+        if (z) {
+            CU(cudaMemcpyAsync(d_z[slot], z + (size_t)r0 * zrow, (size_t)nr * zrow * 8, cudaMemcpyHostToDevice, sk));
+            rp.z = d_z[slot];
+        } else if (dz_all) {
+            rp.z = dz_all + (size_t)r0 * zrow;
+        }
         rp.seed = seed;
         rp.n = n;
-        rp.n_reps = n_reps;
+        rp.n_reps = nr;
+        rp.rep0 = r0;
         rp.mu = mu;
         rp.exp_trans = exp_trans;
-        rp.simX = k == 0 ? dstage : nullptr;
-        rp.simY = k == 1 ? dstage : nullptr;
-        rp.simQ = k == 2 ? dstage : nullptr;
-        CU(kt->rep(rp, 0));
-        dim3 grid((n_reps + 31) / 32, (n + 31) / 32), block(32, 8);
-        transpose_kernel<<<grid, block>>>(dstage, dout, n, n_reps); // [n][reps] -> [reps][n]
-        CU(cudaGetLastError());
-        CU(cudaMemcpy(outs[k], dout, tot * 8, cudaMemcpyDeviceToHost));
+        int k = 0;
+        double *slot_out[3] = {nullptr, nullptr, nullptr};
+        for (int o = 0; o < 3; o++)
+            if (outs[o]) slot_out[o] = d_out[slot] + (size_t)(k++) * chunk * n;
+        rp.simX = slot_out[0];
+        rp.simY = slot_out[1];
+        rp.simQ = slot_out[2];
+        cudaEvent_t ta = nullptr, tb = nullptr;
+        CU(cudaEventCreate(&ta));
+        ev_t.push_back(ta);
+        CU(cudaEventCreate(&tb));
+        ev_t.push_back(tb);
+        CU(cudaEventRecord(ta, sk));
+        CU(kt->rep(rp, sk));
+        CU(cudaEventRecord(tb, sk));
+        CU(cudaEventRecord(ev_k[slot], sk));
+        CU(cudaStreamWaitEvent(sc, ev_k[slot], 0));
+        CU(cudaMemcpyAsync(h_out[slot], d_out[slot], slot_doubles * 8, cudaMemcpyDeviceToHost, sc));
+        CU(cudaEventRecord(ev_c[slot], sc));
+        // the next kernel into this slot must wait for this copy
+        CU(cudaStreamWaitEvent(sk, ev_c[slot], 0));
+    }
+    for (int c = std::max(0, n_chunks - SLOTS); c < n_chunks; c++) {
+        CU(cudaEventSynchronize(ev_c[c % SLOTS]));
+        copy_out(c);
+    }
+    CU(cudaStreamSynchronize(sk));
+    for (size_t i = 0; i + 1 < ev_t.size(); i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev_t[i], ev_t[i + 1]));
+        g_last_device_ms += ms;
     }
     return Err();
 }
@@ -1647,6 +1769,8 @@ struct ldsr_r_rng {
     ldsr::RMersenne g;
     explicit ldsr_r_rng(unsigned seed) : g(seed) {}
 };
+
+double ldsr_last_device_ms(void) { return g_last_device_ms; }
 
 int ldsr_r_rng_create(unsigned int seed, ldsr_r_rng **out, char *errbuf, int errlen) {
     if (!out) return report(fail(LDSR_ERR_ARG, "out is NULL"), errbuf, errlen);

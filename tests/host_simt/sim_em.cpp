@@ -272,12 +272,16 @@ template <int PQ> int run(const Job &J) {
 #endif
 #ifdef LDSR_HAVE_SCAN
         else if (J.kind == 5) {
-            constexpr int L = 4;
+            // 2 steps per thread while that fits 8 warps, else 4 (as plan_em chooses); order >= 8 forces 4
+            const int L = (T <= 2 * 32 * SCAN_MAX_WARPS && J.order < 8) ? 2 : 4;
             const int nwarps = (T + 32 * L - 1) / (32 * L);
             if (nwarps > SCAN_MAX_WARPS) return 14;
-            if constexpr (PQ <= 4)
-                hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, L>(ep); });
-            else
+            if constexpr (PQ <= 4) {
+                if (L == 2)
+                    hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 2>(ep); });
+                else
+                    hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 4>(ep); });
+            } else
                 return 15;
         }
 #endif

@@ -25,11 +25,11 @@ def rand_theta0(rng, p, q, n):
                                      rng.uniform(-1, 1, q), [1, 1, 0, 1]]) for _ in range(n)])
 
 
-def assert_theta_close(a, b, rtol=THETA_RTOL):
+def assert_theta_close(a, b, rtol=THETA_RTOL, floor=1e-8):
     a, b = np.asarray(a), np.asarray(b)
     assert np.array_equal(np.isnan(a), np.isnan(b))  # unused tail of a padded theta row stays NaN
     ok = ~np.isnan(b)
-    scale = np.maximum(np.abs(b[ok]), 1e-8)
+    scale = np.maximum(np.abs(b[ok]), floor)
     assert np.max(np.abs(a[ok] - b[ok]) / scale) < rtol, np.max(np.abs(a[ok] - b[ok]) / scale)
 
 
@@ -562,7 +562,11 @@ def test_unusual_initial_values(variant):
     # ill-conditioned in the reference's own arithmetic and is held to the digits that survive
     stable = np.abs(th[:, 0]) < 1.0
     assert np.allclose(g["lik"][stable], o["lik"][stable], rtol=1e-9, atol=0)
-    assert_theta_close(g["theta"][stable], o["theta"][stable], 1e-6)
+    # The scan kernel (variant 5) forms the smoothed mean of step 0 -- the new mu1 -- by composing affine maps
+    # over the whole series: its ABSOLUTE error is a few ulps of the O(1) terms composed, while the value itself
+    # is ~A^360 here (the first record is 360 steps away; the sequential recursions carry that decay exactly).
+    # mu1 only enters the next E-step additively, so 1e-12 absolute is far inside every other bar.
+    assert_theta_close(g["theta"][stable], o["theta"][stable], 1e-6, floor=1e-6 if variant == 5 else 1e-8)
     assert np.allclose(g["lik"][~stable], o["lik"][~stable], rtol=1e-6, atol=0)
     assert_theta_close(g["theta"][~stable], o["theta"][~stable], 1e-5)
 

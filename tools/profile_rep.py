@@ -24,16 +24,18 @@ for want in (("simX", "simY", "simQ"), ("simQ",)):
         t0 = time.perf_counter()
         r = _lib.rep_batch(th, u, u, T, n_reps, seed=20261018, mu=mu, want=want)
         dt = time.perf_counter() - t0
-    nb = sum(a.nbytes for a in r.values())
-    print("LDS_rep %d replicates x T=%d, outputs %s: %.1f ms wall (%.2f GB to the host, %.1f M triples/s)"
-          % (n_reps, T, "+".join(want), dt * 1e3, nb / 1e9, n_reps * T / dt / 1e6))
+    nb = sum(a.nbytes for k, a in r.items() if k != "device_ms")
+    print("LDS_rep %d replicates x T=%d, outputs %s: %.1f ms wall (%.2f GB to the host, %.1f M triples/s); "
+          "kernels %.3f ms on the device = %.0f GB/s of output"
+          % (n_reps, T, "+".join(want), dt * 1e3, nb / 1e9, n_reps * T / dt / 1e6, r["device_ms"],
+             nb / (r["device_ms"] * 1e-3) / 1e9))
 # the same replicates as `set.seed(1); LDS_rep(...)` in R: R's stream generated on the device (r_rng.cuh)
 for rep in range(2):
     t0 = time.perf_counter()
     r = _lib.rep_batch(th, u, u, T, n_reps, mu=mu, want=("simQ",), r_seed=1)
     dt = time.perf_counter() - t0
 print("LDS_rep %d replicates, simQ, R's own stream (set.seed(1)) generated on the device: %.1f ms wall "
-      "(%.1f M normals)" % (n_reps, dt * 1e3, n_reps * (1 + 2 * T) / 1e6))
+      "(%.1f M normals); replicate kernels %.3f ms" % (n_reps, dt * 1e3, n_reps * (1 + 2 * T) / 1e6, r["device_ms"]))
 # propagate on n_reps thetas (perturbed copies of the NP theta)
 rng = np.random.default_rng(1)
 n_th = min(n_reps, 100_000)

@@ -61,7 +61,7 @@ def main():
         assert np.allclose(s["lik"], so["lik"], rtol=1e-9)
     _lib.propagate_batch(ser, [0], [held[0]], np.zeros(5, dtype=int), th)
     r = _lib.rep_batch(th[0], u, u, y.size, 300, seed=1, mu=mu)
-    assert all(np.isfinite(v).all() for v in r.values())
+    assert all(np.isfinite(v).all() for v in r.values())  # incl. the device_ms scalar
     d, T = 3, 700
     A = 0.5 * np.eye(d)
     thd = np.concatenate([A.ravel(), 0.1 * rng.standard_normal(d * 2), rng.standard_normal(d), [0.1, 0.2],
