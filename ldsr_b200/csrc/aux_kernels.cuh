@@ -366,7 +366,8 @@ template <int PQ> __global__ void __launch_bounds__(REP_WARPS * 32) rep_kernel(c
             }
             __syncwarp();
         }
-        for (int j = 0; j < cnt; ++j) {
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) { // only x chains from step to step: the draws of several steps overlap
             const int t = t0 + j;
             double zq, ze;
             if (have_z) {

@@ -65,6 +65,7 @@ __host__ __device__ inline size_t wide_smem_bytes(int pq, int nw, int max_T, int
     b += (size_t)((max_T + 31) / 32) * 128;     // MW: observed-bit words of the CTA's fits
     b += 2 * (((size_t)max_units * 4 + 15) & ~size_t(15)); // unit table, Dv row of each unit
     b += 256;                                   // piece bounds, slice bounds
+    b += ((size_t)(max_msteps > 0 ? max_msteps : 1) * 4 + 15) & ~size_t(15); // time step of every Dv row
     return b;
 }
 
@@ -349,6 +350,85 @@ __device__ __forceinline__ void wide_smooth_short(double A, double A2, double Q,
     cH = H0;
 }
 
+// ---- phases A and C: register blocking over fits --------------------------------------------------
+// With one fit per lane a broadcast row load delivers 16 bytes to each of 32 lanes -- 512 B through the
+// 128 B/clk shared-memory port, 4 cycles per LDS.128 -- for two multiply-adds per lane: the row phases
+// were bound by that port (8000 cycles of loads per iteration and phase against 2000-4000 cycles of FP64
+// pipe; profiles/em_r02_wide_phase_clocks.txt).  So in these phases a lane takes FPL fits and a
+// sub-warp GROUP of 32 / FPL lanes one time step: an LDS.128 then brings FPL different rows to the warp
+// and every loaded double feeds FPL multiply-adds.  Lane l of group g = l / LG (LG = 32 / FPL lanes) holds
+// the fits (l % LG) + k LG, k < FPL; the groups split the warp's slice of the time axis.  Sums over time
+// come back to the lane-per-fit layout by a transposing shuffle reduction (lane l ends with fit l).
+#ifdef LDSR_WIDE_FPL // development: force the blocking factor
+__host__ __device__ constexpr int wide_fpl(int) { return LDSR_WIDE_FPL; }
+#else
+__host__ __device__ constexpr int wide_fpl(int pq) { return pq <= 16 ? 2 : 1; } // measured at PQ = 10: 2 beats 4 and 1
+#endif
+
+// sum over the FPL groups; on return out[i] is the total of MY fit (k = my group index) in every lane
+template <int FPL, int NV>
+__device__ __forceinline__ void group_transpose_sum(double (&v)[FPL][NV], double (&out)[NV], int lane) {
+    static_assert(FPL == 1 || FPL == 2 || FPL == 4, "fits per lane");
+    if constexpr (FPL == 1) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) out[i] = v[0][i];
+    } else if constexpr (FPL == 2) {
+        const bool upper = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const double send = upper ? v[0][i] : v[1][i], keep = upper ? v[1][i] : v[0][i];
+            out[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+    } else {
+        const bool upper = (lane & 16) != 0, up2 = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            // groups {0,1} keep the fits k = 0, 1 and groups {2,3} k = 2, 3 ...
+            const double s0 = upper ? v[0][i] : v[2][i], k0 = upper ? v[2][i] : v[0][i];
+            const double s1 = upper ? v[1][i] : v[3][i], k1 = upper ? v[3][i] : v[1][i];
+            const double w0 = k0 + __shfl_xor_sync(FULL, s0, 16), w1 = k1 + __shfl_xor_sync(FULL, s1, 16);
+            // ... then each group keeps its own
+            const double send = up2 ? w0 : w1, keep = up2 ? w1 : w0;
+            out[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+}
+
+// dst[m][fit] = coef[fit] . rows[t(m)] for m = 0 .. n-1, t(m) = list ? list[m] : m  (FPL fits per lane, one row per
+// group at a time)
+//   coef: [PQ][32] in shared memory (B or D of the CTA's fits); rows: the series' [t][PQ] rows; dst: [m][32]
+template <int PQ, int FPL>
+__device__ __forceinline__ void rows_times_coef(const double *__restrict__ coef, const double *__restrict__ rows,
+                                                const int *__restrict__ list, double *__restrict__ dst, int n, int lane) {
+    constexpr int LG = 32 / FPL;
+    const int g = lane / LG, lg = lane % LG;
+    double cf[FPL][PQ];
+#pragma unroll
+    for (int k = 0; k < FPL; k++)
+#pragma unroll
+        for (int i = 0; i < PQ; i++) cf[k][i] = coef[i * 32 + lg + k * LG];
+    const int len = (n + FPL - 1) / FPL; // contiguous sub-slices, one per group
+    const int lo = g * len, hi = (lo + len < n) ? lo + len : n;
+#pragma unroll 1
+    for (int m = lo; m < hi; ++m) {
+        const int t = list ? list[m] : m;
+        double r[PQ];
+        load_vec<PQ>(rows + (size_t)t * PQ, r);
+#pragma unroll
+        for (int k = 0; k < FPL; k++) {
+            double a0 = cf[k][0] * r[0], a1 = cf[k][1] * r[1];
+#pragma unroll
+            for (int i = 2; i < PQ; i++) {
+                if (i & 1)
+                    a1 = fma(cf[k][i], r[i], a1);
+                else
+                    a0 = fma(cf[k][i], r[i], a0);
+            }
+            dst[(size_t)m * 32 + lg + k * LG] = a0 + a1;
+        }
+    }
+}
+
 template <int PQ, int NW, int MSEG, int UW>
 __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP) {
     static_assert(MSEG == 4 || MSEG == 8, "observed unit is 4 or 8 steps");
@@ -395,6 +475,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
     int *const ubase = units + ((WP.max_units + 3) & ~3);                           // [max_units] Dv row of the unit
     int *const pbound = ubase + ((WP.max_units + 3) & ~3);                          // [NP + 1]
     int *const sbound = pbound + 32;                                                // [NW + 1]
+    int *const mlist = sbound + 32;                                                 // [max_msteps] time step of Dv row m
     double *const ST = TR; // [NW][NST]: the trajectory is dead after phase C
 
     // ---- per-lane fit state: every warp holds the same 32 fits
@@ -467,7 +548,11 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                         ubase[nu] = nm;
                     }
                     nu++;
-                    if (type != UNIT_US) nm += single ? 1 : MSEG;
+                    if (type != UNIT_US) {
+                        const int len = single ? 1 : MSEG;
+                        if (lane < len) mlist[nm + lane] = t + lane;
+                        nm += len;
+                    }
                 });
             }
         }
@@ -488,12 +573,14 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 sbound[w] = t;
             }
             sbound[NW] = T;
-            pbound[NP + 1] = nu; // number of units (phase A walks the whole table)
+            pbound[NP + 1] = nu; // number of units
+            pbound[NP + 2] = nm; // number of Dv rows = steps inside observed units
         }
     }
     mbar_wait(&bar, phase);
     __syncthreads();
-    const int n_units = pbound[NP + 1];
+    const int n_msteps = pbound[NP + 2];
+    const int ma = (int)(((long long)n_msteps * warp) / NW), mb = (int)(((long long)n_msteps * (warp + 1)) / NW);
     const int sa = sbound[warp], sb = sbound[warp + 1];
     const int ua = pbound[warp], ue = pbound[warp + 1];
 
@@ -506,70 +593,10 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         k.set(th);
 
         // ================= phase A: Bu_t = B.u_t over my slice, Dv_t = D.v_t of the observed units =================
-        {
-            double Bv[PQ];
-#pragma unroll
-            for (int i = 0; i < PQ; i++) Bv[i] = TB[i * 32];
-            const double *__restrict__ row = us + sa * PQ;
-            double *__restrict__ o = TR + sa * 32;
-            int n = sb - sa;
-#pragma unroll 1
-            for (; n >= 4; n -= 4, row += 4 * PQ, o += 4 * 32) {
-                double r[4 * PQ];
-                load_vec<4 * PQ>(row, r);
-                // two partial sums per row: eight independent chains of PQ/2 multiply-adds
-                double lo[4], hi[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    lo[j] = Bv[0] * r[j * PQ];
-                    hi[j] = Bv[1] * r[j * PQ + 1];
-                }
-#pragma unroll
-                for (int i = 2; i < PQ; i++) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (i & 1)
-                            hi[j] = fma(Bv[i], r[j * PQ + i], hi[j]);
-                        else
-                            lo[j] = fma(Bv[i], r[j * PQ + i], lo[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) o[j * 32] = lo[j] + hi[j];
-            }
-#pragma unroll 1
-            for (; n > 0; --n, row += PQ, o += 32) {
-                double a = 0.0;
-#pragma unroll
-                for (int i = 0; i < PQ; i++) a = fma(Bv[i], row[i], a);
-                o[0] = a;
-            }
-        }
-        {
-            double Dq[PQ];
-#pragma unroll
-            for (int i = 0; i < PQ; i++) Dq[i] = TD[i * 32];
-#pragma unroll 1
-            for (int un = warp; un < n_units; un += NW) {
-                const int u0 = units[un];
-                if (!(u0 & (UNIT_M | UNIT_M1))) continue;
-                const int t0 = u0 & UNIT_T0, n = (u0 & UNIT_M) ? MSEG : 1;
-                double *__restrict__ o = YM + (size_t)ubase[un] * 32;
-                const double *__restrict__ row = vs + t0 * PQ;
-#pragma unroll 1
-                for (int j = 0; j < n; ++j, row += PQ) {
-                    double a0 = Dq[0] * row[0], a1 = Dq[1] * row[1];
-#pragma unroll
-                    for (int i = 2; i < PQ; i++) {
-                        if (i & 1)
-                            a1 = fma(Dq[i], row[i], a1);
-                        else
-                            a0 = fma(Dq[i], row[i], a0);
-                    }
-                    o[j * 32] = a0 + a1;
-                }
-            }
-        }
+        constexpr int FPL = wide_fpl(PQ);
+        double *const TRb = TR - lane, *const YMb = YM - lane; // un-offset bases: here a lane is not one fit
+        rows_times_coef<PQ, FPL>(TB - lane, us + (size_t)sa * PQ, nullptr, TRb + (size_t)sa * 32, sb - sa, lane);
+        rows_times_coef<PQ, FPL>(TD - lane, vs, mlist + ma, YMb + (size_t)ma * 32, mb - ma, lane); // my share of the Dv rows
 
         LDSR_PHASE_MARK(16);
         // ================= P1: variance map of my piece =================
@@ -763,56 +790,74 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         // ================= phase C: the row sums of EM.cpp:153-161, 184-193 =================
         Stats<PQ> st;
         st.zero();
-        { // transitions t = 0 .. T-2 of my slice: Tux += u_t Xs_t, Tx1u += u_t Xs_{t+1}
-            const int te = sb < T - 1 ? sb : T - 1;
-            const double *__restrict__ row = us + sa * PQ;
-            const double *__restrict__ zp = TR + sa * 32;
-            int n = te - sa;
-            double z0 = n > 0 ? zp[0] : 0.0;
+        {
+            constexpr int LG = 32 / FPL;
+            const int g = lane / LG, lg = lane % LG;
+            { // transitions t = 0 .. T-2 of my slice: Tux += u_t Xs_t, Tx1u += u_t Xs_{t+1}
+                const int te = sb < T - 1 ? sb : T - 1;
+                const int n = te > sa ? te - sa : 0, len = (n + FPL - 1) / FPL;
+                const int lo = sa + g * len, hi = (lo + len < sa + n) ? lo + len : sa + n;
+                double acc[FPL][2 * PQ];
+                double z[FPL];
+#pragma unroll
+                for (int k = 0; k < FPL; k++) {
+#pragma unroll
+                    for (int i = 0; i < 2 * PQ; i++) acc[k][i] = 0.0;
+                    z[k] = lo < hi ? TRb[(size_t)lo * 32 + lg + k * LG] : 0.0;
+                }
 #pragma unroll 1
-            for (; n >= 4; n -= 4, row += 4 * PQ, zp += 4 * 32) {
-                double r[4 * PQ], z[5];
-                load_vec<4 * PQ>(row, r);
-                z[0] = z0;
+                for (int t = lo; t < hi; ++t) {
+                    double r[PQ];
+                    load_vec<PQ>(us + (size_t)t * PQ, r);
 #pragma unroll
-                for (int j = 1; j <= 4; j++) z[j] = zp[j * 32];
+                    for (int k = 0; k < FPL; k++) {
+                        const double z1 = TRb[(size_t)(t + 1) * 32 + lg + k * LG];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-#pragma unroll
-                    for (int i = 0; i < PQ; i++) {
-                        st.Tux[i] = fma(r[j * PQ + i], z[j], st.Tux[i]);
-                        st.Tx1u[i] = fma(r[j * PQ + i], z[j + 1], st.Tx1u[i]);
+                        for (int i = 0; i < PQ; i++) {
+                            acc[k][i] = fma(r[i], z[k], acc[k][i]);
+                            acc[k][PQ + i] = fma(r[i], z1, acc[k][PQ + i]);
+                        }
+                        z[k] = z1;
                     }
                 }
-                z0 = z[4];
-            }
-#pragma unroll 1
-            for (; n > 0; --n, row += PQ, zp += 32) {
-                const double z1 = zp[32];
+                double tot[2 * PQ];
+                group_transpose_sum<FPL, 2 * PQ>(acc, tot, lane);
 #pragma unroll
                 for (int i = 0; i < PQ; i++) {
-                    st.Tux[i] = fma(row[i], z0, st.Tux[i]);
-                    st.Tx1u[i] = fma(row[i], z1, st.Tx1u[i]);
+                    st.Tux[i] = tot[i];
+                    st.Tx1u[i] = tot[PQ + i];
                 }
-                z0 = z1;
             }
-        }
-#pragma unroll 1
-        for (int un = warp; un < n_units; un += NW) { // observed units, dealt round-robin: Sxv += v_t Xs_t where observed
-            const int u0 = units[un];
-            if (!(u0 & (UNIT_M | UNIT_M1))) continue;
-            const int t0 = u0 & UNIT_T0, n = (u0 & UNIT_M) ? MSEG : 1;
-            const unsigned bits = mask_bits(t0, n);
-            const double *__restrict__ row = vs + t0 * PQ;
-            const double *__restrict__ zp = TR + t0 * 32;
-#pragma unroll 1
-            for (int j = 0; j < n; ++j, row += PQ) {
-                const double xo = ((bits >> j) & 1u) ? zp[j * 32] : 0.0;
+            { // my share of the steps inside observed units: Sxv += v_t Xs_t where the fit observes t
+                double acc[FPL][PQ];
 #pragma unroll
-                for (int i = 0; i < PQ; i++) st.Sxv[i] = fma(xo, row[i], st.Sxv[i]);
+                for (int k = 0; k < FPL; k++)
+#pragma unroll
+                    for (int i = 0; i < PQ; i++) acc[k][i] = 0.0;
+                const unsigned *const MWb = MW - lane;
+                const int n = mb - ma, len = (n + FPL - 1) / FPL;
+                const int lo = ma + g * len, hi = (lo + len < mb) ? lo + len : mb;
+#pragma unroll 1
+                for (int m = lo; m < hi; ++m) {
+                    const int t = mlist[m];
+                    double r[PQ];
+                    load_vec<PQ>(vs + (size_t)t * PQ, r);
+#pragma unroll
+                    for (int k = 0; k < FPL; k++) {
+                        const int f = lg + k * LG;
+                        const bool obs = (MWb[(t >> 5) * 32 + f] >> (t & 31)) & 1u;
+                        const double xo = obs ? TRb[(size_t)t * 32 + f] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < PQ; i++) acc[k][i] = fma(xo, r[i], acc[k][i]);
+                    }
+                }
+                double tot[PQ];
+                group_transpose_sum<FPL, PQ>(acc, tot, lane);
+#pragma unroll
+                for (int i = 0; i < PQ; i++) st.Sxv[i] = tot[i];
             }
         }
-        LDSR_PHASE_MARK(6);
+        LDSR_PHASE_MARK(18);
         __syncthreads(); // B4: nobody reads the trajectory any more: it becomes the partial sums
         LDSR_PHASE_MARK(7);
         st.Syx = ws.Syx;
@@ -854,10 +899,15 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 const double *__restrict__ m = (which == 0 ? svv_inv : tuu_inv) + a * PQ;
                 // the vector, in stats_store order: Sxv at 11, Tx1u at 11 + PQ, Tux at 11 + 2 PQ
                 const double *__restrict__ xv = TOT + (size_t)(which == 0 ? 11 : (which == 1 ? 11 + 2 * PQ : 11 + PQ)) * 32;
-                double acc = 0.0;
+                double a0 = m[0] * xv[0], a1 = m[1] * xv[32];
 #pragma unroll
-                for (int b2 = 0; b2 < PQ; b2++) acc = fma(m[b2], xv[b2 * 32], acc);
-                ZW[rr * 32] = acc;
+                for (int b2 = 2; b2 < PQ; b2++) {
+                    if (b2 & 1)
+                        a1 = fma(m[b2], xv[b2 * 32], a1);
+                    else
+                        a0 = fma(m[b2], xv[b2 * 32], a0);
+                }
+                ZW[rr * 32] = a0 + a1;
             }
         }
         LDSR_PHASE_MARK(12);

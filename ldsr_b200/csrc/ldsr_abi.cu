@@ -672,9 +672,12 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // small batches of narrow inputs: one CTA per fit, the time axis spread over its threads (em_scan_kernel.cuh).
     // A batched kernel needs 10 us per iteration however few fits it holds; the scan kernel 2-3 us for up
     // to one fit per SM and about n/148 times that beyond, so it wins below a few hundred fits.
-    // steps per thread: 2 while the series fits 8 warps that way (T <= 512), else 4 (T <= 1024)
-    int scan_steps = P->max_T <= 2 * 32 * SCAN_MAX_WARPS ? 2 : 4;
-    if (const char *ev = std::getenv("LDSR_SCAN_L")) scan_steps = std::atoi(ev) == 4 ? 4 : scan_steps; // development
+    // steps per thread: 4 (series up to 1024 steps).  Measured on NP-413, 100 fits x 1000 iterations: 2.91 ms with
+    // 4 steps per thread (4 warps), 3.36 ms with 2 (7 warps: the cross-warp chains and barriers outweigh the
+    // shorter per-thread recursions).  LDSR_SCAN_L=2 (development) selects the latter where it fits.
+    int scan_steps = 4;
+    if (const char *ev = std::getenv("LDSR_SCAN_L"))
+        if (std::atoi(ev) == 2 && P->max_T <= 2 * 32 * SCAN_MAX_WARPS) scan_steps = 2;
     const bool scan_ok = P->kt->scan_l > 0 && P->max_T <= scan_steps * 32 * SCAN_MAX_WARPS;
     const bool use_scan = scan_ok && nf <= SCAN_MAX_FITS && (variant == 0 || variant == 5);
     if (variant == 5 && !use_scan)
@@ -816,6 +819,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             // about 8.5 instructions per unobserved step, 90 per step of an observed unit)
             wp.cost_u = P->kt->split_uw * 17 / 2;
             wp.cost_m = P->kt->wide_mseg * 90;
+            if (const char *ev = std::getenv("LDSR_WIDE_COST_M")) wp.cost_m = std::atoi(ev); // development: piece balancing
 #ifdef LDSR_PHASE_CLOCKS
             if (!sp_clk_last) cudaMalloc(&sp_clk_last, sizeof(long long) * 4096 * 21 * 8);
             wp.clk = (c == 1 && grid <= 2048) ? sp_clk_last : nullptr;
@@ -827,11 +831,11 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
                 std::vector<long long> h((size_t)grid * nw * 21);
                 cudaStreamSynchronize(st);
                 cudaMemcpy(h.data(), sp_clk_last, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-                static const char *names[21] = {"P1", "B1 wait", "prefix+P2", "B2 wait", "P4", "B3 wait", "phase C",
+                static const char *names[21] = {"P1", "B1 wait", "prefix+P2", "B2 wait", "P4", "B3 wait", "-",
                                                 "B4 wait", "store sums", "B5 wait", "totals", "B5b wait", "matvec rows",
-                                                "B5c wait", "M-step scalars", "B6 wait", "phase A", "chain+stop", "-", "-", "-"};
+                                                "B5c wait", "M-step scalars", "B6 wait", "phase A", "chain+stop", "phase C", "-", "-"};
                 std::fprintf(stderr, "[ldsr] wide kernel, phase clocks of launch 1 (cycles per iteration, mean over %d CTAs), per warp:\n", grid);
-                for (int i = 0; i < 18; i++) {
+                for (int i = 0; i < 19; i++) {
                     std::fprintf(stderr, "[ldsr]   %-14s", names[i]);
                     for (int w = 0; w < nw; w++) {
                         double sum = 0;
@@ -1534,7 +1538,8 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     for (double *o : outs) n_out += o ? 1 : 0;
     g_last_device_ms = 0.0;
     if (n_out == 0) return Err();
-    int chunk = (int)std::max<size_t>(128, ((size_t)24 << 20) / ((size_t)n * 8)); // ~24 MB per output and chunk
+    // ~48 MB per output and chunk, a multiple of a CTA's 128 replicates (at T = 813: 58 CTAs per launch)
+    int chunk = (int)std::max<size_t>(128, ((size_t)48 << 20) / ((size_t)n * 8));
     chunk = std::min(n_reps, (chunk + 127) / 128 * 128);
     const int n_chunks = (n_reps + chunk - 1) / chunk;
     const size_t slot_doubles = (size_t)n_out * chunk * n;
@@ -1633,8 +1638,7 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
         CU(cudaStreamWaitEvent(sc, ev_k[slot], 0));
         CU(cudaMemcpyAsync(h_out[slot], d_out[slot], slot_doubles * 8, cudaMemcpyDeviceToHost, sc));
         CU(cudaEventRecord(ev_c[slot], sc));
-        // the next kernel into this slot must wait for this copy
-        CU(cudaStreamWaitEvent(sk, ev_c[slot], 0));
+        // (the next kernel into this slot is enqueued only after the host has seen ev_c[slot], above)
     }
     for (int c = std::max(0, n_chunks - SLOTS); c < n_chunks; c++) {
         CU(cudaEventSynchronize(ev_c[c % SLOTS]));

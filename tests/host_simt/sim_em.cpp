@@ -272,8 +272,8 @@ template <int PQ> int run(const Job &J) {
 #endif
 #ifdef LDSR_HAVE_SCAN
         else if (J.kind == 5) {
-            // 2 steps per thread while that fits 8 warps, else 4 (as plan_em chooses); order >= 8 forces 4
-            const int L = (T <= 2 * 32 * SCAN_MAX_WARPS && J.order < 8) ? 2 : 4;
+            // 4 steps per thread (what plan_em chooses); orders >= 8 run the 2-steps-per-thread build
+            const int L = (T <= 2 * 32 * SCAN_MAX_WARPS && J.order >= 8) ? 2 : 4;
             const int nwarps = (T + 32 * L - 1) / (32 * L);
             if (nwarps > SCAN_MAX_WARPS) return 14;
             if constexpr (PQ <= 4) {

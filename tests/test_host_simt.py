@@ -161,7 +161,7 @@ def test_emulated_scan_kernel(T):
         r = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=order, grid_cap=2 if order == 4 else 0)
         for k in ("theta", "lik", "iters"):
             assert np.array_equal(base[k], r[k]), (order, k)
-    # four steps per thread (the kernel of series longer than 512 steps): orders >= 8 select it in the harness
+    # two steps per thread (the LDSR_SCAN_L=2 build): orders >= 8 select it in the harness
     r4 = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=8)
     _check_vs_oracle(r4, y, u, u, held, fg, th0, niter)
     r4b = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=9)
