@@ -1543,6 +1543,12 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     chunk = std::min(n_reps, (chunk + 127) / 128 * 128);
     const int n_chunks = (n_reps + chunk - 1) / chunk;
     const size_t slot_doubles = (size_t)n_out * chunk * n;
+    // When the whole output fits comfortably in HBM (up to 8 GB here) ONE kernel simulates every replicate --
+    // 782 CTAs for 100 000 replicates instead of 58 per chunk, each warp's 813-step chain hidden behind the
+    // others -- and only the copies are chunked.  Otherwise kernel and copies are chunked alike.
+    const size_t tot = (size_t)n * n_reps;
+    const bool whole = (size_t)n_out * tot * 8 + (z ? (size_t)n_reps * zrow * 8 : 0) <= ((size_t)8 << 30);
+    double *d_whole = nullptr;
     constexpr int SLOTS = 2;
     double *d_out[SLOTS] = {nullptr, nullptr}, *h_out[SLOTS] = {nullptr, nullptr}, *d_z[SLOTS] = {nullptr, nullptr};
     cudaEvent_t ev_k[SLOTS] = {nullptr, nullptr}, ev_c[SLOTS] = {nullptr, nullptr};
@@ -1570,11 +1576,11 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     CU(pool->get_stream(&sk));
     CU(pool->get_stream(&sc));
     for (int i = 0; i < SLOTS && i < n_chunks; i++) {
-        CU(dal(slot_doubles * 8, (void **)&d_out[i]));
+        if (!whole) CU(dal(slot_doubles * 8, (void **)&d_out[i]));
         void *hp = nullptr;
         CU(pool->alloc_pinned(slot_doubles * 8, &hp));
         h_out[i] = static_cast<double *>(hp);
-        if (z) CU(dal((size_t)chunk * zrow * 8, (void **)&d_z[i]));
+        if (z && !whole) CU(dal((size_t)chunk * zrow * 8, (void **)&d_z[i]));
         CU(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
     }
@@ -1596,11 +1602,61 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
         }
         for (auto &t : th) t.join();
     };
+    auto launch = [&](int r0, int nr, const double *zdev, double *base, size_t out_stride) -> Err {
+        RepParams rp;
+        rp.theta = dth;
+        rp.u = du;
+        rp.v = dv;
+        rp.z = zdev;
+        rp.seed = seed;
+        rp.n = n;
+        rp.n_reps = nr;
+        rp.rep0 = r0;
+        rp.mu = mu;
+        rp.exp_trans = exp_trans;
+        int k = 0;
+        double *o3[3] = {nullptr, nullptr, nullptr};
+        for (int o = 0; o < 3; o++)
+            if (outs[o]) o3[o] = base + (size_t)(k++) * out_stride;
+        rp.simX = o3[0];
+        rp.simY = o3[1];
+        rp.simQ = o3[2];
+        cudaEvent_t ta = nullptr, tb = nullptr;
+        CU(cudaEventCreate(&ta));
+        ev_t.push_back(ta);
+        CU(cudaEventCreate(&tb));
+        ev_t.push_back(tb);
+        CU(cudaEventRecord(ta, sk));
+        CU(kt->rep(rp, sk));
+        CU(cudaEventRecord(tb, sk));
+        return Err();
+    };
+    if (whole) {
+        CU(dal((size_t)n_out * tot * 8, (void **)&d_whole));
+        const double *zdev = dz_all;
+        if (z) {
+            double *dzw = nullptr;
+            CU(dal((size_t)n_reps * zrow * 8, (void **)&dzw));
+            CU(cudaMemcpyAsync(dzw, z, (size_t)n_reps * zrow * 8, cudaMemcpyHostToDevice, sk));
+            zdev = dzw;
+        }
+        Err e = launch(0, n_reps, zdev, d_whole, tot);
+        if (!e.ok()) return e;
+        CU(cudaEventRecord(ev_k[0], sk));
+        CU(cudaStreamWaitEvent(sc, ev_k[0], 0));
+    }
     for (int c = 0; c < n_chunks; c++) {
         const int slot = c % SLOTS, r0 = c * chunk, nr = std::min(chunk, n_reps - r0);
         if (c >= SLOTS) { // the slot's previous chunk must have left the device, then leave the pinned block
             CU(cudaEventSynchronize(ev_c[slot]));
             copy_out(c - SLOTS);
+        }
+        if (whole) { // the kernel is done (or running ahead of the copy stream's wait): only the copies are chunked
+            for (int k = 0; k < n_out; k++)
+                CU(cudaMemcpyAsync(h_out[slot] + (size_t)k * chunk * n, d_whole + (size_t)k * tot + (size_t)r0 * n,
+                                   (size_t)nr * n * 8, cudaMemcpyDeviceToHost, sc));
+            CU(cudaEventRecord(ev_c[slot], sc));
+            continue;
         }
         RepParams rp;
         rp.theta = dth;
