@@ -2003,9 +2003,9 @@ int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *
             P.L = T; // one chunk: the "down" kernels are the sequential recursion
         } else if (chunk > 0) {
             P.L = std::min(chunk, T);
-        } else { // thread phase ~L combines, warp phase ~T/(16 L): balance, power of two in 8..256
+        } else { // chunk phases ~2 L combines deep, scan phase ~2 T/(256 L) + 14: balance, power of two in 8..64
             int L = 8;
-            while (L < 256 && (long long)L * L * 32 < T) L *= 2;
+            while (L < 64 && (long long)L * L * 256 < T) L *= 2;
             P.L = L;
         }
         P.n_chunks = (T + P.L - 1) / P.L;

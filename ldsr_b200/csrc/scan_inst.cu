@@ -12,12 +12,22 @@ template <int D> cudaError_t run(const ScanParams &P, cudaStream_t st) {
     const unsigned gb = (unsigned)((nc + TB - 1) / TB);
     if (P.n_chunks > 1) {
         scan_filt_agg_kernel<D><<<gb, TB, 0, st>>>(P);
-        scan_filt_scan_kernel<D><<<P.n_fits, 32, (32 * FiltElem<D>::LEN + 1) * sizeof(double), st>>>(P);
+        {
+            const size_t smem = (size_t)(SCAN_NT + SCAN_NT / 32) * FiltElem<D>::LEN * sizeof(double);
+            cudaError_t e = cudaFuncSetAttribute(scan_filt_scan_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            scan_filt_scan_kernel<D><<<P.n_fits, SCAN_NT, smem, st>>>(P);
+        }
     }
     scan_filt_down_kernel<D><<<gb, TB, 0, st>>>(P);
     if (P.n_chunks > 1) {
         scan_smth_agg_kernel<D><<<gb, TB, 0, st>>>(P);
-        scan_smth_scan_kernel<D><<<P.n_fits, 32, (32 * SmthElem<D>::LEN + 1) * sizeof(double), st>>>(P);
+        {
+            const size_t smem = (size_t)(SCAN_NT + SCAN_NT / 32) * SmthElem<D>::LEN * sizeof(double);
+            cudaError_t e = cudaFuncSetAttribute(scan_smth_scan_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            scan_smth_scan_kernel<D><<<P.n_fits, SCAN_NT, smem, st>>>(P);
+        }
     }
     scan_smth_down_kernel<D><<<gb, TB, 0, st>>>(P);
     scan_lik_kernel<D><<<P.n_fits, 32, 0, st>>>(P);

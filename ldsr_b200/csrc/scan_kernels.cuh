@@ -8,7 +8,7 @@
 // Time is cut into chunks of L steps, one THREAD per (fit, chunk):
 //   prep        c_t = B u_{t-1}, dv_t = D v_t for every t (one thread per step, coalesced rows)
 //   filt_agg    each chunk's filtering element a = (A,b,C,eta,J), combined step by step
-//   filt_scan   one warp per fit: prefix over the chunk elements -> (Xu,Vu) entering every chunk
+//   filt_scan   one CTA per fit, three levels: prefix over the chunk elements -> (Xu,Vu) entering every chunk
 //   filt_down   ordinary Kalman filter inside each chunk from that state: Xu_t, Vu_t, lik terms
 //   smth_agg    each chunk's smoothing element (E,g,L) from Xu,Vu
 //   smth_scan   suffix over the chunk elements -> (Xs,Vs) entering every chunk from the right
@@ -190,6 +190,18 @@ template <int D> struct FiltElem {
     }
 };
 
+// the neutral element of filt_combine: (I, 0, 0, 0, 0) -- both combine(a, id) = a and combine(id, e) = e hold
+// exactly (the inverse taken is that of the identity)
+template <int D> __device__ __forceinline__ void filt_identity(FiltElem<D> &a) {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) {
+        a.A[i] = (i % (D + 1) == 0) ? 1.0 : 0.0;
+        a.C[i] = 0.0;
+        a.J[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) a.b[i] = a.eta[i] = 0.0;
+}
 // a <- a (earlier) combined with e (later)
 template <int D> __device__ __forceinline__ void filt_combine(FiltElem<D> &a, const FiltElem<D> &e) {
     double T1[D * D], M[D * D], N[D * D];
@@ -394,65 +406,64 @@ template <int D> __global__ void scan_filt_agg_kernel(const ScanParams P) {
     a.store(P.fagg + ((size_t)f * P.n_chunks + ch) * FiltElem<D>::LEN);
 }
 
-// prefix over the chunk elements: one warp per fit, lane l owns a contiguous range of chunks
-template <int D> __global__ void scan_filt_scan_kernel(const ScanParams P) {
-    extern __shared__ double sh[]; // [32][LEN] lane aggregates, then their exclusive prefixes
+// prefix over the chunk elements: one CTA of SCAN_NT threads per fit, three levels.
+//   (1) thread t combines its contiguous range of chunk elements (n_chunks / SCAN_NT of them) serially;
+//   (2) Kogge-Stone over the 32 thread aggregates of a warp through shared memory (5 rounds), warp totals;
+//   (3) every thread combines the totals of the warps before its own (< SCAN_NT / 32 of them) with the inclusive
+//       prefix of the lane before it, then walks its range again writing the filtered state entering each chunk.
+// Serial depth n_chunks/SCAN_NT + 5 + SCAN_NT/32 + 1 + n_chunks/SCAN_NT combines (round 1: one warp per fit,
+// n_chunks/32 + 32 + n_chunks/32).  Empty ranges hold the neutral element, so no lane needs a special case.
+constexpr int SCAN_NT = 256;
+template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_filt_scan_kernel(const ScanParams P) {
+    extern __shared__ double sh[]; // [SCAN_NT][LEN] thread aggregates -> inclusive prefixes in the warp; [SCAN_NT/32][LEN] warp totals
     constexpr int LEN = FiltElem<D>::LEN;
-    const int f = blockIdx.x, lane = threadIdx.x;
-    const int per = (P.n_chunks + 31) / 32;
-    const int k0 = min(P.n_chunks, lane * per), k1 = min(P.n_chunks, k0 + per);
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (P.n_chunks + SCAN_NT - 1) / SCAN_NT;
+    const int k0 = min(P.n_chunks, tid * per), k1 = min(P.n_chunks, k0 + per);
     const double *__restrict__ agg = P.fagg + (size_t)f * P.n_chunks * LEN;
-    FiltElem<D> a;
+    FiltElem<D> a, e;
+    filt_identity<D>(a);
     for (int k = k0; k < k1; k++) {
-        FiltElem<D> e;
         e.load(agg + (size_t)k * LEN);
-        if (k == k0)
+        filt_combine<D>(a, e);
+    }
+    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)SCAN_NT * LEN;
+    a.store(mine);
+    __syncwarp();
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool act = lane >= o;
+        if (act) { // new_i = old_{i-o} o old_i
+            e.load(sh + (size_t)(tid - o) * LEN);
+            filt_combine<D>(e, a);
             a = e;
-        else
-            filt_combine<D>(a, e);
-    }
-    if (k1 > k0) a.store(sh + lane * LEN);
-    __syncwarp();
-    if (lane == 0) { // exclusive prefixes of the lane aggregates, in place (slot l <- prefix before lane l)
-        FiltElem<D> run, nxt;
-        bool have = false;
-        for (int l = 0; l < 32; l++) {
-            const int a0 = min(P.n_chunks, l * per), a1 = min(P.n_chunks, a0 + per);
-            if (a1 <= a0) break;
-            nxt.load(sh + l * LEN);
-            if (have) run.store(sh + l * LEN);
-            if (!have) {
-                run = nxt;
-                have = true;
-            } else {
-                filt_combine<D>(run, nxt);
-            }
         }
+        __syncwarp();
+        if (act) a.store(mine);
+        __syncwarp();
     }
-    __syncwarp();
+    if (lane == 31) a.store(wt + (size_t)warp * LEN);
+    __syncthreads();
+    FiltElem<D> run; // exclusive prefix before my range
+    filt_identity<D>(run);
+    for (int w = 0; w < warp; ++w) {
+        e.load(wt + (size_t)w * LEN);
+        filt_combine<D>(run, e);
+    }
+    if (lane > 0) {
+        e.load(sh + (size_t)(tid - 1) * LEN);
+        filt_combine<D>(run, e);
+    }
     // walk the range again: the filtered state entering chunk k is (b, C) of the prefix before it
     double *__restrict__ pre = P.pre + (size_t)f * P.n_chunks * (D + D * D);
-    FiltElem<D> run;
-    bool have = false;
-    if (lane > 0 && k1 > k0) {
-        run.load(sh + lane * LEN);
-        have = true;
-    }
     for (int k = k0; k < k1; k++) {
-        if (have) {
+        if (k > 0) {
 #pragma unroll
             for (int i = 0; i < D; i++) pre[(size_t)k * (D + D * D) + i] = run.b[i];
 #pragma unroll
             for (int i = 0; i < D * D; i++) pre[(size_t)k * (D + D * D) + D + i] = run.C[i];
         }
-        FiltElem<D> e;
         e.load(agg + (size_t)k * LEN);
-        if (have)
-            filt_combine<D>(run, e);
-        else {
-            run = e;
-            have = true;
-        }
+        filt_combine<D>(run, e);
     }
 }
 
@@ -526,6 +537,15 @@ template <int D> struct SmthElem {
         for (int i = 0; i < D; i++) g[i] = o[D * D + i];
     }
 };
+template <int D> __device__ __forceinline__ void smth_identity(SmthElem<D> &a) { // neutral element: (I, 0, 0)
+#pragma unroll
+    for (int i = 0; i < D * D; i++) {
+        a.E[i] = (i % (D + 1) == 0) ? 1.0 : 0.0;
+        a.L[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) a.g[i] = 0.0;
+}
 // a (earlier) <- a combined with e (later): E = E_i E_j, g = E_i g_j + g_i, L = E_i L_j E_i' + L_i
 template <int D> __device__ __forceinline__ void smth_combine(SmthElem<D> &a, const SmthElem<D> &e) {
     double nE[D * D], t[D], T1[D * D], nL[D * D];
@@ -604,71 +624,60 @@ template <int D> __global__ void scan_smth_agg_kernel(const ScanParams P) {
     a.store(P.sagg + ((size_t)f * P.n_chunks + ch) * SmthElem<D>::LEN);
 }
 
-// suffix over the chunk elements: (g, L) of the suffix right of chunk k = smoothed state of its first step
-template <int D> __global__ void scan_smth_scan_kernel(const ScanParams P) {
+// suffix over the chunk elements: (g, L) of the suffix right of chunk k = smoothed state of its first step.
+// Same three levels as scan_filt_scan_kernel, mirrored.
+template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_smth_scan_kernel(const ScanParams P) {
     extern __shared__ double sh[];
     constexpr int LEN = SmthElem<D>::LEN;
-    const int f = blockIdx.x, lane = threadIdx.x;
-    const int per = (P.n_chunks + 31) / 32;
-    const int k0 = min(P.n_chunks, lane * per), k1 = min(P.n_chunks, k0 + per);
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (P.n_chunks + SCAN_NT - 1) / SCAN_NT;
+    const int k0 = min(P.n_chunks, tid * per), k1 = min(P.n_chunks, k0 + per);
     const double *__restrict__ agg = P.sagg + (size_t)f * P.n_chunks * LEN;
-    SmthElem<D> a;
-    for (int k = k1 - 1; k >= k0; k--) { // a = e_k0 * ... * e_{k1-1}, built from the right
-        SmthElem<D> e;
+    SmthElem<D> a, e;
+    smth_identity<D>(a);
+    for (int k = k1 - 1; k >= k0; k--) { // a = e_k0 o ... o e_{k1-1}, built from the right
         e.load(agg + (size_t)k * LEN);
-        if (k == k1 - 1)
-            a = e;
-        else {
-            smth_combine<D>(e, a);
-            a = e;
-        }
+        smth_combine<D>(e, a);
+        a = e;
     }
-    if (k1 > k0) a.store(sh + lane * LEN);
+    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)SCAN_NT * LEN;
+    a.store(mine);
     __syncwarp();
-    if (lane == 0) { // exclusive suffixes of the lane aggregates: slot l <- product of lanes l+1 ..
-        int last = -1;
-        for (int l = 0; l < 32; l++)
-            if (min(P.n_chunks, l * per) < P.n_chunks) last = l;
-        SmthElem<D> run, cur;
-        bool have = false;
-        for (int l = last; l >= 0; l--) {
-            cur.load(sh + l * LEN);
-            if (have) run.store(sh + l * LEN);
-            if (!have) {
-                run = cur;
-                have = true;
-            } else {
-                smth_combine<D>(cur, run);
-                run = cur;
-            }
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool act = lane + o < 32;
+        if (act) { // new_i = old_i o old_{i+o}
+            e.load(sh + (size_t)(tid + o) * LEN);
+            smth_combine<D>(a, e);
         }
-        if (last >= 0) sh[32 * LEN] = (double)last;
+        __syncwarp();
+        if (act) a.store(mine);
+        __syncwarp();
     }
-    __syncwarp();
-    const int last = (int)sh[32 * LEN];
+    if (lane == 0) a.store(wt + (size_t)warp * LEN);
+    __syncthreads();
+    SmthElem<D> run; // exclusive suffix right of my range
+    smth_identity<D>(run);
+    for (int w = SCAN_NT / 32 - 1; w > warp; --w) {
+        e.load(wt + (size_t)w * LEN);
+        smth_combine<D>(e, run);
+        run = e;
+    }
+    if (lane < 31) {
+        e.load(sh + (size_t)(tid + 1) * LEN);
+        smth_combine<D>(e, run);
+        run = e;
+    }
     double *__restrict__ suf = P.suf + (size_t)f * P.n_chunks * (D + D * D);
-    SmthElem<D> run;
-    bool have = false;
-    if (lane < last && k1 > k0) {
-        run.load(sh + lane * LEN);
-        have = true;
-    }
     for (int k = k1 - 1; k >= k0; k--) {
-        if (have) {
+        if (k < P.n_chunks - 1) {
 #pragma unroll
             for (int i = 0; i < D; i++) suf[(size_t)k * (D + D * D) + i] = run.g[i];
 #pragma unroll
             for (int i = 0; i < D * D; i++) suf[(size_t)k * (D + D * D) + D + i] = run.L[i];
         }
-        SmthElem<D> e;
         e.load(agg + (size_t)k * LEN);
-        if (have) {
-            smth_combine<D>(e, run);
-            run = e;
-        } else {
-            run = e;
-            have = true;
-        }
+        smth_combine<D>(e, run);
+        run = e;
     }
 }
 

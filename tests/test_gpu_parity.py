@@ -440,6 +440,26 @@ def test_wide_kernel_full_length_convergence_matches_oracle():
     assert np.array_equal(s["iters"], o["iters"]) and np.array_equal(s["best"], o["best"])
 
 
+@pytest.mark.parametrize("variant", [2, 3, 5])
+def test_result_of_a_fit_does_not_depend_on_its_neighbours(variant):
+    """Every EM kernel classifies segments / units from the SERIES (is y finite?), never from a vote over the
+    hold-out masks of the fits that happen to share a warp or CTA, so listing the groups in reverse order and
+    changing the chunk length (another compaction pattern) gives bit-identical results -- for the lane-per-fit
+    kernel too (it used a warp vote)."""
+    from ldsr_b200 import workloads as W
+    w = W.np_cv(12, 20)
+    a = em_variant(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 150, 1e-5,
+                   want_traj=False, variant=variant)
+    ng = len(w["group_series"])
+    perm = np.arange(ng)[::-1]
+    src = np.concatenate([np.nonzero(w["fit_group"] == g)[0] for g in perm])
+    fg2 = np.repeat(np.arange(ng), 20)
+    b = em_variant(w["series"], w["group_series"][perm], [w["held"][g] for g in perm], fg2, w["theta0"][src], 150, 1e-5,
+                   chunk_iters=13, want_traj=False, variant=variant)
+    assert np.array_equal(b["iters"], a["iters"][src]) and np.array_equal(b["lik"], a["lik"][src])
+    assert np.array_equal(b["theta"], a["theta"][src], equal_nan=True)
+
+
 def test_full_size_cvlds_job_properties():
     """BASELINE config 2 at full size (10 000 fits: 100 folds x 100 restarts on NP-413), where the
     oracle would take minutes: size-independent properties instead.
