@@ -409,8 +409,31 @@ __device__ __forceinline__ void rows_times_coef(const double *__restrict__ coef,
         for (int i = 0; i < PQ; i++) cf[k][i] = coef[i * 32 + lg + k * LG];
     const int len = (n + FPL - 1) / FPL; // contiguous sub-slices, one per group
     const int lo = g * len, hi = (lo + len < n) ? lo + len : n;
+    int m = lo;
 #pragma unroll 1
-    for (int m = lo; m < hi; ++m) {
+    for (; m + 2 <= hi; m += 2) { // two rows in flight: 4 FPL independent chains, the loads of one row behind the other's math
+        const int t0 = list ? list[m] : m, t1 = list ? list[m + 1] : m + 1;
+        double r0[PQ], r1[PQ];
+        load_vec<PQ>(rows + (size_t)t0 * PQ, r0);
+        load_vec<PQ>(rows + (size_t)t1 * PQ, r1);
+#pragma unroll
+        for (int k = 0; k < FPL; k++) {
+            double a0 = cf[k][0] * r0[0], a1 = cf[k][1] * r0[1], b0 = cf[k][0] * r1[0], b1 = cf[k][1] * r1[1];
+#pragma unroll
+            for (int i = 2; i < PQ; i++) {
+                if (i & 1) {
+                    a1 = fma(cf[k][i], r0[i], a1);
+                    b1 = fma(cf[k][i], r1[i], b1);
+                } else {
+                    a0 = fma(cf[k][i], r0[i], a0);
+                    b0 = fma(cf[k][i], r1[i], b0);
+                }
+            }
+            dst[(size_t)m * 32 + lg + k * LG] = a0 + a1;
+            dst[(size_t)(m + 1) * 32 + lg + k * LG] = b0 + b1;
+        }
+    }
+    if (m < hi) {
         const int t = list ? list[m] : m;
         double r[PQ];
         load_vec<PQ>(rows + (size_t)t * PQ, r);
@@ -805,8 +828,30 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                     for (int i = 0; i < 2 * PQ; i++) acc[k][i] = 0.0;
                     z[k] = lo < hi ? TRb[(size_t)lo * 32 + lg + k * LG] : 0.0;
                 }
+                int t = lo;
 #pragma unroll 1
-                for (int t = lo; t < hi; ++t) {
+                for (; t + 2 <= hi; t += 2) { // two steps per trip: the second row's loads behind the first row's math
+                    double r0[PQ], r1[PQ];
+                    load_vec<PQ>(us + (size_t)t * PQ, r0);
+                    load_vec<PQ>(us + (size_t)(t + 1) * PQ, r1);
+#pragma unroll
+                    for (int k = 0; k < FPL; k++) {
+                        const double z1 = TRb[(size_t)(t + 1) * 32 + lg + k * LG];
+                        const double z2 = TRb[(size_t)(t + 2) * 32 + lg + k * LG];
+#pragma unroll
+                        for (int i = 0; i < PQ; i++) {
+                            acc[k][i] = fma(r0[i], z[k], acc[k][i]);
+                            acc[k][PQ + i] = fma(r0[i], z1, acc[k][PQ + i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < PQ; i++) {
+                            acc[k][i] = fma(r1[i], z1, acc[k][i]);
+                            acc[k][PQ + i] = fma(r1[i], z2, acc[k][PQ + i]);
+                        }
+                        z[k] = z2;
+                    }
+                }
+                if (t < hi) {
                     double r[PQ];
                     load_vec<PQ>(us + (size_t)t * PQ, r);
 #pragma unroll

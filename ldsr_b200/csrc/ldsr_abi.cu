@@ -1547,7 +1547,10 @@ static Err rep_batch(ldsr_ctx *ctx, const double *theta, const double *u, const 
     // 782 CTAs for 100 000 replicates instead of 58 per chunk, each warp's 813-step chain hidden behind the
     // others -- and only the copies are chunked.  Otherwise kernel and copies are chunked alike.
     const size_t tot = (size_t)n * n_reps;
-    const bool whole = (size_t)n_out * tot * 8 + (z ? (size_t)n_reps * zrow * 8 : 0) <= ((size_t)8 << 30);
+    // (LDSR_REP_CHUNKED=1, development / tests: take the chunked path whatever the size)
+    static const bool force_chunked = std::getenv("LDSR_REP_CHUNKED") != nullptr;
+    const bool whole =
+        !force_chunked && (size_t)n_out * tot * 8 + (z ? (size_t)n_reps * zrow * 8 : 0) <= ((size_t)8 << 30);
     double *d_whole = nullptr;
     constexpr int SLOTS = 2;
     double *d_out[SLOTS] = {nullptr, nullptr}, *h_out[SLOTS] = {nullptr, nullptr}, *d_z[SLOTS] = {nullptr, nullptr};

@@ -2,10 +2,14 @@
 oracle and the reference's golden values.  Tolerances are BASELINE.json's: log-likelihood
 relative 1e-9, theta and reconstructed flow relative 1e-6 at the same iteration count, identical
 selected restart."""
+import os
+
 import numpy as np
 import pytest
 
 import ldsr_b200 as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from ldsr_b200 import _lib
 from oracle import oracle as O
 from tests import data
@@ -518,6 +522,24 @@ def test_task_loop_when_later_chunks_have_more_tasks_than_ctas():
         for k in ("iters", "lik", "best"):
             assert np.array_equal(a[k], b[k]), (variant, k)
         assert np.array_equal(a["theta"], b["theta"], equal_nan=True)
+
+
+def test_lds_rep_chunked_pipeline_equals_the_single_kernel_path(tmp_path):
+    """ldsr_rep_batch simulates every replicate in one kernel when the output fits HBM and in pipelined chunks
+    otherwise; the device generator is keyed by (seed, replicate, step), so both give the same bits.  The
+    chunked path is forced through LDSR_REP_CHUNKED in a child process (the switch is read once)."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from ldsr_b200 import _lib; from tests import data\n"
+            "d = data.load('np.json'); th = data.theta_of(d['theta']); y, u, mu, inst = data.np_case(1, 1200)\n"
+            "r = _lib.rep_batch(th, u, u, y.size, 9000, seed=7, mu=mu)\n"
+            "np.save(sys.argv[1], np.stack([r['simX'], r['simY'], r['simQ']]))\n") % ROOT
+    outs = []
+    for k, env in enumerate(({}, {"LDSR_REP_CHUNKED": "1"})):
+        f = str(tmp_path / ("rep%d.npy" % k))
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env), timeout=300)
+        outs.append(np.load(f))
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
 
 
 def test_construct_rec_kernel_reproduces_the_stored_reconstruction():
