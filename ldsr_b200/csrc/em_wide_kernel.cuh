@@ -45,16 +45,32 @@ struct WideParams {
 #endif
 };
 
-// rows of the trajectory area: one per step, and room for what aliases it after phase C (the NW slots
-// of partial sums, their totals, the matrix-vector rows of the M-step)
-__host__ __device__ inline size_t wide_traj_rows(int pq, int nw, int max_T) {
-    const size_t st = (size_t)(nw + 1) * (11 + 3 * pq) + 3 * pq; // NW slots, the totals, the 3 PQ rows of the M-step
-    return (size_t)max_T > st ? (size_t)max_T : st;
+// Where phases A and C read the input rows from.  0: the whole series blob (y, u, v) is staged in shared memory;
+// 1: only y is staged and the rows come from global memory (warp-uniform addresses, L1/L2 hits: every CTA of a
+// series reads the same 32 KB) -- which frees 32 KB per CTA for more warps (pieces).  Build-time switch.
+#ifndef LDSR_WIDE_ROWS_GLOBAL
+#define LDSR_WIDE_ROWS_GLOBAL 0
+#endif
+__host__ __device__ constexpr bool wide_rows_global() { return LDSR_WIDE_ROWS_GLOBAL != 0; }
+// bytes reserved at the start of dynamic shared memory for the staged part of the blob
+__host__ __device__ inline size_t wide_blob_smem(size_t max_blob_bytes, int max_T) {
+    const size_t b = wide_rows_global() ? (size_t)((max_T + 1) & ~1) * 8 : max_blob_bytes;
+    return (b + 127) & ~size_t(127);
+}
+
+// Rows of the trajectory area: one per step.  After phase C the partial sums (NW slots), their totals and the
+// 3 PQ matrix-vector rows of the M-step alias the trajectory AND the two areas that follow it in the carve-up
+// (Dv rows, checkpoints: both dead by then); the trajectory is only enlarged when even that is too small.
+__host__ __device__ inline size_t wide_traj_rows(int pq, int nw, int max_T, int max_units, int max_msteps) {
+    const size_t need = (size_t)(nw + 1) * (11 + 3 * pq) + 3 * pq;
+    const size_t behind = (size_t)(max_msteps > 0 ? max_msteps : 1) + (size_t)3 * max_units;
+    const size_t extra = need > behind ? need - behind : 0;
+    return (size_t)max_T > extra ? (size_t)max_T : extra;
 }
 // dynamic shared memory after the series blob, in bytes
 __host__ __device__ inline size_t wide_smem_bytes(int pq, int nw, int max_T, int max_units, int max_msteps) {
     size_t b = 0;
-    b += wide_traj_rows(pq, nw, max_T) * 256;   // TR: Bu_t, then Xs_t; later the partial sums
+    b += wide_traj_rows(pq, nw, max_T, max_units, max_msteps) * 256; // TR: Bu_t, then Xs_t; later the partial sums
     b += (size_t)(max_msteps > 0 ? max_msteps : 1) * 256; // YM: Dv of the steps of observed units
     b += (size_t)max_units * 3 * 256;           // CK: checkpoints (Vq, q, P) per unit
     b += (size_t)nw * 4 * 256;                  // MC: variance maps of the pieces
@@ -476,15 +492,19 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
     const int4 task = P.tasks[ti];
     const SeriesDev S = P.series[task.x];
     const int T = S.T;
-    if (threadIdx.x == 0) stage_blob(smem_raw, P.blobs + S.blob_off, (unsigned)S.blob_doubles * 8u, &bar);
+    constexpr bool ROWS_GLOBAL = wide_rows_global();
+    // y sits first in the blob (u_off doubles, even): with ROWS_GLOBAL only that part is staged
+    if (threadIdx.x == 0)
+        stage_blob(smem_raw, P.blobs + S.blob_off, (unsigned)(ROWS_GLOBAL ? S.u_off : S.blob_doubles) * 8u, &bar);
 
     const double *__restrict__ ser = reinterpret_cast<const double *>(smem_raw);
+    const double *__restrict__ gser = P.blobs + S.blob_off;
     const double *__restrict__ ys = ser + S.y_off;
-    const double *__restrict__ us = ser + S.u_off;
-    const double *__restrict__ vs = ser + S.v_off;
+    const double *__restrict__ us = (ROWS_GLOBAL ? gser : ser) + S.u_off;
+    const double *__restrict__ vs = (ROWS_GLOBAL ? gser : ser) + S.v_off;
     // shared-memory carve-up after the blob; every per-lane array is [..][32] doubles, already offset by lane
     double *const TR = reinterpret_cast<double *>(smem_raw + WP.blob_smem) + lane;  // [rows]
-    double *const YM = TR + wide_traj_rows(PQ, NW, WP.max_T) * 32;                  // [max_msteps]
+    double *const YM = TR + wide_traj_rows(PQ, NW, WP.max_T, WP.max_units, WP.max_msteps) * 32; // [max_msteps]
     double *const CK = YM + (size_t)(WP.max_msteps > 0 ? WP.max_msteps : 1) * 32;   // [unit][3]
     double *const MC = CK + (size_t)WP.max_units * 96;                              // [NP][4]
     double *const CH = MC + (size_t)NP * 4 * 32;                                    // [NP][WIDE_NCH]
@@ -499,7 +519,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
     int *const pbound = ubase + ((WP.max_units + 3) & ~3);                          // [NP + 1]
     int *const sbound = pbound + 32;                                                // [NW + 1]
     int *const mlist = sbound + 32;                                                 // [max_msteps] time step of Dv row m
-    double *const ST = TR; // [NW][NST]: the trajectory is dead after phase C
+    double *const ST = TR; // [NW][NST]: the trajectory (and the Dv rows and checkpoints behind it) is dead after phase C
 
     // ---- per-lane fit state: every warp holds the same 32 fits
     const bool valid = lane < task.z;

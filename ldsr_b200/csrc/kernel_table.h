@@ -39,7 +39,10 @@ constexpr int split_minb_for(int pq) {
 
 // wide-input kernel (em_wide_kernel.cuh): compiled for PQ >= WIDE_MIN_PQ, one CTA of WIDE_NW warps per SM
 constexpr int WIDE_MIN_PQ = 5;
-constexpr int WIDE_NW = 8;
+#ifndef LDSR_WIDE_NW
+#define LDSR_WIDE_NW 8
+#endif
+constexpr int WIDE_NW = LDSR_WIDE_NW;
 constexpr int WIDE_MSEG = 8;
 
 // small-batch scan kernel (em_scan_kernel.cuh): one CTA per fit, SCAN_L steps per thread; compiled for PQ <= SCAN_MAX_PQ

@@ -662,8 +662,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     const int variant = opt ? opt->variant : 0;
     const int max_uunits = (P->max_T + P->kt->split_uw - 1) / P->kt->split_uw;
     const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units, max_uunits);
+    const size_t wide_blob_sm = wide_blob_smem(P->max_blob_bytes, P->max_T);
     const size_t wide_sm = P->kt->wide_nw > 0
-                               ? blob_sm + wide_smem_bytes(P->PQ, P->kt->wide_nw, P->max_T, P->wide_units, P->wide_msteps)
+                               ? wide_blob_sm + wide_smem_bytes(P->PQ, P->kt->wide_nw, P->max_T, P->wide_units, P->wide_msteps)
                                : ~size_t(0);
     const bool use_wide = P->kt->wide_nw > 0 && P->blob_in_smem && wide_sm <= 227 * 1024 && (variant == 0 || variant == 4);
     if (variant == 4 && !use_wide)
@@ -814,7 +815,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             wp.max_units = P->wide_units;
             wp.max_msteps = P->wide_msteps;
             wp.max_T = P->max_T;
-            wp.blob_smem = (int)blob_sm;
+            wp.blob_smem = (int)wide_blob_sm;
             // relative cost of an unobserved word and of an observed unit in P2 + P4 (scalar work only:
             // about 8.5 instructions per unobserved step, 90 per step of an observed unit)
             wp.cost_u = P->kt->split_uw * 17 / 2;

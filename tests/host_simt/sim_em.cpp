@@ -85,7 +85,10 @@ struct Job {
 #ifdef LDSR_HAVE_WIDE
 template <int PQ> int launch_wide_hostsim(const EmParams &ep, const SeriesDev &S, const double *y, size_t blob_sm,
                                           int grid, int order) {
-    constexpr int NW = 8, MSEG = 8, UW = 32;
+#ifndef LDSR_WIDE_NW
+#define LDSR_WIDE_NW 8
+#endif
+    constexpr int NW = LDSR_WIDE_NW, MSEG = 8, UW = 32;
     int nu = 0, nm = 0;
     wide_count_units(y, S.T, MSEG, UW, &nu, &nm);
     WideParams wp;
@@ -93,10 +96,12 @@ template <int PQ> int launch_wide_hostsim(const EmParams &ep, const SeriesDev &S
     wp.max_units = nu;
     wp.max_msteps = nm;
     wp.max_T = S.T;
-    wp.blob_smem = (int)blob_sm;
+    const size_t wblob = wide_blob_smem((size_t)S.blob_doubles * 8, S.T);
+    (void)blob_sm;
+    wp.blob_smem = (int)wblob;
     wp.cost_u = UW * 17 / 2;
     wp.cost_m = MSEG * 90;
-    const size_t smem = blob_sm + wide_smem_bytes(PQ, NW, S.T, nu, nm);
+    const size_t smem = wblob + wide_smem_bytes(PQ, NW, S.T, nu, nm);
     hostsim::launch(grid, NW * 32, smem, order, [&] { em_wide_kernel<PQ, NW, MSEG, UW>(wp); });
     return 0;
 }
