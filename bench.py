@@ -226,7 +226,7 @@ def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak, c
                "per_rank_ms": [round(float(x), 3) for x in per_rank_ms],
                "per_rank_em_kernel_ms": [round(float(x), 3) for x in allv[:, 3]],
                "imbalance": float(per_rank_ms.max() / per_rank_ms.mean() - 1.0),
-               "mean_iters": float(allv[:, 1].sum() / nf),
+               "mean_iters": float(allv[:, 1].sum() / nf), "kernel": stats[0]["kernel"],
                "roofline": {"bound": "fp64", "achieved": flops / (step * 1e-3) / 1e12, "peak": fp64_peak * world,
                             "unit": "TFLOP/s", "frac": flops / (step * 1e-3) / 1e12 / (fp64_peak * world),
                             "note": "algorithmic flops of all ranks / slowest rank's step time / (N x DFMA peak)"},

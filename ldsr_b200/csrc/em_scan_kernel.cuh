@@ -31,7 +31,12 @@ namespace ldsr {
 constexpr int SCAN_MAX_WARPS = 8;
 
 template <int PQ> __host__ __device__ constexpr int scan_nsum() { return 7 + 3 * PQ; }
-template <int PQ> __host__ __device__ constexpr int scan_nsum_pad() { return scan_nsum<PQ>() <= 16 ? 16 : 32; }
+template <int PQ> __host__ __device__ constexpr int scan_nsum_pad() {
+    return scan_nsum<PQ>() <= 16 ? 16 : (scan_nsum<PQ>() <= 32 ? 32 : 48); // reduced as 16, 32 or 32 + 16 values
+}
+constexpr int SCAN_SUM_ROW = 64; // doubles per warp in the partial-sum area
+// wide inputs (PQ > SCAN_SHARE_UV_FROM) keep ONE set of rows in registers: the plan must have v == u
+constexpr int SCAN_SHARE_UV_FROM = 5;
 
 // ---- warp scans (Hillis-Steele over the 32 lanes) -------------------------------------------------
 // inclusive prefix product of 2x2 matrices: lane l ends with M_l M_{l-1} ... M_0
@@ -110,13 +115,15 @@ template <int PQ, int L>
 __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
     static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
     constexpr int NS = scan_nsum<PQ>(), NSP = scan_nsum_pad<PQ>();
+    static_assert(NS <= 48 && NSP <= SCAN_SUM_ROW, "7 + 3 PQ sums are reduced as 32 + 16 values at most");
+    constexpr bool SHARE_UV = PQ >= SCAN_SHARE_UV_FROM;
     constexpr int TL = theta_pad_len<PQ>();
     LDSR_STATIC_SMEM(double, S1[SCAN_MAX_WARPS * 4]);  // variance-map totals of the warps
     LDSR_STATIC_SMEM(double, S2[SCAN_MAX_WARPS * 2]);  // mean-map totals
     LDSR_STATIC_SMEM(double, S3[SCAN_MAX_WARPS]);      // likelihood partial sums
     LDSR_STATIC_SMEM(double, S4[SCAN_MAX_WARPS * 3]);  // backward-map totals
-    LDSR_STATIC_SMEM(double, S5[SCAN_MAX_WARPS * 32]); // M-step partial sums [warp][NSP]
-    LDSR_STATIC_SMEM(double, TOTS[2 * 32]);            // their totals, one copy per M-step warp
+    LDSR_STATIC_SMEM(double, S5[SCAN_MAX_WARPS * SCAN_SUM_ROW]); // M-step partial sums [warp][NSP]
+    LDSR_STATIC_SMEM(double, TOTS[2 * SCAN_SUM_ROW]);            // their totals, one copy per M-step warp
     LDSR_STATIC_SMEM(double, ENDS[4]);                 // X0, V0, XT, VT
     LDSR_STATIC_SMEM(double, THS[TL]);                 // theta after the M-step
 
@@ -135,7 +142,8 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 
     // ---- this thread's steps: rows and mask bits, in registers for the whole launch
     const int t0 = (int)threadIdx.x * L;
-    double yr[L], ur[L * PQ], vr[L * PQ];
+    double yr[L], ur[L * PQ], vr_own[SHARE_UV ? 1 : L * PQ];
+    double(&vr)[L * PQ] = *reinterpret_cast<double(*)[L * PQ]>(SHARE_UV ? ur : vr_own); // v == u: one set of rows
     unsigned bits = 0u; // observed steps (the group's mask: finite(y) minus the hold-outs)
     {
         const double *__restrict__ blob = P.blobs + S.blob_off;
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 #pragma unroll
             for (int i = 0; i < PQ; i++) {
                 ur[j * PQ + i] = real ? blob[S.u_off + (size_t)t * PQ + i] : 0.0;
-                vr[j * PQ + i] = real ? blob[S.v_off + (size_t)t * PQ + i] : 0.0;
+                if (!SHARE_UV) vr_own[j * PQ + i] = real ? blob[S.v_off + (size_t)t * PQ + i] : 0.0;
             }
             if (real && ((mw[t >> 5] >> (t & 31)) & 1u)) bits |= 1u << j;
         }
@@ -433,26 +441,38 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             }
         }
         {
-            const double r = scan_reduce_many<NSP>(sums, lane);
-            if (NSP == 32)
-                S5[warp * 32 + lane] = r;
-            else if ((lane & 1) == 0)
-                S5[warp * 32 + (lane >> 1)] = r;
+            double *const row = S5 + warp * SCAN_SUM_ROW;
+            if constexpr (NSP == 16) {
+                const double r = scan_reduce_many<16>(sums, lane);
+                if ((lane & 1) == 0) row[lane >> 1] = r;
+            } else {
+                const double r = scan_reduce_many<32>(*reinterpret_cast<double(*)[32]>(&sums[0]), lane);
+                row[lane] = r;
+                if constexpr (NSP == 48) {
+                    const double r2 = scan_reduce_many<16>(*reinterpret_cast<double(*)[16]>(&sums[32]), lane);
+                    if ((lane & 1) == 0) row[32 + (lane >> 1)] = r2;
+                }
+            }
         }
         __syncthreads(); // B4
 
-        // ================= M-step (EM.cpp:139-229): thread 0 the observation block, thread 32 the transition block ====
+        // ================= M-step (EM.cpp:139-229): warp 0 the observation block, warp 1 the transition block ======
+        // (one warp: warp 0 does both).  Lane a < PQ takes row a of the matrix-vector products of the block
+        // elimination (lds_math.cuh); the dot products over a are warp sums.
+        if constexpr (PQ <= 4) {
+        // narrow inputs: thread 0 does the observation block, thread 32 the transition block (measured on NP-413:
+        // 2.91 ms per 1000 iterations against 3.15 ms with the rows spread over lanes and warp sums)
         const bool do_obs = warp == 0, do_trans = nw > 1 ? warp == 1 : warp == 0; // one warp: warp 0 does both
         if (do_obs || do_trans) {
             if (lane < NS) {
                 double a = 0.0;
-                for (int w = 0; w < nw; ++w) a += S5[w * 32 + lane];
-                TOTS[warp * 32 + lane] = a;
+                for (int w = 0; w < nw; ++w) a += S5[w * SCAN_SUM_ROW + lane];
+                TOTS[warp * SCAN_SUM_ROW + lane] = a;
             }
             __syncwarp();
             if (lane == 0) {
                 Stats<PQ> st;
-                const double *o = TOTS + warp * 32;
+                const double *o = TOTS + warp * SCAN_SUM_ROW;
                 st.Syx = o[0];
                 st.Sxx = o[1];
                 st.Sxxv = o[2];
@@ -488,6 +508,63 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                     THS[5 + 2 * PQ] = tn.V1;
                 }
             }
+        }
+        } else {
+        const bool do_obs = warp == 0, do_trans = nw > 1 ? warp == 1 : warp == 0;
+        if (do_obs || do_trans) {
+            double *const o = TOTS + warp * SCAN_SUM_ROW;
+            for (int i = lane; i < NS; i += 32) {
+                double a = 0.0;
+                for (int w = 0; w < nw; ++w) a += S5[w * SCAN_SUM_ROW + i];
+                o[i] = a;
+            }
+            __syncwarp();
+            const bool row = lane < PQ;
+            const int la = row ? lane : 0;
+            if (do_obs) {
+                const double *Syv = gc + 2, *wy = gc + 2 + PQ, *svv_inv = gc + 2 + 2 * PQ;
+                const double sxv = row ? o[7 + la] : 0.0, wya = row ? wy[la] : 0.0, syva = row ? Syv[la] : 0.0;
+                double z = 0.0;
+#pragma unroll
+                for (int b2 = 0; b2 < PQ; b2++) z = fma(svv_inv[la * PQ + b2], o[7 + b2], z);
+                if (!row) z = 0.0;
+                const double num = o[0] - scan_warp_sum(wya * sxv);
+                const double den = (o[1] + o[2]) - scan_warp_sum(sxv * z); // Sxx + sum V over observed steps (EM.cpp:152)
+                const double Cn = num / den;
+                const double d = fma(-Cn, z, wya);
+                const double racc = fma(-Cn, o[0], gc[0]) - scan_warp_sum(d * syva);
+                if (row) THS[2 + PQ + la] = d;
+                if (lane == 0) {
+                    THS[1 + PQ] = Cn;
+                    THS[3 + 2 * PQ] = racc / n_obs;
+                }
+            }
+            if (do_trans) {
+                const double tx1u = row ? o[7 + PQ + la] : 0.0, tux = row ? o[7 + 2 * PQ + la] : 0.0;
+                double z = 0.0, w2 = 0.0;
+#pragma unroll
+                for (int b2 = 0; b2 < PQ; b2++) {
+                    const double m = tuu_inv[la * PQ + b2];
+                    z = fma(m, o[7 + 2 * PQ + b2], z);
+                    w2 = fma(m, o[7 + PQ + b2], w2);
+                }
+                if (!row) z = w2 = 0.0;
+                const double Txx = o[5] + o[6], Tx1x = o[3] + o[4]; // EM.cpp:180,181
+                const double num = Tx1x - scan_warp_sum(tx1u * z), den = Txx - scan_warp_sum(tux * z);
+                const double An = num / den;
+                // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
+                const double Tx1x1 = Txx - fma(ENDS[0], ENDS[0], ENDS[1]) + fma(ENDS[2], ENDS[2], ENDS[3]);
+                const double bb = fma(-An, z, w2);
+                const double qacc = fma(-An, Tx1x, Tx1x1) - scan_warp_sum(bb * tx1u);
+                if (row) THS[1 + la] = bb;
+                if (lane == 0) {
+                    THS[0] = An;
+                    THS[2 + 2 * PQ] = qacc / (double)(T - 1);
+                    THS[4 + 2 * PQ] = ENDS[0]; // EM.cpp:218-219
+                    THS[5 + 2 * PQ] = ENDS[1];
+                }
+            }
+        }
         }
         __syncthreads(); // B5: the new theta is published
         load_theta<PQ>(th, THS);

@@ -46,8 +46,8 @@ constexpr int WIDE_NW = LDSR_WIDE_NW;
 constexpr int WIDE_MSEG = 8;
 
 // small-batch scan kernel (em_scan_kernel.cuh): one CTA per fit, SCAN_L steps per thread; compiled for PQ <= SCAN_MAX_PQ
-constexpr int SCAN_MAX_PQ = 4;
-constexpr int SCAN_L = 4;
+constexpr int SCAN_MAX_PQ = 10;
+constexpr int SCAN_L = 4; // steps per thread for width <= 4 (T <= 1024); wider inputs take 2 (T <= 512, v == u)
 
 struct KernelTable {
     int pq;

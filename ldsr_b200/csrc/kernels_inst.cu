@@ -119,12 +119,16 @@ template <int PQV> struct ScanLaunch<PQV, true> {
     static cudaError_t launch(const EmParams &p, int n_tasks, int steps_per_thread, cudaStream_t st) {
         // one thread per `steps_per_thread` steps, whole warps
         const int threads = (((p.max_seg + steps_per_thread - 1) / steps_per_thread + 31) / 32) * 32;
-        if (steps_per_thread == 2)
+        if (steps_per_thread == 2) {
             em_scan_kernel<PQV, 2><<<n_tasks, threads, 0, st>>>(p);
-        else if (steps_per_thread == 4)
-            em_scan_kernel<PQV, 4><<<n_tasks, threads, 0, st>>>(p);
-        else
+        } else if (steps_per_thread == 4) {
+            if constexpr (PQV <= 4)
+                em_scan_kernel<PQV, 4><<<n_tasks, threads, 0, st>>>(p);
+            else
+                return cudaErrorNotSupported; // wide inputs: two steps per thread only (registers)
+        } else {
             return cudaErrorNotSupported;
+        }
         return cudaGetLastError();
     }
 };

@@ -676,14 +676,19 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // steps per thread: 4 (series up to 1024 steps).  Measured on NP-413, 100 fits x 1000 iterations: 2.91 ms with
     // 4 steps per thread (4 warps), 3.36 ms with 2 (7 warps: the cross-warp chains and barriers outweigh the
     // shorter per-thread recursions).  LDSR_SCAN_L=2 (development) selects the latter where it fits.
-    int scan_steps = 4;
+    // Wider inputs (5 .. SCAN_MAX_PQ) keep one set of rows in registers: 2 steps per thread (T <= 512), v == u.
+    int scan_steps = P->PQ <= 4 ? 4 : 2;
     if (const char *ev = std::getenv("LDSR_SCAN_L"))
         if (std::atoi(ev) == 2 && P->max_T <= 2 * 32 * SCAN_MAX_WARPS) scan_steps = 2;
-    const bool scan_ok = P->kt->scan_l > 0 && P->max_T <= scan_steps * 32 * SCAN_MAX_WARPS;
+    bool scan_uv_ok = true;
+    if (P->PQ >= SCAN_SHARE_UV_FROM)
+        for (const SeriesDev &S : P->h_series) scan_uv_ok = scan_uv_ok && S.same_uv != 0 && S.has_u != 0;
+    const bool scan_ok = P->kt->scan_l > 0 && scan_uv_ok && P->max_T <= scan_steps * 32 * SCAN_MAX_WARPS;
     const bool use_scan = scan_ok && nf <= SCAN_MAX_FITS && (variant == 0 || variant == 5);
     if (variant == 5 && !use_scan)
-        return fail(LDSR_ERR_UNSUPPORTED, "variant 5 (scan kernel) needs input width <= %d, T <= %d and at most %d fits",
-                    SCAN_MAX_PQ, 32 * SCAN_L * SCAN_MAX_WARPS, SCAN_MAX_FITS);
+        return fail(LDSR_ERR_UNSUPPORTED,
+                    "variant 5 (scan kernel) needs input width <= %d, T <= %d (%d and v == u for width > 4) and at most %d fits",
+                    SCAN_MAX_PQ, 32 * SCAN_L * SCAN_MAX_WARPS, 32 * 2 * SCAN_MAX_WARPS, SCAN_MAX_FITS);
     bool use_split = !use_scan && !use_wide && P->blob_in_smem && split_sm <= 227 * 1024 && (variant == 0 || variant == 3);
     if (variant == 3 && !use_split)
         return fail(LDSR_ERR_UNSUPPORTED, "variant 3 (time-split kernel) needs %zu bytes of shared memory", split_sm);

@@ -286,8 +286,11 @@ template <int PQ> int run(const Job &J) {
                     hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 2>(ep); });
                 else
                     hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 4>(ep); });
-            } else
-                return 15;
+            } else { // wide inputs: two steps per thread, v == u
+                if (!S.same_uv || T > 2 * 32 * SCAN_MAX_WARPS) return 15;
+                const int nw2 = (T + 63) / 64;
+                hostsim::launch(grid, nw2 * 32, 0, J.order, [&] { em_scan_kernel<PQ, 2>(ep); });
+            }
         }
 #endif
         else

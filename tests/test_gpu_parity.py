@@ -379,12 +379,12 @@ def _run_variant(fn, variant):
     try:
         return fn()
     except _lib.LdsrError as e:
-        if variant == 4 and e.code == _lib.ERR_UNSUPPORTED:
-            pytest.skip("the wide-input kernel's shared-memory plan does not fit this case")
+        if variant in (4, 5) and e.code == _lib.ERR_UNSUPPORTED:
+            pytest.skip("kernel variant %d does not cover this case (shared-memory plan / width / v != u)" % variant)
         raise
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 0])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 0])
 @pytest.mark.parametrize("p,q", [(5, 5), (7, 6), (10, 10), (12, 11), (16, 16), (18, 20), (32, 29)])
 def test_wide_inputs(variant, p, q):
     # the padded widths 5 .. 32 (24 and 32 are built as several translation units)

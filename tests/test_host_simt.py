@@ -167,3 +167,18 @@ def test_emulated_scan_kernel(T):
     r4b = sim_em(5, y, u, u, held, fg, th0, niter, chunk=4, order=9)
     for k in ("theta", "lik", "iters"):
         assert np.array_equal(r4[k], r4b[k]), k
+
+
+@pytest.mark.parametrize("p,T", [(10, 150), (7, 85), (6, 40)])
+def test_emulated_scan_kernel_wide_inputs(p, T):
+    """The scan kernel with 5..10 inputs (v == u, two steps per thread, 32 + 16-value sum reduction, the M-step's
+    matrix-vector rows spread over the lanes)."""
+    y, u, held, fg, th0 = _wide_job(p, T, 9, seed=100 + p, first_obs=T // 3)
+    th0[:, 1:1 + p] *= 0.2
+    th0[:, 2 + p:2 + 2 * p] *= 0.2
+    niter = 8
+    base = sim_em(5, y, u, u, held, fg, th0, niter, chunk=5, order=0)
+    _check_vs_oracle(base, y, u, u, held, fg, th0, niter)
+    r = sim_em(5, y, u, u, held, fg, th0, niter, chunk=5, order=3)
+    for k in ("theta", "lik", "iters"):
+        assert np.array_equal(base[k], r[k]), k
