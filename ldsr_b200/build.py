@@ -56,13 +56,11 @@ def build(force=False, verbose=False, ptxas_info=False):
     if os.environ.get("LDSR_PQ_LIST"):
         PQ_LIST = tuple(int(x) for x in os.environ["LDSR_PQ_LIST"].split(","))
     deps = _sources()
-    if not force and not _stale(SO, deps):
-        return SO
     # per-object dependencies, so that touching the ABI or the scan kernels does not recompile the
     # thirteen per-width EM translation units (minutes)
     c = lambda *names: [os.path.join(CSRC, n) for n in names]
     em_deps = c("kernels_inst.cu", "kernel_table.h", "em_kernel.cuh", "em_split_kernel.cuh", "em_wide_kernel.cuh",
-                "aux_kernels.cuh", "lds_math.cuh", "common.cuh")
+                "em_scan_kernel.cuh", "aux_kernels.cuh", "lds_math.cuh", "common.cuh")
     scan_deps = c("scan_inst.cu", "scan_kernels.cuh", "common.cuh")
     obj_deps = {}
     os.makedirs(OBJ, exist_ok=True)
@@ -93,7 +91,9 @@ def build(force=False, verbose=False, ptxas_info=False):
         for out in ex.map(lambda j: _run(j[1]), todo):
             logs.append(out)
     objs = [o for o, _ in jobs]
-    logs.append(_run([NVCC, "-shared", "-o", SO] + objs + ["-cudart", "static", "-lpthread"]))
+    # staleness is decided per object (above); the library is relinked when an object is newer than it
+    if force or todo or _stale(SO, objs):
+        logs.append(_run([NVCC, "-shared", "-o", SO] + objs + ["-cudart", "static", "-lpthread"]))
     if verbose:
         sys.stderr.write("".join(logs))
     return SO

@@ -111,6 +111,16 @@ template <int N> __device__ __forceinline__ double scan_reduce_many(double (&v)[
     return r;
 }
 
+// element idx of the thread's v rows: its own copy, or the u rows when the plan has v == u (no pointer games:
+// both arrays must stay plain register arrays)
+template <bool SHARE, int N>
+__device__ __forceinline__ double scan_vrow(const double (&u)[N], const double (&v)[SHARE ? 1 : N], int idx) {
+    if constexpr (SHARE)
+        return u[idx];
+    else
+        return v[idx];
+}
+
 template <int PQ, int L>
 __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
     static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
@@ -142,8 +152,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 
     // ---- this thread's steps: rows and mask bits, in registers for the whole launch
     const int t0 = (int)threadIdx.x * L;
-    double yr[L], ur[L * PQ], vr_own[SHARE_UV ? 1 : L * PQ];
-    double(&vr)[L * PQ] = *reinterpret_cast<double(*)[L * PQ]>(SHARE_UV ? ur : vr_own); // v == u: one set of rows
+    double yr[L], ur[L * PQ], vr_own[SHARE_UV ? 1 : L * PQ]; // v == u (wide inputs): one set of rows, see scan_vrow
     unsigned bits = 0u; // observed steps (the group's mask: finite(y) minus the hold-outs)
     {
         const double *__restrict__ blob = P.blobs + S.blob_off;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 #pragma unroll
             for (int i = 0; i < PQ; i++) {
                 ur[j * PQ + i] = real ? blob[S.u_off + (size_t)t * PQ + i] : 0.0;
-                if (!SHARE_UV) vr_own[j * PQ + i] = real ? blob[S.v_off + (size_t)t * PQ + i] : 0.0;
+                if constexpr (!SHARE_UV) vr_own[j * PQ + i] = real ? blob[S.v_off + (size_t)t * PQ + i] : 0.0;
             }
             if (real && ((mw[t >> 5] >> (t & 31)) & 1u)) bits |= 1u << j;
         }
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 #pragma unroll
                 for (int i = 0; i < PQ; i++) {
                     b = fma(th.B[i], ur[j * PQ + i], b);
-                    dv = fma(th.D[i], vr[j * PQ + i], dv);
+                    dv = fma(th.D[i], scan_vrow<SHARE_UV, L * PQ>(ur, vr_own, j * PQ + i), dv);
                 }
                 Bu[j] = b;
                 ymd[j] = yr[j] - dv;
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 sums[2] += obs ? Vs[j] : 0.0;
 #pragma unroll
                 for (int i = 0; i < PQ; i++) {
-                    sums[7 + i] = fma(xo, vr[j * PQ + i], sums[7 + i]);
+                    sums[7 + i] = fma(xo, scan_vrow<SHARE_UV, L * PQ>(ur, vr_own, j * PQ + i), sums[7 + i]);
                     sums[7 + PQ + i] = fma(xb, ur[j * PQ + i], sums[7 + PQ + i]);
                     sums[7 + 2 * PQ + i] = fma(ur[j * PQ + i], xa, sums[7 + 2 * PQ + i]);
                 }
