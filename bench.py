@@ -201,7 +201,7 @@ def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak, c
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
         dist.barrier()
-    step_ms, stats = device_steps(plan, args, args.strong_steps, 1, torch, flush, stream)
+    step_ms, stats = device_steps(plan, args, args.strong_steps, 3, torch, flush, stream)  # 3 warm-up steps
     res = plan.fetch(want_traj=False)
     my = torch.tensor([sum(step_ms) / len(step_ms), float(res["iters"].sum()), total_flops(mine, res["iters"]),
                        float(np.mean([st["em_kernel_ns"] for st in stats])) * 1e-6], dtype=torch.float64, device=dev)
@@ -222,7 +222,8 @@ def strong_block(args, rank, world, local, dev, torch, dist, flush, fp64_peak, c
     if rank == 0:
         flops = float(allv[:, 2].sum())
         out = {"workload": w3["name"], "scaling": "strong", "n_fits": nf, "n_groups": ng, "n_gpus": world,
-               "steps": args.strong_steps, "value": nf / (step * 1e-3), "unit": "fits/s", "ms_per_step": step,
+               "steps": args.strong_steps, "warmup": 3, "l2": "flushed (256 MiB write) between timed steps",
+               "value": nf / (step * 1e-3), "unit": "fits/s", "ms_per_step": step,
                "per_rank_ms": [round(float(x), 3) for x in per_rank_ms],
                "per_rank_em_kernel_ms": [round(float(x), 3) for x in allv[:, 3]],
                "imbalance": float(per_rank_ms.max() / per_rank_ms.mean() - 1.0),
@@ -266,7 +267,7 @@ def config1_block(args, local, torch, flush):
     for name, n in (("restarts_100", 100), ("single_fit", 1)):
         sub = dict(w, fit_group=w["fit_group"][:n], theta0=w["theta0"][:n])
         plan = _lib.Plan(sub["series"], sub["group_series"], sub["held"], sub["fit_group"], sub["theta0"], device=local)
-        ms, stats = device_steps(plan, args, 5, 2, torch, flush, stream)
+        ms, stats = device_steps(plan, args, 5, 3, torch, flush, stream)
         res = plan.fetch(want_traj=False)
         rec = {"n_fits": n, "ms": float(np.median(ms)), "value": n / (float(np.median(ms)) * 1e-3), "unit": "fits/s",
                "mean_iters": float(res["iters"].mean()), "kernel": stats[0]["kernel"]}
