@@ -14,6 +14,35 @@
 #define LDSR_STATIC_SMEM(type, name) static type name
 #endif
 
+// Plan-consistency checks inside the kernels (compute-sanitizer is not available on the GPU pool): always on in
+// the CPU emulation (tests/host_simt), on the device only in a -DLDSR_DEBUG_CHECKS build (tools/gpu_jobs/
+// debug_checks.sh runs the GPU test suite against it).  They assert, once per task, that everything the shared-
+// memory carve-up was sized from on the host (units, observed-unit steps, series length, aliased scratch) holds
+// for what the kernel derives on the device -- every index used afterwards is bounded by these.
+#if defined(LDSR_HOST_SIM)
+#define LDSR_CHECK(cond)                                                                          \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            std::fprintf(stderr, "LDSR_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);   \
+            std::abort();                                                                         \
+        }                                                                                         \
+    } while (0)
+#elif defined(LDSR_DEBUG_CHECKS)
+#include <cstdio>
+#define LDSR_CHECK(cond)                                                                                          \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            printf("LDSR_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                             \
+            __trap();                                                                                             \
+        }                                                                                                         \
+    } while (0)
+#else
+#define LDSR_CHECK(cond) \
+    do {                 \
+    } while (0)
+#endif
+
 namespace ldsr {
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     const int4 task = P.tasks[ti];
     const SeriesDev S = P.series[task.x];
     const int T = S.T;
+    LDSR_CHECK((int)blockDim.x * L >= T && nw <= SCAN_MAX_WARPS && task.z == 1); // the block covers the series
+    LDSR_CHECK(!SHARE_UV || S.same_uv);
     const int fit = P.active[task.y];
     const int grp = P.f_group[fit];
     const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);

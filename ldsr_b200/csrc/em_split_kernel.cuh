@@ -903,6 +903,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             }
             split_range<NW>(units, 0, best, SP.cost_u, SP.cost_m, MSEG, pbound);
             split_range<NW>(units, best, nu, SP.cost_u, SP.cost_m, MSEG, pbound + NW);
+            LDSR_CHECK(nu <= SP.max_units && (T + UW - 1) / UW <= SP.max_uunits); // what the host sized the carve-up from
+            for (int w = 0; w < 2 * NW; ++w) LDSR_CHECK(pbound[w] >= 0 && pbound[w] <= pbound[w + 1] && pbound[w + 1] <= nu);
         }
     }
     mbar_wait(&bar, phase);

@@ -618,6 +618,19 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             sbound[NW] = T;
             pbound[NP + 1] = nu; // number of units
             pbound[NP + 2] = nm; // number of Dv rows = steps inside observed units
+            // the host sized the carve-up from these (wide_count_units, wide_smem_bytes)
+            LDSR_CHECK(nu <= WP.max_units && nm <= WP.max_msteps && T <= WP.max_T);
+            LDSR_CHECK((size_t)(NW + 1) * NST + 3 * PQ <=
+                       wide_traj_rows(PQ, NW, WP.max_T, WP.max_units, WP.max_msteps) +
+                           (size_t)(WP.max_msteps > 0 ? WP.max_msteps : 1) + (size_t)3 * WP.max_units);
+            for (int w = 0; w < NW; ++w) {
+                LDSR_CHECK(pbound[w] >= 0 && pbound[w] <= pbound[w + 1] && pbound[w + 1] <= nu);
+                LDSR_CHECK(sbound[w] >= 0 && sbound[w] <= sbound[w + 1] && sbound[w + 1] <= T && (sbound[w] & 3) == 0);
+            }
+            for (int i = 0; i < nu; ++i)
+                if (units[i] & (UNIT_M | UNIT_M1))
+                    LDSR_CHECK(ubase[i] >= 0 && ubase[i] + ((units[i] & UNIT_M) ? MSEG : 1) <= nm);
+            for (int i = 0; i < nm; ++i) LDSR_CHECK(mlist[i] >= 0 && mlist[i] < T);
         }
     }
     mbar_wait(&bar, phase);
