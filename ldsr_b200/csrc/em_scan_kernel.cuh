@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     const int grp = P.f_group[fit];
     const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);
     const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
-    const double n_obs = gc[1];
+    const double n_obs = gc[1], inv_n_obs = 1.0 / n_obs;
 
     // ---- this thread's steps: rows and mask bits, in registers for the whole launch
     const int t0 = (int)threadIdx.x * L;
@@ -187,6 +187,20 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
 
     for (int it = 0; live && it < P.chunk; ++it) {
         const double A = th.A, Q = th.Q, Cc = th.C, R = th.R;
+
+        // the input terms of my steps do not wait for anything: issued here, they overlap the first scan
+        double Bu[L], ymd[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            double b = 0.0, dv = 0.0;
+#pragma unroll
+            for (int i = 0; i < PQ; i++) {
+                b = fma(th.B[i], ur[j * PQ + i], b);
+                dv = fma(th.D[i], scan_vrow<SHARE_UV, L * PQ>(ur, vr_own, j * PQ + i), dv);
+            }
+            Bu[j] = b;
+            ymd[j] = yr[j] - dv;
+        }
 
         // ================= P1: variance map of my steps, scan =================
         double e11, e12, e21, e22; // exclusive prefix inside the warp
@@ -260,18 +274,6 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         double acc_l0, acc_l1, acc_l2;             // sum_obs delta^2/Sigma = l0 - 2 C x l1 + C^2 x^2 l2
         double PJ, G0, GG, Lc;                     // my backward map
         {
-            double Bu[L], ymd[L];
-#pragma unroll
-            for (int j = 0; j < L; j++) {
-                double b = 0.0, dv = 0.0;
-#pragma unroll
-                for (int i = 0; i < PQ; i++) {
-                    b = fma(th.B[i], ur[j * PQ + i], b);
-                    dv = fma(th.D[i], scan_vrow<SHARE_UV, L * PQ>(ur, vr_own, j * PQ + i), dv);
-                }
-                Bu[j] = b;
-                ymd[j] = yr[j] - dv;
-            }
             // gains: the variance in homogeneous coordinates (n, d), all reciprocals after the chain
             double nj[L], dj[L], nn[L], dd[L];
             {
@@ -382,7 +384,9 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         __syncthreads(); // B3
         double acc = 0.0;
         for (int w = 0; w < nw; ++w) acc += S3[w];
-        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs; // EM.cpp:122-124
+        // EM.cpp:122-124: (-n/2 log 2pi - acc/2) / n, the division by n as a multiplication by its (once per task,
+        // correctly rounded) reciprocal: it sits on the critical path of every thread
+        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
 
         // ================= stop rule (EM.cpp:259-275): the same in every thread =================
         lik = lik_new;
@@ -503,14 +507,14 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 st.VT = ENDS[3];
                 Theta<PQ> tn = th;
                 if (do_obs) {
-                    mstep_obs_block<PQ>(st, gc, tn);
+                    mstep_obs_block<PQ, true>(st, gc, tn);
                     THS[1 + PQ] = tn.C;
 #pragma unroll
                     for (int i = 0; i < PQ; i++) THS[2 + PQ + i] = tn.D[i];
                     THS[3 + 2 * PQ] = tn.R;
                 }
                 if (do_trans) {
-                    mstep_trans_block<PQ>(st, tuu_inv, T, tn);
+                    mstep_trans_block<PQ, true>(st, tuu_inv, T, tn);
                     THS[0] = tn.A;
 #pragma unroll
                     for (int i = 0; i < PQ; i++) THS[1 + i] = tn.B[i];

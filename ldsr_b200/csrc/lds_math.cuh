@@ -123,8 +123,17 @@ template <int PQ> struct Stats {
 //   Q = (Tx1x1 - A Tx1x - B.Tx1u)/(T-1)                                     (EM.cpp:210)
 // With TuuInv = 0 (no u) this reduces to A = Tx1x/Txx, B = 0 (EM.cpp:212-213); likewise C, D.
 // gc -> [Syy, n_obs, Syv[PQ], wy[PQ], SvvInv[PQ*PQ]] (per group), tuu_inv -> [PQ*PQ] (per series).
+// a / b.  FAST: a * fast_rcp(b) (about 1 ulp; for the latency path of the scan kernel, where the M-step is a
+// serial section of one thread and an IEEE division costs ~130 cycles)
+template <bool FAST> __device__ __forceinline__ double mstep_div(double a, double b) {
+    if constexpr (FAST)
+        return a * fast_rcp(b);
+    else
+        return a / b;
+}
+
 // The observation block: C, D, R (EM.cpp:164-177).
-template <int PQ>
+template <int PQ, bool FAST = false>
 __device__ __forceinline__ void mstep_obs_block(const Stats<PQ> &s, const double *__restrict__ gc, Theta<PQ> &th) {
     const double Syy = gc[0], n_obs = gc[1];
     const double *Syv = gc + 2, *wy = gc + 2 + PQ, *svv_inv = gc + 2 + 2 * PQ;
@@ -143,7 +152,7 @@ __device__ __forceinline__ void mstep_obs_block(const Stats<PQ> &s, const double
         num = fma(-wy[a], s.Sxv[a], num);
         den = fma(-s.Sxv[a], z[a], den);
     }
-    const double Cn = num / den;
+    const double Cn = mstep_div<FAST>(num, den);
     double racc = fma(-Cn, s.Syx, Syy);
 #pragma unroll
     for (int a = 0; a < PQ; a++) {
@@ -152,10 +161,10 @@ __device__ __forceinline__ void mstep_obs_block(const Stats<PQ> &s, const double
         racc = fma(-d, Syv[a], racc);
     }
     th.C = Cn;
-    th.R = racc / n_obs;
+    th.R = mstep_div<FAST>(racc, n_obs);
 }
 // The transition block: A, B, Q, mu1, V1 (EM.cpp:180-219).
-template <int PQ>
+template <int PQ, bool FAST = false>
 __device__ __forceinline__ void mstep_trans_block(const Stats<PQ> &s, const double *__restrict__ tuu_inv, int T,
                                                   Theta<PQ> &th) {
     const double Txx = s.Txx + s.Txxv, Tx1x = s.Tx1x + s.Tx1xv; // EM.cpp:180,181
@@ -178,7 +187,7 @@ __device__ __forceinline__ void mstep_trans_block(const Stats<PQ> &s, const doub
         num = fma(-s.Tx1u[a], z[a], num);
         den = fma(-s.Tux[a], z[a], den);
     }
-    const double An = num / den;
+    const double An = mstep_div<FAST>(num, den);
     // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
     const double Tx1x1 = Txx - fma(s.X0, s.X0, s.V0) + fma(s.XT, s.XT, s.VT);
     double qacc = fma(-An, Tx1x, Tx1x1);
@@ -189,7 +198,7 @@ __device__ __forceinline__ void mstep_trans_block(const Stats<PQ> &s, const doub
         qacc = fma(-b, s.Tx1u[a], qacc);
     }
     th.A = An;
-    th.Q = qacc / (double)(T - 1);
+    th.Q = mstep_div<FAST>(qacc, (double)(T - 1));
     th.mu1 = s.X0; // EM.cpp:218-219
     th.V1 = s.V0;
 }
