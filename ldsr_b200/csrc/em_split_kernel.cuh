@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     const unsigned *__restrict__ mw = P.masks + P.g_mask_off[grp];
     const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);
     const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
-    const double n_obs = gc[1];
+    const double n_obs = gc[1], inv_n_obs = 1.0 / n_obs;
     constexpr int TL = theta_pad_len<PQ>();
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta + (size_t)fit * TL);
@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 }
             }
         }
-        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs; // EM.cpp:122-124
+        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs; // EM.cpp:122-124 (x 1/n, rounded once per task)
 
         // ================= stop rule (EM.cpp:259-275) =================
         if (live) {
@@ -1160,7 +1160,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         }
         LDSR_PHASE_MARK(11);
         if (!PAIR) {
-            if (live) mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
+            if (live) mstep_from_stats<PQ, true>(st, gc, tuu_inv, T, th); // reciprocal multiplies: a serial section
         } else {
             // Wide inputs: the M-step is two (PQ+1)-dimensional solves, thousands of instructions.  Done once,
             // by warp 0, and published through shared memory (the partial-sum slots are dead once warp 0
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                         th.D[i] = TD[i * 32];
                     }
                 }
-                if (live) mstep_from_stats<PQ>(st, gc, tuu_inv, T, th);
+                if (live) mstep_from_stats<PQ, true>(st, gc, tuu_inv, T, th); // reciprocal multiplies: a serial section
                 if (BD_SMEM) {
 #pragma unroll
                     for (int i = 0; i < PQ; i++) {

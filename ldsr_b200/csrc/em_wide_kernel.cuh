@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
     const int grp = P.f_group[fit];
     const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);
     const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
-    const double n_obs = gc[1];
+    const double n_obs = gc[1], inv_n_obs = 1.0 / n_obs;
     constexpr int TL = theta_pad_len<PQ>();
     Theta<PQ> th;
     th.sb = TB;
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                 Vr = vend;
             }
         }
-        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) / n_obs; // EM.cpp:122-124
+        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs; // EM.cpp:122-124 (x 1/n, rounded once per task)
 
         // ================= stop rule (EM.cpp:259-275) =================
         if (live) {
@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                     num = fma(-wy[a], sxv, num);
                     den = fma(-sxv, ZW[a * 32], den);
                 }
-                const double Cn = num / den;
+                const double Cn = mstep_div<true>(num, den); // reciprocal multiplies: a serial section
                 double racc = fma(-Cn, Syx, Syy);
 #pragma unroll
                 for (int a = 0; a < PQ; a++) {
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                     racc = fma(-d, Syv[a], racc);
                 }
                 th.C = Cn;
-                th.R = racc / n_obs;
+                th.R = racc * inv_n_obs;
             }
             TH[1 * 32] = th.C;
             TH[3 * 32] = th.R;
@@ -1028,7 +1028,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                     num = fma(-TOT[(11 + PQ + a) * 32], z, num);     // Tx1u . z
                     den = fma(-TOT[(11 + 2 * PQ + a) * 32], z, den); // Tux . z
                 }
-                const double An = num / den;
+                const double An = mstep_div<true>(num, den);
                 // Tx1x1 = sum_{t=1}^{T-1} (X_t^2+V_t) = Txx - (X_0^2+V_0) + (X_{T-1}^2+V_{T-1})   (EM.cpp:181,183)
                 const double Tx1x1 = Txx - fma(X0, X0, V0) + fma(XT, XT, VT);
                 double qacc = fma(-An, Tx1x, Tx1x1);
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
                     qacc = fma(-bb, TOT[(11 + PQ + a) * 32], qacc);
                 }
                 th.A = An;
-                th.Q = qacc / (double)(T - 1);
+                th.Q = mstep_div<true>(qacc, (double)(T - 1));
                 th.mu1 = X0; // EM.cpp:218-219
                 th.V1 = V0;
             }

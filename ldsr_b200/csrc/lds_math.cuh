@@ -202,11 +202,11 @@ __device__ __forceinline__ void mstep_trans_block(const Stats<PQ> &s, const doub
     th.mu1 = s.X0; // EM.cpp:218-219
     th.V1 = s.V0;
 }
-template <int PQ>
+template <int PQ, bool FAST = false>
 __device__ __forceinline__ void mstep_from_stats(const Stats<PQ> &s, const double *__restrict__ gc,
                                                  const double *__restrict__ tuu_inv, int T, Theta<PQ> &th) {
-    mstep_obs_block<PQ>(s, gc, th);
-    mstep_trans_block<PQ>(s, tuu_inv, T, th);
+    mstep_obs_block<PQ, FAST>(s, gc, th);
+    mstep_trans_block<PQ, FAST>(s, tuu_inv, T, th);
 }
 
 } // namespace ldsr
