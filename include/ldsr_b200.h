@@ -149,7 +149,9 @@ int ldsr_plan_create(const ldsr_batch *batch, int device, ldsr_plan **out, char 
  * are returned through the optional long long[8] `stats`:
  * {kernel launches issued, EM chunks (= em_chunk_kernel launches), total E-steps executed (all
  *  fits), summed device time of the EM kernel launches in ns (CUDA events on `stream`),
- *  which EM kernel ran: 0 lane-per-fit, 1 time-split, 2 wide-input time-split, 3 small-batch scan; 0, 0, 0}. */
+ *  which EM kernel ran: 0 lane-per-fit, 1 time-split, 2 wide-input time-split, 3 small-batch scan;
+ *  CTAs of the co-resident grid that shared the tasks by iterations (time-split kernel, batches of one to four
+ *  waves; 0 = one CTA per task); 0, 0}. */
 int ldsr_plan_em(ldsr_plan *plan, int niter, double tol, const ldsr_options *opt, void *stream,
                  long long *stats, char *errbuf, int errlen);
 int ldsr_plan_set_theta0(ldsr_plan *plan, const double *theta0_host, char *errbuf, int errlen);

@@ -265,7 +265,8 @@ class Plan:
         self.niter = niter
         self.trace = bool(trace_liks)
         return dict(launches=stats[0], chunks=stats[1], esteps=stats[2], em_kernel_ns=stats[3],
-                    kernel=("em_chunk_kernel", "em_split_kernel", "em_wide_kernel", "em_scan_kernel")[stats[4]])
+                    kernel=("em_chunk_kernel", "em_split_kernel", "em_wide_kernel", "em_scan_kernel")[stats[4]],
+                    shared_slots=stats[5])
 
     def set_theta0(self, theta0):
         th = np.ascontiguousarray(theta0, dtype=np.float64)

@@ -115,6 +115,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 }
 #endif
 
+// ---- hand-over of a fit's state between CTAs of one (co-resident) launch (em_split_kernel.cuh, task loop)
+#ifndef LDSR_HOST_SIM
+template <class T> __device__ __forceinline__ T ld_l2(const T *p) { return __ldcg(p); } // L1 is not coherent across SMs
+__device__ __forceinline__ void flag_raise(int *flag, int value) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const int *flag, int value) {
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == value) break;
+        __nanosleep(200);
+    }
+}
+#else
+template <class T> __device__ __forceinline__ T ld_l2(const T *p) { return *p; }
+__device__ __forceinline__ void flag_raise(int *flag, int value) { *flag = value; }
+// the emulator runs one CTA at a time, the harness the highest CTA first: the producer has always finished
+__device__ __forceinline__ void flag_wait(const int *flag, int value) { LDSR_CHECK(*flag == value); }
+#endif
+
 // Stage `bytes` (multiple of 16) from global to shared with TMA bulk copies issued by one thread.
 // Pieces of <= 32 KB keep each transaction well inside the mbarrier tx-count range.
 __device__ __forceinline__ void stage_blob(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {

@@ -730,6 +730,10 @@ struct SplitParams {
     int max_uunits;     // number of UW-step windows of the longest series
     int blob_smem;      // bytes reserved for the series blob at the start of dynamic shared memory
     int cost_u, cost_m; // relative cost of a U unit and an M unit (piece balancing)
+    // Iteration-level sharing of the tasks between the CTAs of a CO-RESIDENT grid (cooperative launch), for batches of
+    // a little more than one wave; NULL: CTA b takes tasks b, b + gridDim.x, ... whole.  See the kernel's task loop.
+    int *flags; // [n_tasks] flags[j] == epoch: the first part of task j has been written back
+    int epoch;  // differs from every value left in flags by earlier launches
 #ifdef LDSR_PHASE_CLOCKS
     long long *clk; // development build: [CTA][NW][21] cycles per phase / unit type of the iteration loop
 #endif
@@ -800,10 +804,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     __syncthreads();
     // The grid is an upper bound on (or, with fewer CTAs than tasks, a divisor of) the task count,
     // which the launch reads from device memory: CTA b takes tasks b, b + gridDim.x, ...
+    //
+    // With SP.flags the grid is co-resident (cooperative launch) and shares the tasks by ITERATIONS, so that a batch
+    // of a little more than one wave costs its share of a wave instead of two (10 000 fits are 313 tasks for 296
+    // slots).  A fit's state lives in global memory between launches anyway, so a task can stop after any
+    // iteration and continue elsewhere with identical results.  McNaughton's wrap-around rule: the n * chunk
+    // task-iterations are laid on a line, task j on [j chunk, (j+1) chunk), and cut into gridDim.x slots of
+    // M = max(chunk, ceil(n chunk / gridDim.x)); a task cut by a slot boundary runs its FIRST iterations at
+    // the start of the later slot and its remaining ones at the end of the earlier slot, which waits for the flag
+    // the first part raises (M >= chunk: the two parts never overlap in a balanced run, so the wait is short).
     const int n_tasks = *P.n_tasks;
     unsigned phase = 0;
-    for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x, phase ^= 1u) {
-    if (ti != (int)blockIdx.x) __syncthreads(); // the previous task's shared memory is dead
+    // (few registers may live across the iteration loop: only w_lo and n_it do; the rest is recomputed)
+    int w_lo = 0; // where on the line of task-iterations my next segment starts (the host keeps n chunk < 2^31)
+    const auto slot_len = [&]() -> int {
+        const int W = n_tasks * P.chunk, M = (W + (int)gridDim.x - 1) / (int)gridDim.x;
+        return M < P.chunk ? P.chunk : M;
+    };
+    if (SP.flags) w_lo = (int)blockIdx.x * slot_len();
+    for (int seg = 0;; ++seg, phase ^= 1u) {
+    int ti, n_it = P.chunk;
+    bool wait_first = false;
+    if (SP.flags) {
+        const int W = n_tasks * P.chunk, hi = ((int)blockIdx.x + 1) * slot_len(), w_hi = hi < W ? hi : W;
+        if (w_lo >= w_hi) break;
+        ti = w_lo / P.chunk;
+        const int t_end = (ti + 1) * P.chunk, end = t_end < w_hi ? t_end : w_hi;
+        n_it = end - w_lo;
+        // starting inside a task: its first n_it iterations (the slot before mine does the rest, and waits for the
+        // flag raised below); stopping inside a task: its last n_it iterations, after the next slot's CTA has done
+        // the first ones
+        wait_first = w_lo == ti * P.chunk && end < t_end;
+    } else {
+        ti = (int)blockIdx.x + seg * (int)gridDim.x;
+        if (ti >= n_tasks) break;
+    }
+    if (seg > 0) __syncthreads(); // the previous task's shared memory is dead
+    if (wait_first) {
+        if (threadIdx.x == 0) flag_wait(SP.flags + ti, SP.epoch);
+        __syncthreads();
+    }
     const int4 task = P.tasks[ti];
     const SeriesDev S = P.series[task.x];
     const int T = S.T;
@@ -836,8 +876,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
     const double n_obs = gc[1], inv_n_obs = 1.0 / n_obs;
     constexpr int TL = theta_pad_len<PQ>();
+    // a fit's state may have been written by another CTA of this launch (SP.flags): read it past L1
     Theta<PQ> th;
-    load_theta<PQ>(th, P.theta + (size_t)fit * TL);
+    {
+        double g[TL];
+#pragma unroll
+        for (int i = 0; i < TL; i++) g[i] = ld_l2(P.theta + (size_t)fit * TL + i);
+        load_theta<PQ>(th, g);
+    }
     th.sb = TB;
     th.sd = TD;
     if (BD_SMEM && warp == 0) { // visible to the other warps after the barrier that ends the set-up
@@ -847,9 +893,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             TD[i * 32] = th.D[i];
         }
     }
-    double l1 = P.l1[fit], l2 = P.l2[fit], lik = P.lik[fit];
-    int ne = P.ne[fit];
-    bool live = valid && (P.done[fit] == 0);
+    double l1 = ld_l2(P.l1 + fit), l2 = ld_l2(P.l2 + fit), lik = ld_l2(P.lik + fit);
+    int ne = ld_l2(P.ne + fit);
+    bool live = valid && (ld_l2(P.done + fit) == 0);
     if (live && P.g_status[grp] != 0) { // Gram block not invertible: the reference would throw
         live = false;
         lik = __longlong_as_double(0x7ff8000000000000ULL);
@@ -913,7 +959,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
 #ifdef LDSR_PHASE_CLOCKS
     long long pc[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
-    for (int it = 0; it < P.chunk; ++it) {
+    for (int it = 0; it < n_it; ++it) {
         if (!__any_sync(FULL, live)) break;
         SplitConst<PQ, UW> k;
         k.set(th);
@@ -1219,6 +1265,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         P.lik[fit] = lik;
         P.ne[fit] = ne;
         P.done[fit] = live ? 0 : 1;
+    }
+    if (SP.flags) {
+        if (w_lo % P.chunk != 0 && warp == 0) { // the first part of a task: release every lane's stores, then the flag
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) flag_raise(SP.flags + w_lo / P.chunk, SP.epoch);
+        }
+        w_lo += n_it;
     }
     } // task loop
 }

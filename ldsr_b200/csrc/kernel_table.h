@@ -59,7 +59,9 @@ struct KernelTable {
     cudaError_t (*em_split)(const SplitParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
     // the same kernel compiled for 2 CTAs/SM (255 registers): 9 % faster per launch when the batch
     // needs no more than two CTAs per SM; the same function as em_split when split_minb == 2
+    // With SplitParams.flags the launch is cooperative (the CTAs hand tasks over to one another).
     cudaError_t (*em_split_wide)(const SplitParams &, int n_tasks, size_t smem_bytes, cudaStream_t);
+    int (*em_split_resident)(size_t smem_bytes); // CTAs of em_split_wide one SM holds at once (0: unknown)
     // wide-input kernel: wide_nw == 0 when this width has none (PQ < WIDE_MIN_PQ)
     int wide_nw, wide_mseg;
     cudaError_t (*em_wide_prepare)(size_t smem_bytes);

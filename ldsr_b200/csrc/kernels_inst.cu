@@ -38,6 +38,8 @@ template <> cudaError_t split_prepare<PQ, 0>(size_t);
 template <> cudaError_t split_prepare<PQ, 1>(size_t);
 template <> cudaError_t split_launch<PQ, 0>(const SplitParams &, int, size_t, cudaStream_t);
 template <> cudaError_t split_launch<PQ, 1>(const SplitParams &, int, size_t, cudaStream_t);
+template <int PQV> int split_resident(size_t smem_bytes);
+template <> int split_resident<PQ>(size_t);
 
 #define LDSR_DEFINE_CHUNK(M)                                                                       \
     template <> cudaError_t chunk_prepare<PQ, M>(size_t smem_bytes) {                              \
@@ -75,8 +77,32 @@ template <> cudaError_t split_prepare<PQ, 1>(size_t smem_bytes) {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
 template <> cudaError_t split_launch<PQ, 1>(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
+    if (p.flags) {
+        // CTAs wait for one another (iteration-level task sharing): the grid must be co-resident, which a
+        // cooperative launch guarantees (it fails instead of dead-locking when the grid does not fit)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_tasks);
+        cfg.blockDim = dim3(SPLIT_NW * 32);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeCooperative;
+        at.val.cooperative = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW>, p);
+    }
     em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW><<<n_tasks, SPLIT_NW * 32, smem_bytes, st>>>(p);
     return cudaGetLastError();
+}
+template <> int split_resident<PQ>(size_t smem_bytes) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, em_split_kernel<PQ, SPLIT_NW, MINB_WIDE, SPLIT_MSEG, SPLIT_UW>,
+                                                      SPLIT_NW * 32, smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 #endif
 
@@ -159,6 +185,7 @@ cudaError_t em_split(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaS
 cudaError_t em_split_wide(const SplitParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     return split_launch<PQ, 1>(p, n_tasks, smem_bytes, st);
 }
+int em_split_resident(size_t smem_bytes) { return split_resident<PQ>(smem_bytes); }
 cudaError_t em_wide_prepare(size_t smem_bytes) { return wide_prepare<PQ>(smem_bytes); }
 cudaError_t em_wide(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStream_t st) {
     return wide_launch<PQ>(p, n_tasks, smem_bytes, st);
@@ -199,6 +226,7 @@ const KernelTable table = {PQ,
                            em_split_prepare,
                            em_split,
                            em_split_wide,
+                           em_split_resident,
                            PQ >= WIDE_MIN_PQ ? WIDE_NW : 0,
                            WIDE_MSEG,
                            em_wide_prepare,

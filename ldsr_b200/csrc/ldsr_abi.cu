@@ -244,6 +244,8 @@ struct ldsr_plan {
     int max_tasks = 0;
     unsigned long long *d_sum = nullptr;
     unsigned *d_ticket = nullptr; // compact_kernel's last-block counter (0 between launches)
+    int *d_share_flags = nullptr; // [max_tasks] hand-over flags of em_split_kernel's iteration-level task sharing
+    int share_epoch = 0;          // one value per launch: the flags need no reset
     double *d_ckpt = nullptr;
     size_t ckpt_cap = 0;
     int *d_best = nullptr;
@@ -566,6 +568,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     // the time-split kernels take 32 fits per CTA; the small-batch scan kernel one fit per CTA
     P->max_tasks = std::max(nf / 32, std::min(nf, SCAN_MAX_FITS)) + ns + 1;
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_share_flags, P->max_tasks)).ok()) return e;
+    CU(cudaMemsetAsync(P->d_share_flags, 0, (size_t)P->max_tasks * sizeof(int), P->stream));
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
 
     // ---- set-up kernel: masks + Gram constants
@@ -752,6 +756,21 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     int grid0 = 0; // task count of the first chunk: every fit is live
     for (int s = 0; s < ns; s++)
         grid0 += (P->h_series[s].fit_end - P->h_series[s].fit_begin + fits_per_cta - 1) / fits_per_cta;
+    // Batches of one to four waves of the time-split kernel (10 000 fits: 313 tasks for 2 x 148 CTAs): a co-resident
+    // grid shares the tasks by ITERATIONS (em_split_kernel.cuh, task loop), so the chunk costs its share of a
+    // wave (313/296) instead of a second wave or a third CTA per SM with 168 registers.  Beyond four waves the
+    // hardware's dealing of whole tasks balances better: tasks end early as their fits converge.
+    int share_slots = 0;
+    if (use_split && P->kt->em_split_resident) {
+        static const bool no_share = std::getenv("LDSR_NO_SHARE") != nullptr; // development: A/B measurement
+        int coop = 0, dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        const int slots = P->kt->em_split_resident(smem) * P->n_sm;
+        if (!no_share && coop && slots > 0 && grid0 > slots && grid0 <= 4 * slots &&
+            (long long)(grid0 + 1) * chunk < (1ll << 31)) // the kernel's line of task-iterations is an int
+            share_slots = slots;
+    }
     if ((int)P->counts_cap < 2 * max_chunks) {
         Err e = P->drealloc(&P->d_counts, (size_t)2 * max_chunks);
         if (!e.ok()) return e;
@@ -791,6 +810,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         // the wide-input kernel holds one CTA per SM: one CTA per task, dealt to the SMs by the hardware as
         // they finish (tasks differ in length: fits stop at different iterations)
         if (use_wide || use_scan) grid = grid0;
+        if (share_slots > 0) grid = share_slots;
         // development: LDSR_MAX_GRID caps the grid so that a small batch exercises the task loop of the
         // kernels (tools/sanitize.py runs it under compute-sanitizer)
         static const int grid_cap = std::getenv("LDSR_MAX_GRID") ? std::atoi(std::getenv("LDSR_MAX_GRID")) : 0;
@@ -799,6 +819,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             CU(cudaMemcpyAsync(P->h_counts + 2 * c, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             grid = std::max(1, P->h_counts[2 * c]);
+            if (share_slots > 0) grid = std::min(grid, share_slots);
             if (P->h_counts[2 * c + 1] == 0) break;
             if (abort_flag) {
                 if (abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
@@ -870,8 +891,10 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             if (!sp_clk_last) cudaMalloc(&sp_clk_last, sizeof(long long) * 4096 * 21 * 8);
             sp.clk = (c == 1 && grid <= 4096) ? sp_clk_last : nullptr; // the second launch: a two-per-SM wave
 #endif
+            sp.flags = share_slots > 0 ? P->d_share_flags : nullptr;
+            sp.epoch = ++P->share_epoch;
             // one wave of at most two CTAs per SM: the 255-register build of the kernel
-            if (grid <= 2 * P->n_sm)
+            if (grid <= 2 * P->n_sm || sp.flags)
                 CU(P->kt->em_split_wide(sp, grid, smem, st));
             else
                 CU(P->kt->em_split(sp, grid, smem, st));
@@ -997,7 +1020,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         stats[2] = (long long)total;
         stats[3] = (long long)(em_ms * 1e6);
         stats[4] = use_scan ? 3 : (use_wide ? 2 : (use_split ? 1 : 0)); // which EM kernel ran
-        stats[5] = stats[6] = stats[7] = 0;
+        stats[5] = share_slots; // > 0: the CTAs of a co-resident grid shared the tasks by iterations
+        stats[6] = stats[7] = 0;
     }
     return Err();
 }

@@ -109,7 +109,9 @@ inline void trampoline() {
 }
 
 // order: 0 forward, 1 reverse, >= 2 seed of a shuffle re-drawn every round
-template <class F> void launch(unsigned grid, unsigned block, size_t smem_bytes, int order, F kernel_call) {
+// highest_cta_first: for kernels whose CTAs wait for flags raised by higher-numbered CTAs (one CTA runs at a time)
+template <class F>
+void launch(unsigned grid, unsigned block, size_t smem_bytes, int order, F kernel_call, bool highest_cta_first = false) {
     State &s = st();
     const size_t page = (size_t)sysconf(_SC_PAGESIZE);
     const size_t need = (smem_bytes + 127) & ~size_t(127);
@@ -125,7 +127,8 @@ template <class F> void launch(unsigned grid, unsigned block, size_t smem_bytes,
     std::mt19937 rng((unsigned)order * 2654435761u + 12345u);
     gridDim = {grid, 1, 1};
     blockDim = {block, 1, 1};
-    for (unsigned b = 0; b < grid; b++) {
+    for (unsigned bi = 0; bi < grid; bi++) {
+        const unsigned b = highest_cta_first ? grid - 1 - bi : bi;
         std::memset(dyn, 0xFF, need);
         s.dyn = dyn;
         s.block = Group();
@@ -193,6 +196,7 @@ template <class T> inline T warp_exchange(T v, int src_lane) {
 static inline void __syncthreads() {
     hostsim::sync_group(hostsim::st().block, (int)blockDim.x);
 }
+static inline void __threadfence() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     hostsim::sync_group(hostsim::st().warps[hostsim::warp_id()], hostsim::warp_width());
 }

@@ -239,6 +239,7 @@ template <int PQ> int run(const Job &J) {
     const int max_uunits = (T + UW - 1) / UW;
 
     const int max_chunks = (J.niter + J.chunk - 1) / J.chunk;
+    std::vector<int> share_flags;
     for (int c = 0; c < max_chunks; c++) {
         // compact_kernel: live fits in order, 32 (or 128) per CTA
         const int per = J.kind == 2 ? 32 * 4 : (J.kind == 5 ? 1 : 32);
@@ -253,6 +254,15 @@ template <int PQ> int run(const Job &J) {
         if (J.grid_cap > 0) grid = std::min(grid, J.grid_cap);
         if (J.kind == 3) {
             SplitParams sp;
+            // grid_cap < 0: -grid_cap CTAs share the tasks by iterations (hand-over flags); the emulator runs one CTA
+            // at a time, the highest first, so the part of a task that must run first always has
+            const bool share = J.grid_cap < 0;
+            if (share) {
+                grid = -J.grid_cap;
+                share_flags.resize(std::max<size_t>(share_flags.size(), (size_t)n_tasks), 0);
+            }
+            sp.flags = share ? share_flags.data() : nullptr;
+            sp.epoch = c + 1;
             sp.em = ep;
             sp.max_units = max_units;
             sp.max_uunits = max_uunits;
@@ -260,7 +270,7 @@ template <int PQ> int run(const Job &J) {
             sp.cost_u = UW * 22;
             sp.cost_m = MSEG * 168;
             const size_t smem = blob_sm + split_smem_bytes(PQ, NW, max_units, max_uunits);
-            hostsim::launch(grid, NW * 32, smem, J.order, [&] { em_split_kernel<PQ, NW, 2, MSEG, UW>(sp); });
+            hostsim::launch(grid, NW * 32, smem, J.order, [&] { em_split_kernel<PQ, NW, 2, MSEG, UW>(sp); }, share);
         } else if (J.kind == 2) {
             constexpr int SEG = 8, W = 4;
             ep.max_seg = (T + SEG - 1) / SEG;

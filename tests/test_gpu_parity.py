@@ -524,6 +524,28 @@ def test_task_loop_when_later_chunks_have_more_tasks_than_ctas():
         assert np.array_equal(a["theta"], b["theta"], equal_nan=True)
 
 
+def test_tasks_shared_by_iterations_equal_separate_runs():
+    """Between one and four waves the time-split kernel's co-resident grid shares the tasks by iterations (a task's
+    first iterations on one CTA, the rest on another, handed over through global memory and a flag: 375 and 313
+    tasks on 296 CTAs).  The results must equal, bit for bit, those of the same fits run as two batches that
+    each fit one wave (one CTA per task, no hand-over), and the call must report the time-split kernel."""
+    from ldsr_b200 import workloads as W
+    for folds, niter in ((120, 130), (100, 230)):
+        w = W.np_cv(folds, 100)
+        a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], niter, 1e-5,
+                          want_traj=False)
+        st = _lib.Plan(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"]).em(niter=3)
+        assert st["kernel"] == "em_split_kernel" and 0 < st["shared_slots"] < folds * 100 // 32
+        for half in (np.arange(0, folds // 2), np.arange(folds // 2, folds)):
+            h = W.take_groups(w, half)
+            b = _lib.em_batch(h["series"], h["group_series"], h["held"], h["fit_group"], h["theta0"], niter, 1e-5,
+                              want_traj=False)
+            f = h["fits"]
+            assert np.array_equal(b["iters"], a["iters"][f]) and np.array_equal(b["lik"], a["lik"][f])
+            assert np.array_equal(b["theta"], a["theta"][f], equal_nan=True)
+            assert np.array_equal(f[b["best"]], a["best"][half])
+
+
 def test_lds_rep_chunked_pipeline_equals_the_single_kernel_path(tmp_path):
     """ldsr_rep_batch simulates every replicate in one kernel when the output fits HBM and in pipelined chunks
     otherwise; the device generator is keyed by (seed, replicate, step), so both give the same bits.  The

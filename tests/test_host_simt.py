@@ -101,6 +101,19 @@ def test_emulated_task_loop_reuses_shared_memory_safely():
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("slots,chunk,n_rest", [(2, 5, 35), (2, 4, 35), (4, 5, 35), (3, 5, 70)])
+def test_emulated_tasks_shared_by_iterations(slots, chunk, n_rest):
+    """Iteration-level task sharing (SplitParams.flags): 3 tasks on 2 CTAs -- a task's first iterations at the
+    start of one CTA's slot, the rest at the end of the previous one's --, on more CTAs than tasks, and 5 tasks
+    on 3 CTAs (the middle CTA: end of one task, a whole task, start of another); results are bit-identical to
+    one CTA per task, whatever the chunk length."""
+    y, u, held, fg, th0 = _np_job(n_folds=2, n_rest=n_rest)  # 70 fits = 3 tasks, 140 = 5
+    a = sim_em(3, y, u, u, held, fg, th0, 7, chunk=chunk, order=2, grid_cap=-slots)
+    b = sim_em(3, y, u, u, held, fg, th0, 7, chunk=7, order=0, grid_cap=0)
+    for k in ("theta", "lik", "iters"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def _wide_job(p=10, T=150, n_fits=40, seed=3, first_obs=60):
     rng = np.random.default_rng(seed)
     u = rng.standard_normal((p, T)) * np.sqrt(4.0 / np.arange(1, p + 1))[:, None]
