@@ -115,6 +115,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 }
 #endif
 
+// Control block (ints) of em_split_kernel's ranked task assignment, zeroed before every launch by compact_kernel:
+// [0] SMs seen, [1] CTAs that have done their share, [2 + smid] CTAs arrived on the SM, [2 + 1024 + smid] 1 + rank of the SM,
+// [2 + 2048 + smid] CTAs of the SM that have done their share
+constexpr int SHARE_CTL_SMS = 0, SHARE_CTL_FINISHED = 1, SHARE_CTL_SLOT = 2, SHARE_MAX_SMID = 1024,
+              SHARE_CTL_RANK = SHARE_CTL_SLOT + SHARE_MAX_SMID, SHARE_CTL_DONE = SHARE_CTL_RANK + SHARE_MAX_SMID,
+              SHARE_CTL_LEN = SHARE_CTL_DONE + SHARE_MAX_SMID;
+
 // ---- hand-over of a fit's state between CTAs of one (co-resident) launch (em_split_kernel.cuh, task loop)
 #ifndef LDSR_HOST_SIM
 template <class T> __device__ __forceinline__ T ld_l2(const T *p) { return __ldcg(p); } // L1 is not coherent across SMs
@@ -129,8 +136,27 @@ __device__ __forceinline__ void flag_wait(const int *flag, int value) {
         __nanosleep(200);
     }
 }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned sm_id(int /*slots_per_sm*/) {
+    unsigned v;
+    asm("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
 #else
 template <class T> __device__ __forceinline__ T ld_l2(const T *p) { return *p; }
+__device__ __forceinline__ int ld_acquire(const int *p) { return *p; }
+__device__ __forceinline__ int ld_relaxed(const int *p) { return *p; }
+// the emulated grid fills "SMs" of slots_per_sm CTAs in launch order: CTA b sits on SM b mod (grid / slots_per_sm)
+__device__ __forceinline__ unsigned sm_id(int slots_per_sm) { return blockIdx.x % (gridDim.x / slots_per_sm); }
 __device__ __forceinline__ void flag_raise(int *flag, int value) { *flag = value; }
 // the emulator runs one CTA at a time, the harness the highest CTA first: the producer has always finished
 __device__ __forceinline__ void flag_wait(const int *flag, int value) { LDSR_CHECK(*flag == value); }

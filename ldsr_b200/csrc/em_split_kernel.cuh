@@ -734,6 +734,12 @@ struct SplitParams {
     // a little more than one wave; NULL: CTA b takes tasks b, b + gridDim.x, ... whole.  See the kernel's task loop.
     int *flags; // [n_tasks] flags[j] == epoch: the first part of task j has been written back
     int epoch;  // differs from every value left in flags by earlier launches
+    // With at most one task per CTA (and exactly two CTAs per SM): which CTA takes which task is decided by the
+    // progress of the tasks (order[]: most advanced first) and by where the CTAs landed (ctl: SHARE_CTL_*), and
+    // CTAs that are done early keep iterating until every CTA has done its `chunk`.  NULL: CTA b takes task b.
+    int *ctl;
+    const int *order;
+    int n_sm;
 #ifdef LDSR_PHASE_CLOCKS
     long long *clk; // development build: [CTA][NW][21] cycles per phase / unit type of the iteration loop
 #endif
@@ -815,6 +821,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
     // the first part raises (M >= chunk: the two parts never overlap in a balanced run, so the wait is short).
     const int n_tasks = *P.n_tasks;
     unsigned phase = 0;
+    //
+    // With at most one task per CTA (later launches: fits have converged, the tasks were re-packed) the launch
+    // takes as long as an SM that still holds two live CTAs needs for `chunk` iterations (1.37 ms against 1.0 ms
+    // for a CTA that has its SM to itself), so (SP.ctl) (a) the CTAs find out where they landed (%smid, an
+    // arrival counter per SM) and the 2x most advanced tasks go to x = n - n_sm SMs, one task each to the others:
+    // the fits with the longest way to go run alone; (b) a CTA that has done its `chunk` iterations keeps going
+    // until every CTA has (a counter in global memory, looked at once per iteration): the extra iterations are
+    // the fits' own next iterations, done now instead of in the next launch.  How many iterations a fit
+    // advances per launch thus depends on the run; its results do not (the state written back is exact).
     // (few registers may live across the iteration loop: only w_lo and n_it do; the rest is recomputed)
     int w_lo = 0; // where on the line of task-iterations my next segment starts (the host keeps n chunk < 2^31)
     const auto slot_len = [&]() -> int {
@@ -822,10 +837,40 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         return M < P.chunk ? P.chunk : M;
     };
     if (SP.flags) w_lo = (int)blockIdx.x * slot_len();
+    const bool ranked = SP.ctl != nullptr && n_tasks <= (int)gridDim.x;
+    LDSR_STATIC_SMEM(int, s_ti);
+    LDSR_STATIC_SMEM(int, s_more);
+    LDSR_STATIC_SMEM(int, s_on_sm);
     for (int seg = 0;; ++seg, phase ^= 1u) {
     int ti, n_it = P.chunk;
     bool wait_first = false;
-    if (SP.flags) {
+    if (ranked) {
+        if (seg > 0) break;
+        if (threadIdx.x == 0) {
+            const unsigned sm = sm_id(2);
+            LDSR_CHECK(sm < (unsigned)SHARE_MAX_SMID);
+            const int local = atomicAdd(SP.ctl + SHARE_CTL_SLOT + sm, 1); // 0: first CTA on this SM, 1: second
+            int r;
+            if (local == 0) {
+                r = atomicAdd(SP.ctl + SHARE_CTL_SMS, 1);
+                flag_raise(SP.ctl + SHARE_CTL_RANK + sm, r + 1);
+            } else {
+                while ((r = ld_acquire(SP.ctl + SHARE_CTL_RANK + sm)) == 0) {
+                }
+                r -= 1;
+            }
+            // SMs of rank < x hold two tasks (the 2x most advanced), the others one
+            const int x = n_tasks > SP.n_sm ? n_tasks - SP.n_sm : 0;
+            int qi = -1;
+            if (local < 2 && r < SP.n_sm) qi = r < x ? 2 * r + local : (local == 0 ? x + r : -1);
+            s_ti = (qi >= 0 && qi < n_tasks) ? SP.order[qi] : -1;
+            s_on_sm = r < x ? 2 : 1; // CTAs with a task on my SM
+            s_more = 1;
+        }
+        __syncthreads();
+        ti = s_ti;
+        if (ti < 0) break;
+    } else if (SP.flags) {
         const int W = n_tasks * P.chunk, hi = ((int)blockIdx.x + 1) * slot_len(), w_hi = hi < W ? hi : W;
         if (w_lo >= w_hi) break;
         ti = w_lo / P.chunk;
@@ -959,7 +1004,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
 #ifdef LDSR_PHASE_CLOCKS
     long long pc[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
-    for (int it = 0; it < n_it; ++it) {
+    bool counted = false; // (ranked) this CTA has reported its `chunk` iterations done
+    for (int it = 0;; ++it) {
+        if (it >= n_it) {
+            if (!ranked) break;
+            if (!counted) {
+                if (threadIdx.x == 0) {
+                    atomicAdd(SP.ctl + SHARE_CTL_FINISHED, 1);
+                    // the SM's other CTA still at its share: leave the SM to it (it runs 1.4x faster alone)
+                    if (atomicAdd(SP.ctl + SHARE_CTL_DONE + sm_id(2), 1) + 1 < s_on_sm) s_more = 0;
+                }
+                counted = true;
+                __syncthreads();
+            }
+            if (!s_more) break; // written before the last barrier of the previous iteration
+        }
         if (!__any_sync(FULL, live)) break;
         SplitConst<PQ, UW> k;
         k.set(th);
@@ -1182,6 +1241,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
             }
         }
         LDSR_PHASE_MARK(6);
+        // (ranked) may another iteration follow the `chunk`-th?  While some CTA still has not done its share.
+        if (ranked && it + 1 >= n_it && threadIdx.x == 0)
+            s_more = ld_relaxed(SP.ctl + SHARE_CTL_FINISHED) + (counted ? 0 : 1) < n_tasks;
         if (!PAIR) {
             stats_store<PQ>(st, ST + (size_t)warp * NST * 32);
             __syncthreads();
@@ -1251,6 +1313,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         for (int i = 0; i < 21; i++) SP.clk[((size_t)blockIdx.x * NW + warp) * 21 + i] = pc[i];
 #endif
 
+    if (ranked && !counted && threadIdx.x == 0) { // left the loop early: every fit of the task is done
+        atomicAdd(SP.ctl + SHARE_CTL_FINISHED, 1);
+        atomicAdd(SP.ctl + SHARE_CTL_DONE + sm_id(2), 1);
+    }
     if (BD_SMEM && warp == 0) {
 #pragma unroll
         for (int i = 0; i < PQ; i++) {

@@ -217,9 +217,13 @@ __global__ void select_kernel(int n_groups, const int *g_fit_ptr, const double *
 // count to n_live[series].  Each thread owns a contiguous run of fits (count, block scan, write).
 // The last block to finish turns the per-series counts into the CTA task list:
 // counts[0] = number of CTA tasks, counts[1] = number of live fits; *ticket is left at 0 again.
+// With share_ctl (time-split kernel, ranked task assignment): the control block is zeroed and order[] lists the
+// tasks by progress, most advanced first (key: E-steps done by the task's least advanced fit; ties in task order).
 __global__ void compact_kernel(const SeriesDev *series, int n_series, const int *done, int *active, int *n_live,
-                               int fits_per_cta, int4 *tasks, int *task_off, int *counts, unsigned *ticket) {
+                               int fits_per_cta, int4 *tasks, int *task_off, int *counts, unsigned *ticket,
+                               const int *ne = nullptr, int *share_ctl = nullptr, int *order = nullptr) {
     __shared__ int warp_sums[32];
+    __shared__ int keys[1024];
     __shared__ bool last;
     const SeriesDev S = series[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -269,6 +273,25 @@ __global__ void compact_kernel(const SeriesDev *series, int n_series, const int 
             const int first = i * fits_per_cta;
             tasks[t0 + i] = make_int4(s, series[s].fit_begin + first, min(fits_per_cta, live - first), 0);
         }
+    }
+    if (!share_ctl) return;
+    for (int i = threadIdx.x; i < SHARE_CTL_LEN; i += blockDim.x) share_ctl[i] = 0;
+    __syncthreads(); // the task list of this block's threads
+    const int nt = task_off[n_series];
+    if (nt > 1024 || blockDim.x < 1024) return; // more tasks than any co-resident grid: the ranked mode is off
+    const int t = threadIdx.x;
+    if (t < nt) { // the task's least advanced fit
+        const int4 tk = tasks[t];
+        int k = 0x7fffffff;
+        for (int i = 0; i < tk.z; i++) k = min(k, ne[__ldcg(active + tk.y + i)]);
+        keys[t] = k;
+    }
+    __syncthreads();
+    if (t < nt) {
+        int rank = 0;
+        const int mine = keys[t];
+        for (int j = 0; j < nt; j++) rank += (keys[j] > mine) || (keys[j] == mine && j < t);
+        order[rank] = t;
     }
 }
 

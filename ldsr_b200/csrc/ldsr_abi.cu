@@ -245,6 +245,7 @@ struct ldsr_plan {
     unsigned long long *d_sum = nullptr;
     unsigned *d_ticket = nullptr; // compact_kernel's last-block counter (0 between launches)
     int *d_share_flags = nullptr; // [max_tasks] hand-over flags of em_split_kernel's iteration-level task sharing
+    int *d_share_ctl = nullptr, *d_share_order = nullptr; // its ranked task assignment (SHARE_CTL_LEN, max_tasks)
     int share_epoch = 0;          // one value per launch: the flags need no reset
     double *d_ckpt = nullptr;
     size_t ckpt_cap = 0;
@@ -570,6 +571,8 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     if (!(e = P->dalloc(&P->d_tasks, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_share_flags, P->max_tasks)).ok()) return e;
     CU(cudaMemsetAsync(P->d_share_flags, 0, (size_t)P->max_tasks * sizeof(int), P->stream));
+    if (!(e = P->dalloc(&P->d_share_ctl, SHARE_CTL_LEN)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_share_order, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
 
     // ---- set-up kernel: masks + Gram constants
@@ -761,15 +764,20 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     // wave (313/296) instead of a second wave or a third CTA per SM with 168 registers.  Beyond four waves the
     // hardware's dealing of whole tasks balances better: tasks end early as their fits converge.
     int share_slots = 0;
+    bool share_ranked = false;
     if (use_split && P->kt->em_split_resident) {
         static const bool no_share = std::getenv("LDSR_NO_SHARE") != nullptr; // development: A/B measurement
         int coop = 0, dev = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         const int slots = P->kt->em_split_resident(smem) * P->n_sm;
-        if (!no_share && coop && slots > 0 && grid0 > slots && grid0 <= 4 * slots &&
+        if (!no_share && !std::getenv("LDSR_MAX_GRID") && coop && slots > 0 && grid0 > P->n_sm && grid0 <= 4 * slots &&
             (long long)(grid0 + 1) * chunk < (1ll << 31)) // the kernel's line of task-iterations is an int
             share_slots = slots;
+        // later launches (at most one task per CTA): ranked assignment + extra iterations, see the kernel.  Needs
+        // exactly two CTAs on every SM.
+        static const bool no_rank = std::getenv("LDSR_NO_RANK") != nullptr; // development: A/B measurement
+        share_ranked = share_slots == 2 * P->n_sm && share_slots <= 1024 && !no_rank;
     }
     if ((int)P->counts_cap < 2 * max_chunks) {
         Err e = P->drealloc(&P->d_counts, (size_t)2 * max_chunks);
@@ -800,7 +808,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     for (int c = 0; c < max_chunks; ++c) {
         int *cnt = P->d_counts + 2 * c;
         compact_kernel<<<ns, 1024, 0, st>>>(P->d_series, ns, P->d_done, P->d_active, P->d_n_live, fits_per_cta,
-                                            P->d_tasks, P->d_task_off, cnt, P->d_ticket);
+                                            P->d_tasks, P->d_task_off, cnt, P->d_ticket, P->d_ne,
+                                            share_ranked ? P->d_share_ctl : nullptr, P->d_share_order);
         launches++;
         // Later chunks have at most grid0 tasks.  For a batch that fits the machine in one wave the
         // grid is capped at two CTAs per SM: CTAs are dealt to SMs in launch order, so idle CTAs
@@ -819,7 +828,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             CU(cudaMemcpyAsync(P->h_counts + 2 * c, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             grid = std::max(1, P->h_counts[2 * c]);
-            if (share_slots > 0) grid = std::min(grid, share_slots);
+            if (share_slots > 0) grid = share_ranked ? share_slots : std::min(grid, share_slots);
             if (P->h_counts[2 * c + 1] == 0) break;
             if (abort_flag) {
                 if (abort_flag->load()) return fail(LDSR_ERR_INTERRUPTED, "interrupted");
@@ -893,6 +902,9 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
 #endif
             sp.flags = share_slots > 0 ? P->d_share_flags : nullptr;
             sp.epoch = ++P->share_epoch;
+            sp.ctl = share_ranked ? P->d_share_ctl : nullptr;
+            sp.order = P->d_share_order;
+            sp.n_sm = P->n_sm;
             // one wave of at most two CTAs per SM: the 255-register build of the kernel
             if (grid <= 2 * P->n_sm || sp.flags)
                 CU(P->kt->em_split_wide(sp, grid, smem, st));

@@ -197,6 +197,11 @@ static inline void __syncthreads() {
     hostsim::sync_group(hostsim::st().block, (int)blockDim.x);
 }
 static inline void __threadfence() {}
+static inline int atomicAdd(int *p, int v) { // one thread runs at a time
+    const int old = *p;
+    *p += v;
+    return old;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     hostsim::sync_group(hostsim::st().warps[hostsim::warp_id()], hostsim::warp_width());
 }

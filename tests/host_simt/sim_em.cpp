@@ -239,7 +239,7 @@ template <int PQ> int run(const Job &J) {
     const int max_uunits = (T + UW - 1) / UW;
 
     const int max_chunks = (J.niter + J.chunk - 1) / J.chunk;
-    std::vector<int> share_flags;
+    std::vector<int> share_flags, share_ctl, share_order;
     for (int c = 0; c < max_chunks; c++) {
         // compact_kernel: live fits in order, 32 (or 128) per CTA
         const int per = J.kind == 2 ? 32 * 4 : (J.kind == 5 ? 1 : 32);
@@ -263,6 +263,26 @@ template <int PQ> int run(const Job &J) {
             }
             sp.flags = share ? share_flags.data() : nullptr;
             sp.epoch = c + 1;
+            sp.ctl = nullptr;
+            sp.order = nullptr;
+            sp.n_sm = grid / 2;
+            if (share && grid % 2 == 0 && n_tasks <= grid) { // what compact_kernel prepares for the ranked assignment
+                share_ctl.assign(SHARE_CTL_LEN, 0);
+                share_order.resize(n_tasks);
+                auto key = [&](int t) { // the task's least advanced fit
+                    int k = 0x7fffffff;
+                    for (int i = 0; i < tasks[t].z; i++) k = std::min(k, ne[active[tasks[t].y + i]]);
+                    return k;
+                };
+                for (int t = 0; t < n_tasks; t++) {
+                    int rank = 0;
+                    const int mine = key(t);
+                    for (int j = 0; j < n_tasks; j++) rank += (key(j) > mine) || (key(j) == mine && j < t);
+                    share_order[rank] = t;
+                }
+                sp.ctl = share_ctl.data();
+                sp.order = share_order.data();
+            }
             sp.em = ep;
             sp.max_units = max_units;
             sp.max_uunits = max_uunits;

@@ -114,6 +114,18 @@ def test_emulated_tasks_shared_by_iterations(slots, chunk, n_rest):
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("slots,order", [(4, 0), (6, 3), (2, 1)])
+def test_emulated_ranked_assignment_and_extra_iterations(slots, order):
+    """At most one task per CTA, two CTAs per (emulated) SM: tasks are dealt by progress and by where the CTAs
+    landed, and a CTA keeps iterating past its chunk while others have not finished theirs (the emulator runs
+    the CTAs one after the other, so the first ones run their fits to the end).  Results equal the plain run's."""
+    y, u, held, fg, th0 = _np_job(n_folds=2, n_rest=35)  # 3 tasks; slots = 2: the first launch shares by iterations
+    a = sim_em(3, y, u, u, held, fg, th0, 9, chunk=4, order=order, grid_cap=-slots)
+    b = sim_em(3, y, u, u, held, fg, th0, 9, chunk=9, order=0, grid_cap=0)
+    for k in ("theta", "lik", "iters"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def _wide_job(p=10, T=150, n_fits=40, seed=3, first_obs=60):
     rng = np.random.default_rng(seed)
     u = rng.standard_normal((p, T)) * np.sqrt(4.0 / np.arange(1, p + 1))[:, None]
