@@ -146,6 +146,7 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void share_trap() { __trap(); }
 __device__ __forceinline__ unsigned sm_id(int /*slots_per_sm*/) {
     unsigned v;
     asm("mov.u32 %0, %%smid;" : "=r"(v));
@@ -157,6 +158,7 @@ __device__ __forceinline__ int ld_acquire(const int *p) { return *p; }
 __device__ __forceinline__ int ld_relaxed(const int *p) { return *p; }
 // the emulated grid fills "SMs" of slots_per_sm CTAs in launch order: CTA b sits on SM b mod (grid / slots_per_sm)
 __device__ __forceinline__ unsigned sm_id(int slots_per_sm) { return blockIdx.x % (gridDim.x / slots_per_sm); }
+__device__ __forceinline__ void share_trap() { LDSR_CHECK(!"CTAs are not two per SM"); }
 __device__ __forceinline__ void flag_raise(int *flag, int value) { *flag = value; }
 // the emulator runs one CTA at a time, the harness the highest CTA first: the producer has always finished
 __device__ __forceinline__ void flag_wait(const int *flag, int value) { LDSR_CHECK(*flag == value); }

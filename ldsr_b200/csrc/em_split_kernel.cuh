@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         if (seg > 0) break;
         if (threadIdx.x == 0) {
             const unsigned sm = sm_id(2);
-            LDSR_CHECK(sm < (unsigned)SHARE_MAX_SMID);
+            if (sm >= (unsigned)SHARE_MAX_SMID) share_trap();
             const int local = atomicAdd(SP.ctl + SHARE_CTL_SLOT + sm, 1); // 0: first CTA on this SM, 1: second
             int r;
             if (local == 0) {
@@ -859,6 +859,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
                 }
                 r -= 1;
             }
+            // exactly two CTAs on each of n_sm SMs, or tasks would be left out: fail loudly (the host launches this
+            // mode only with a co-resident grid of 2 n_sm CTAs of a kernel that fits twice on an SM)
+            if (local >= 2 || r >= SP.n_sm) share_trap();
             // SMs of rank < x hold two tasks (the 2x most advanced), the others one
             const int x = n_tasks > SP.n_sm ? n_tasks - SP.n_sm : 0;
             int qi = -1;

@@ -819,6 +819,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         // the wide-input kernel holds one CTA per SM: one CTA per task, dealt to the SMs by the hardware as
         // they finish (tasks differ in length: fits stop at different iterations)
         if (use_wide || use_scan) grid = grid0;
+        int plain_grid = grid; // one CTA per task (first launch) / the task loop of a capped grid
         if (share_slots > 0) grid = share_slots;
         // development: LDSR_MAX_GRID caps the grid so that a small batch exercises the task loop of the
         // kernels (tools/sanitize.py runs it under compute-sanitizer)
@@ -827,7 +828,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         if (sync_each) {
             CU(cudaMemcpyAsync(P->h_counts + 2 * c, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            grid = std::max(1, P->h_counts[2 * c]);
+            grid = plain_grid = std::max(1, P->h_counts[2 * c]);
             if (share_slots > 0) grid = share_ranked ? share_slots : std::min(grid, share_slots);
             if (P->h_counts[2 * c + 1] == 0) break;
             if (abort_flag) {
@@ -906,10 +907,20 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
             sp.order = P->d_share_order;
             sp.n_sm = P->n_sm;
             // one wave of at most two CTAs per SM: the 255-register build of the kernel
-            if (grid <= 2 * P->n_sm || sp.flags)
-                CU(P->kt->em_split_wide(sp, grid, smem, st));
-            else
-                CU(P->kt->em_split(sp, grid, smem, st));
+            cudaError_t le = (grid <= 2 * P->n_sm || sp.flags) ? P->kt->em_split_wide(sp, grid, smem, st)
+                                                               : P->kt->em_split(sp, grid, smem, st);
+            if (le == cudaErrorCooperativeLaunchTooLarge && sp.flags) {
+                // fewer SMs than the device reports are ours (a partitioned GPU): one CTA per task from here on.
+                // Nothing of this launch ran; the control block compact_kernel prepared is simply not used.
+                cudaGetLastError();
+                share_slots = 0;
+                share_ranked = false;
+                sp.flags = nullptr;
+                sp.ctl = nullptr;
+                grid = plain_grid;
+                le = grid <= 2 * P->n_sm ? P->kt->em_split_wide(sp, grid, smem, st) : P->kt->em_split(sp, grid, smem, st);
+            }
+            CU(le);
         } else {
             CU(P->kt->em_chunk(ep, grid, smem, st));
         }
