@@ -131,8 +131,10 @@ class PackedBatch:
             hp = np.zeros(ng + 1, dtype=np.int32)
             hp[1:] = np.cumsum([len(h) for h in held])
             self.held_ptr = hp
-            self.held_idx = (np.concatenate([np.asarray(h, dtype=np.int32).ravel() for h in held])
-                             if hp[-1] > 0 else np.zeros(1, dtype=np.int32)).astype(np.int32)
+            if hp[-1] > 0:  # one conversion of the concatenation, not one per group
+                self.held_idx = np.ascontiguousarray(np.concatenate(held, axis=None), dtype=np.int32)
+            else:
+                self.held_idx = np.zeros(1, dtype=np.int32)
         self.fit_group = np.ascontiguousarray(fit_group, dtype=np.int32)
         self.theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
         if self.theta0.ndim != 2 or self.theta0.shape[0] != self.fit_group.size:
@@ -142,11 +144,21 @@ class PackedBatch:
         self.stride = self.theta0.shape[1]
         self.traj_ptr = np.zeros(ng + 1, dtype=np.int64)
         self.traj_ptr[1:] = np.cumsum(self.T[self.group_series])
-        self.fit_ptr = np.zeros(self.n_fits + 1, dtype=np.int64)
-        self.fit_ptr[1:] = np.cumsum(self.T[self.group_series[self.fit_group]])
+        self._fit_ptr = None
         self.c = Batch(ns, _i(self.T), _i(self.p), _i(self.q), self.yp, self.up, self.vp,
                        ng, _i(self.group_series), _i(self.held_ptr), _i(self.held_idx),
                        self.n_fits, _i(self.fit_group), _d(self.theta0), self.stride)
+
+
+def _fit_ptr(self):
+    """Row offsets of per-FIT trajectories (smoother / propagate outputs); made on first use."""
+    if self._fit_ptr is None:
+        self._fit_ptr = np.zeros(self.n_fits + 1, dtype=np.int64)
+        self._fit_ptr[1:] = np.cumsum(self.T[self.group_series[self.fit_group]])
+    return self._fit_ptr
+
+
+PackedBatch.fit_ptr = property(_fit_ptr)
 
 
 def _check(rc, err):
@@ -208,7 +220,8 @@ class EmOutputs:
         nf, ng = pb.n_fits, pb.n_groups
         # the library writes every element of every output except the tail of a theta row beyond
         # its series' p + q + 6 (kept NaN here)
-        self.theta = np.full((nf, pb.stride), np.nan)
+        same_width = bool(np.all(pb.p + pb.q + 6 == pb.stride))
+        self.theta = np.empty((nf, pb.stride)) if same_width else np.full((nf, pb.stride), np.nan)
         self.lik = np.empty(nf)
         self.iters = np.empty(nf, dtype=np.int32)
         self.status = np.empty(nf, dtype=np.int32)

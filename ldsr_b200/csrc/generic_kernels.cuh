@@ -219,9 +219,13 @@ __global__ void select_kernel(int n_groups, const int *g_fit_ptr, const double *
 // counts[0] = number of CTA tasks, counts[1] = number of live fits; *ticket is left at 0 again.
 // With share_ctl (time-split kernel, ranked task assignment): the control block is zeroed and order[] lists the
 // tasks by progress, most advanced first (key: E-steps done by the task's least advanced fit; ties in task order).
+// The keys are gathered while compacting (ne[f] is loaded next to done[f]; a shared-memory atomicMin per live fit)
+// and handed to the last block through task_key[fit_begin/fits_per_cta + series + local task] -- slots of different series
+// never collide and stay below n_fits/32 + n_series.
 __global__ void compact_kernel(const SeriesDev *series, int n_series, const int *done, int *active, int *n_live,
                                int fits_per_cta, int4 *tasks, int *task_off, int *counts, unsigned *ticket,
-                               const int *ne = nullptr, int *share_ctl = nullptr, int *order = nullptr) {
+                               const int *ne = nullptr, int *share_ctl = nullptr, int *order = nullptr,
+                               int *task_key = nullptr) {
     __shared__ int warp_sums[32];
     __shared__ int keys[1024];
     __shared__ bool last;
@@ -229,6 +233,8 @@ __global__ void compact_kernel(const SeriesDev *series, int n_series, const int 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n = S.fit_end - S.fit_begin, per = (n + blockDim.x - 1) / blockDim.x;
     const int lo = S.fit_begin + min(n, (int)threadIdx.x * per), hi = S.fit_begin + min(n, ((int)threadIdx.x + 1) * per);
+    const bool rank_tasks = share_ctl != nullptr && (n + fits_per_cta - 1) / fits_per_cta <= 1024 && blockDim.x == 1024;
+    if (rank_tasks) keys[threadIdx.x] = 0x7fffffff;
     int mine = 0;
     for (int f = lo; f < hi; f++) mine += done[f] == 0;
     int incl = mine;
@@ -244,7 +250,16 @@ __global__ void compact_kernel(const SeriesDev *series, int n_series, const int 
         total += warp_sums[w];
     }
     for (int f = lo; f < hi; f++)
-        if (done[f] == 0) active[S.fit_begin + off++] = f;
+        if (done[f] == 0) {
+            if (rank_tasks) atomicMin(&keys[off / fits_per_cta], ne[f]);
+            active[S.fit_begin + off++] = f;
+        }
+    if (rank_tasks) {
+        __syncthreads();
+        const int my_tasks = (total + fits_per_cta - 1) / fits_per_cta;
+        if ((int)threadIdx.x < my_tasks) task_key[S.fit_begin / fits_per_cta + blockIdx.x + threadIdx.x] = keys[threadIdx.x];
+    }
+    __syncthreads(); // every thread's writes, before thread 0's fence and ticket
     if (threadIdx.x == 0) {
         n_live[blockIdx.x] = total;
         __threadfence();
@@ -280,17 +295,15 @@ __global__ void compact_kernel(const SeriesDev *series, int n_series, const int 
     const int nt = task_off[n_series];
     if (nt > 1024 || blockDim.x < 1024) return; // more tasks than any co-resident grid: the ranked mode is off
     const int t = threadIdx.x;
-    if (t < nt) { // the task's least advanced fit
-        const int4 tk = tasks[t];
-        int k = 0x7fffffff;
-        for (int i = 0; i < tk.z; i++) k = min(k, ne[__ldcg(active + tk.y + i)]);
-        keys[t] = k;
+    if (t < nt) {
+        const int s = tasks[t].x;
+        keys[t] = __ldcg(task_key + series[s].fit_begin / fits_per_cta + s + (t - task_off[s]));
     }
     __syncthreads();
     if (t < nt) {
         int rank = 0;
-        const int mine = keys[t];
-        for (int j = 0; j < nt; j++) rank += (keys[j] > mine) || (keys[j] == mine && j < t);
+        const int mine_key = keys[t];
+        for (int j = 0; j < nt; j++) rank += (keys[j] > mine_key) || (keys[j] == mine_key && j < t);
         order[rank] = t;
     }
 }

@@ -245,7 +245,8 @@ struct ldsr_plan {
     unsigned long long *d_sum = nullptr;
     unsigned *d_ticket = nullptr; // compact_kernel's last-block counter (0 between launches)
     int *d_share_flags = nullptr; // [max_tasks] hand-over flags of em_split_kernel's iteration-level task sharing
-    int *d_share_ctl = nullptr, *d_share_order = nullptr; // its ranked task assignment (SHARE_CTL_LEN, max_tasks)
+    int *d_share_ctl = nullptr, *d_share_order = nullptr, *d_share_key = nullptr; // its ranked task assignment
+                                                                                  // (SHARE_CTL_LEN, max_tasks, max_tasks)
     int share_epoch = 0;          // one value per launch: the flags need no reset
     double *d_ckpt = nullptr;
     size_t ckpt_cap = 0;
@@ -573,6 +574,7 @@ static Err plan_build(const ldsr_batch *b, int device, DevicePool *pool, ldsr_pl
     CU(cudaMemsetAsync(P->d_share_flags, 0, (size_t)P->max_tasks * sizeof(int), P->stream));
     if (!(e = P->dalloc(&P->d_share_ctl, SHARE_CTL_LEN)).ok()) return e;
     if (!(e = P->dalloc(&P->d_share_order, P->max_tasks)).ok()) return e;
+    if (!(e = P->dalloc(&P->d_share_key, P->max_tasks)).ok()) return e;
     if (!(e = P->dalloc(&P->d_best, ng)).ok()) return e;
 
     // ---- set-up kernel: masks + Gram constants
@@ -809,7 +811,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         int *cnt = P->d_counts + 2 * c;
         compact_kernel<<<ns, 1024, 0, st>>>(P->d_series, ns, P->d_done, P->d_active, P->d_n_live, fits_per_cta,
                                             P->d_tasks, P->d_task_off, cnt, P->d_ticket, P->d_ne,
-                                            share_ranked ? P->d_share_ctl : nullptr, P->d_share_order);
+                                            share_ranked ? P->d_share_ctl : nullptr, P->d_share_order, P->d_share_key);
         launches++;
         // Later chunks have at most grid0 tasks.  For a batch that fits the machine in one wave the
         // grid is capped at two CTAs per SM: CTAs are dealt to SMs in launch order, so idle CTAs
