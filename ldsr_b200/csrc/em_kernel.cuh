@@ -49,6 +49,12 @@ struct EmParams {
     int niter, chunk;
     double tol;
     int mode;                 // kernel MODE (see em_chunk_kernel)
+    // em_scan_kernel<PQ, L, EMIT = true> only: the smoothed trajectories (EM.cpp:94-110 outputs) of n_jobs (group, fit)
+    // pairs -- the winners of the groups -- one CTA per job; theta is read from theta[job_theta[job]] (< 0: NaN rows)
+    int n_jobs;
+    const int *job_group, *job_theta;
+    const long long *job_row; // first element of the job's rows in tX / tY / tV / tJ
+    double *tX, *tY, *tV, *tJ;
 };
 
 __device__ __forceinline__ unsigned seg_bits(const unsigned *__restrict__ mw, int t0, int seg_len) {

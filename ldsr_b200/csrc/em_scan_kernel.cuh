@@ -121,7 +121,10 @@ __device__ __forceinline__ double scan_vrow(const double (&u)[N], const double (
         return v[idx];
 }
 
-template <int PQ, int L>
+// EMIT = true: not EM but its E-step once, for the winners of the groups: the smoothed X, V, the gains J and
+// Y = C X + D v of every step are written out (what smoother_kernel computes with one thread per job in
+// 2 T dependent steps -- 0.12 ms at T = 413 whatever the number of jobs; here about 3 us).
+template <int PQ, int L, bool EMIT = false>
 __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
     static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
     constexpr int NS = scan_nsum<PQ>(), NSP = scan_nsum_pad<PQ>();
@@ -138,16 +141,25 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     LDSR_STATIC_SMEM(double, THS[TL]);                 // theta after the M-step
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int n_tasks = *P.n_tasks;
+    const int n_tasks = EMIT ? P.n_jobs : *P.n_tasks;
     for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x) {
     if (ti != (int)blockIdx.x) __syncthreads();
-    const int4 task = P.tasks[ti];
+    const int4 task = EMIT ? make_int4(P.g_series[P.job_group[ti]], 0, 1, 0) : P.tasks[ti];
     const SeriesDev S = P.series[task.x];
     const int T = S.T;
     LDSR_CHECK((int)blockDim.x * L >= T && nw <= SCAN_MAX_WARPS && task.z == 1); // the block covers the series
     LDSR_CHECK(!SHARE_UV || S.same_uv);
-    const int fit = P.active[task.y];
-    const int grp = P.f_group[fit];
+    const int fit = EMIT ? P.job_theta[ti] : P.active[task.y];
+    if (EMIT && fit < 0) { // no restart of the group qualified: NaN rows (uniform over the CTA)
+        const double nan = __longlong_as_double(0x7ff8000000000000ULL);
+        const long long row = P.job_row[ti];
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            P.tX[row + t] = P.tY[row + t] = P.tV[row + t] = nan;
+            if (P.tJ) P.tJ[row + t] = nan;
+        }
+        continue;
+    }
+    const int grp = EMIT ? P.job_group[ti] : P.f_group[fit];
     const double *__restrict__ gc = P.gconst + (size_t)grp * gconst_stride(PQ);
     const double *__restrict__ tuu_inv = P.sconst + S.sconst_off;
     const double n_obs = gc[1], inv_n_obs = 1.0 / n_obs;
@@ -177,15 +189,20 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     }
     Theta<PQ> th;
     load_theta<PQ>(th, P.theta + (size_t)fit * TL);
-    double l1 = P.l1[fit], l2 = P.l2[fit], lik = P.lik[fit];
-    int ne = P.ne[fit];
-    bool live = P.done[fit] == 0;
-    if (live && P.g_status[grp] != 0) { // Gram block not invertible: the reference would throw
-        live = false;
-        lik = __longlong_as_double(0x7ff8000000000000ULL);
+    double l1 = 0.0, l2 = 0.0, lik = 0.0;
+    int ne = 0;
+    bool live = true;
+    if constexpr (!EMIT) {
+        l1 = P.l1[fit], l2 = P.l2[fit], lik = P.lik[fit];
+        ne = P.ne[fit];
+        live = P.done[fit] == 0;
+        if (live && P.g_status[grp] != 0) { // Gram block not invertible: the reference would throw
+            live = false;
+            lik = __longlong_as_double(0x7ff8000000000000ULL);
+        }
     }
 
-    for (int it = 0; live && it < P.chunk; ++it) {
+    for (int it = 0; live && it < (EMIT ? 1 : P.chunk); ++it) {
         const double A = th.A, Q = th.Q, Cc = th.C, R = th.R;
 
         // the input terms of my steps do not wait for anything: issued here, they overlap the first scan
@@ -389,14 +406,16 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
 
         // ================= stop rule (EM.cpp:259-275): the same in every thread =================
-        lik = lik_new;
-        ne += 1;
-        if (threadIdx.x == 0 && P.liks) P.liks[(size_t)P.f_user[fit] * P.niter + (ne - 1)] = lik_new;
-        {
-            const bool conv = (ne >= 3) && (fabs(lik_new - l1) < P.tol) && (fabs(l1 - l2) < P.tol);
-            if (conv || ne >= P.niter) live = false;
+        if constexpr (!EMIT) {
+            lik = lik_new;
+            ne += 1;
+            if (threadIdx.x == 0 && P.liks) P.liks[(size_t)P.f_user[fit] * P.niter + (ne - 1)] = lik_new;
+            {
+                const bool conv = (ne >= 3) && (fabs(lik_new - l1) < P.tol) && (fabs(l1 - l2) < P.tol);
+                if (conv || ne >= P.niter) live = false;
+            }
+            if (!live) break;
         }
-        if (!live) break;
 
         // ---- smoothed state entering my steps from the right: the chain starts from the prior of the
         //      virtual step after the last one, Xs_{T-1} = Xu_{T-1} (EM.cpp:94-95)
@@ -425,6 +444,23 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             for (int j = L - 1; j >= 0; j--) {
                 Xs[j] = fma(Jg[j], Xs[j + 1], fma(gP[j], xin, g0[j]));
                 Vs[j] = fma(Jg[j] * Jg[j], Vs[j + 1], Lg[j]);
+            }
+            if constexpr (EMIT) { // the outputs of EM.cpp:94-110 for my steps, and that is all
+                const long long row = P.job_row[ti];
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    const int t = t0 + j;
+                    if (t < T) {
+                        double dv = 0.0;
+#pragma unroll
+                        for (int i = 0; i < PQ; i++) dv = fma(th.D[i], scan_vrow<SHARE_UV, L * PQ>(ur, vr_own, j * PQ + i), dv);
+                        P.tX[row + t] = Xs[j];
+                        P.tV[row + t] = Vs[j];
+                        P.tY[row + t] = fma(Cc, Xs[j], dv);
+                        if (P.tJ) P.tJ[row + t] = Jg[j]; // A Vu_t / Vp_{t+1}, also at t = T - 1 (EM.cpp:98)
+                    }
+                }
+                break;
             }
 #pragma unroll
             for (int j = 0; j < L; j++) {
@@ -587,7 +623,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         l1 = lik;
     }
 
-    if (threadIdx.x == 0) {
+    if (!EMIT && threadIdx.x == 0) {
         store_theta<PQ>(th, P.theta + (size_t)fit * TL);
         P.l1[fit] = l1;
         P.l2[fit] = l2;

@@ -71,6 +71,8 @@ struct KernelTable {
     // the longest series of the plan (the block is sized from it).
     int scan_l;
     cudaError_t (*em_scan)(const EmParams &, int n_tasks, int steps_per_thread, cudaStream_t);
+    // the same kernel's E-step once, writing the smoothed trajectories of EmParams.n_jobs (group, fit) pairs
+    cudaError_t (*em_scan_traj)(const EmParams &, int steps_per_thread, cudaStream_t);
     cudaError_t (*smoother)(const SmootherParams &, cudaStream_t);
     cudaError_t (*mstep)(const MstepParams &, cudaStream_t);
     cudaError_t (*propagate)(const SmootherParams &, cudaStream_t);

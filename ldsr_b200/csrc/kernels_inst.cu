@@ -137,11 +137,29 @@ template <> cudaError_t wide_launch<PQ>(const WideParams &p, int n_tasks, size_t
 // small-batch scan kernel
 template <int PQV> cudaError_t scan_launch(const EmParams &, int, int, cudaStream_t);
 template <> cudaError_t scan_launch<PQ>(const EmParams &, int, int, cudaStream_t);
+template <int PQV> cudaError_t scan_traj_launch(const EmParams &, int, cudaStream_t);
+template <> cudaError_t scan_traj_launch<PQ>(const EmParams &, int, cudaStream_t);
 #if LDSR_HAS_PART(5)
 template <int PQV, bool HAVE> struct ScanLaunch { // widths above SCAN_MAX_PQ have no scan kernel
     static cudaError_t launch(const EmParams &, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+    static cudaError_t traj(const EmParams &, int, cudaStream_t) { return cudaErrorNotSupported; }
 };
 template <int PQV> struct ScanLaunch<PQV, true> {
+    // EMIT mode: the smoothed trajectories of p.n_jobs winners, one CTA each
+    static cudaError_t traj(const EmParams &p, int steps_per_thread, cudaStream_t st) {
+        const int threads = (((p.max_seg + steps_per_thread - 1) / steps_per_thread + 31) / 32) * 32;
+        if (steps_per_thread == 2) {
+            em_scan_kernel<PQV, 2, true><<<p.n_jobs, threads, 0, st>>>(p);
+        } else if (steps_per_thread == 4) {
+            if constexpr (PQV <= 4)
+                em_scan_kernel<PQV, 4, true><<<p.n_jobs, threads, 0, st>>>(p);
+            else
+                return cudaErrorNotSupported;
+        } else {
+            return cudaErrorNotSupported;
+        }
+        return cudaGetLastError();
+    }
     static cudaError_t launch(const EmParams &p, int n_tasks, int steps_per_thread, cudaStream_t st) {
         // one thread per `steps_per_thread` steps, whole warps
         const int threads = (((p.max_seg + steps_per_thread - 1) / steps_per_thread + 31) / 32) * 32;
@@ -160,6 +178,9 @@ template <int PQV> struct ScanLaunch<PQV, true> {
 };
 template <> cudaError_t scan_launch<PQ>(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
     return ScanLaunch<PQ, (PQ <= SCAN_MAX_PQ)>::launch(p, n_tasks, warps, st);
+}
+template <> cudaError_t scan_traj_launch<PQ>(const EmParams &p, int steps_per_thread, cudaStream_t st) {
+    return ScanLaunch<PQ, (PQ <= SCAN_MAX_PQ)>::traj(p, steps_per_thread, st);
 }
 #endif
 
@@ -192,6 +213,9 @@ cudaError_t em_wide(const WideParams &p, int n_tasks, size_t smem_bytes, cudaStr
 }
 cudaError_t em_scan(const EmParams &p, int n_tasks, int warps, cudaStream_t st) {
     return scan_launch<PQ>(p, n_tasks, warps, st);
+}
+cudaError_t em_scan_traj(const EmParams &p, int steps_per_thread, cudaStream_t st) {
+    return scan_traj_launch<PQ>(p, steps_per_thread, st);
 }
 cudaError_t smoother(const SmootherParams &p, cudaStream_t st) {
     smoother_kernel<PQ><<<(p.n_jobs + 63) / 64, 64, 0, st>>>(p);
@@ -233,6 +257,7 @@ const KernelTable table = {PQ,
                            em_wide,
                            PQ <= SCAN_MAX_PQ ? SCAN_L : 0,
                            em_scan,
+                           em_scan_traj,
                            smoother,
                            mstep,
                            propagate,

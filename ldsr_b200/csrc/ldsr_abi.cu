@@ -1020,7 +1020,24 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     sp.lik = nullptr;
     sp.stdlik = 1;
     sp.aux = nullptr;
-    CU(P->kt->smoother(sp, st));
+    // One thread per winner walks 2 T dependent steps (0.12 ms at T = 413, however few the groups); where the scan
+    // kernel applies (its width / length / v == u conditions, whatever the batch size) its E-step does it in a few us
+    static const bool seq_traj = std::getenv("LDSR_SEQ_TRAJ") != nullptr; // development: A/B measurement
+    if (scan_ok && !seq_traj) {
+        EmParams tp = ep;
+        tp.max_seg = P->max_T;
+        tp.n_jobs = ng;
+        tp.job_group = sp.job_group;
+        tp.job_theta = sp.job_theta;
+        tp.job_row = sp.job_row;
+        tp.tX = sp.X;
+        tp.tY = sp.Y;
+        tp.tV = sp.V;
+        tp.tJ = sp.J;
+        CU(P->kt->em_scan_traj(tp, scan_steps, st));
+    } else {
+        CU(P->kt->smoother(sp, st));
+    }
     launches++;
     if (tail_a) cudaEventRecord(tail_b, st);
     CU(cudaMemsetAsync(P->d_sum, 0, sizeof(unsigned long long), st));

@@ -80,6 +80,7 @@ struct Job {
     double tol;
     double *theta_out, *lik_out;
     int *iters_out;
+    double *traj_out = nullptr; // optional [4][n_fits][T]: X, Y, V, J of every fit's final theta (scan kernel, EMIT mode)
 };
 
 #ifdef LDSR_HAVE_WIDE
@@ -326,6 +327,39 @@ template <int PQ> int run(const Job &J) {
         else
             return 12;
     }
+#ifdef LDSR_HAVE_SCAN
+    if (J.traj_out) { // the E-step once more, writing the trajectories: one job per fit
+        if (J.kind != 5) return 16;
+        std::vector<int> job_theta(nf);
+        std::vector<long long> job_row(nf);
+        for (int f = 0; f < nf; f++) {
+            job_theta[f] = f;
+            job_row[f] = (long long)f * T;
+        }
+        if (nf > 1) job_theta[nf - 1] = -1; // a group without a winner: NaN rows
+        EmParams tp = ep;
+        tp.n_jobs = nf;
+        tp.job_group = f_group.data();
+        tp.job_theta = job_theta.data();
+        tp.job_row = job_row.data();
+        tp.tX = J.traj_out;
+        tp.tY = J.traj_out + (size_t)nf * T;
+        tp.tV = J.traj_out + (size_t)2 * nf * T;
+        tp.tJ = J.traj_out + (size_t)3 * nf * T;
+        const int grid = J.grid_cap > 0 ? std::min(nf, J.grid_cap) : nf;
+        if constexpr (PQ <= 4) {
+            const int L = (T <= 2 * 32 * SCAN_MAX_WARPS && J.order >= 8) ? 2 : 4;
+            const int nwarps = (T + 32 * L - 1) / (32 * L);
+            if (L == 2)
+                hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 2, true>(tp); });
+            else
+                hostsim::launch(grid, nwarps * 32, 0, J.order, [&] { em_scan_kernel<PQ, 4, true>(tp); });
+        } else {
+            if (!S.same_uv || T > 2 * 32 * SCAN_MAX_WARPS) return 15;
+            hostsim::launch(grid, ((T + 63) / 64) * 32, 0, J.order, [&] { em_scan_kernel<PQ, 2, true>(tp); });
+        }
+    }
+#endif
     for (int f = 0; f < nf; f++) {
         const double *src = &theta[(size_t)f * TL];
         double *dst = J.theta_out + (size_t)f * stride;
@@ -352,6 +386,20 @@ extern "C" int hostsim_em(int kind, int T, int p, int q, const double *y, const 
                           double *theta_out, double *lik_out, int *iters_out) {
     Job J{kind, T, p, q, n_groups, n_fits, niter, chunk, order, grid_cap, y, u, v, held_ptr, held_idx, fit_group, theta0,
           tol, theta_out, lik_out, iters_out};
+    const int need = std::max(u ? p : 1, v ? q : 1);
+    if (need <= 3) return run<3>(J);
+    if (need <= 10) return run<10>(J);
+    return 13;
+}
+
+// hostsim_em for the scan kernel, followed by its trajectory mode on every fit's final theta (the last fit's job
+// is marked "no winner"): traj_out is [4][n_fits][T] = X, Y, V, J.
+extern "C" int hostsim_em_traj(int T, int p, int q, const double *y, const double *u, const double *v, int n_groups,
+                               const int *held_ptr, const int *held_idx, int n_fits, const int *fit_group,
+                               const double *theta0, int niter, double tol, int chunk, int order, int grid_cap,
+                               double *theta_out, double *lik_out, int *iters_out, double *traj_out) {
+    Job J{5, T, p, q, n_groups, n_fits, niter, chunk, order, grid_cap, y, u, v, held_ptr, held_idx, fit_group, theta0,
+          tol, theta_out, lik_out, iters_out, traj_out};
     const int need = std::max(u ? p : 1, v ? q : 1);
     if (need <= 3) return run<3>(J);
     if (need <= 10) return run<10>(J);

@@ -546,6 +546,72 @@ def test_tasks_shared_by_iterations_equal_separate_runs():
             assert np.array_equal(f[b["best"]], a["best"][half])
 
 
+def test_ranked_assignment_with_several_series_equals_separate_runs():
+    """Five stations of narrow inputs, 6 000 fits = 190 tasks: more than one task per SM, so the co-resident
+    grid deals the tasks by progress and lets early CTAs run ahead (the iterations a fit advances per launch
+    depend on the run).  Each station run alone is 38 tasks (one CTA per task, plain launches): results must
+    agree bit for bit; and the first groups agree with the oracle."""
+    from ldsr_b200 import workloads as W
+    w = W.synthetic_stations(n_stations=5, T=200, p=3, n_folds=12, n_restarts=100, seed=77)
+    niter = 260
+    st = _lib.Plan(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"]).em(niter=3)
+    assert st["kernel"] == "em_split_kernel" and st["shared_slots"] > 0
+    a = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], niter, 1e-5, want_traj=False)
+    for s_ in range(5):
+        h = W.take_groups(w, np.arange(12 * s_, 12 * (s_ + 1)))
+        b = _lib.em_batch(h["series"], h["group_series"], h["held"], h["fit_group"], h["theta0"], niter, 1e-5,
+                          want_traj=False)
+        f = h["fits"]
+        assert np.array_equal(b["iters"], a["iters"][f]) and np.array_equal(b["lik"], a["lik"][f])
+        assert np.array_equal(b["theta"], a["theta"][f], equal_nan=True)
+    h = W.take_groups(w, np.arange(2))
+    o = O.em_batch(h["series"], h["group_series"], h["held"], h["fit_group"], h["theta0"], niter, 1e-5)
+    f = h["fits"]
+    assert np.array_equal(a["iters"][f], o["iters"]) and np.array_equal(f[o["best"]], a["best"][:2])
+    assert np.allclose(a["lik"][f], o["lik"], rtol=LIK_RTOL, atol=0)
+    assert_theta_close(a["theta"][f], o["theta"])
+
+
+@pytest.mark.parametrize("case", ["np413", "narrow_separate_v", "wide10", "wide10_separate_v", "long1500"])
+def test_winner_trajectories_equal_the_oracle_estep_with_the_same_theta(case):
+    """X, Y, V, J returned by ldsr_em_batch are the E-step (EM.cpp:43-110) of the selected restart's theta on the
+    group's y: compared with the oracle's smoother run with the GPU's OWN theta, so the tolerance is that of one
+    E-step (1e-10), not of a whole EM run.  Covers both trajectory paths: the scan kernel's trajectory mode
+    (narrow inputs, or wide with v == u, series up to 1024 / 512 steps) and the one-thread-per-winner kernel."""
+    rng = np.random.default_rng(21)
+    if case == "np413":
+        from ldsr_b200 import workloads as W
+        w = W.np_cv(4, 10)
+    else:
+        T, p, q, same = dict(narrow_separate_v=(150, 3, 2, False), wide10=(300, 10, 10, True),
+                             wide10_separate_v=(120, 10, 4, False), long1500=(1500, 3, 3, True))[case]
+        u = rng.standard_normal((p, T))
+        v = u if same else rng.standard_normal((q, T))
+        x = np.zeros(T)
+        for t in range(1, T):
+            x[t] = 0.7 * x[t - 1] + 0.1 * u[0, t - 1] + 0.4 * rng.standard_normal()
+        y = 0.6 * x + 0.05 * v[0] + 0.2 * rng.standard_normal(T)
+        y[: T // 2] = np.nan
+        y[T // 2 + 7] = np.nan
+        inst = np.arange(T // 2, T)
+        inst = inst[np.isfinite(y[inst])]
+        held = [np.sort(rng.choice(inst, 9, replace=False)) for _ in range(3)] + [np.array([], dtype=int)]
+        th0 = rand_theta0(rng, p, q, 4 * 6)
+        th0[:, 1:1 + p] *= 0.2
+        th0[:, 2 + p:2 + p + q] *= 0.2
+        w = dict(series=[dict(y=y, u=u, v=v)], group_series=np.zeros(4, dtype=np.int32), held=held,
+                 fit_group=np.repeat(np.arange(4), 6), theta0=th0)
+    g = _lib.em_batch(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"], 40, 1e-5)
+    s0 = w["series"][0]
+    for k in range(len(w["group_series"])):
+        yy = np.array(s0["y"], dtype=float)
+        yy[w["held"][k]] = np.nan
+        s = O.kalman_smoother(yy, s0["u"], s0["v"], g["theta"][g["best"][k]])
+        row = slice(g["traj_ptr"][k], g["traj_ptr"][k + 1])
+        for name in ("X", "Y", "V", "J"):
+            assert np.allclose(g[name][row], s[name], rtol=1e-10, atol=1e-13), (k, name)
+
+
 def test_lds_rep_chunked_pipeline_equals_the_single_kernel_path(tmp_path):
     """ldsr_rep_batch simulates every replicate in one kernel when the output fits HBM and in pipelined chunks
     otherwise; the device generator is keyed by (seed, replicate, step), so both give the same bits.  The

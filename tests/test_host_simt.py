@@ -60,6 +60,29 @@ def sim_em(kind, y, u, v, held, fit_group, theta0, niter, tol=1e-5, chunk=100, o
     return dict(theta=th, lik=lik, iters=it)
 
 
+def sim_em_traj(y, u, v, held, fit_group, theta0, niter, tol=1e-5, chunk=100, order=0, grid_cap=0):
+    """The scan kernel's EM, then its trajectory mode on every fit's final theta (last fit: 'no winner')."""
+    L = _lib()
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    T = y.size
+    uf = np.ascontiguousarray(np.asarray(u, dtype=np.float64).T)
+    vf = np.ascontiguousarray(np.asarray(v, dtype=np.float64).T)
+    hp = np.zeros(len(held) + 1, dtype=np.int32)
+    hp[1:] = np.cumsum([len(h) for h in held])
+    hi = np.ascontiguousarray(np.concatenate([np.asarray(h, dtype=np.int32) for h in held] + [np.zeros(1, np.int32)]))
+    fg = np.ascontiguousarray(fit_group, dtype=np.int32)
+    th0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    nf = fg.size
+    th, lik, it = np.full_like(th0, np.nan), np.empty(nf), np.empty(nf, dtype=np.int32)
+    traj = np.full((4, nf, T), 12345.0)
+    d = lambda a: a.ctypes.data_as(_dp)
+    i = lambda a: a.ctypes.data_as(_ip)
+    rc = L.hostsim_em_traj(T, uf.shape[1], vf.shape[1], d(y), d(uf), d(vf), len(held), i(hp), i(hi), nf, i(fg), d(th0),
+                           niter, C.c_double(tol), chunk, order, grid_cap, d(th), d(lik), i(it), d(traj))
+    assert rc == 0, rc
+    return dict(theta=th, lik=lik, iters=it, X=traj[0], Y=traj[1], V=traj[2], J=traj[3])
+
+
 def rand_theta0(rng, p, q, n):
     return np.stack([np.concatenate([[rng.uniform()], rng.uniform(-1, 1, p), [rng.uniform()],
                                      rng.uniform(-1, 1, q), [1, 1, 0, 1]]) for _ in range(n)])
@@ -207,3 +230,38 @@ def test_emulated_scan_kernel_wide_inputs(p, T):
     r = sim_em(5, y, u, u, held, fg, th0, niter, chunk=5, order=3)
     for k in ("theta", "lik", "iters"):
         assert np.array_equal(base[k], r[k]), k
+
+
+@pytest.mark.parametrize("case", ["np213", "np40_separate_v", "wide10", "wide7_ragged"])
+def test_emulated_scan_kernel_trajectory_mode(case):
+    """em_scan_kernel<.., EMIT>: the smoothed X, Y, V, J of a (group, theta) pair against the oracle's E-step with the
+    same theta on the group's y (held-out steps missing); a job without a winner gives NaN rows; schedule
+    independence; CTAs that take several jobs."""
+    rng = np.random.default_rng(3)
+    if case.startswith("np"):
+        y, u, held, fg, th0 = _np_job(n_folds=2, n_rest=3)
+        v = u
+        if case == "np40_separate_v":
+            y, u = y[213 - 40:], u[:, 213 - 40:]
+            v = rng.standard_normal((2, 40))
+            held = [np.array([39]), np.array([], dtype=int)]
+            th0 = rand_theta0(rng, 3, 2, 6)
+    else:
+        p, T = (10, 150) if case == "wide10" else (7, 85)
+        y, u, held, fg, th0 = _wide_job(p, T, 7, seed=50 + p, first_obs=T // 3)
+        th0[:, 1:1 + p] *= 0.2
+        th0[:, 2 + p:2 + 2 * p] *= 0.2
+        v = u
+    a = sim_em_traj(y, u, v, held, fg, th0, 6, chunk=6, order=0)
+    nf = fg.size
+    for f in range(nf - 1):
+        yy = np.array(y, dtype=float)
+        yy[held[fg[f]]] = np.nan
+        s = O.kalman_smoother(yy, u, v, a["theta"][f])
+        for k in ("X", "Y", "V", "J"):
+            assert np.allclose(a[k][f], s[k], rtol=1e-10, atol=1e-13), (f, k, np.max(np.abs(a[k][f] - s[k])))
+    for k in ("X", "Y", "V", "J"):
+        assert np.isnan(a[k][nf - 1]).all()
+    b = sim_em_traj(y, u, v, held, fg, th0, 6, chunk=6, order=3, grid_cap=2)
+    for k in ("X", "Y", "V", "J"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
