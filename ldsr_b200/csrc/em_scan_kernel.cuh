@@ -25,6 +25,9 @@
 // Five barriers per iteration; nothing per step goes to shared or global memory.
 #pragma once
 #include "em_split_kernel.cuh"
+#ifdef LDSR_PHASE_CLOCKS
+#include <cstdio>
+#endif
 
 namespace ldsr {
 
@@ -124,6 +127,17 @@ __device__ __forceinline__ double scan_vrow(const double (&u)[N], const double (
 // EMIT = true: not EM but its E-step once, for the winners of the groups: the smoothed X, V, the gains J and
 // Y = C X + D v of every step are written out (what smoother_kernel computes with one thread per job in
 // 2 T dependent steps -- 0.12 ms at T = 413 whatever the number of jobs; here about 3 us).
+#ifdef LDSR_PHASE_CLOCKS // development build: cycles per phase of the iteration, threads 0 and 32 of CTA 0 (printf)
+#define SCAN_MARK(kk)                                \
+    do {                                             \
+        const long long c_ = clock64();              \
+        pc[kk] += c_ - tprev;                        \
+        tprev = c_;                                  \
+    } while (0)
+#else
+#define SCAN_MARK(kk) ((void)0)
+#endif
+
 template <int PQ, int L, bool EMIT = false>
 __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
     static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
@@ -202,7 +216,12 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         }
     }
 
+#ifdef LDSR_PHASE_CLOCKS
+    long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    int n_it_done = 0;
+#endif
     for (int it = 0; live && it < (EMIT ? 1 : P.chunk); ++it) {
+        SCAN_MARK(0);
         const double A = th.A, Q = th.Q, Cc = th.C, R = th.R;
 
         // the input terms of my steps do not wait for anything: issued here, they overlap the first scan
@@ -261,30 +280,41 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 e12 = e21 = 0.0;
             }
         }
+        SCAN_MARK(1);
         __syncthreads(); // B1
-        double Vin, vend; // prior variance entering my steps; prior variance of the virtual step after the last
+        SCAN_MARK(2);
+        // prior variance entering my steps in homogeneous coordinates (Vin = ni / di: P2 only uses ratios, so the
+        // division stays off the critical path); prior variance of the virtual step after the last
+        double ni, di, vend;
         {
+            // the warps' maps first (independent loads), then the chain; every map was normalised to entries
+            // summing to [1,2), so at most SCAN_MAX_WARPS of them cannot leave the double range
+            double a11[SCAN_MAX_WARPS], a12[SCAN_MAX_WARPS], a21[SCAN_MAX_WARPS], a22[SCAN_MAX_WARPS];
+#pragma unroll
+            for (int w = 0; w < SCAN_MAX_WARPS; ++w) {
+                const bool on = w < nw;
+                a11[w] = on ? S1[w * 4 + 0] : 1.0;
+                a12[w] = on ? S1[w * 4 + 1] : 0.0;
+                a21[w] = on ? S1[w * 4 + 2] : 0.0;
+                a22[w] = on ? S1[w * 4 + 3] : 1.0;
+            }
             double n = th.V1, d = 1.0, nwp = th.V1, dwp = 1.0;
-            for (int w = 0; w < nw; ++w) {
+#pragma unroll
+            for (int w = 0; w < SCAN_MAX_WARPS; ++w) {
                 if (w == warp) {
                     nwp = n;
                     dwp = d;
                 }
-                const double nn = fma(S1[w * 4 + 0], n, S1[w * 4 + 1] * d), dd = fma(S1[w * 4 + 2], n, S1[w * 4 + 3] * d);
+                const double nn = fma(a11[w], n, a12[w] * d), dd = fma(a21[w], n, a22[w] * d);
                 n = nn;
                 d = dd;
-                if ((w & 1) == 1) { // keep the pair in range (ratios only matter)
-                    const int e = ((__double2hiint(n + d) >> 20) & 0x7ff) - 1023;
-                    const double sc = __hiloint2double((1023 - e) << 20, 0);
-                    n *= sc;
-                    d *= sc;
-                }
             }
             vend = n * fast_rcp(d);
-            const double ni = fma(e11, nwp, e12 * dwp), di = fma(e21, nwp, e22 * dwp);
-            Vin = ni * fast_rcp(di);
+            ni = fma(e11, nwp, e12 * dwp);
+            di = fma(e21, nwp, e22 * dwp);
         }
 
+        SCAN_MARK(3);
         // ================= P2: forward over my steps (EM.cpp:70-90), mean in the (P, q) basis =================
         double Kg[L], Jg[L], Lg[L], g0[L], gP[L]; // kept for P4
         double Pth, qth;                           // my affine map of the mean
@@ -294,7 +324,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             // gains: the variance in homogeneous coordinates (n, d), all reciprocals after the chain
             double nj[L], dj[L], nn[L], dd[L];
             {
-                double n = Vin, d = 1.0;
+                double n = ni, d = di;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     nj[j] = n;
@@ -353,8 +383,13 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             }
             Pth = Pc[L];
             qth = q[L];
-            if (bits) acc_l0 += log(dend); // sum_obs log Sigma = log prod Sigma (d started at 1)
+            // sum_obs log Sigma = log prod Sigma = log(d_end / d_in).  Branch-free, in every thread: a warp whose
+            // steps are unobserved would otherwise wait at the next barrier for the others' logarithm.
+            // (Multiplying the ratios up over the CTA -- mantissas and exponents apart -- and taking ONE logarithm
+            // after barrier 3, with the stop rule applied after barrier 4, was measured: 2.73 against 2.67 ms.)
+            acc_l0 += log(bits ? dend * fast_rcp(di) : 1.0);
         }
+        SCAN_MARK(4);
         double xin, xend; // prior mean entering my steps; prior mean of the virtual step after the last
         {
             double Pi = Pth, qi = qth;
@@ -368,15 +403,24 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 Pe = 1.0;
                 qe = 0.0;
             }
+            SCAN_MARK(5);
             __syncthreads(); // B2
+            double wp[SCAN_MAX_WARPS], wq[SCAN_MAX_WARPS];
+#pragma unroll
+            for (int w = 0; w < SCAN_MAX_WARPS; ++w) {
+                wp[w] = w < nw ? S2[w * 2 + 0] : 1.0;
+                wq[w] = w < nw ? S2[w * 2 + 1] : 0.0;
+            }
             double x = th.mu1, xw = th.mu1; // prior of step 0 (EM.cpp:48)
-            for (int w = 0; w < nw; ++w) {
+#pragma unroll
+            for (int w = 0; w < SCAN_MAX_WARPS; ++w) {
                 if (w == warp) xw = x;
-                x = fma(S2[w * 2 + 0], x, S2[w * 2 + 1]);
+                x = fma(wp[w], x, wq[w]);
             }
             xend = x;
             xin = fma(Pe, xw, qe);
         }
+        SCAN_MARK(6);
         // ---- likelihood partial sums and the backward maps, one barrier for both
         const double gk = fma(GG, xin, G0);
         double PJs = PJ, gs = gk, Ls = Lc;
@@ -398,9 +442,11 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             ge = 0.0;
             Le = 0.0;
         }
+        SCAN_MARK(7);
         __syncthreads(); // B3
         double acc = 0.0;
-        for (int w = 0; w < nw; ++w) acc += S3[w];
+#pragma unroll
+        for (int w = 0; w < SCAN_MAX_WARPS; ++w) acc += w < nw ? S3[w] : 0.0; // warp order: the same sum in every thread
         // EM.cpp:122-124: (-n/2 log 2pi - acc/2) / n, the division by n as a multiplication by its (once per task,
         // correctly rounded) reciprocal: it sits on the critical path of every thread
         const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
@@ -417,15 +463,18 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             if (!live) break;
         }
 
+        SCAN_MARK(8);
         // ---- smoothed state entering my steps from the right: the chain starts from the prior of the
         //      virtual step after the last one, Xs_{T-1} = Xu_{T-1} (EM.cpp:94-95)
         double Xs1, Vs1;
         {
             double X = xend, V = vend;
-            for (int w = nw - 1; w > warp; --w) {
-                const double pj = S4[w * 3 + 0];
-                X = fma(pj, X, S4[w * 3 + 1]);
-                V = fma(pj * pj, V, S4[w * 3 + 2]);
+#pragma unroll
+            for (int w = SCAN_MAX_WARPS - 1; w > 0; --w) {
+                const bool on = w < nw && w > warp;
+                const double pj = on ? S4[w * 3 + 0] : 1.0;
+                X = fma(pj, X, on ? S4[w * 3 + 1] : 0.0);
+                V = fma(pj * pj, V, on ? S4[w * 3 + 2] : 0.0);
             }
             Xs1 = fma(PJe, X, ge);
             Vs1 = fma(PJe * PJe, V, Le);
@@ -460,8 +509,8 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                         if (P.tJ) P.tJ[row + t] = Jg[j]; // A Vu_t / Vp_{t+1}, also at t = T - 1 (EM.cpp:98)
                     }
                 }
-                break;
             }
+            if constexpr (!EMIT) {
 #pragma unroll
             for (int j = 0; j < L; j++) {
                 const int t = t0 + j;
@@ -490,7 +539,10 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 ENDS[0] = Xs[0];
                 ENDS[1] = Vs[0];
             }
+            } // !EMIT
         }
+        if constexpr (EMIT) break; // nothing else of the iteration is needed (no barrier is pending)
+        SCAN_MARK(9);
         {
             double *const row = S5 + warp * SCAN_SUM_ROW;
             if constexpr (NSP == 16) {
@@ -505,7 +557,9 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
                 }
             }
         }
+        SCAN_MARK(10);
         __syncthreads(); // B4
+        SCAN_MARK(11);
 
         // ================= M-step (EM.cpp:139-229): warp 0 the observation block, warp 1 the transition block ======
         // (one warp: warp 0 does both).  Lane a < PQ takes row a of the matrix-vector products of the block
@@ -517,7 +571,8 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         if (do_obs || do_trans) {
             if (lane < NS) {
                 double a = 0.0;
-                for (int w = 0; w < nw; ++w) a += S5[w * SCAN_SUM_ROW + lane];
+#pragma unroll
+                for (int w = 0; w < SCAN_MAX_WARPS; ++w) a += w < nw ? S5[w * SCAN_SUM_ROW + lane] : 0.0; // loads first
                 TOTS[warp * SCAN_SUM_ROW + lane] = a;
             }
             __syncwarp();
@@ -617,11 +672,26 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             }
         }
         }
+        SCAN_MARK(12);
         __syncthreads(); // B5: the new theta is published
         load_theta<PQ>(th, THS);
         l2 = l1;
         l1 = lik;
+        SCAN_MARK(13);
+#ifdef LDSR_PHASE_CLOCKS
+        n_it_done++;
+#endif
     }
+#ifdef LDSR_PHASE_CLOCKS
+    if (!EMIT && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32) && n_it_done > 0) {
+        static const char *names[14] = {"loop top", "Bu + P1 compose + scan", "B1 wait", "warp chain + Vin", "P2", "affine scan",
+                                        "B2 wait + xin", "lik sum + backward scan", "B3 wait + lik + stop", "Xs1 + P4 + sums",
+                                        "reduce", "B4 wait", "M-step", "B5 wait + theta"};
+        for (int i = 0; i < 14; i++)
+            printf("[scan clocks] thread %2d  %-26s %8.0f cycles/iteration\n", (int)threadIdx.x, names[i],
+                   (double)pc[i] / n_it_done);
+    }
+#endif
 
     if (!EMIT && threadIdx.x == 0) {
         store_theta<PQ>(th, P.theta + (size_t)fit * TL);
