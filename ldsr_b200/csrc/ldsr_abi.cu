@@ -2082,9 +2082,19 @@ int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *
             P.L = T; // one chunk: the "down" kernels are the sequential recursion
         } else if (chunk > 0) {
             P.L = std::min(chunk, T);
-        } else { // chunk phases ~2 L combines deep, scan phase ~2 T/(256 L) + 14: balance, power of two in 8..64
+        } else {
+            // One CTA per fit in the scan stages (short series): chunk phases ~2 L combines deep, scan phase
+            // ~2 T/(256 L) + 14: balance, power of two in 8..64.
             int L = 8;
             while (L < 64 && (long long)L * L * 256 < T) L *= 2;
+            // Long series (SCAN_GROUPS CTAs per fit): the scan stages cost a few combines per chunk ELEMENT, spread
+            // over the machine, the chunk phases 2 L steps of latency: L ~ 0.05 sqrt(n_fits T), the power of two
+            // nearest in ratio, 4..64 (measured optima, d = 4: T = 20 000 / 100 000 / 1 000 000 with one
+            // parameter set: 4-8 / 16 / 64; T = 100 000 with 8 / 32 sets: 32 / 32-64 -- profiles/scan_smoother_r02.txt)
+            const double want = 0.05 * std::sqrt((double)n_fits * (double)T);
+            int Lg = 4;
+            while (Lg < 64 && (double)Lg * 1.41421356 < want) Lg *= 2;
+            if (scan_groups_for((T + Lg - 1) / Lg) > 1) L = Lg;
             P.L = L;
         }
         P.n_chunks = (T + P.L - 1) / P.L;
@@ -2133,6 +2143,16 @@ int ldsr_smoother_d_batch(int device, int d, int T, int p, int q, const double *
         CU(dalloc(&P.pre, nC * (D + D * D)));
         CU(dalloc(&P.suf, nC * (D + D * D)));
         CU(dalloc(&P.likp, nC * 2));
+        P.n_groups = scan_groups_for(P.n_chunks);
+        if (const char *ev = std::getenv("LDSR_SCAN_GROUPS")) // development: 1 = one CTA per fit scans all chunks
+            if (std::atoi(ev) == 1) P.n_groups = 1;
+        if (P.n_groups > 1) {
+            const size_t nG = (size_t)n_fits * P.n_groups;
+            CU(dalloc(&P.fgagg, nG * (3 * D * D + 2 * D)));
+            CU(dalloc(&P.fgpre, nG * (3 * D * D + 2 * D)));
+            CU(dalloc(&P.sgagg, nG * (2 * D * D + D)));
+            CU(dalloc(&P.sgsuf, nG * (2 * D * D + D)));
+        }
         CU(dalloc(&P.X, nT * D));
         CU(dalloc(&P.V, nT * D * D));
         CU(dalloc(&P.Y, nT));

@@ -35,6 +35,10 @@ struct ScanParams {
     double *pre;         // [n_fits][n_chunks][D+D^2]  filtered state entering the chunk
     double *suf;         // [n_fits][n_chunks][D+D^2]  smoothed state right of the chunk
     double *likp;        // [n_fits][n_chunks][2]      (sum of terms, n_obs)
+    // long series: the chunk elements are scanned by n_groups CTAs per fit (SCAN_GROUPS), in three launches
+    int n_groups;
+    double *fgagg, *fgpre; // [n_fits][n_groups][3D^2+2D] totals of the groups, prefix before each group
+    double *sgagg, *sgsuf; // [n_fits][n_groups][2D^2+D]  totals of the groups, suffix right of each group
     double *X, *V, *Y;   // outputs [n_fits][T][D], [n_fits][T][D*D], [n_fits][T]
     double *lik;         // [n_fits]
 };
@@ -406,20 +410,28 @@ template <int D> __global__ void scan_filt_agg_kernel(const ScanParams P) {
     a.store(P.fagg + ((size_t)f * P.n_chunks + ch) * FiltElem<D>::LEN);
 }
 
-// prefix over the chunk elements: one CTA of SCAN_NT threads per fit, three levels.
-//   (1) thread t combines its contiguous range of chunk elements (n_chunks / SCAN_NT of them) serially;
+// prefix over the chunk elements: one CTA of NT threads per fit (MODE 0) or per group of chunks (MODES 1, 2), three levels.
+//   (1) thread t combines its contiguous range of chunk elements serially;
 //   (2) Kogge-Stone over the 32 thread aggregates of a warp through shared memory (5 rounds), warp totals;
-//   (3) every thread combines the totals of the warps before its own (< SCAN_NT / 32 of them) with the inclusive
+//   (3) every thread combines the totals of the warps before its own (< NT / 32 of them) with the inclusive
 //       prefix of the lane before it, then walks its range again writing the filtered state entering each chunk.
-// Serial depth n_chunks/SCAN_NT + 5 + SCAN_NT/32 + 1 + n_chunks/SCAN_NT combines (round 1: one warp per fit,
-// n_chunks/32 + 32 + n_chunks/32).  Empty ranges hold the neutral element, so no lane needs a special case.
-constexpr int SCAN_NT = 256;
-template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_filt_scan_kernel(const ScanParams P) {
-    extern __shared__ double sh[]; // [SCAN_NT][LEN] thread aggregates -> inclusive prefixes in the warp; [SCAN_NT/32][LEN] warp totals
+// Serial depth n/NT + 5 + NT/32 + 1 + n/NT combines for n elements (round 1: one warp per fit, n/32 + 32 + n/32).
+// Empty ranges hold the neutral element, so no lane needs a special case.
+// A combine is ~600 multiply-adds per thread, so ONE CTA is bound by the FP64 pipe of its one SM (T = 100 000,
+// L = 32: 39 combines deep, 0.20 ms).  Long series therefore cut the chunk elements into SCAN_GROUPS groups:
+//   MODE 1  one CTA per (fit, group): levels (1), (2) and the group's total -> fgagg          (many SMs)
+//   top     one warp per fit: exclusive prefix over the group totals -> fgpre                  (5 rounds)
+//   MODE 2  one CTA per (fit, group) again: levels (1)-(3) starting from the group's prefix    (many SMs)
+constexpr int SCAN_NT = 256, SCAN_NT_GROUP = 128, SCAN_GROUPS = 32, SCAN_GROUPS_FROM = 512; // chunks from which groups pay
+template <int D, int NT, int MODE>
+__global__ void __launch_bounds__(NT) scan_filt_scan_kernel(const ScanParams P) {
+    extern __shared__ double sh[]; // [NT][LEN] thread aggregates -> inclusive prefixes in the warp; [NT/32][LEN] warp totals
     constexpr int LEN = FiltElem<D>::LEN;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (P.n_chunks + SCAN_NT - 1) / SCAN_NT;
-    const int k0 = min(P.n_chunks, tid * per), k1 = min(P.n_chunks, k0 + per);
+    const int f = blockIdx.x, g = MODE == 0 ? 0 : blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = MODE == 0 ? P.n_chunks : (P.n_chunks + P.n_groups - 1) / P.n_groups; // chunks per group
+    const int c_lo = min(P.n_chunks, g * S), n = min(P.n_chunks, c_lo + S) - c_lo;
+    const int per = (n + NT - 1) / NT;
+    const int k0 = c_lo + min(n, tid * per), k1 = c_lo + min(n, tid * per + per);
     const double *__restrict__ agg = P.fagg + (size_t)f * P.n_chunks * LEN;
     FiltElem<D> a, e;
     filt_identity<D>(a);
@@ -427,7 +439,7 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_filt_scan_kerne
         e.load(agg + (size_t)k * LEN);
         filt_combine<D>(a, e);
     }
-    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)SCAN_NT * LEN;
+    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)NT * LEN;
     a.store(mine);
     __syncwarp();
     for (int o = 1; o < 32; o <<= 1) {
@@ -443,8 +455,22 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_filt_scan_kerne
     }
     if (lane == 31) a.store(wt + (size_t)warp * LEN);
     __syncthreads();
+    if (MODE == 1) { // the group's total
+        if (tid == 0) {
+            e.load(wt);
+            for (int w = 1; w < NT / 32; ++w) {
+                a.load(wt + (size_t)w * LEN);
+                filt_combine<D>(e, a);
+            }
+            e.store(P.fgagg + ((size_t)f * P.n_groups + g) * LEN);
+        }
+        return;
+    }
     FiltElem<D> run; // exclusive prefix before my range
-    filt_identity<D>(run);
+    if (MODE == 2)
+        run.load(P.fgpre + ((size_t)f * P.n_groups + g) * LEN);
+    else
+        filt_identity<D>(run);
     for (int w = 0; w < warp; ++w) {
         e.load(wt + (size_t)w * LEN);
         filt_combine<D>(run, e);
@@ -464,6 +490,39 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_filt_scan_kerne
         }
         e.load(agg + (size_t)k * LEN);
         filt_combine<D>(run, e);
+    }
+}
+// exclusive prefix over the SCAN_GROUPS group totals of a fit: one warp, Kogge-Stone through shared memory
+template <int D> __global__ void __launch_bounds__(SCAN_GROUPS) scan_filt_top_kernel(const ScanParams P) {
+    static_assert(SCAN_GROUPS == 32, "one warp");
+    extern __shared__ double sh[]; // [32][LEN]
+    constexpr int LEN = FiltElem<D>::LEN;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    FiltElem<D> a, e;
+    if (lane < P.n_groups)
+        a.load(P.fgagg + ((size_t)f * P.n_groups + lane) * LEN);
+    else
+        filt_identity<D>(a);
+    double *const mine = sh + (size_t)lane * LEN;
+    a.store(mine);
+    __syncwarp();
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool act = lane >= o;
+        if (act) {
+            e.load(sh + (size_t)(lane - o) * LEN);
+            filt_combine<D>(e, a);
+            a = e;
+        }
+        __syncwarp();
+        if (act) a.store(mine);
+        __syncwarp();
+    }
+    if (lane < P.n_groups) {
+        if (lane > 0)
+            e.load(sh + (size_t)(lane - 1) * LEN);
+        else
+            filt_identity<D>(e);
+        e.store(P.fgpre + ((size_t)f * P.n_groups + lane) * LEN);
     }
 }
 
@@ -625,13 +684,16 @@ template <int D> __global__ void scan_smth_agg_kernel(const ScanParams P) {
 }
 
 // suffix over the chunk elements: (g, L) of the suffix right of chunk k = smoothed state of its first step.
-// Same three levels as scan_filt_scan_kernel, mirrored.
-template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_smth_scan_kernel(const ScanParams P) {
+// Same levels and modes as scan_filt_scan_kernel, mirrored.
+template <int D, int NT, int MODE>
+__global__ void __launch_bounds__(NT) scan_smth_scan_kernel(const ScanParams P) {
     extern __shared__ double sh[];
     constexpr int LEN = SmthElem<D>::LEN;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (P.n_chunks + SCAN_NT - 1) / SCAN_NT;
-    const int k0 = min(P.n_chunks, tid * per), k1 = min(P.n_chunks, k0 + per);
+    const int f = blockIdx.x, g = MODE == 0 ? 0 : blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = MODE == 0 ? P.n_chunks : (P.n_chunks + P.n_groups - 1) / P.n_groups;
+    const int c_lo = min(P.n_chunks, g * S), n = min(P.n_chunks, c_lo + S) - c_lo;
+    const int per = (n + NT - 1) / NT;
+    const int k0 = c_lo + min(n, tid * per), k1 = c_lo + min(n, tid * per + per);
     const double *__restrict__ agg = P.sagg + (size_t)f * P.n_chunks * LEN;
     SmthElem<D> a, e;
     smth_identity<D>(a);
@@ -640,7 +702,7 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_smth_scan_kerne
         smth_combine<D>(e, a);
         a = e;
     }
-    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)SCAN_NT * LEN;
+    double *const mine = sh + (size_t)tid * LEN, *const wt = sh + (size_t)NT * LEN;
     a.store(mine);
     __syncwarp();
     for (int o = 1; o < 32; o <<= 1) {
@@ -655,9 +717,24 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_smth_scan_kerne
     }
     if (lane == 0) a.store(wt + (size_t)warp * LEN);
     __syncthreads();
+    if (MODE == 1) { // the group's total: e_first o ... o e_last
+        if (tid == 0) {
+            a.load(wt + (size_t)(NT / 32 - 1) * LEN);
+            for (int w = NT / 32 - 2; w >= 0; --w) {
+                e.load(wt + (size_t)w * LEN);
+                smth_combine<D>(e, a);
+                a = e;
+            }
+            a.store(P.sgagg + ((size_t)f * P.n_groups + g) * LEN);
+        }
+        return;
+    }
     SmthElem<D> run; // exclusive suffix right of my range
-    smth_identity<D>(run);
-    for (int w = SCAN_NT / 32 - 1; w > warp; --w) {
+    if (MODE == 2)
+        run.load(P.sgsuf + ((size_t)f * P.n_groups + g) * LEN);
+    else
+        smth_identity<D>(run);
+    for (int w = NT / 32 - 1; w > warp; --w) {
         e.load(wt + (size_t)w * LEN);
         smth_combine<D>(e, run);
         run = e;
@@ -678,6 +755,37 @@ template <int D> __global__ void __launch_bounds__(SCAN_NT) scan_smth_scan_kerne
         e.load(agg + (size_t)k * LEN);
         smth_combine<D>(e, run);
         run = e;
+    }
+}
+// exclusive suffix over the group totals of a fit: one warp
+template <int D> __global__ void __launch_bounds__(SCAN_GROUPS) scan_smth_top_kernel(const ScanParams P) {
+    extern __shared__ double sh[];
+    constexpr int LEN = SmthElem<D>::LEN;
+    const int f = blockIdx.x, lane = threadIdx.x;
+    SmthElem<D> a, e;
+    if (lane < P.n_groups)
+        a.load(P.sgagg + ((size_t)f * P.n_groups + lane) * LEN);
+    else
+        smth_identity<D>(a);
+    double *const mine = sh + (size_t)lane * LEN;
+    a.store(mine);
+    __syncwarp();
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool act = lane + o < 32;
+        if (act) {
+            e.load(sh + (size_t)(lane + o) * LEN);
+            smth_combine<D>(a, e);
+        }
+        __syncwarp();
+        if (act) a.store(mine);
+        __syncwarp();
+    }
+    if (lane < P.n_groups) {
+        if (lane < 31)
+            e.load(sh + (size_t)(lane + 1) * LEN);
+        else
+            smth_identity<D>(e);
+        e.store(P.sgsuf + ((size_t)f * P.n_groups + lane) * LEN);
     }
 }
 
@@ -741,12 +849,24 @@ template <int D> __global__ void scan_smth_down_kernel(const ScanParams P) {
 
 // likelihood: the chunk terms of a fit are added by one warp, lane-strided then a shuffle tree --
 // a fixed order, so the result does not depend on the launch (EM.cpp:115-124)
-template <int D> __global__ void scan_lik_kernel(const ScanParams P) {
-    const int f = blockIdx.x, lane = threadIdx.x;
+// sum of the chunks' likelihood terms: one CTA of SCAN_LIK_NT threads per fit (strided partial sums with the loads
+// of four chunks in flight, then a fixed-order tree: the result does not depend on the launch)
+constexpr int SCAN_LIK_NT = 256;
+template <int D> __global__ void __launch_bounds__(SCAN_LIK_NT) scan_lik_kernel(const ScanParams P) {
+    __shared__ double sa[SCAN_LIK_NT / 32], sn[SCAN_LIK_NT / 32];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 *__restrict__ lp = reinterpret_cast<const double2 *>(P.likp) + (size_t)f * P.n_chunks;
     double acc = 0.0, n = 0.0;
-    for (int k = lane; k < P.n_chunks; k += 32) {
-        acc += P.likp[((size_t)f * P.n_chunks + k) * 2];
-        n += P.likp[((size_t)f * P.n_chunks + k) * 2 + 1];
+    int k = tid;
+    for (; k + 3 * SCAN_LIK_NT < P.n_chunks; k += 4 * SCAN_LIK_NT) {
+        const double2 a0 = lp[k], a1 = lp[k + SCAN_LIK_NT], a2 = lp[k + 2 * SCAN_LIK_NT], a3 = lp[k + 3 * SCAN_LIK_NT];
+        acc += (a0.x + a1.x) + (a2.x + a3.x);
+        n += (a0.y + a1.y) + (a2.y + a3.y);
+    }
+    for (; k < P.n_chunks; k += SCAN_LIK_NT) {
+        const double2 a0 = lp[k];
+        acc += a0.x;
+        n += a0.y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -754,6 +874,17 @@ template <int D> __global__ void scan_lik_kernel(const ScanParams P) {
         n += __shfl_xor_sync(FULL, n, o);
     }
     if (lane == 0) {
+        sa[warp] = acc;
+        sn[warp] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        acc = n = 0.0;
+#pragma unroll
+        for (int w = 0; w < SCAN_LIK_NT / 32; w++) {
+            acc += sa[w];
+            n += sn[w];
+        }
         double lik = -0.5 * n * LOG_2PI - 0.5 * acc;
         if (P.stdlik) lik /= n;
         P.lik[f] = lik;
@@ -761,5 +892,6 @@ template <int D> __global__ void scan_lik_kernel(const ScanParams P) {
 }
 
 cudaError_t scan_smoother_launch(int D, const ScanParams &P, cudaStream_t st); // scan_inst.cu
+int scan_groups_for(int n_chunks); // CTAs per fit in the scan stages (ScanParams.n_groups): 1 or SCAN_GROUPS
 
 } // namespace ldsr

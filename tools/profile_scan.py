@@ -38,7 +38,7 @@ for nf in fits:
     _lib.smoother_d(d, y, u, v, th, method=1, want=())  # warm-up
     seq = _lib.smoother_d(d, y, u, v, th, method=0, want=want)
     best = {}
-    for chunk in (0, 16, 32, 64, 128):
+    for chunk in (0, 4, 8, 16, 32, 64, 128):
         r = _lib.smoother_d(d, y, u, v, th, method=1, chunk=chunk, want=want)
         best[chunk] = r["kernel_ms"]
     sc = _lib.smoother_d(d, y, u, v, th, method=1, want=want)
