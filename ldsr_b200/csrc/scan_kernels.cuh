@@ -344,6 +344,137 @@ __device__ __forceinline__ void filt_element(const double (&F)[D * D], const dou
     }
 }
 
+// a <- a combined with the element of ONE step (what filt_agg does L times per chunk), without forming that
+// element: the generic combine needs (I + C_a J_e)^-1, a d x d inverse, but a step with a scalar observation has
+// J_e = s w w' (w = (H F)', s = 1/S) and Sherman-Morrison gives it in closed form,
+//   (I + s C_a w w')^-1 = I - kappa g w',  g = C_a w,  kappa = s / (1 + s w'g),
+// which turns combine(a, e) into (K = Q H'/S the step's gain, A_e = F - K w', z = A_a' w, Y = C_a - kappa g g')
+//   A   <- F A_a - (K + kappa A_e g) z'
+//   b   <- A_e (t - kappa g (w't)) + c + K rr,            t = b_a + s rr g,  rr = r - H c
+//   C   <- A_e Y A_e' + Q - K (Q H')'
+//   eta <- eta_a + kappa (rr - w'b_a) z
+//   J   <- J_a + kappa z z'
+// (three d x d products and a dozen matrix-vector ones instead of eight products and an inverse; no element, no
+// inverse, a third of the live values -- filt_agg spilled 1 008 B per thread).  An unobserved step has J_e = 0,
+// eta_e = 0: A <- F A_a, b <- F b_a + c, C <- F C_a F' + Q, eta and J unchanged.  Same map as filt_combine(a,
+// filt_element(..)) in exact arithmetic.
+template <int D>
+__device__ __forceinline__ void filt_append_step(FiltElem<D> &a, const double (&F)[D * D], const double (&Q)[D * D],
+                                                 const double (&Cc)[D], double R, bool obs, double r,
+                                                 const double (&c)[D]) {
+    double FA[D * D], P[D * D], nC[D * D];
+    mm<D>(F, a.A, FA);
+    if (!obs) {
+        double nb[D];
+        mv<D>(F, a.b, nb);
+        mm<D>(F, a.C, P);
+        mmt<D>(P, F, nC);
+#pragma unroll
+        for (int i = 0; i < D * D; i++) {
+            a.A[i] = FA[i];
+            nC[i] += Q[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D * D; i++) a.C[i] = 0.5 * (nC[i] + nC[(i % D) * D + i / D]);
+#pragma unroll
+        for (int i = 0; i < D; i++) a.b[i] = nb[i] + c[i];
+        return;
+    }
+    double qh[D], w[D], S = R, hc = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double sq = 0.0, sw = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            sq = fma(Q[i * D + k], Cc[k], sq);
+            sw = fma(Cc[k], F[k * D + i], sw);
+        }
+        qh[i] = sq; // Q H'
+        w[i] = sw;  // (H F)'
+        hc = fma(Cc[i], c[i], hc);
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) S = fma(Cc[k], qh[k], S);
+    const double s = 1.0 / S, rr = r - hc;
+    double K[D], g[D], z[D];
+    mv<D>(a.C, w, g);
+    mtv<D>(a.A, w, z);
+    double wg = 0.0, wb = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        K[i] = qh[i] * s;
+        wg = fma(w[i], g[i], wg);
+        wb = fma(w[i], a.b[i], wb);
+    }
+    const double kappa = s / fma(s, wg, 1.0);
+    // b: A_e x = F x - K (w'x)
+    {
+        double t[D], Ft[D], wt = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) t[i] = fma(s * rr, g[i], a.b[i]);
+#pragma unroll
+        for (int i = 0; i < D; i++) wt = fma(w[i], t[i], wt);
+#pragma unroll
+        for (int i = 0; i < D; i++) t[i] = fma(-kappa * wt, g[i], t[i]);
+        wt = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) wt = fma(w[i], t[i], wt);
+        mv<D>(F, t, Ft);
+#pragma unroll
+        for (int i = 0; i < D; i++) a.b[i] = fma(K[i], rr - wt, Ft[i]) + c[i];
+    }
+    // eta, J (rank one)
+    {
+        const double ke = kappa * (rr - wb);
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            a.eta[i] = fma(ke, z[i], a.eta[i]);
+#pragma unroll
+            for (int j = 0; j < D; j++) a.J[i * D + j] = fma(kappa * z[i], z[j], a.J[i * D + j]);
+        }
+    }
+    // A = F A_a - (K + kappa A_e g) z',  A_e g = F g - K (w'g)
+    {
+        double Fg[D];
+        mv<D>(F, g, Fg);
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double col = fma(kappa, fma(-K[i], wg, Fg[i]), K[i]);
+#pragma unroll
+            for (int j = 0; j < D; j++) a.A[i * D + j] = fma(-col, z[j], FA[i * D + j]);
+        }
+    }
+    // C = A_e Y A_e' + Q - K qh',  Y = C_a - kappa g g' (symmetric), yv = Y w = g / (1 + s w'g)
+    //   A_e Y A_e' = P F' - (F yv) K' - K (F yv)' + (yv'w) K K',  P = F Y
+    {
+        double Y[D * D], yv[D], Fy[D];
+        const double sh = 1.0 / fma(s, wg, 1.0);
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            yv[i] = g[i] * sh;
+#pragma unroll
+            for (int j = 0; j < D; j++) Y[i * D + j] = fma(-kappa * g[i], g[j], a.C[i * D + j]);
+        }
+        mm<D>(F, Y, P);
+        mmt<D>(P, F, nC);
+        mv<D>(F, yv, Fy);
+        const double yw = wg * sh;
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                double x = nC[i * D + j] + Q[i * D + j];
+                x = fma(-Fy[i], K[j], x);
+                x = fma(-K[i], Fy[j], x);
+                x = fma(yw * K[i], K[j], x);
+                x = fma(-K[i], qh[j], x);
+                nC[i * D + j] = x;
+            }
+#pragma unroll
+        for (int i = 0; i < D * D; i++) a.C[i] = 0.5 * (nC[i] + nC[(i % D) * D + i / D]);
+    }
+}
+
 // ---- kernels --------------------------------------------------------------------------------
 // c_t = B u_{t-1}, dv_t = D v_t : one thread per (fit, t)
 template <int D> __global__ void scan_prep_kernel(const ScanParams P) {
@@ -388,24 +519,22 @@ template <int D> __global__ void scan_filt_agg_kernel(const ScanParams P) {
         const double yt = P.y[t];
         const bool obs = yt == yt;
         const double r = obs ? yt - P.dv[(size_t)f * P.T + t] : 0.0;
-        FiltElem<D> e;
         if (t == 0) { // (0, Xu_0, Vu_0, 0, 0): the ordinary update of the prior
-            vec_load<D>(th.mu1, e.b);
-            mat_load<D>(th.V1, e.C);
-            if (obs) meas_update<D>(Cc, th.R, r, e.b, e.C);
+            vec_load<D>(th.mu1, a.b);
+            mat_load<D>(th.V1, a.C);
+            if (obs) meas_update<D>(Cc, th.R, r, a.b, a.C);
 #pragma unroll
-            for (int i = 0; i < D * D; i++) e.A[i] = e.J[i] = 0.0;
+            for (int i = 0; i < D * D; i++) a.A[i] = a.J[i] = 0.0;
 #pragma unroll
-            for (int i = 0; i < D; i++) e.eta[i] = 0.0;
+            for (int i = 0; i < D; i++) a.eta[i] = 0.0;
         } else {
             double c[D];
             vec_load<D>(P.c + ((size_t)f * P.T + t) * D, c);
-            filt_element<D>(F, Q, Cc, th.R, obs, r, c, e);
+            if (t == t0)
+                filt_element<D>(F, Q, Cc, th.R, obs, r, c, a); // the chunk's first step: its element
+            else
+                filt_append_step<D>(a, F, Q, Cc, th.R, obs, r, c); // == filt_combine(a, element of step t)
         }
-        if (t == t0)
-            a = e;
-        else
-            filt_combine<D>(a, e);
     }
     a.store(P.fagg + ((size_t)f * P.n_chunks + ch) * FiltElem<D>::LEN);
 }
