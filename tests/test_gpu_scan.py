@@ -40,7 +40,9 @@ def random_model(rng, d, p, q, T, miss=0.3, lead=0):
 
 
 @pytest.mark.parametrize("d", [1, 2, 3, 4])
-@pytest.mark.parametrize("T,chunk", [(2, 0), (37, 8), (200, 0), (513, 16), (1000, 7)])
+# (2600, 4), (4133, 5), (6000, 0): 512 chunks and more -- the scan stages run as 32 groups per fit in three launches
+# (group totals, one-warp scan of the totals, apply), with ragged last groups; 6000 with the automatic chunk length
+@pytest.mark.parametrize("T,chunk", [(2, 0), (37, 8), (200, 0), (513, 16), (1000, 7), (2600, 4), (4133, 5), (6000, 0)])
 def test_scan_and_sequential_match_oracle(d, T, chunk):
     rng = np.random.default_rng(1000 * d + T)
     p, q = 5, 4
