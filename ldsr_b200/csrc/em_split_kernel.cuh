@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) em_split_kernel(const SplitPara
         ti = (int)blockIdx.x + seg * (int)gridDim.x;
         if (ti >= n_tasks) break;
     }
+    LDSR_CHECK(ti >= 0 && ti < n_tasks && n_it >= 1 && n_it <= P.chunk); // my segment is a piece of one task's chunk
     if (seg > 0) __syncthreads(); // the previous task's shared memory is dead
     if (wait_first) {
         if (threadIdx.x == 0) flag_wait(SP.flags + ti, SP.epoch);
