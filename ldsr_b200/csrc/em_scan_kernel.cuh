@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
     LDSR_STATIC_SMEM(double, S1[SCAN_MAX_WARPS * 4]);  // variance-map totals of the warps
     LDSR_STATIC_SMEM(double, S2[SCAN_MAX_WARPS * 2]);  // mean-map totals
     LDSR_STATIC_SMEM(double, S3[SCAN_MAX_WARPS]);      // likelihood partial sums
+    LDSR_STATIC_SMEM(double, S3M[SCAN_MAX_WARPS]);     // prod Sigma of the warps: mantissa product ...
+    LDSR_STATIC_SMEM(int, S3E[SCAN_MAX_WARPS]);        // ... and exponent sum
+    LDSR_STATIC_SMEM(double, S_LIK[1]);                // the iteration's likelihood and whether the fit goes on
+    LDSR_STATIC_SMEM(int, S_LIVE[1]);
     LDSR_STATIC_SMEM(double, S4[SCAN_MAX_WARPS * 3]);  // backward-map totals
     LDSR_STATIC_SMEM(double, S5[SCAN_MAX_WARPS * SCAN_SUM_ROW]); // M-step partial sums [warp][NSP]
     LDSR_STATIC_SMEM(double, TOTS[2 * SCAN_SUM_ROW]);            // their totals, one copy per M-step warp
@@ -319,6 +323,7 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         double Kg[L], Jg[L], Lg[L], g0[L], gP[L]; // kept for P4
         double Pth, qth;                           // my affine map of the mean
         double acc_l0, acc_l1, acc_l2;             // sum_obs delta^2/Sigma = l0 - 2 C x l1 + C^2 x^2 l2
+        double dratio;                             // prod_obs Sigma over my steps
         double PJ, G0, GG, Lc;                     // my backward map
         {
             // gains: the variance in homogeneous coordinates (n, d), all reciprocals after the chain
@@ -383,11 +388,9 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
             }
             Pth = Pc[L];
             qth = q[L];
-            // sum_obs log Sigma = log prod Sigma = log(d_end / d_in).  Branch-free, in every thread: a warp whose
-            // steps are unobserved would otherwise wait at the next barrier for the others' logarithm.
-            // (Multiplying the ratios up over the CTA -- mantissas and exponents apart -- and taking ONE logarithm
-            // after barrier 3, with the stop rule applied after barrier 4, was measured: 2.73 against 2.67 ms.)
-            acc_l0 += log(bits ? dend * fast_rcp(di) : 1.0);
+            // sum_obs log Sigma = log prod Sigma = log(d_end / d_in): the ratios are multiplied up over the CTA
+            // (mantissas and exponents apart) and ONE thread takes ONE logarithm, beside the M-step (see there)
+            dratio = bits ? dend * fast_rcp(di) : 1.0;
         }
         SCAN_MARK(4);
         double xin, xend; // prior mean entering my steps; prior mean of the virtual step after the last
@@ -427,8 +430,19 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         {
             const double tC = Cc * xin;
             const double accw = scan_warp_sum(fma(tC, fma(tC, acc_l2, -2.0 * acc_l1), acc_l0));
+            // prod Sigma over the warp: 32 mantissas in [1,2) (product < 2^32) and the sum of the exponents
+            const int dhi = __double2hiint(dratio);
+            int pe = ((dhi >> 20) & 0x7ff) - 1023;
+            double pm = __hiloint2double((dhi & 0x000fffff) | 0x3ff00000, __double2loint(dratio));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pm *= __shfl_xor_sync(FULL, pm, o);
+                pe += __shfl_xor_sync(FULL, pe, o);
+            }
             scan_backward_incl(PJs, gs, Ls, lane);
             if (lane == 0) {
+                S3M[warp] = pm;
+                S3E[warp] = pe;
                 S3[warp] = accw;
                 S4[warp * 3 + 0] = PJs;
                 S4[warp * 3 + 1] = gs;
@@ -444,25 +458,8 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         }
         SCAN_MARK(7);
         __syncthreads(); // B3
-        double acc = 0.0;
-#pragma unroll
-        for (int w = 0; w < SCAN_MAX_WARPS; ++w) acc += w < nw ? S3[w] : 0.0; // warp order: the same sum in every thread
-        // EM.cpp:122-124: (-n/2 log 2pi - acc/2) / n, the division by n as a multiplication by its (once per task,
-        // correctly rounded) reciprocal: it sits on the critical path of every thread
-        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
-
-        // ================= stop rule (EM.cpp:259-275): the same in every thread =================
-        if constexpr (!EMIT) {
-            lik = lik_new;
-            ne += 1;
-            if (threadIdx.x == 0 && P.liks) P.liks[(size_t)P.f_user[fit] * P.niter + (ne - 1)] = lik_new;
-            {
-                const bool conv = (ne >= 3) && (fabs(lik_new - l1) < P.tol) && (fabs(l1 - l2) < P.tol);
-                if (conv || ne >= P.niter) live = false;
-            }
-            if (!live) break;
-        }
-
+        // (the likelihood and the stop rule are computed by one thread beside the M-step and applied after barrier 5:
+        //  nothing of the backward pass depends on them)
         SCAN_MARK(8);
         // ---- smoothed state entering my steps from the right: the chain starts from the prior of the
         //      virtual step after the last one, Xs_{T-1} = Xu_{T-1} (EM.cpp:94-95)
@@ -673,7 +670,35 @@ __global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const E
         }
         }
         SCAN_MARK(12);
-        __syncthreads(); // B5: the new theta is published
+        // ---- likelihood (EM.cpp:122-124) and stop rule (EM.cpp:259-275): the last thread of the last warp, while
+        //      threads 0 and 32 do the M-step -- off everybody's critical path (as part of every thread's own
+        //      instruction stream the logarithm alone cost 230 cycles of an iteration of 5 100).  The M-step is
+        //      speculative: when the fit has converged or is out of iterations, its theta is simply not loaded.
+        if constexpr (!EMIT) {
+            if (warp == nw - 1 && lane == 31) {
+                double acc = 0.0, pmt = 1.0; // in warp order
+                int pet = 0;
+#pragma unroll
+                for (int w = 0; w < SCAN_MAX_WARPS; ++w) {
+                    acc += w < nw ? S3[w] : 0.0;
+                    pmt *= w < nw ? S3M[w] : 1.0; // < 2^(32 SCAN_MAX_WARPS)
+                    pet += w < nw ? S3E[w] : 0;
+                }
+                acc += fma((double)pet, 0.693147180559945309417, log_pos(pmt));
+                const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
+                if (P.liks) P.liks[(size_t)P.f_user[fit] * P.niter + ne] = lik_new;
+                const bool conv = (ne + 1 >= 3) && (fabs(lik_new - l1) < P.tol) && (fabs(l1 - l2) < P.tol);
+                S_LIK[0] = lik_new;
+                S_LIVE[0] = (conv || ne + 1 >= P.niter) ? 0 : 1;
+            }
+        }
+        __syncthreads(); // B5: the new theta and the stop decision are published
+        if constexpr (!EMIT) {
+            lik = S_LIK[0];
+            ne += 1;
+            live = S_LIVE[0] != 0;
+            if (!live) break; // theta stays as it entered this iteration
+        }
         load_theta<PQ>(th, THS);
         l2 = l1;
         l1 = lik;

@@ -76,6 +76,33 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
+// Natural logarithm of a POSITIVE NORMAL double (no zero / subnormal / infinity / NaN handling), 2 ulp, straight-line
+// code.  x = 2^e m with m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m - 1)/(m + 1), |s| <= 0.172: odd series
+// up to s^21.
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    const bool upper = hi >= 0x3ff6a09e; // m > sqrt(2) (to 20 bits): halve it
+    hi = upper ? hi - 0x00100000 : hi;
+    e = upper ? e + 1 : e;
+    const double m = __hiloint2double(hi, lo);
+    const double s = (m - 1.0) * fast_rcp(m + 1.0), z = s * s;
+    double p = 1.0 / 21.0;
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    const double r = fma(2.0 * s * z, p, 2.0 * s);
+    return fma((double)e, 0.693147180559945309417, r);
+}
+
 template <int PQ> __device__ __forceinline__ double dot_row(const double (&w)[PQ], const double *__restrict__ row) {
     double s = 0.0;
 #pragma unroll
