@@ -749,27 +749,54 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         __syncthreads(); // B2
         LDSR_PHASE_MARK(3);
 
-        // ---- chain the pieces: x_in of every piece, likelihood (identical in every warp)
-        double gk[NP];
-        double xin = 0.0, Xr = 0.0, Vr = 0.0; // prior mean entering my piece; prior right of it
-        double acc = 0.0;
-        double x = th.mu1; // prior of step 0 (EM.cpp:48)
-        double vend = th.V1;
+        // ---- chain the pieces: the prior mean entering every piece, the likelihood, the smoothed state entering
+        //      every piece from the right.  ONE warp walks the two chains and publishes what each piece needs in the
+        //      piece summaries themselves (their P, q, l0, l1, l2 are dead once read): the chains are serial and short,
+        //      and eight warps walking them redundantly were 8 x 80 shared-memory loads of 256 B through one port,
+        //      1 400 - 2 900 cycles of an iteration (profiles/em_r02_wide_v4_balance_and_clocks.txt).
+        if (warp == 0) {
+            double gk[NP];
+            double acc = 0.0;
+            double x = th.mu1; // prior of step 0 (EM.cpp:48)
+            double vend = th.V1;
 #pragma unroll
-        for (int pj = 0; pj < NP; ++pj) {
-            const double *o = CH + (size_t)pj * WIDE_NCH * 32;
-            if (pj == warp) xin = x;
-            gk[pj] = fma(o[7 * 32], x, o[6 * 32]);
-            const double tC = th.C * x;
-            acc += fma(tC, fma(tC, o[4 * 32], -2.0 * o[3 * 32]), o[2 * 32]);
-            x = fma(o[0 * 32], x, o[1 * 32]);
-            vend = o[9 * 32];
-            if (pj == warp) {
-                Xr = x;
-                Vr = vend;
+            for (int pj = 0; pj < NP; ++pj) {
+                double *o = CH + (size_t)pj * WIDE_NCH * 32;
+                const double x_in = x;
+                gk[pj] = fma(o[7 * 32], x, o[6 * 32]);
+                const double tC = th.C * x;
+                acc += fma(tC, fma(tC, o[4 * 32], -2.0 * o[3 * 32]), o[2 * 32]);
+                x = fma(o[0 * 32], x, o[1 * 32]);
+                vend = o[9 * 32];
+                o[0 * 32] = x_in; // prior mean entering the piece
+                o[1 * 32] = x;    // prior mean of the first step right of it
+            }
+            // EM.cpp:122-124 (x 1/n, rounded once per task)
+            CH[4 * 32] = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs;
+            // the backward chain starts from the prior of the virtual step T: Xs_{T-1} = Xu + J (Xp_T - Xp_T) = Xu_{T-1}
+            // (EM.cpp:94-95)
+            double Xs = x, Vs = vend;
+#pragma unroll
+            for (int pj = NP - 1; pj >= 0; --pj) {
+                double *o = CH + (size_t)pj * WIDE_NCH * 32;
+                o[2 * 32] = Xs; // smoothed state of the first step right of the piece
+                o[3 * 32] = Vs;
+                const double pjv = o[5 * 32];
+                Xs = fma(pjv, Xs, gk[pj]);
+                Vs = fma(pjv * pjv, Vs, o[8 * 32]);
             }
         }
-        const double lik_new = (-0.5 * n_obs * LOG_2PI - 0.5 * acc) * inv_n_obs; // EM.cpp:122-124 (x 1/n, rounded once per task)
+        __syncthreads(); // B2b
+        const double lik_new = CH[4 * 32];
+        double xin, Xr, Vr, Xs1, Vs1; // prior mean entering my piece; prior right of it; smoothed state right of it
+        {
+            const double *o = CH + (size_t)warp * WIDE_NCH * 32;
+            xin = o[0 * 32];
+            Xr = o[1 * 32];
+            Vr = o[9 * 32];
+            Xs1 = o[2 * 32];
+            Vs1 = o[3 * 32];
+        }
 
         // ================= stop rule (EM.cpp:259-275) =================
         if (live) {
@@ -780,24 +807,6 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
             if (conv || ne >= P.niter) live = false;
         }
         if (!__any_sync(FULL, live)) break;
-
-        // ---- smoothed state entering my piece from the right.  The chain starts from the prior of
-        //      the virtual step T: Xs_{T-1} = Xu + J (Xp_T - Xp_T) = Xu_{T-1}   (EM.cpp:94-95)
-        double Xs1 = 0.0, Vs1 = 0.0;
-        {
-            double Xs = x, Vs = vend;
-#pragma unroll
-            for (int pj = NP - 1; pj >= 0; --pj) {
-                if (pj == warp) {
-                    Xs1 = Xs;
-                    Vs1 = Vs;
-                }
-                const double *o = CH + (size_t)pj * WIDE_NCH * 32;
-                const double pjv = o[5 * 32];
-                Xs = fma(pjv, Xs, gk[pj]);
-                Vs = fma(pjv * pjv, Vs, o[8 * 32]);
-            }
-        }
 
         LDSR_PHASE_MARK(17);
         // ================= P4: backward over my piece: scalar sums, Xs_t -> shared memory =================
