@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         // (1) totals: warp w adds the NW partial sums of the entries w, w + NW, ...
         double *const TOT = ST + (size_t)NW * NST * 32; // [NST]
         double *const ZW = TOT + (size_t)NST * 32;      // [3 PQ]: SvvInv Sxv | TuuInv Tux | TuuInv Tx1u
-#pragma unroll 1
+#pragma unroll 2
         for (int j = warp; j < NST; j += NW) {
             double a = ST[j * 32];
 #pragma unroll
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(NW * 32, 1) em_wide_kernel(const WideParams WP
         // (2) the three matrix-vector products of the block elimination (lds_math.cuh), one row per warp at a time
         {
             const double *__restrict__ svv_inv = gc + 2 + 2 * PQ;
-#pragma unroll 1
+#pragma unroll 2 // two rows in flight (measured: 1 -> 2: config 3 1.128 -> 1.117 s; 4: 1.125 s)
             for (int rr = warp; rr < 3 * PQ; rr += NW) {
                 const int which = rr / PQ, a = rr - which * PQ;
                 const double *__restrict__ m = (which == 0 ? svv_inv : tuu_inv) + a * PQ;
