@@ -457,22 +457,6 @@ __global__ void construct_rec_kernel(int n, int T, const double *__restrict__ X,
     mean[T + t] = sq / n;
 }
 
-// [rows][cols] -> [cols][rows] through a padded shared-memory tile.
-__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int cols) {
-    __shared__ double tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
-    }
-}
-
-
 // initial EM state: theta <- theta0, no E-step done, lik = NaN
 __global__ void init_state_kernel(int n_fits, int theta_len, const double *theta0, double *theta, double *l1,
                                   double *l2, double *lik, int *ne, int *done) {
