@@ -546,6 +546,28 @@ def test_tasks_shared_by_iterations_equal_separate_runs():
             assert np.array_equal(f[b["best"]], a["best"][half])
 
 
+def test_repeated_runs_of_the_shared_launches_are_bit_identical():
+    """Which CTA runs which iterations of which task depends on the run (hand-over between CTAs, CTAs that run ahead);
+    the results must not: 25 runs of the full 10 000-fit job (313 tasks on 296 CTAs, then ranked launches) and of a
+    12 000-fit job (375 tasks) give bit-identical theta, lik, iteration counts and selections -- a lost hand-over or
+    a stale state read would show as a difference."""
+    from ldsr_b200 import workloads as W
+    for folds, niter, reps in ((100, 1000, 25), (120, 330, 10)):
+        w = W.np_cv(folds, 100)
+        plan = _lib.Plan(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"])
+        ref = None
+        for _ in range(reps):
+            st = plan.em(niter=niter)
+            assert st["shared_slots"] > 0
+            r = plan.fetch(want_traj=False)
+            if ref is None:
+                ref = {k: np.array(r[k], copy=True) for k in ("theta", "lik", "iters", "best")}
+            else:
+                for k in ("lik", "iters", "best"):
+                    assert np.array_equal(r[k], ref[k]), k
+                assert np.array_equal(r["theta"], ref["theta"], equal_nan=True)
+
+
 def test_ranked_assignment_with_several_series_equals_separate_runs():
     """Five stations of narrow inputs, 6 000 fits = 190 tasks: more than one task per SM, so the co-resident
     grid deals the tasks by progress and lets early CTAs run ahead (the iterations a fit advances per launch
