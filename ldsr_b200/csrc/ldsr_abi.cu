@@ -201,7 +201,13 @@ struct ldsr_ctx {
 };
 
 // ---- plan -----------------------------------------------------------------------------------
-constexpr int SCAN_MAX_FITS = 600; // batches up to this size run the scan kernel (one CTA per fit) when it exists
+// Batches up to this size may run the scan kernel (one CTA per fit), `variant = 5` forces it up to here.  Chosen
+// automatically below the measured crossover with the batched kernels (tools/profile_crossover.py, NP-413, 1000
+// iterations: scan 3.1 / 4.6 / 6.1 ms for 200 / 400 / 600 fits, +0.75 ms per 100, against 10.6 ms for the time-split
+// kernel whatever the batch up to 4 700 fits): 1000 fits of narrow inputs; 500 of wide ones (one CTA per SM:
+// 4.4 ms per wave of 148 against 16.3 ms for the wide-input kernel)
+constexpr int SCAN_MAX_FITS = 1000;
+inline int scan_auto_fits(int pq) { return pq <= 4 ? 1000 : 500; }
 constexpr size_t COUNTS_CAP = 256; // (tasks, live fits) per chunk: room for 128 chunks without regrowing
 struct ldsr_plan {
     int device = 0;
@@ -668,7 +674,11 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     //   the kernel of wide inputs (PQ >= 5) whenever its shared-memory plan fits.
     // variant: 0 auto, 1 lane kernel with global checkpoints, 2 lane kernel, 3 time-split kernel,
     //          4 wide-input time-split kernel
-    const int variant = opt ? opt->variant : 0;
+    // 6 = automatic, but never the small-batch scan kernel: what the workers of a sharded call get when the WHOLE
+    // batch is above the scan kernel's range, so that the kernel family -- and with it the last bits of the
+    // results -- does not depend on the number of devices the batch is shared by
+    const bool no_scan = opt && opt->variant == 6;
+    const int variant = (opt && !no_scan) ? opt->variant : 0;
     const int max_uunits = (P->max_T + P->kt->split_uw - 1) / P->kt->split_uw;
     const size_t split_sm = blob_sm + split_smem_bytes(P->PQ, P->kt->split_nw, P->max_units, max_uunits);
     const size_t wide_blob_sm = wide_blob_smem(P->max_blob_bytes, P->max_T);
@@ -693,7 +703,8 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
     if (P->PQ >= SCAN_SHARE_UV_FROM)
         for (const SeriesDev &S : P->h_series) scan_uv_ok = scan_uv_ok && S.same_uv != 0 && S.has_u != 0;
     const bool scan_ok = P->kt->scan_l > 0 && scan_uv_ok && P->max_T <= scan_steps * 32 * SCAN_MAX_WARPS;
-    const bool use_scan = scan_ok && nf <= SCAN_MAX_FITS && (variant == 0 || variant == 5);
+    const bool use_scan = scan_ok && !no_scan &&
+                          ((variant == 0 && nf <= scan_auto_fits(P->PQ)) || (variant == 5 && nf <= SCAN_MAX_FITS));
     if (variant == 5 && !use_scan)
         return fail(LDSR_ERR_UNSUPPORTED,
                     "variant 5 (scan kernel) needs input width <= %d, T <= %d (%d and v == u for width > 4) and at most %d fits",
@@ -1324,6 +1335,15 @@ static Err em_batch(ldsr_ctx *ctx, const ldsr_batch *b, int niter, double tol, c
     if (opt) wopt = *opt;
     wopt.poll = nullptr;
     wopt.poll_arg = nullptr;
+    if (wopt.variant == 0) { // the kernel follows the whole batch, not the shard (see plan_em, variant 6)
+        int width = 1;
+        for (int s = 0; s < b->n_series; s++) {
+            if (b->u && b->u[s]) width = std::max(width, b->p[s]);
+            if (b->v && b->v[s]) width = std::max(width, b->q[s]);
+        }
+        const KernelTable *kt_all = kernel_table_for(width);
+        if (kt_all && b->n_fits > scan_auto_fits(kt_all->pq)) wopt.variant = 6;
+    }
     const bool caller_polls = opt && opt->poll;
     std::vector<SubBatch> subs(nd);
     std::vector<Err> errs(nd);
