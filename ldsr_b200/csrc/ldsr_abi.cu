@@ -204,10 +204,10 @@ struct ldsr_ctx {
 // Batches up to this size may run the scan kernel (one CTA per fit), `variant = 5` forces it up to here.  Chosen
 // automatically below the measured crossover with the batched kernels (tools/profile_crossover.py, NP-413, 1000
 // iterations: scan 3.1 / 4.6 / 6.1 ms for 200 / 400 / 600 fits, +0.75 ms per 100, against 10.6 ms for the time-split
-// kernel whatever the batch up to 4 700 fits): 1000 fits of narrow inputs; 500 of wide ones (one CTA per SM:
-// 4.4 ms per wave of 148 against 16.3 ms for the wide-input kernel)
+// kernel whatever the batch up to 4 700 fits): 1000 fits of narrow inputs; 900 of wide ones (p = q = 10, T = 400:
+// 3.8 / 5.9 / 10.8 / 13.3 ms for 100 / 300 / 600 / 800 fits against 15.9 ms for the wide-input kernel)
 constexpr int SCAN_MAX_FITS = 1000;
-inline int scan_auto_fits(int pq) { return pq <= 4 ? 1000 : 500; }
+inline int scan_auto_fits(int pq) { return pq <= 4 ? 1000 : 900; }
 constexpr size_t COUNTS_CAP = 256; // (tasks, live fits) per chunk: room for 128 chunks without regrowing
 struct ldsr_plan {
     int device = 0;
