@@ -118,7 +118,7 @@ typedef struct {
                             lane-per-fit kernel); 1 = lane-per-fit kernel with checkpoints in global
                             memory; 2 = lane-per-fit kernel; 3 = time-split kernel, 4 = wide-input
                             time-split kernel, 5 = small-batch scan kernel (one CTA per fit; auto for
-                            up to 1000 fits of width <= 4, 900 of width 5..10), or LDSR_ERR_UNSUPPORTED;
+                            up to 1200 fits of width <= 4, 900 of width 5..10), or LDSR_ERR_UNSUPPORTED;
                             6 = auto without the scan kernel (what a sharded call gives its workers when
                             the whole batch is above that range).  DESIGN.md section 4. */
     int trace_liks;      /* ldsr_plan_em only: record the likelihood trace so that

@@ -138,8 +138,12 @@ __device__ __forceinline__ double scan_vrow(const double (&u)[N], const double (
 #define SCAN_MARK(kk) ((void)0)
 #endif
 
-template <int PQ, int L, bool EMIT = false>
-__global__ void __launch_bounds__(SCAN_MAX_WARPS * 32, 1) em_scan_kernel(const EmParams P) {
+// DENSE = true: compiled for three CTAs of at most 128 threads per SM (168 registers, 32 B of stack at PQ = 3) instead
+// of two (244 registers): for batches of more than two fits per SM the third resident CTA hides more latency
+// than the spills cost (NP-413, 1000 iterations: 400 / 900 fits 4.63 -> 3.92 / 8.76 -> 7.49 ms), for smaller
+// ones it is 2.5 % slower (200 fits 3.11 -> 3.19 ms) and not used.
+template <int PQ, int L, bool EMIT = false, bool DENSE = false>
+__global__ void __launch_bounds__(DENSE ? 128 : SCAN_MAX_WARPS * 32, DENSE ? 3 : 1) em_scan_kernel(const EmParams P) {
     static_assert(L == 1 || L == 2 || L == 4 || L == 8, "steps per thread");
     constexpr int NS = scan_nsum<PQ>(), NSP = scan_nsum_pad<PQ>();
     static_assert(NS <= 48 && NSP <= SCAN_SUM_ROW, "7 + 3 PQ sums are reduced as 32 + 16 values at most");

@@ -166,10 +166,15 @@ template <int PQV> struct ScanLaunch<PQV, true> {
         if (steps_per_thread == 2) {
             em_scan_kernel<PQV, 2><<<n_tasks, threads, 0, st>>>(p);
         } else if (steps_per_thread == 4) {
-            if constexpr (PQV <= 4)
-                em_scan_kernel<PQV, 4><<<n_tasks, threads, 0, st>>>(p);
-            else
+            if constexpr (PQV <= 4) {
+                // p.mode = 1: more than two fits per SM (plan_em): the build for three CTAs per SM, if the block fits it
+                if (p.mode == 1 && threads <= 128)
+                    em_scan_kernel<PQV, 4, false, true><<<n_tasks, threads, 0, st>>>(p);
+                else
+                    em_scan_kernel<PQV, 4><<<n_tasks, threads, 0, st>>>(p);
+            } else {
                 return cudaErrorNotSupported; // wide inputs: two steps per thread only (registers)
+            }
         } else {
             return cudaErrorNotSupported;
         }

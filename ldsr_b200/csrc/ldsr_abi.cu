@@ -202,12 +202,13 @@ struct ldsr_ctx {
 
 // ---- plan -----------------------------------------------------------------------------------
 // Batches up to this size may run the scan kernel (one CTA per fit), `variant = 5` forces it up to here.  Chosen
-// automatically below the measured crossover with the batched kernels (tools/profile_crossover.py, NP-413, 1000
-// iterations: scan 3.1 / 4.6 / 6.1 ms for 200 / 400 / 600 fits, +0.75 ms per 100, against 10.6 ms for the time-split
-// kernel whatever the batch up to 4 700 fits): 1000 fits of narrow inputs; 900 of wide ones (p = q = 10, T = 400:
-// 3.8 / 5.9 / 10.8 / 13.3 ms for 100 / 300 / 600 / 800 fits against 15.9 ms for the wide-input kernel)
-constexpr int SCAN_MAX_FITS = 1000;
-inline int scan_auto_fits(int pq) { return pq <= 4 ? 1000 : 900; }
+// automatically below the measured crossover with the batched kernels (tools/profile_crossover.py, profiles/
+// scan_r02_crossover.txt; NP-413, 1000 iterations: scan 3.1 / 3.9 / 5.8 / 7.5 / 9.5 / 10.1 / 10.8 ms for 200 / 400 /
+// 600 / 900 / 1200 / 1300 / 1400 fits against 10.3-10.4 ms for the time-split kernel whatever the batch up to
+// 4 700 fits): 1200 fits of narrow inputs; 900 of wide ones (p = q = 10, T = 400: 3.8 / 5.9 / 10.8 / 13.3 ms for
+// 100 / 300 / 600 / 800 fits against 15.9 ms for the wide-input kernel)
+constexpr int SCAN_MAX_FITS = 1500;
+inline int scan_auto_fits(int pq) { return pq <= 4 ? 1200 : 900; }
 constexpr size_t COUNTS_CAP = 256; // (tasks, live fits) per chunk: room for 128 chunks without regrowing
 struct ldsr_plan {
     int device = 0;
@@ -861,6 +862,7 @@ static Err plan_em(ldsr_plan *P, int niter, double tol, const ldsr_options *opt,
         }
         if (use_scan) {
             ep.max_seg = P->max_T; // the scan kernel sizes its block from the longest series
+            ep.mode = nf > 2 * P->n_sm ? 1 : 0; // more than two fits per SM: the three-CTAs-per-SM build (em_scan_kernel.cuh)
             CU(P->kt->em_scan(ep, grid, scan_steps, st));
         } else if (use_wide) {
             WideParams wp;

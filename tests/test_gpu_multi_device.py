@@ -93,11 +93,11 @@ def test_sharded_call_with_two_series_of_different_width_and_trace():
 
 
 def test_kernel_choice_follows_the_whole_batch_not_the_shard():
-    """1 200 fits are above the small-batch scan kernel's automatic range, 600 per device are inside it: the workers
+    """1 400 fits are above the small-batch scan kernel's automatic range, 700 per device are inside it: the workers
     of the sharded call must take the kernel the whole batch takes, or the last bits of the results would
     depend on the number of devices."""
     _need2()
-    ser, gs, held, fg, th0 = _job(n_folds=12, n_rest=100)
+    ser, gs, held, fg, th0 = _job(n_folds=14, n_rest=100)
     a = _lib.em_batch(ser, gs, held, fg, th0, 150, 1e-5, n_devices=1)
     b = _lib.em_batch(ser, gs, held, fg, th0, 150, 1e-5, n_devices=2)
     for k in ("theta", "lik", "iters", "best", "X", "Y", "V", "J"):

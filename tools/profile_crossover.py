@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ldsr_b200 import _lib, workloads as W  # noqa: E402
 
 wide = len(sys.argv) > 1 and sys.argv[1] == "wide"  # one synthetic station, ten inputs, T = 400 (config 3's shape)
-for folds in ((5, 10, 15, 20, 30, 40) if wide else (10, 20, 30, 45, 60, 90, 120)):
+for folds in ((5, 10, 15, 20, 30, 40) if wide else (10, 20, 30, 45, 55, 60, 65, 70, 90, 120)):
     w = W.synthetic_stations(n_stations=1, n_folds=folds, n_restarts=20) if wide else W.np_cv(folds, 20)
     plan = _lib.Plan(w["series"], w["group_series"], w["held"], w["fit_group"], w["theta0"])
     out = []
